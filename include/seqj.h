@@ -1,0 +1,171 @@
+/*
+ * seqj.h -- C ABI of the B200-native Sequencer hot path (libseqj_b200.so).
+ *
+ * The reference (turingtest37/SequencerJ.jl) is pure Julia and has no FFI of its own; this ABI
+ * is what a Julia `ccall` (see INTEGRATION.md and sequencerj.jl_b200/julia/SequencerJB200.jl) or
+ * a Python ctypes binding (sequencerj.jl_b200/_lib.py) binds to replace the reference's hot
+ * path.  Each entry point cites the reference code it replaces (paths relative to the
+ * reference repository root).
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = ok, <0 = error class (SEQJ_E_*);
+ *     seqj_last_error(handle) returns a human-readable message for the last failure.
+ *   - the library owns handle/result objects; the caller owns every array buffer.
+ *   - matrices are passed exactly as Julia stores them: `A` is M x N column-major, i.e. object
+ *     (column) j is the contiguous run A[j*M .. j*M+M-1].  N x N matrices are column-major too
+ *     (for symmetric matrices this equals row-major).
+ *   - all vertex / column indices are 0-based on the C side; the Julia wrapper adds 1.
+ *   - calls are blocking; a handle is not thread-safe; there is no global state.
+ *   - there is NO CPU fallback: every compute entry point fails with SEQJ_E_CUDA when no
+ *     sm_100 device is usable.
+ */
+#ifndef SEQJ_H
+#define SEQJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEQJ_VERSION 100 /* 0.1.0 */
+
+/* status codes */
+#define SEQJ_OK 0
+#define SEQJ_E_BADARG (-1)
+#define SEQJ_E_CUDA (-2)
+#define SEQJ_E_NCCL (-3)
+#define SEQJ_E_OOM (-4)
+#define SEQJ_E_INTERNAL (-5)
+
+/* metric ids, in the order of the reference's ALL_METRICS (src/distancemetrics.jl:234-257) */
+#define SEQJ_L2 0     /* L2 = Distances.Euclidean(1e-7)   src/distancemetrics.jl:234 */
+#define SEQJ_EMD 1    /* WASS1D = EMD()                   src/distancemetrics.jl:247 */
+#define SEQJ_KLD 2    /* KLD = Distances.KLDivergence()   src/distancemetrics.jl:239 */
+#define SEQJ_ENERGY 3 /* ENERGY = Energy()                src/distancemetrics.jl:254 */
+
+/* phase timers returned by seqj_result_timings (milliseconds, CUDA events on the library's streams) */
+#define SEQJ_T_TOTAL 0    /* whole seqj_sequence call, device side (H2D .. results ready) */
+#define SEQJ_T_H2D 1      /* host -> device copy of A */
+#define SEQJ_T_PREP 2     /* normalise + prefix-scan kernels */
+#define SEQJ_T_DIST_L2 3  /* distance kernels per metric */
+#define SEQJ_T_DIST_EMD 4
+#define SEQJ_T_DIST_KLD 5
+#define SEQJ_T_DIST_ENERGY 6
+#define SEQJ_T_PRIM 7     /* batched dense Prim */
+#define SEQJ_T_TREE 8     /* root / elongation / BFS-tree kernels */
+#define SEQJ_T_COMBINE 9  /* eta-weighted accumulation */
+#define SEQJ_T_FUSE 10    /* proximity fuse + final MST / order */
+#define SEQJ_T_D2H 11     /* result copy-out */
+#define SEQJ_NTIMERS 12
+
+typedef struct seqj_handle seqj_handle;
+typedef struct seqj_result seqj_result;
+
+/* ---- lifecycle ----------------------------------------------------------------------- */
+
+int seqj_version(void);
+
+/* Create a handle driving `ndev` CUDA devices (devices == NULL or ndev <= 0: current device).
+ * Round 1 drives devices[0]; multi-GPU sharding is done one process per GPU above this ABI. */
+int seqj_create(seqj_handle** out, const int* devices, int ndev);
+void seqj_destroy(seqj_handle* h);
+const char* seqj_last_error(const seqj_handle* h);
+
+/* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
+int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
+
+/* ---- the hot call --------------------------------------------------------------------
+ * Replaces `_sequence(A, scales, metrics, grid)`  (src/sequencer.jl:184-276) for the metric
+ * instances of ALL_METRICS on the shared unit grid:  _splitnorm (:383-407), the metric x scale x
+ * chunk loop with `abs.(pairwise(alg, m; dims=2)) .+ eps` (:194-236), `_measure_dm` (:284-290)
+ * per chunk and per (metric, scale), the eta-weighted combination (:231-247), the proximity
+ * fuse `_weighted_p_matrix` (:310-328), `inv.(Pw)` (:269), the final `_measure_dm` (:271) and
+ * `unroll` (src/utils.jl:15-24).
+ *
+ * A          host pointer, M x N column-major, read-only.  The caller (Julia wrapper) has already
+ *            validated it and applied `clamp!(A, eps(), Inf)` (src/sequencer.jl:111,130).
+ * metric_ids caller order is kept (it fixes the order of groups, src/sequencer.jl:253-254).
+ * scales     number of chunks per column for each scale (src/sequencer.jl:389).
+ * eps_floor  the reference's `const eps = 1e-6` (src/distancemetrics.jl:3).
+ * l2_thresh  the reference's `L2THR = 1e-7`     (src/distancemetrics.jl:6).
+ * group_mask NULL, or nmetrics*nscales flags (metric-major): only groups with a non-zero flag
+ *            are computed and the final fuse is skipped (used to shard groups across processes;
+ *            finish with seqj_fuse).
+ */
+int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N,
+                  const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
+                  double eps_floor, double l2_thresh, const uint8_t* group_mask,
+                  seqj_result** out);
+
+/* Same, with A already resident on the handle's device (device pointer, same layout). */
+int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M, int64_t N,
+                      const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
+                      double eps_floor, double l2_thresh, const uint8_t* group_mask,
+                      seqj_result** out);
+
+/* Final fuse from per-group MSTs gathered by the caller: `_weighted_p_matrix` + `inv.` + final
+ * `_measure_dm` + `unroll` (src/sequencer.jl:266-273).  mst_* hold ngroups*(N-1) entries. */
+int seqj_fuse(seqj_handle* h, int64_t N, int ngroups, const double* eta_group,
+              const int32_t* mst_i, const int32_t* mst_j, const double* mst_w,
+              double eps_floor, seqj_result** out);
+
+/* ---- result copy-out ------------------------------------------------------------------
+ * Mirrors SequencerResult (src/sequencer.jl:13-20): EOSeg -> group chunks, EOAlgScale -> group,
+ * D / mst / eta / order -> final.  NULL output pointers are skipped. */
+int seqj_result_dims(const seqj_result* r, int64_t* N, int* ngroups);
+int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale, int* nchunks,
+                           int* computed);
+/* eta_chunk[nchunks], root_chunk[nchunks], parents_chunk[nchunks*N] (BFS-tree parent of each
+ * vertex, root -> itself): EOSeg[(alg, l)] = (etas, bfs trees)   (src/sequencer.jl:257) */
+int seqj_result_group_chunks(const seqj_result* r, int g, double* eta_chunk, int32_t* root_chunk,
+                             int32_t* parents_chunk);
+/* EOAlgScale[(alg, l)] = (eta_kl, BFS_kl) (src/sequencer.jl:258) plus the group's MST edges
+ * (i<j, weight), which feed `_weighted_p_matrix` */
+int seqj_result_group(const seqj_result* r, int g, double* eta, int32_t* root, int32_t* parents,
+                      int32_t* mst_i, int32_t* mst_j, double* mst_w);
+/* final: eta (elong), root (stidx), order[N] (src/utils.jl:15-24), parents[N], mst edges[N-1] */
+int seqj_result_final(const seqj_result* r, double* eta, int32_t* root, int32_t* order,
+                      int32_t* parents, int32_t* mst_i, int32_t* mst_j, double* mst_w);
+/* final distance matrix D (src/sequencer.jl:269) as triplets on the edge union (i<j); every
+ * other off-diagonal entry is +Inf and the diagonal is eps_floor. */
+int seqj_result_D_nnz(const seqj_result* r, int64_t* nnz);
+int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double* val);
+int seqj_result_timings(const seqj_result* r, double* ms /* SEQJ_NTIMERS */);
+/* number of kernels the library launched for this result */
+int seqj_result_launches(const seqj_result* r, int64_t* launches);
+void seqj_result_free(seqj_result* r);
+
+/* ---- unit-level entry points (each layer parity-testable in isolation) ---------------- */
+
+/* `_splitnorm(A, grid, scale)` (src/sequencer.jl:383-407) plus the ECDF on the shared unit grid
+ * (`ecdf` inside EMD/Energy, src/distancemetrics.jl:86,147).  Outputs are M x N column-major like
+ * A: P_out = normalised chunks stacked in row order, U_out = per-chunk CDFs.  nchunks_out = number
+ * of chunks (can be < scale).  Any output may be NULL. */
+int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M, int64_t N, int32_t scale,
+                   double* P_out, double* U_out, int32_t* nchunks_out);
+
+/* `abs.(pairwise(alg, m; dims=2)) .+ eps` (src/sequencer.jl:226) for one chunk `m` (m x N
+ * column-major).  normalize != 0 applies the _splitnorm column normalisation first.
+ * kl_full != 0 computes both triangles of the (asymmetric) KL matrix as Distances.pairwise does;
+ * otherwise the upper triangle is mirrored (what `Symmetric(dm)`, src/sequencer.jl:365, consumes).
+ * D_out is N x N. */
+int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m, int64_t N,
+                  int normalize, int kl_full, double eps_floor, double l2_thresh, double* D_out);
+
+/* `_measure_dm(D)` (src/sequencer.jl:284-290): `_mst` (:358-374; clamp to [eps, Inf], upper
+ * triangle wins), `_leastcentralpt` (:331), `elongation` (:348-354), `bfs_tree` (:288), and
+ * optionally `unroll` (src/utils.jl:15-24).  D is N x N column-major; +Inf marks a non-edge. */
+int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N, double eps_floor, double* eta,
+                    int32_t* root, int32_t* parents, int32_t* mst_i, int32_t* mst_j,
+                    double* mst_w, int32_t* order);
+
+/* `Dklms .+= clamp(eta .* Dklm, eps(), Inf)` over chunks, then `/ sum(etas)`
+ * (src/sequencer.jl:231-235,247).  Dchunks = n stacked N x N matrices. */
+int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, int n, int64_t N,
+                    double* Dkl_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQJ_H */

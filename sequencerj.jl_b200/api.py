@@ -1,0 +1,444 @@
+"""Host-side mirror of the SequencerJ API above the C ABI (include/seqj.h).
+
+Mirrors, name for name, what the reference exports (src/SequencerJ.jl:24-31) for the hot path:
+``sequence(A; scales, metrics, grid)`` (src/sequencer.jl:105-145), ``SequencerResult`` and its
+accessors ``D, mst, elong, order`` (:13-52), the metric constants ``L2, WASS1D, KLD, ENERGY,
+ALL_METRICS`` (src/distancemetrics.jl:234-257), ``EMD`` / ``Energy`` / ``emd`` / ``energy`` on the
+unit grid, ``elongation``, ``ensuregrid``, ``autoscale`` and ``prettyp``.  Julia is not installed
+in this image, so this Python module plays the role of the Julia wrapper in
+``sequencerj.jl_b200/julia/SequencerJB200.jl``; both are thin shells over the same C entry points.
+
+Differences from Julia, by design: indices are 0-based (the Julia wrapper adds 1); the input is
+converted to Float64 up front.  All compute happens in libseqj_b200.so on a
+B200; nothing here falls back to the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+logger = logging.getLogger("sequencerj_b200")
+
+EPS_FLOOR = 1e-6           # const ϵ            (src/distancemetrics.jl:3)
+L2THR = 1e-7               # const L2THR        (src/distancemetrics.jl:6)
+JULIA_EPS = 2.220446049250313e-16
+FIB = [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 5168]  # sequencer.jl:148
+
+
+@dataclass(frozen=True)
+class Metric:
+    """A metric instance as the reference passes to `sequence` (Distances.PreMetric objects)."""
+    id: int
+    name: str
+
+    def __repr__(self):
+        return self.name
+
+
+L2 = Metric(0, "Euclidean(1.0e-7)")        # Distances.Euclidean(L2THR)   distancemetrics.jl:234
+WASS1D = Metric(1, "EMD(nothing)")         # EMD()                        distancemetrics.jl:247
+KLD = Metric(2, "KLDivergence()")          # Distances.KLDivergence()     distancemetrics.jl:239
+ENERGY = Metric(3, "Energy(nothing)")      # Energy()                     distancemetrics.jl:254
+ALL_METRICS = (L2, WASS1D, KLD, ENERGY)    # distancemetrics.jl:257
+_BY_ID = {m.id: m for m in ALL_METRICS}
+
+_default_handle = None
+
+
+def default_handle() -> _lib.Handle:
+    global _default_handle
+    if _default_handle is None:
+        _default_handle = _lib.Handle()
+    return _default_handle
+
+
+# ------------------------------------------------------------------------------------------
+@dataclass
+class WeightedTree:
+    """Minimum spanning tree as an edge list (stands in for the SimpleWeightedGraph of the reference)."""
+    nv: int
+    src: np.ndarray
+    dst: np.ndarray
+    weight: np.ndarray
+
+    def edges(self):
+        return list(zip(self.src.tolist(), self.dst.tolist(), self.weight.tolist()))
+
+
+@dataclass
+class BFSTree:
+    """Directed BFS tree (parent -> child) rooted at the least central vertex; `parents[root] == root`."""
+    root: int
+    parents: np.ndarray
+
+    def outneighbors(self, v):
+        return [int(c) for c in np.nonzero(self.parents == v)[0] if c != self.root]
+
+    def edges(self):
+        return [(int(self.parents[c]), int(c)) for c in range(len(self.parents)) if c != self.root]
+
+
+class SequencerResult:
+    """Mirror of the reference's SequencerResult (src/sequencer.jl:13-20).
+
+    EOSeg[(metric, scale)]      = (etas, [BFSTree per chunk])
+    EOAlgScale[(metric, scale)] = (eta, BFSTree)
+    D, mst, eta (η), order      = final distance matrix, MST, elongation, column order (0-based)
+    """
+
+    def __init__(self, N, EOSeg, EOAlgScale, D_triplets, mst, eta, order, root, parents, timings, launches,
+                 group_msts):
+        self.N = N
+        self.EOSeg = EOSeg
+        self.EOAlgScale = EOAlgScale
+        self._D_triplets = D_triplets
+        self.mst = mst
+        self.eta = eta
+        self.η = eta
+        self.order = order
+        self.root = root
+        self.parents = parents
+        self.timings = timings
+        self.launches = launches
+        self.group_msts = group_msts
+        self._D = None
+
+    @property
+    def D(self):
+        """Dense final distance matrix: +Inf off the edge union, 1e-6 on the diagonal (sequencer.jl:269,360)."""
+        if self._D is None:
+            i, j, v = self._D_triplets
+            D = np.full((self.N, self.N), np.inf)
+            np.fill_diagonal(D, EPS_FLOOR)
+            D[i, j] = v
+            D[j, i] = v
+            self._D = D
+        return self._D
+
+    @property
+    def D_triplets(self):
+        return self._D_triplets
+
+    def __repr__(self):
+        return f"Sequencer Result: η = {self.eta:.4g}, order = {prettyp(self.order, 5)}"
+
+
+def D(r: SequencerResult):
+    return r.D
+
+
+def mst(r: SequencerResult):
+    return r.mst
+
+
+def elong(r: SequencerResult):
+    return r.eta
+
+
+def order(r: SequencerResult):
+    return r.order
+
+
+def prettyp(v, length: int = 3) -> str:
+    """src/utils.jl:48-53."""
+    v = list(v)
+    if len(v) < 7:
+        return ",".join(str(x) for x in v)
+    head = ",".join(str(x) for x in v[:length])
+    tail = ",".join(str(x) for x in v[len(v) - length:])
+    return head + "..." + tail
+
+
+def ensuregrid(A, grid=None):
+    """src/sequencer.jl:296-304. With the ALL_METRICS instances the grid is never used by the
+    distance functors; only its length is checked."""
+    M = A.shape[0]
+    if grid is None:
+        grid = np.arange(1, M + 1, dtype=np.float64)
+    grid = np.asarray(grid, dtype=np.float64)
+    assert len(grid) == M, f"Grid length must match dims 1 (row count) of A. Got grid:{len(grid)} and A:{M}"
+    return grid
+
+
+def _tuplify(x):
+    if isinstance(x, (Metric, int, np.integer)):
+        return (x,)
+    return tuple(x)
+
+
+def _prepare_input(A):
+    """Validation + clamp of `sequence` (src/sequencer.jl:111-130). Returns an (N, M) C-contiguous
+    float64 array = Julia column-major M x N. Clamps the caller's array in place when it is a
+    writable float64 array (the reference's clamp! is caller-visible)."""
+    if isinstance(A, (list, tuple)):
+        A = np.stack([np.asarray(c, dtype=np.float64) for c in A], axis=1)     # hcat(A...)
+    A = np.asarray(A)
+    if A.ndim == 1:
+        A = A.reshape(1, -1)
+    if A.ndim != 2:
+        raise ValueError("A must be a vector or an M x N matrix")
+    if not (np.all(np.isfinite(A)) and np.all(A >= 0)):
+        raise AssertionError("Input data cannot contain negative, NaN or infinite values.")
+    if A.dtype == np.float64 and A.flags.writeable:
+        np.maximum(A, JULIA_EPS, out=A)                                         # clamp!(A, eps(), typemax)
+        Af = A
+    else:
+        Af = np.maximum(A.astype(np.float64), JULIA_EPS)
+    return np.ascontiguousarray(Af.T)                                           # object-major (N, M)
+
+
+def _collect(handle, res, N, metrics, scales, want_final=True):
+    lib = handle.lib
+    ngroups = C.c_int()
+    n64 = C.c_int64()
+    handle.check(lib.seqj_result_dims(res, C.byref(n64), C.byref(ngroups)))
+    EOSeg, EOAlgScale, group_msts = {}, {}, {}
+    for g in range(ngroups.value):
+        met, sc, nch, comp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        handle.check(lib.seqj_result_group_info(res, g, C.byref(met), C.byref(sc), C.byref(nch), C.byref(comp)))
+        if not comp.value:
+            continue
+        key = (_BY_ID[met.value], sc.value)
+        etas = np.empty(nch.value)
+        roots = np.empty(nch.value, dtype=np.int32)
+        pars = np.empty((nch.value, N), dtype=np.int32)
+        handle.check(lib.seqj_result_group_chunks(res, g, _lib.dptr(etas), _lib.iptr(roots), _lib.iptr(pars)))
+        EOSeg[key] = (etas.tolist(), [BFSTree(int(roots[c]), pars[c]) for c in range(nch.value)])
+        eta = C.c_double(); root = C.c_int32()
+        par = np.empty(N, dtype=np.int32)
+        mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
+        handle.check(lib.seqj_result_group(res, g, C.byref(eta), C.byref(root), _lib.iptr(par), _lib.iptr(mi),
+                                           _lib.iptr(mj), _lib.dptr(mw)))
+        EOAlgScale[key] = (eta.value, BFSTree(root.value, par))
+        group_msts[key] = WeightedTree(N, mi, mj, mw)
+    tm = np.zeros(_lib.SEQJ_NTIMERS)
+    handle.check(lib.seqj_result_timings(res, _lib.dptr(tm)))
+    launches = C.c_int64()
+    handle.check(lib.seqj_result_launches(res, C.byref(launches)))
+    timings = dict(zip(_lib.TIMER_NAMES, tm.tolist()))
+    if not want_final:
+        return SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
+                               group_msts)
+    eta = C.c_double(); root = C.c_int32()
+    order_ = np.empty(N, dtype=np.int32); par = np.empty(N, dtype=np.int32)
+    mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
+    handle.check(lib.seqj_result_final(res, C.byref(eta), C.byref(root), _lib.iptr(order_), _lib.iptr(par),
+                                       _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw)))
+    nnz = C.c_int64()
+    handle.check(lib.seqj_result_D_nnz(res, C.byref(nnz)))
+    ti = np.empty(nnz.value, dtype=np.int32); tj = np.empty(nnz.value, dtype=np.int32); tv = np.empty(nnz.value)
+    handle.check(lib.seqj_result_D_triplets(res, _lib.iptr(ti), _lib.iptr(tj), _lib.dptr(tv)))
+    return SequencerResult(N, EOSeg, EOAlgScale, (ti, tj, tv), WeightedTree(N, mi, mj, mw), eta.value, order_,
+                           root.value, par, timings, launches.value, group_msts)
+
+
+def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None):
+    """`_sequence` (src/sequencer.jl:184-276) through the C ABI. At: (N, M) float64 C-contiguous host
+    array, or (with device_ptr) the shape only."""
+    handle = handle or default_handle()
+    N, M = At.shape
+    mids = np.array([m.id for m in metrics], dtype=np.int32)
+    scs = np.array(scales, dtype=np.int32)
+    res = C.c_void_p()
+    mask = None
+    if group_mask is not None:
+        mask = np.ascontiguousarray(group_mask, dtype=np.uint8).reshape(-1)
+        assert mask.size == len(mids) * len(scs)
+    maskp = mask.ctypes.data_as(_lib.c_u8p) if mask is not None else None
+    if device_ptr is not None:
+        st = handle.lib.seqj_sequence_dev(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
+                                          _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
+    else:
+        st = handle.lib.seqj_sequence(handle.h, At.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(mids), len(mids),
+                                      _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
+    handle.check(st)
+    try:
+        return _collect(handle, res, N, metrics, scales, want_final=group_mask is None)
+    finally:
+        handle.lib.seqj_result_free(res)
+
+
+def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=None) -> SequencerResult:
+    """Drop-in for `sequence(A; scales, metrics, grid)` (src/sequencer.jl:105-145).
+
+    A: M x N (rows = samples, columns = objects), non-negative and finite.
+    """
+    At = _prepare_input(A)
+    N, M = At.shape
+    logger.info("Sequencing data with\n    shape: (%d, %d)\n    metric(s): %s\n    scale(s): %s", M, N, metrics, scales)
+    ensuregrid(At.T, grid)
+    metrics = _tuplify(metrics) if metrics is not None else ALL_METRICS
+    for m in metrics:
+        if not isinstance(m, Metric):
+            raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY")
+    if scales is None:
+        scales = autoscale(At.T, metrics=metrics, grid=grid, handle=handle, rng=rng, _At=At)
+        logger.info("After autoscaling, best scale = %s", scales)
+    scales = tuple(int(s) for s in _tuplify(scales))
+    for s in scales:
+        assert 1 <= s <= M, f"Scale ({s}) cannot be larger than the number of data elements ({M})."
+    r = _sequence(At, scales, metrics, handle)
+    for (m, l), (eta, _) in r.EOAlgScale.items():
+        logger.info("%s at scale %d: η = %.4g", m, l, eta)
+    logger.info("Final: η = %.4g sequence = %s", r.eta, prettyp(r.order, 5))
+    return r
+
+
+def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None, rng=None, _At=None):
+    """src/sequencer.jl:158-179: run the Sequencer on a random p-sample of the columns for each
+    Fibonacci scale < M ÷ 10 and keep the scale with the largest elongation.  The reference samples
+    with an unseeded StatsBase.sample; pass `rng` (numpy Generator or seed) for reproducibility."""
+    At = _At if _At is not None else _prepare_input(A)
+    N, M = At.shape
+    nsamp = int(np.floor(N * p))
+    assert nsamp > 1, f"Matrix A contains too few columns ({N}) to sample with p = {p}. Use a larger p."
+    maxscale = M // 10
+    assert maxscale > 0, (f"Matrix A contains too few rows ({M}) for autoscale. The minimum is 10 rows. "
+                          "It is recommended to set scale=(1,).")
+    gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
+    idx = np.sort(gen.choice(N, size=nsamp, replace=False))                   # sample(..., ordered=true)
+    Asamp = np.ascontiguousarray(At[idx])
+    metrics = _tuplify(metrics)
+    best, max_eta = 1, 0.0
+    for s in [f for f in FIB if f < maxscale]:
+        r = _sequence(Asamp, (s,), metrics, handle)
+        if r.eta > max_eta:
+            max_eta, best = r.eta, s
+    return best
+
+
+# ---- unit-level wrappers (each layer testable in isolation) -----------------------------------
+def splitnorm(A, scale, handle=None):
+    """`_splitnorm` (src/sequencer.jl:383-407) + per-chunk ECDF. Returns (P, U, nchunks), both M x N."""
+    handle = handle or default_handle()
+    A = np.asarray(A, dtype=np.float64)
+    M, N = A.shape
+    if scale > M:
+        raise AssertionError(f"Scale ({scale}) cannot be larger than the number of data elements ({M}).")
+    At = np.ascontiguousarray(A.T)
+    P = np.empty((N, M)); U = np.empty((N, M))
+    nch = C.c_int32()
+    handle.check(handle.lib.seqj_splitnorm(handle.h, _lib.dptr(At), M, N, int(scale), _lib.dptr(P), _lib.dptr(U),
+                                           C.byref(nch)))
+    return P.T.copy(), U.T.copy(), nch.value
+
+
+def pairwise(metric, chunk, normalize=True, kl_full=True, eps_floor=EPS_FLOOR, l2_thresh=L2THR, handle=None):
+    """`abs.(pairwise(alg, m; dims=2)) .+ ϵ` (src/sequencer.jl:226) for one m x N chunk."""
+    handle = handle or default_handle()
+    mid = metric.id if isinstance(metric, Metric) else int(metric)
+    chunk = np.asarray(chunk, dtype=np.float64)
+    m, N = chunk.shape
+    Ct = np.ascontiguousarray(chunk.T)
+    Dm = np.empty((N, N))
+    handle.check(handle.lib.seqj_pairwise(handle.h, mid, _lib.dptr(Ct), m, N, int(bool(normalize)), int(bool(kl_full)),
+                                          eps_floor, l2_thresh, _lib.dptr(Dm)))
+    return Dm.T.copy()      # column-major N x N -> numpy [i, j]
+
+
+@dataclass
+class MeasureResult:
+    mst: WeightedTree
+    root: int
+    eta: float
+    bfs: BFSTree
+    order: np.ndarray = None
+
+
+def measure_dm(Dm, want_order=False, eps_floor=EPS_FLOOR, handle=None) -> MeasureResult:
+    """`_measure_dm(D)` (src/sequencer.jl:284-290) [+ `unroll`, src/utils.jl:15-24]."""
+    handle = handle or default_handle()
+    Dm = np.asarray(Dm, dtype=np.float64)
+    N = Dm.shape[0]
+    Dcm = np.ascontiguousarray(Dm.T)         # column-major storage of D
+    eta = C.c_double(); root = C.c_int32()
+    par = np.empty(N, dtype=np.int32)
+    mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
+    od = np.empty(N, dtype=np.int32) if want_order else None
+    handle.check(handle.lib.seqj_measure_dm(handle.h, _lib.dptr(Dcm), N, eps_floor, C.byref(eta), C.byref(root),
+                                            _lib.iptr(par), _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw),
+                                            _lib.iptr(od)))
+    return MeasureResult(WeightedTree(N, mi, mj, mw), root.value, eta.value, BFSTree(root.value, par), od)
+
+
+def elongation(Dm, handle=None) -> float:
+    """Elongation of the MST of a distance matrix (reference `elongation(g, startidx)`, sequencer.jl:348-354,
+    composed with `_mst` and `_leastcentralpt` as `_measure_dm` does)."""
+    return measure_dm(Dm, handle=handle).eta
+
+
+def accumulate(Dchunks, etas, handle=None):
+    """eta-weighted combination of chunk matrices (src/sequencer.jl:231-235,247)."""
+    handle = handle or default_handle()
+    Dchunks = np.asarray(Dchunks, dtype=np.float64)
+    n, N, _ = Dchunks.shape
+    Dt = np.ascontiguousarray(np.transpose(Dchunks, (0, 2, 1)))
+    etas = np.ascontiguousarray(etas, dtype=np.float64)
+    out = np.empty((N, N))
+    handle.check(handle.lib.seqj_accumulate(handle.h, _lib.dptr(Dt), _lib.dptr(etas), n, N, _lib.dptr(out)))
+    return out.T.copy()
+
+
+def fuse(N, etas, msts, eps_floor=EPS_FLOOR, handle=None) -> SequencerResult:
+    """Final fuse (src/sequencer.jl:266-273) from per-group (eta, MST) lists."""
+    handle = handle or default_handle()
+    G = len(etas)
+    etas = np.ascontiguousarray(etas, dtype=np.float64)
+    mi = np.ascontiguousarray(np.concatenate([t.src for t in msts]), dtype=np.int32)
+    mj = np.ascontiguousarray(np.concatenate([t.dst for t in msts]), dtype=np.int32)
+    mw = np.ascontiguousarray(np.concatenate([t.weight for t in msts]), dtype=np.float64)
+    res = C.c_void_p()
+    handle.check(handle.lib.seqj_fuse(handle.h, N, G, _lib.dptr(etas), _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw),
+                                      eps_floor, C.byref(res)))
+    try:
+        return _collect(handle, res, N, None, None, want_final=True)
+    finally:
+        handle.lib.seqj_result_free(res)
+
+
+class EMD:
+    """`EMD()` functor on the shared unit grid (src/distancemetrics.jl:16-21,46-50,90)."""
+
+    def __init__(self, grids=None):
+        if grids is not None:
+            raise NotImplementedError("explicit grids are a 'next' row (SURVEY.md §8f)")
+
+    def __call__(self, u, v=None):
+        return emd(u, v)
+
+
+class Energy:
+    """`Energy()` functor on the shared unit grid (src/distancemetrics.jl:121-132,158-162)."""
+
+    def __init__(self, grids=None):
+        if grids is not None:
+            raise NotImplementedError("explicit grids are a 'next' row (SURVEY.md §8f)")
+
+    def __call__(self, u, v=None):
+        return energy(u, v)
+
+
+def _pair(metric, u, v, handle=None):
+    u = np.asarray(u, dtype=np.float64)
+    v = u if v is None else np.asarray(v, dtype=np.float64)
+    if u.ndim != 1 or v.ndim != 1:
+        raise ValueError("Only 1-d data vectors are supported.")
+    if len(u) != len(v):
+        raise ValueError("u and v must have the same length on the shared unit grid")
+    Dm = pairwise(metric, np.stack([u, v], axis=1), normalize=False, eps_floor=0.0, handle=handle)
+    return float(Dm[0, 1])
+
+
+def emd(u, v=None, handle=None):
+    """`emd(u, v)` (src/distancemetrics.jl:101): EMD on the default unit grid."""
+    return _pair(WASS1D, u, v, handle)
+
+
+def energy(u, v=None, handle=None):
+    """`energy(u, v)` (src/distancemetrics.jl:172): Energy distance on the default unit grid."""
+    return _pair(ENERGY, u, v, handle)

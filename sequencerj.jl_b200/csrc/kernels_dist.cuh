@@ -1,0 +1,349 @@
+// K2/K3/K4: pairwise distance tile kernels.
+// Replace `abs.(pairwise(alg, m; dims=2)) .+ eps` (reference src/sequencer.jl:226) for the four
+// ALL_METRICS instances (src/distancemetrics.jl:234-257):
+//   Euclidean / Energy / KL : dense contractions -> FP64 tensor cores (DMMA.8x8x4), TMA-staged
+//                             operands (SWIZZLE_128B), fused norm / sqrt / entropy epilogue.
+//   EMD                     : L1 between CDFs, not a contraction -> CUDA-core FP64 (DADD x2 per
+//                             element), same TMA pipeline, register-tiled 8x8 per thread.
+// Both exploit symmetry: only tiles touching the upper triangle are computed, every value is
+// stored at (i,j) and mirrored to (j,i) (the reference evaluates i>j and mirrors for SemiMetrics;
+// for KL only the upper triangle is ever consumed, src/sequencer.jl:365).
+//
+// Tile = 64 (i) x 128 (j) x 16 (k) doubles, 4 warps (thread 0 also issues the TMA loads), 4 stages,
+// 2 CTAs / SM so that one CTA's epilogue overlaps the other's main loop.
+//
+// Accuracy: Gram forms cancel when two objects are close.  Entries whose Gram value is small
+// relative to the norms are recomputed directly (sum of squared differences / sum p log(p/q)) by a
+// fix-up kernel, exactly the Distances.jl `Euclidean(thresh)` recipe (src/distancemetrics.jl:6,234)
+// with a safer relative threshold, so results stay within 1e-9 of the reference's direct formulas
+// (Energy: src/distancemetrics.jl:219; KL: Distances.KLDivergence).
+#pragma once
+#include "common.cuh"
+
+namespace seqj {
+
+enum DistMode { MODE_L2 = 0, MODE_EMD = 1, MODE_KL = 2, MODE_ENERGY = 3 };
+
+struct DistParams {
+  int N;
+  int64_t ldD;          // leading dimension of every output matrix (doubles)
+  int64_t strideD;      // elements between consecutive chunk matrices in the batch
+  double* D;            // output of the first chunk in this launch
+  int nk;               // k-stages per chunk (= cl_pad / 16)
+  int cl_pad;
+  int chunk0;           // first chunk of this launch (blockIdx.y = chunk - chunk0)
+  const double* normA;  // [nchunks][ldn]: row norms (L2: sum p^2; Energy: sum Uc^2; KL: H)
+  int64_t ldn;
+  const int2* tiles;    // (i0, j0) of each CTA tile
+  double eps_floor;
+  double tau;           // relative fix-up threshold
+  int mirror;           // 1: write (i,j) and (j,i) for i<j only;  0: write every (i,j) (KL full)
+  int kl_swap;          // KL full mode: operand A = log P, B = P, so that D[r][c] = KL(p_c || p_r), i.e. the
+                        // row-major buffer is the column-major pairwise matrix of the C ABI
+  // fix-up list
+  int4* fix_list;       // (chunk, i, j, 0)
+  unsigned int* fix_count;
+  unsigned int fix_cap;
+  int* fix_overflow;
+};
+
+// rho: logical fragment row g -> physical row inside an 8-row group, chosen so that the two rows
+// read by one quarter-warp differ in bit 2 (=> their SWIZZLE_128B chunks never collide).
+__device__ __forceinline__ int rho(int g) { return (g >> 1) + ((g & 1) << 2); }
+
+template <int MODE>
+__global__ void __launch_bounds__(kTileThreads, 2)
+gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const TileSmem s = carve_tile_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int2 tile = p.tiles[blockIdx.x];
+  const int i0 = tile.x, j0 = tile.y;
+  const int chunk = p.chunk0 + blockIdx.y;
+  const int kbase = chunk * p.cl_pad;
+
+  if (threadIdx.x == 0) {
+    tile_barriers_init(s);
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0)
+    for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmA, &tmB, s, it, kbase, i0, j0);
+
+  // ---- consumers: warp w owns columns [32w, 32w+32) of the 64 x 128 tile ----
+  const int g = lane >> 2, t = lane & 3;
+  const int rg = rho(g);
+  // byte offset of this lane's 16 B chunk for k-half p (chunks 4p+t), swizzled by the row
+  uint32_t off[2];
+  off[0] = rg * 128 + (((0 + t) ^ rg) << 4);
+  off[1] = rg * 128 + (((4 + t) ^ rg) << 4);
+
+  double acc[8][4][2];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+  const uint32_t stages_u32 = smem_u32(s.stages);
+  for (int it = 0; it < p.nk; ++it) {
+    const int st = it % kStages;
+    const uint32_t ph = (it / kStages) & 1;
+    if (threadIdx.x == 0) tile_refill(&tmA, &tmB, s, it, p.nk, kbase, i0, j0);
+    mbar_wait(&s.full[st], ph);
+    const uint32_t sa = stages_u32 + st * kStageBytes;
+    const uint32_t sb = sa + kStageBytesA + warp * (32 * 128);
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      double2 fa[8], fb[4];
+#pragma unroll
+      for (int a = 0; a < 8; ++a) fa[a] = lds128(sa + a * 1024 + off[half]);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) fb[b] = lds128(sb + b * 1024 + off[half]);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a].x, fb[b].x);
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a].y, fb[b].y);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.empty[st]);
+  }
+
+  // ---- fused epilogue ----
+  // acc[a][b][e] = C[i][j] with i = i0 + 8a + rho(g), j = j0 + 32*warp + 8b + t + 4e
+  const double* __restrict__ nrm = p.normA + (int64_t)chunk * p.ldn;
+  double* __restrict__ D = p.D + (int64_t)blockIdx.y * p.strideD;
+  const int N = p.N;
+  double nj[4][2];
+#pragma unroll
+  for (int b = 0; b < 4; ++b)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int j = j0 + 32 * warp + 8 * b + t + 4 * e;
+      nj[b][e] = (j < N) ? nrm[j] : 0.0;
+    }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + 8 * a + rg;
+    if (i >= N) continue;
+    const double ni = nrm[i];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 32 * warp + 8 * b + t + 4 * e;
+        if (j >= N) continue;
+        if (p.mirror && i > j) continue;
+        double out;
+        if (i == j) {
+          out = p.eps_floor;     // pairwise sets the diagonal to 0, then .+ eps
+        } else {
+          const double c = acc[a][b][e];
+          bool flag;
+          double d;
+          if (MODE == MODE_KL) {
+            const double hh = p.kl_swap ? nj[b][e] : ni;
+            d = hh - c;                                   // H_i - sum_k p_ik log p_jk
+            flag = d < p.tau * fabs(hh);
+          } else {
+            const double selfterms = ni + nj[b][e];
+            const double v = selfterms - 2.0 * c;
+            flag = v < p.tau * selfterms;
+            d = sqrt(fmax(v, 0.0));
+            if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;   // sqrt(2) * sqrt(sum)
+          }
+          out = fabs(d) + p.eps_floor;
+          if (flag) {
+            const unsigned int idx = atomicAdd(p.fix_count, 1u);
+            if (idx < p.fix_cap) {
+              p.fix_list[idx] = make_int4((int)blockIdx.y, i, j, p.kl_swap);
+            } else {
+              *p.fix_overflow = 1;
+              out = -1.0;     // marker for the dense fix-up pass
+            }
+          }
+        }
+        D[(int64_t)i * p.ldD + j] = out;
+        if (p.mirror && i != j) D[(int64_t)j * p.ldD + i] = out;
+      }
+    }
+  }
+}
+
+// ---- EMD: sum_k |U_ik - U_jk| on CUDA cores -------------------------------------------------
+// thread T of the 128 consumers: ti = T>>4 (rows 8ti..8ti+7), tj = T&15 (cols (tj&7)+8(tj>>3)+16bb).
+__global__ void __launch_bounds__(kTileThreads, 2)
+emd_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const TileSmem s = carve_tile_smem(smem_raw);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int2 tile = p.tiles[blockIdx.x];
+  const int i0 = tile.x, j0 = tile.y;
+  const int chunk = p.chunk0 + blockIdx.y;
+  const int kbase = chunk * p.cl_pad;
+
+  if (threadIdx.x == 0) {
+    tile_barriers_init(s);
+    tma_prefetch_desc(&tmU);
+  }
+  __syncthreads();
+
+  if (threadIdx.x == 0)
+    for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmU, &tmU, s, it, kbase, i0, j0);
+
+  const int T = threadIdx.x;
+  const int ti = T >> 4, tj = T & 15;
+  const int jrow0 = (tj & 7) + 8 * (tj >> 3);   // + 16*bb ; (row & 7) == (tj & 7)
+  const int jsw = tj & 7;
+
+  double acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+  const uint32_t stages_u32 = smem_u32(s.stages);
+  for (int it = 0; it < p.nk; ++it) {
+    const int st = it % kStages;
+    const uint32_t ph = (it / kStages) & 1;
+    if (threadIdx.x == 0) tile_refill(&tmU, &tmU, s, it, p.nk, kbase, i0, j0);
+    mbar_wait(&s.full[st], ph);
+    const uint32_t sa = stages_u32 + st * kStageBytes + (8 * ti) * 128;
+    const uint32_t sb = stages_u32 + st * kStageBytes + kStageBytesA + jrow0 * 128;
+#pragma unroll 2
+    for (int c = 0; c < 8; ++c) {    // 16 B chunk = 2 consecutive k
+      double2 fb[8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
+#pragma unroll
+      for (int a = 0; a < 8; ++a) {
+        const double2 fa = lds128(sa + a * 128 + ((c ^ a) << 4));
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          acc[a][b] += fabs(fa.x - fb[b].x);
+          acc[a][b] += fabs(fa.y - fb[b].y);
+        }
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&s.empty[st]);
+  }
+
+  double* __restrict__ D = p.D + (int64_t)blockIdx.y * p.strideD;
+  const int N = p.N;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + 8 * ti + a;
+    if (i >= N) continue;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int j = j0 + jrow0 + 16 * b;
+      if (j >= N || i > j) continue;
+      const double out = (i == j) ? p.eps_floor : fabs(acc[a][b]) + p.eps_floor;
+      D[(int64_t)i * p.ldD + j] = out;
+      if (i != j) D[(int64_t)j * p.ldD + i] = out;
+    }
+  }
+}
+
+// ---- fix-up: direct recomputation of flagged entries (one warp per entry) ---------------------
+struct FixParams {
+  int mode;
+  int N;
+  int64_t ldD, strideD;
+  double* D;
+  const double* X;      // L2: P ; Energy: Uc ; KL: P
+  int64_t ldX;
+  int cl_pad, chunk0;
+  const int* m_of_chunk;   // valid length of every chunk
+  double eps_floor;
+  int mirror;
+  const int4* fix_list;
+  const unsigned int* fix_count;
+  unsigned int fix_cap;
+  const int* fix_overflow;
+  int kl_swap;
+};
+
+__device__ __forceinline__ double direct_pair(int mode, const double* __restrict__ xi, const double* __restrict__ xj,
+                                              int m, int lane) {
+  double sacc = 0.0;
+  if (mode == MODE_KL) {
+    for (int k = lane; k < m; k += 32) {
+      const double a = xi[k], b = xj[k];
+      sacc += a * log(a / b);               // Distances.KLDivergence term
+    }
+    return warp_sum(sacc);
+  }
+  for (int k = lane; k < m; k += 32) {
+    const double d = xi[k] - xj[k];
+    sacc += d * d;
+  }
+  sacc = warp_sum(sacc);
+  double d = sqrt(sacc);
+  if (mode == MODE_ENERGY) d = 1.4142135623730951 * d;
+  return d;
+}
+
+__global__ void __launch_bounds__(256) fixup_list_kernel(FixParams p) {
+  const int lane = threadIdx.x & 31;
+  const unsigned int nwarps = gridDim.x * (blockDim.x >> 5);
+  const unsigned int count = min(*p.fix_count, p.fix_cap);
+  for (unsigned int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); e < count; e += nwarps) {
+    const int4 f = p.fix_list[e];
+    const int chunk = p.chunk0 + f.x;
+    const int m = p.m_of_chunk[chunk];
+    const double* xr = p.X + (int64_t)f.y * p.ldX + (int64_t)chunk * p.cl_pad;
+    const double* xc = p.X + (int64_t)f.z * p.ldX + (int64_t)chunk * p.cl_pad;
+    const double d = f.w ? direct_pair(p.mode, xc, xr, m, lane) : direct_pair(p.mode, xr, xc, m, lane);
+    if (lane == 0) {
+      const double out = fabs(d) + p.eps_floor;
+      double* D = p.D + (int64_t)f.x * p.strideD;
+      D[(int64_t)f.y * p.ldD + f.z] = out;
+      if (p.mirror) D[(int64_t)f.z * p.ldD + f.y] = out;
+    }
+  }
+}
+
+// Dense fallback, only does work when the list overflowed: every entry marked -1 is recomputed.
+__global__ void __launch_bounds__(256) fixup_dense_kernel(FixParams p, int nchunks_batch) {
+  if (*p.fix_overflow == 0) return;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t total = (int64_t)nchunks_batch * p.N;
+  for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < total; r += nwarps) {
+    const int cb = (int)(r / p.N);
+    const int i = (int)(r % p.N);
+    const int chunk = p.chunk0 + cb;
+    const int m = p.m_of_chunk[chunk];
+    double* Drow = p.D + (int64_t)cb * p.strideD + (int64_t)i * p.ldD;
+    const double* xi = p.X + (int64_t)i * p.ldX + (int64_t)chunk * p.cl_pad;
+    for (int jb = 0; jb < p.N; jb += 32) {
+      const int j = jb + lane;
+      const bool marked = (j < p.N) && (Drow[j] < 0.0) && (!p.mirror || i < j);
+      unsigned int mask = __ballot_sync(0xffffffffu, marked);
+      while (mask) {
+        const int l = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const int jj = jb + l;
+        const double* xj = p.X + (int64_t)jj * p.ldX + (int64_t)chunk * p.cl_pad;
+        const double d = p.kl_swap ? direct_pair(p.mode, xj, xi, m, lane) : direct_pair(p.mode, xi, xj, m, lane);
+        if (lane == 0) {
+          const double out = fabs(d) + p.eps_floor;
+          Drow[jj] = out;
+          if (p.mirror) p.D[(int64_t)cb * p.strideD + (int64_t)jj * p.ldD + i] = out;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace seqj

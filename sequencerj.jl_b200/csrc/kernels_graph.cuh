@@ -1,0 +1,399 @@
+// K5-K8: graph layer.  Replaces `_measure_dm` (reference src/sequencer.jl:284-290):
+//   _mst            (:358-374, LightGraphs.kruskal_mst)      -> batched dense Prim, one CTA per graph
+//   _leastcentralpt (:331, closeness_centrality)             -> O(N) rerooted tree-distance sums
+//   elongation      (:334-354)                               -> hop depths by pointer jumping
+//   bfs_tree        (:288, src/bfs.jl:6-9)                   -> re-rooted parent vector
+//   unroll          (src/utils.jl:15-24)                     -> reverse DFS preorder, children ascending
+// plus the eta-weighted combine (:231-247) and the proximity fuse (:310-328, :269).
+//
+// The MST is unique whenever edge weights are distinct, so Prim and the reference's Kruskal agree;
+// ties are broken by (weight, vertex index) to keep the result deterministic.
+#pragma once
+#include <math_constants.h>
+#include "common.cuh"
+
+namespace seqj {
+
+constexpr int kPrimThreads = 1024;
+constexpr int kPrimUnroll = 8;
+constexpr double kJuliaEps = 2.220446049250313e-16;       // eps(Float64)
+constexpr double kFloatMax32 = 3.4028234663852886e38;     // floatmax(Float32)
+
+struct PrimParams {
+  const double* D;      // batch of dense symmetric N x N matrices (row r at D + r*ldD)
+  int64_t ldD, strideD;
+  int N;
+  double eps_floor;     // _mst clamps to [eps, Inf] (src/sequencer.jl:360)
+  int* parent;          // [graph][ldv]  Prim parent (start vertex 0 -> itself)
+  double* weight;       // [graph][ldv]  weight of the edge (v, parent[v])
+  int* order;           // [graph][ldv]  insertion order, order[0] = 0
+  int64_t ldv;
+  double* key_g;        // global scratch [graph][ldv] (used when the keys do not fit in smem)
+  int* from_g;
+  int use_smem;
+};
+
+__device__ __forceinline__ void argmin_combine(double& k, int& v, double ok, int ov) {
+  if (ok < k || (ok == k && ov < v)) { k = ok; v = ov; }
+}
+
+// HBM-bound: each of the N-1 steps streams one 8N-byte row; 8*N^2 bytes per graph in total.
+__global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
+  extern __shared__ double prim_sm[];
+  __shared__ double rk[2][32];
+  __shared__ int rv[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
+  const double* __restrict__ D = p.D + (int64_t)blockIdx.x * p.strideD;
+  double* key;
+  int* from;
+  if (p.use_smem) {
+    key = prim_sm;
+    from = reinterpret_cast<int*>(prim_sm + ((N + 1) & ~1));
+  } else {
+    key = p.key_g + gofs;
+    from = p.from_g + gofs;
+  }
+  int* parent = p.parent + gofs;
+  double* weight = p.weight + gofs;
+  int* order = p.order + gofs;
+
+  for (int v = tid; v < N; v += kPrimThreads) { key[v] = CUDART_INF; from[v] = 0; }
+  __syncthreads();
+  if (tid == 0) { key[0] = -1.0; parent[0] = 0; weight[0] = 0.0; order[0] = 0; }
+  __syncthreads();
+
+  int u = 0, par = 0;
+  for (int step = 1; step < N; ++step) {
+    const double* __restrict__ row = D + (int64_t)u * p.ldD;
+    double bk = CUDART_INF;
+    int bv = 0x7fffffff;
+    for (int base = tid; base < N; base += kPrimThreads * kPrimUnroll) {
+      double dv[kPrimUnroll];
+#pragma unroll
+      for (int r = 0; r < kPrimUnroll; ++r) {
+        const int v = base + r * kPrimThreads;
+        dv[r] = (v < N) ? __ldg(row + v) : CUDART_INF;
+      }
+#pragma unroll
+      for (int r = 0; r < kPrimUnroll; ++r) {
+        const int v = base + r * kPrimThreads;
+        if (v < N) {
+          double k = key[v];
+          if (k >= 0.0) {                       // not yet in the tree
+            const double d = fmax(dv[r], p.eps_floor);
+            if (d < k) { k = d; key[v] = d; from[v] = u; }
+            if (k < bk || bv == 0x7fffffff) { bk = k; bv = v; }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      argmin_combine(bk, bv, ok, ov);
+    }
+    if (lane == 0) { rk[par][warp] = bk; rv[par][warp] = bv; }
+    __syncthreads();
+    bk = rk[par][lane];
+    bv = rv[par][lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      argmin_combine(bk, bv, ok, ov);
+    }
+    u = bv;
+    if ((u % kPrimThreads) == tid) {            // the owner of key[u] retires it
+      order[step] = u;
+      parent[u] = from[u];
+      weight[u] = bk;
+      key[u] = -1.0;
+    }
+    par ^= 1;
+  }
+}
+
+// ---- tree measurement -------------------------------------------------------------------------
+struct TreeParams {
+  int N;
+  int64_t ldv;
+  const int* parent;      // Prim outputs [graph][ldv]
+  const double* weight;
+  const int* order;
+  // scratch, each [graph][ldv]
+  int* size;
+  double* wd;
+  double* S;
+  int* anc0;
+  int* anc1;
+  int* dep0;
+  int* dep1;
+  // outputs (per graph g: index out0 + g)
+  double* eta;            // [ngraphs]
+  int* root;              // [ngraphs]
+  int* newparent;         // [ngraphs][ldp]
+  int64_t ldp;
+  int* mst_i;             // optional [ngraphs][ldp]
+  int* mst_j;
+  double* mst_w;
+  int* dfs_order;         // optional [ngraphs][ldp]
+};
+
+constexpr int kTreeThreads = 1024;
+
+__global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
+  __shared__ double sred_d[32];
+  __shared__ int sred_i[32];
+  __shared__ long long sred_l[32];
+  __shared__ int s_root;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
+  const int64_t oofs = (int64_t)blockIdx.x * p.ldp;
+  const int* __restrict__ parent = p.parent + gofs;
+  const double* __restrict__ weight = p.weight + gofs;
+  const int* __restrict__ order = p.order + gofs;
+  int* size = p.size + gofs;
+  double* wd = p.wd + gofs;
+  double* S = p.S + gofs;
+  int* newparent = p.newparent + oofs;
+  const int r0 = 0;   // Prim start vertex
+
+  for (int v = tid; v < N; v += kTreeThreads) { size[v] = 1; newparent[v] = parent[v]; }
+  if (p.mst_i) {
+    for (int t = 1 + tid; t < N; t += kTreeThreads) {
+      const int v = order[t], q = parent[v];
+      p.mst_i[oofs + t - 1] = min(v, q);
+      p.mst_j[oofs + t - 1] = max(v, q);
+      p.mst_w[oofs + t - 1] = weight[v];
+    }
+  }
+  __syncthreads();
+
+  // Sequential O(N) passes in Prim insertion order (parents always precede children).
+  if (tid == 0) {
+    for (int t = N - 1; t >= 1; --t) {          // subtree sizes
+      const int v = order[t];
+      size[parent[v]] += size[v];
+    }
+    double tot = 0.0;                            // weighted depth from r0 and its sum
+    wd[r0] = 0.0;
+    for (int t = 1; t < N; ++t) {
+      const int v = order[t];
+      const double x = wd[parent[v]] + weight[v];
+      wd[v] = x;
+      tot += x;
+    }
+    S[r0] = tot;                                 // rerooting: S(v) = S(parent) + w * (N - 2 size(v))
+    for (int t = 1; t < N; ++t) {
+      const int v = order[t];
+      S[v] = S[parent[v]] + weight[v] * (double)(N - 2 * size[v]);
+    }
+  }
+  __syncthreads();
+
+  // root = first argmin of closeness (N-1)/S(v)   (LightGraphs.closeness_centrality + findmin)
+  {
+    double bk = CUDART_INF;
+    int bv = 0x7fffffff;
+    for (int v = tid; v < N; v += kTreeThreads) {
+      const double c = (N > 1) ? (double)(N - 1) / S[v] : 0.0;
+      if (c < bk || bv == 0x7fffffff) { bk = c; bv = v; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+      const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      argmin_combine(bk, bv, ok, ov);
+    }
+    if (lane == 0) { sred_d[warp] = bk; sred_i[warp] = bv; }
+    __syncthreads();
+    if (warp == 0) {
+      bk = sred_d[lane];
+      bv = sred_i[lane];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
+        const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        argmin_combine(bk, bv, ok, ov);
+      }
+      if (lane == 0) s_root = bv;
+    }
+    __syncthreads();
+  }
+  const int root = s_root;
+
+  // re-root: reverse the parent pointers on the path root -> r0
+  if (tid == 0) {
+    int v = root, prev = root;
+    while (true) {
+      const int nxt = parent[v];
+      newparent[v] = prev;
+      if (v == r0) break;
+      prev = v;
+      v = nxt;
+    }
+  }
+  __syncthreads();
+
+  // hop depths from the new root by pointer jumping (ceil(log2 N) rounds)
+  int* anc_a = p.anc0 + gofs;
+  int* anc_b = p.anc1 + gofs;
+  int* dep_a = p.dep0 + gofs;
+  int* dep_b = p.dep1 + gofs;
+  for (int v = tid; v < N; v += kTreeThreads) {
+    anc_a[v] = newparent[v];
+    dep_a[v] = (v == root) ? 0 : 1;
+  }
+  __syncthreads();
+  for (int span = 1; span < N; span <<= 1) {
+    for (int v = tid; v < N; v += kTreeThreads) {
+      const int a = anc_a[v];
+      dep_b[v] = dep_a[v] + dep_a[a];
+      anc_b[v] = anc_a[a];
+    }
+    __syncthreads();
+    int* ti = anc_a; anc_a = anc_b; anc_b = ti;
+    ti = dep_a; dep_a = dep_b; dep_b = ti;
+  }
+
+  // eta = mean(h) / (mean count per level / 2) + 1     (src/sequencer.jl:334-354)
+  {
+    long long sh = 0;
+    int mx = 0;
+    for (int v = tid; v < N; v += kTreeThreads) { sh += dep_a[v]; mx = max(mx, dep_a[v]); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      sh += __shfl_xor_sync(0xffffffffu, sh, o);
+      mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if (lane == 0) { sred_l[warp] = sh; sred_i[warp] = mx; }
+    __syncthreads();
+    if (tid == 0) {
+      long long tot = 0;
+      int m = 0;
+      for (int w = 0; w < kTreeThreads / 32; ++w) { tot += sred_l[w]; m = max(m, sred_i[w]); }
+      double hlen = (double)tot / (double)N;
+      double hwid = ((double)N / (double)(m + 1)) / 2.0;
+      hlen = fmin(fmax(hlen, kJuliaEps), kFloatMax32);
+      hwid = fmin(fmax(hwid, kJuliaEps), kFloatMax32);
+      p.eta[blockIdx.x] = hlen / hwid + 1.0;
+      p.root[blockIdx.x] = root;
+    }
+  }
+
+  // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24)
+  if (p.dfs_order) {
+    __syncthreads();
+    if (tid == 0) {
+      int* cstart = size;          // reuse scratch: children CSR
+      int* clist = anc_a;
+      int* stack = anc_b;
+      int* pre = dep_b;
+      for (int v = 0; v <= N; ++v) if (v < N) cstart[v] = 0;
+      for (int v = 0; v < N; ++v) if (v != root) cstart[newparent[v]]++;
+      int run = 0;
+      for (int v = 0; v < N; ++v) { const int c = cstart[v]; cstart[v] = run; run += c; }
+      int* fill = dep_a;           // next free slot per vertex
+      for (int v = 0; v < N; ++v) fill[v] = cstart[v];
+      for (int v = 0; v < N; ++v) if (v != root) clist[fill[newparent[v]]++] = v;   // ascending v
+      int sp = 0, np = 0;
+      stack[sp++] = root;
+      while (sp > 0) {
+        const int x = stack[--sp];
+        pre[np++] = x;
+        const int b = cstart[x], e = fill[x];
+        for (int q = e - 1; q >= b; --q) stack[sp++] = clist[q];
+      }
+      for (int k = 0; k < N; ++k) p.dfs_order[oofs + k] = pre[N - 1 - k];
+    }
+  }
+}
+
+// ---- eta-weighted combine ---------------------------------------------------------------------
+// S = (first ? 0 : S) + sum_c clamp(eta_c * D_c, eps(), Inf)  in chunk order; if last: S /= sum(eta_all)
+// HBM-bound: 8*(nb+1..2) bytes per entry.
+__global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ S, const double* __restrict__ Db,
+                                                      int64_t strideD, int nb, const double* __restrict__ eta_b,
+                                                      int first, int last, const double* __restrict__ eta_all,
+                                                      int n_all, int64_t total) {
+  double e[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) e[c] = (c < nb) ? eta_b[c] : 0.0;
+  double tot = 0.0;
+  if (last)
+    for (int c = 0; c < n_all; ++c) tot += eta_all[c];
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    double s = first ? 0.0 : S[idx];
+#pragma unroll
+    for (int c = 0; c < 32; ++c)
+      if (c < nb) s += fmax(e[c] * Db[(int64_t)c * strideD + idx], kJuliaEps);
+    if (last) s /= tot;
+    S[idx] = s;
+  }
+}
+
+// ---- proximity fuse ---------------------------------------------------------------------------
+// P[i,j] = P[j,i] += eta * inv(w) for every MST edge of one group (src/sequencer.jl:313-322).
+__global__ void fuse_scatter_kernel(double* __restrict__ P, int64_t ldD, const int* __restrict__ mi,
+                                    const int* __restrict__ mj, const double* __restrict__ mw,
+                                    const double* __restrict__ eta, int nedges) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nedges) return;
+  const int i = mi[e], j = mj[e];
+  const double t = eta[0] * (1.0 / mw[e]);
+  const double v = P[(int64_t)j * ldD + i] + t;
+  P[(int64_t)j * ldD + i] = v;
+  P[(int64_t)i * ldD + j] = v;
+}
+
+// D = inv.(P / sum(eta)) with +Inf diagonal proximity (=> 0 -> clamped to eps by _mst); non-edges stay +Inf
+// (src/sequencer.jl:324-326,269,360).
+__global__ void fuse_finalize_kernel(double* __restrict__ P, int64_t ldD, int N, const double* __restrict__ eta_g,
+                                     int ngroups, double eps_floor) {
+  double tot = 0.0;
+  for (int g = 0; g < ngroups; ++g) tot += eta_g[g];
+  const int64_t total = (int64_t)N * ldD;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / ldD), j = (int)(idx % ldD);
+    if (j >= N) continue;
+    const double pv = P[idx];
+    double out;
+    if (i == j) out = eps_floor;
+    else if (pv != 0.0) out = fmax(1.0 / (pv / tot), eps_floor);
+    else out = CUDART_INF;
+    P[idx] = out;
+  }
+}
+
+__global__ void gather_edges_kernel(const double* __restrict__ D, int64_t ldD, const int* __restrict__ mi,
+                                    const int* __restrict__ mj, double* __restrict__ val, int nedges) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nedges) return;
+  val[e] = D[(int64_t)mi[e] * ldD + mj[e]];
+}
+
+// Unit-level: Symmetric(dm) view of a column-major upload (upper triangle wins), clamped to eps.
+__global__ void symmetrize_kernel(const double* __restrict__ up, int N, double* __restrict__ out, int64_t ldD,
+                                  double eps_floor) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)N * N) return;
+  const int r = (int)(idx / N), c = (int)(idx % N);
+  const int lo = min(r, c), hi = max(r, c);
+  out[(int64_t)r * ldD + c] = fmax(up[(int64_t)hi * N + lo], eps_floor);   // D[lo, hi] column-major
+}
+
+__global__ void copy_strided_kernel(const double* __restrict__ in, int64_t ld_in, double* __restrict__ out,
+                                    int64_t ld_out, int rows, int cols) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)rows * cols) return;
+  const int r = (int)(idx / cols), c = (int)(idx % cols);
+  out[(int64_t)r * ld_out + c] = in[(int64_t)r * ld_in + c];
+}
+
+}  // namespace seqj

@@ -1,0 +1,122 @@
+// K1: per-chunk normalisation + prefix scan.
+// Replaces _splitnorm (reference src/sequencer.jl:383-407) and the weighted ECDF evaluated on the
+// shared unit grid inside EMD/Energy (src/distancemetrics.jl:86,147,206-209; StatsBase.ecdf).
+//
+// One warp per (object j, chunk c).  Input A is object-major [N][ldA] (= Julia column-major M x N).
+// Outputs, all K-contiguous [N][ldX] with chunk c at columns [c*cl_pad, c*cl_pad + m_c) and zero
+// padding up to cl_pad (a multiple of 16 doubles so TMA boxes never straddle chunks):
+//   P    = a / sum(a)                    (PDF; Euclidean operand, KL left operand)
+//   logP = log(P)                        (KL right operand)
+//   Uc   = cumsum(P)/sum(P) - (k+1)/m    (CDF centred on the uniform ramp; EMD / Energy operand.
+//                                         Differences U_i - U_j are unchanged by the centring, and
+//                                         |Uc|^2 << |U|^2 removes the Gram-form cancellation.)
+//   U    = cumsum(P)/sum(P), last = 1    (optional, uncentred; unit-level API only)
+// and per-chunk vectors [nchunks][ldn]:  sP = sum P^2, sU = sum Uc^2, H = sum P log P.
+// HBM-bound: 8*M*N bytes read, up to 3 * 8*M*N written per scale.
+#pragma once
+#include "common.cuh"
+
+namespace seqj {
+
+struct PrepParams {
+  const double* A;
+  int64_t ldA;
+  int M, N;
+  int cl, cl_pad, nchunks;
+  int64_t ldX, ldn;
+  double* P;
+  double* logP;
+  double* Uc;
+  double* U;
+  double* sP;
+  double* sU;
+  double* H;
+  int normalize;
+};
+
+__global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wid = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= (int64_t)p.N * p.nchunks) return;
+  const int j = (int)(wid / p.nchunks);
+  const int c = (int)(wid % p.nchunks);
+  const int r0 = c * p.cl;
+  const int m = min(p.cl, p.M - r0);
+  const double* __restrict__ src = p.A + (int64_t)j * p.ldA + r0;
+  const int64_t dst = (int64_t)j * p.ldX + (int64_t)c * p.cl_pad;
+
+  // pass 1: chunk mass
+  double s = 0.0;
+  for (int k = lane; k < m; k += 32) s += src[k];
+  s = warp_sum(s);
+
+  // pass 2: PDF, log PDF, moments
+  double w = 0.0, sq = 0.0, h = 0.0;
+  for (int k = lane; k < p.cl_pad; k += 32) {
+    double pv = 0.0, lp = 0.0;
+    if (k < m) {
+      const double a = src[k];
+      pv = p.normalize ? a / s : a;
+      lp = log(pv);
+      w += pv;
+      sq += pv * pv;
+      h += pv * lp;
+    }
+    if (p.P) p.P[dst + k] = pv;
+    if (p.logP) p.logP[dst + k] = lp;
+  }
+  w = warp_sum(w);
+  sq = warp_sum(sq);
+  h = warp_sum(h);
+
+  // pass 3: CDF by warp-shuffle inclusive scan with a running carry
+  double su = 0.0;
+  if (p.Uc || p.U || p.sU) {
+    double carry = 0.0;
+    for (int base = 0; base < p.cl_pad; base += 32) {
+      const int k = base + lane;
+      double x = 0.0;
+      if (k < m) {
+        const double a = src[k];
+        x = p.normalize ? a / s : a;
+      }
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const double y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+      }
+      const double cum = carry + x;
+      carry = __shfl_sync(0xffffffffu, cum, 31);
+      double u = 0.0, uc = 0.0;
+      if (k < m) {
+        u = (k == m - 1) ? 1.0 : cum / w;
+        uc = u - (double)(k + 1) / (double)m;
+        su += uc * uc;
+      }
+      if (k < p.cl_pad) {            // cl_pad is a multiple of 16, not of the 32-wide scan step
+        if (p.Uc) p.Uc[dst + k] = uc;
+        if (p.U) p.U[dst + k] = u;
+      }
+    }
+    su = warp_sum(su);
+  }
+  if (lane == 0) {
+    const int64_t o = (int64_t)c * p.ldn + j;
+    if (p.sP) p.sP[o] = sq;
+    if (p.sU) p.sU[o] = su;
+    if (p.H) p.H[o] = h;
+  }
+}
+
+// Unit-level copy-out: padded K-contiguous [N][ldX] chunk layout -> dense M x N column-major.
+__global__ void unpad_kernel(const double* __restrict__ X, int64_t ldX, int cl, int cl_pad, int M, int N,
+                             double* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)M * N) return;
+  const int j = (int)(idx / M);
+  const int r = (int)(idx % M);
+  const int c = r / cl;
+  out[idx] = X[(int64_t)j * ldX + (int64_t)c * cl_pad + (r - c * cl)];
+}
+
+}  // namespace seqj

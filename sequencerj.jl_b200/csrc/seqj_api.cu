@@ -1,0 +1,903 @@
+// C ABI + host orchestration of the B200-native Sequencer hot path (see include/seqj.h).
+// Replaces the reference's `_sequence` driver loop (src/sequencer.jl:184-276): scale-major
+// iteration, per (metric, scale) group: distance tile kernels over a batch of chunks -> batched
+// Prim -> tree measurement (eta) -> eta-weighted combine -> group Prim/tree; then the proximity
+// fuse and the final MST / order.  Everything is asynchronous on one stream: eta values never
+// leave the device between kernels, and the host only synchronises to read the final results.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/seqj.h"
+#include "common.cuh"
+#include "kernels_dist.cuh"
+#include "kernels_graph.cuh"
+#include "kernels_prep.cuh"
+
+using namespace seqj;
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct seqj_handle {
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  uint64_t ws_limit = 0;
+  EncodeTiledFn encode = nullptr;
+  int sm_count = 0;
+  size_t max_smem = 0;
+};
+
+struct GroupRes {
+  int metric = 0, scale = 0, nchunks = 0, computed = 0;
+  std::vector<double> eta_chunk;
+  std::vector<int32_t> root_chunk, parents_chunk;
+  double eta = 0;
+  int32_t root = 0;
+  std::vector<int32_t> parents, mst_i, mst_j;
+  std::vector<double> mst_w;
+};
+
+struct seqj_result {
+  int64_t N = 0;
+  std::vector<GroupRes> groups;
+  int has_final = 0;
+  double eta = 0;
+  int32_t root = 0;
+  std::vector<int32_t> order, parents, mst_i, mst_j, Di, Dj;
+  std::vector<double> mst_w, Dv;
+  double timers[SEQJ_NTIMERS] = {0};
+  int64_t launches = 0;
+};
+
+// --------------------------------------------------------------------------------------------
+namespace {
+
+int fail(seqj_handle* h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define CU_TRY(call)                                                                              \
+  do {                                                                                            \
+    cudaError_t e__ = (call);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? SEQJ_E_OOM : SEQJ_E_CUDA,                 \
+                  std::string(#call) + ": " + cudaGetErrorString(e__));                           \
+  } while (0)
+
+#define ST_TRY(call)          \
+  do {                        \
+    int s__ = (call);         \
+    if (s__ != SEQJ_OK) return s__; \
+  } while (0)
+
+inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+// RAII device allocations, freed when the owning call returns.
+struct DevPool {
+  std::vector<void*> ptrs;
+  ~DevPool() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+  template <typename T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) ptrs.push_back(p);
+    *out = static_cast<T*>(p);
+    return e;
+  }
+};
+
+struct PhaseTimer {
+  struct Span { int phase; cudaEvent_t a, b; };
+  std::vector<Span> spans;
+  cudaStream_t st;
+  bool enabled = true;
+  explicit PhaseTimer(cudaStream_t s) : st(s) {}
+  ~PhaseTimer() {
+    for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  }
+  int begin(int phase) {
+    Span s; s.phase = phase;
+    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
+    cudaEventRecord(s.a, st);
+    spans.push_back(s);
+    return (int)spans.size() - 1;
+  }
+  void end(int id) { cudaEventRecord(spans[id].b, st); }
+  void collect(double* timers) {
+    for (auto& s : spans) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) timers[s.phase] += ms;
+    }
+  }
+};
+
+struct ScaleLayout {
+  int scale = 1, cl = 0, cl_pad = 0, nchunks = 0;
+  int64_t ldX = 0;
+  std::vector<int> m_of_chunk;
+};
+
+// _splitnorm chunking (reference src/sequencer.jl:389-397): chunklen = cld(M, scale); starts 1:chunklen:M
+ScaleLayout make_layout(int M, int scale) {
+  ScaleLayout L;
+  L.scale = scale;
+  L.cl = (M + scale - 1) / scale;
+  L.cl_pad = (int)round_up(L.cl, kTileK);
+  for (int r0 = 0; r0 < M; r0 += L.cl) L.m_of_chunk.push_back(std::min(L.cl, M - r0));
+  L.nchunks = (int)L.m_of_chunk.size();
+  L.ldX = (int64_t)L.nchunks * L.cl_pad;
+  return L;
+}
+
+std::vector<int2> make_tiles(int N, bool upper) {
+  std::vector<int2> t;
+  for (int j0 = 0; j0 < N; j0 += kTileN)
+    for (int i0 = 0; i0 < N; i0 += kTileM)
+      if (!upper || i0 < j0 + kTileN) t.push_back(make_int2(i0, j0));
+  return t;
+}
+
+int make_tmap(seqj_handle* h, CUtensorMap* tm, const double* base, int64_t ldX, int64_t rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)ldX, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ldX * 8};
+  cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kTileM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SEQJ_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
+  return SEQJ_OK;
+}
+
+// Everything the graph layer needs for up to `cap` graphs of N vertices.
+struct GraphWS {
+  int cap = 0, N = 0;
+  int64_t ldv = 0;
+  int use_smem = 1;
+  size_t prim_smem = 0;
+  int *parent = nullptr, *order = nullptr, *size = nullptr, *anc0 = nullptr, *anc1 = nullptr, *dep0 = nullptr,
+      *dep1 = nullptr, *from_g = nullptr;
+  double *weight = nullptr, *wd = nullptr, *S = nullptr, *key_g = nullptr;
+};
+
+struct Ctx {
+  seqj_handle* h;
+  cudaStream_t st;
+  DevPool pool;
+  PhaseTimer timer;
+  int64_t launches = 0;
+  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), timer(hh->st) {}
+};
+
+int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
+  seqj_handle* h = c.h;
+  g.cap = cap; g.N = N; g.ldv = round_up(N, 32);
+  const size_t n = (size_t)cap * g.ldv;
+  CU_TRY(c.pool.alloc(&g.parent, n)); CU_TRY(c.pool.alloc(&g.order, n)); CU_TRY(c.pool.alloc(&g.size, n));
+  CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
+  CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
+  CU_TRY(c.pool.alloc(&g.S, n));
+  g.prim_smem = (size_t)((N + 1) & ~1) * 8 + (size_t)N * 4;
+  g.use_smem = g.prim_smem + 1024 <= h->max_smem;
+  if (!g.use_smem) {
+    g.prim_smem = 0;
+    CU_TRY(c.pool.alloc(&g.key_g, n)); CU_TRY(c.pool.alloc(&g.from_g, n));
+  }
+  CU_TRY(cudaFuncSetAttribute(prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
+  return SEQJ_OK;
+}
+
+// _measure_dm for `nb` dense matrices: Prim + tree kernels.  Outputs go to device arrays.
+int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t strideD, int nb, double eps_floor,
+                double* eta_out, int* root_out, int* parents_out, int64_t ldp, int* mst_i, int* mst_j, double* mst_w,
+                int* dfs_order) {
+  seqj_handle* h = c.h;
+  PrimParams pp;
+  pp.D = D; pp.ldD = ldD; pp.strideD = strideD; pp.N = g.N; pp.eps_floor = eps_floor;
+  pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
+  pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
+  int t = c.timer.begin(SEQJ_T_PRIM);
+  prim_kernel<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
+  c.timer.end(t); c.launches++;
+  CU_TRY(cudaGetLastError());
+  TreeParams tp;
+  tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
+  tp.size = g.size; tp.wd = g.wd; tp.S = g.S; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
+  tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
+  tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
+  t = c.timer.begin(SEQJ_T_TREE);
+  tree_kernel<<<nb, kTreeThreads, 0, c.st>>>(tp);
+  c.timer.end(t); c.launches++;
+  CU_TRY(cudaGetLastError());
+  return SEQJ_OK;
+}
+
+struct PrepBufs {
+  double *P = nullptr, *logP = nullptr, *Uc = nullptr, *U = nullptr, *sP = nullptr, *sU = nullptr, *H = nullptr;
+  int64_t ldn = 0, rows_pad = 0;
+  int* m_of_chunk = nullptr;
+};
+
+int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const ScaleLayout& L, PrepBufs& b,
+             int normalize) {
+  seqj_handle* h = c.h;
+  PrepParams pp;
+  pp.A = A_dev; pp.ldA = ldA; pp.M = M; pp.N = N; pp.cl = L.cl; pp.cl_pad = L.cl_pad; pp.nchunks = L.nchunks;
+  pp.ldX = L.ldX; pp.ldn = b.ldn; pp.P = b.P; pp.logP = b.logP; pp.Uc = b.Uc; pp.U = b.U;
+  pp.sP = b.sP; pp.sU = b.sU; pp.H = b.H; pp.normalize = normalize;
+  int t = c.timer.begin(SEQJ_T_PREP);
+  // rows [N, rows_pad) are read by TMA boxes of the last tiles: keep them zero
+  const size_t tail = (size_t)(b.rows_pad - N) * L.ldX * 8;
+  if (tail) {
+    if (b.P) CU_TRY(cudaMemsetAsync(b.P + (size_t)N * L.ldX, 0, tail, c.st));
+    if (b.logP) CU_TRY(cudaMemsetAsync(b.logP + (size_t)N * L.ldX, 0, tail, c.st));
+    if (b.Uc) CU_TRY(cudaMemsetAsync(b.Uc + (size_t)N * L.ldX, 0, tail, c.st));
+  }
+  CU_TRY(cudaMemcpyAsync(b.m_of_chunk, L.m_of_chunk.data(), sizeof(int) * L.nchunks, cudaMemcpyHostToDevice, c.st));
+  const int64_t warps = (int64_t)N * L.nchunks;
+  const int wpb = 8;
+  prep_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, c.st>>>(pp);
+  c.timer.end(t); c.launches++;
+  CU_TRY(cudaGetLastError());
+  return SEQJ_OK;
+}
+
+struct FixBufs {
+  int4* list = nullptr;
+  unsigned int* count = nullptr;
+  int* overflow = nullptr;
+  unsigned int cap = 0;
+};
+
+constexpr double kTauGram = 1e-3;   // relative fix-up threshold for the Gram forms (see kernels_dist.cuh)
+constexpr double kTauKL = 1e-3;
+
+// distance matrices of chunks [chunk0, chunk0+nb) of one scale into D (stride strideD)
+int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const int2* tiles_dev, int ntiles,
+                 int N, double* D, int64_t ldD, int64_t strideD, int chunk0, int nb, double eps_floor,
+                 double l2_thresh, int kl_full, FixBufs& fb) {
+  seqj_handle* h = c.h;
+  DistParams dp;
+  dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.D = D; dp.nk = L.cl_pad / kTileK; dp.cl_pad = L.cl_pad;
+  dp.chunk0 = chunk0; dp.ldn = pb.ldn; dp.tiles = tiles_dev; dp.eps_floor = eps_floor;
+  dp.mirror = 1; dp.kl_swap = 0;
+  dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  const int phase = SEQJ_T_DIST_L2 + metric;
+  int t = c.timer.begin(phase);
+  dim3 grid(ntiles, nb);
+  if (metric == SEQJ_EMD) {
+    CUtensorMap tmU;
+    ST_TRY(make_tmap(h, &tmU, pb.Uc, L.ldX, pb.rows_pad));
+    dp.normA = nullptr; dp.tau = 0;
+    emd_dist_kernel<<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmU, dp);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+    c.timer.end(t);
+    return SEQJ_OK;
+  }
+  CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
+  CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
+  CUtensorMap tmA, tmB;
+  FixParams fp;
+  fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
+  fp.chunk0 = chunk0; fp.m_of_chunk = pb.m_of_chunk; fp.eps_floor = eps_floor; fp.mirror = 1; fp.kl_swap = 0;
+  fp.fix_list = fb.list; fp.fix_count = fb.count; fp.fix_cap = fb.cap; fp.fix_overflow = fb.overflow;
+  if (metric == SEQJ_L2) {
+    ST_TRY(make_tmap(h, &tmA, pb.P, L.ldX, pb.rows_pad));
+    dp.normA = pb.sP; dp.tau = std::max(kTauGram, l2_thresh); fp.X = pb.P;
+    gemm_dist_kernel<MODE_L2><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
+  } else if (metric == SEQJ_ENERGY) {
+    ST_TRY(make_tmap(h, &tmA, pb.Uc, L.ldX, pb.rows_pad));
+    dp.normA = pb.sU; dp.tau = kTauGram; fp.X = pb.Uc;
+    gemm_dist_kernel<MODE_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
+  } else {  // KL
+    ST_TRY(make_tmap(h, &tmA, pb.P, L.ldX, pb.rows_pad));
+    ST_TRY(make_tmap(h, &tmB, pb.logP, L.ldX, pb.rows_pad));
+    dp.normA = pb.H; dp.tau = kTauKL; fp.X = pb.P;
+    if (kl_full) {
+      dp.mirror = 0; dp.kl_swap = 1; fp.mirror = 0; fp.kl_swap = 1;
+      gemm_dist_kernel<MODE_KL><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmB, tmA, dp);
+    } else {
+      gemm_dist_kernel<MODE_KL><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmB, dp);
+    }
+  }
+  c.launches++;
+  CU_TRY(cudaGetLastError());
+  fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
+  fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, nb);
+  c.launches += 2;
+  CU_TRY(cudaGetLastError());
+  c.timer.end(t);
+  return SEQJ_OK;
+}
+
+int set_kernel_attrs(seqj_handle* h) {
+  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(emd_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  return SEQJ_OK;
+}
+
+int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, bool needP, bool needLog, bool needUc,
+               bool needU) {
+  seqj_handle* h = c.h;
+  pb.rows_pad = round_up(N, kTileN);
+  pb.ldn = round_up(N, 8);
+  const size_t n = (size_t)pb.rows_pad * max_ldX;
+  if (needP) CU_TRY(c.pool.alloc(&pb.P, n));
+  if (needLog) CU_TRY(c.pool.alloc(&pb.logP, n));
+  if (needUc) CU_TRY(c.pool.alloc(&pb.Uc, n));
+  if (needU) CU_TRY(c.pool.alloc(&pb.U, n));
+  const size_t nn = (size_t)max_chunks * pb.ldn;
+  CU_TRY(c.pool.alloc(&pb.sP, nn)); CU_TRY(c.pool.alloc(&pb.sU, nn)); CU_TRY(c.pool.alloc(&pb.H, nn));
+  CU_TRY(c.pool.alloc(&pb.m_of_chunk, (size_t)max_chunks));
+  return SEQJ_OK;
+}
+
+int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap) {
+  seqj_handle* h = c.h;
+  fb.cap = cap;
+  CU_TRY(c.pool.alloc(&fb.list, (size_t)cap));
+  CU_TRY(c.pool.alloc(&fb.count, 1));
+  CU_TRY(c.pool.alloc(&fb.overflow, 1));
+  return SEQJ_OK;
+}
+
+// final fuse on device: group MSTs (device arrays, [G][ldp]) -> D (in Sbuf) -> final measure
+int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, const double* eta_g, const int* mst_i,
+             const int* mst_j, const double* mst_w, int64_t ldp, double eps_floor, double* eta_f, int* root_f,
+             int* parents_f, int* fmst_i, int* fmst_j, double* fmst_w, int* order_f, double* edge_val) {
+  seqj_handle* h = c.h;
+  int t = c.timer.begin(SEQJ_T_FUSE);
+  CU_TRY(cudaMemsetAsync(Sbuf, 0, (size_t)N * ldD * 8, c.st));
+  const int ne = N - 1;
+  for (int g = 0; g < G; ++g) {
+    fuse_scatter_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
+                                                          mst_w + (int64_t)g * ldp, eta_g + g, ne);
+    c.launches++;
+  }
+  fuse_finalize_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, ldD, N, eta_g, G, eps_floor);
+  c.launches++;
+  for (int g = 0; g < G; ++g) {
+    gather_edges_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
+                                                          edge_val + (int64_t)g * ldp, ne);
+    c.launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  ST_TRY(run_measure(c, gws, Sbuf, ldD, 0, 1, eps_floor, eta_f, root_f, parents_f, ldp, fmst_i, fmst_j, fmst_w, order_f));
+  c.timer.end(t);
+  return SEQJ_OK;
+}
+
+void dedup_triplets(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
+                    const std::vector<double>& val) {
+  std::map<std::pair<int, int>, double> m;
+  for (int g = 0; g < G; ++g)
+    for (int e = 0; e < N - 1; ++e) {
+      const int64_t k = (int64_t)g * ldp + e;
+      m[std::make_pair(mi[k], mj[k])] = val[k];
+    }
+  for (auto& kv : m) {
+    r->Di.push_back(kv.first.first);
+    r->Dj.push_back(kv.first.second);
+    r->Dv.push_back(kv.second);
+  }
+}
+
+template <typename T>
+void copy_out(T* dst, const std::vector<T>& v) {
+  if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(T));
+}
+
+}  // namespace
+
+// --------------------------------------------------------------------------------------------
+extern "C" {
+
+int seqj_version(void) { return SEQJ_VERSION; }
+
+int seqj_create(seqj_handle** out, const int* devices, int ndev) {
+  if (!out) return SEQJ_E_BADARG;
+  *out = nullptr;
+  seqj_handle* h = new seqj_handle();
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    // keep the handle so the caller can read the message; every compute call will fail loudly
+    h->err = std::string("no CUDA device: ") + cudaGetErrorString(e);
+    *out = h;
+    return SEQJ_E_CUDA;
+  }
+  if (devices && ndev > 0) h->dev = devices[0];
+  else cudaGetDevice(&h->dev);
+  cudaDeviceProp prop;
+  if (cudaSetDevice(h->dev) != cudaSuccess || cudaGetDeviceProperties(&prop, h->dev) != cudaSuccess) {
+    h->err = "cudaSetDevice failed";
+    *out = h;
+    return SEQJ_E_CUDA;
+  }
+  if (prop.major != 10) {
+    h->err = std::string("device is not sm_100 (Blackwell B200): ") + prop.name;
+    *out = h;
+    return SEQJ_E_CUDA;
+  }
+  h->sm_count = prop.multiProcessorCount;
+  h->max_smem = prop.sharedMemPerBlockOptin;
+  cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
+    h->err = "cuTensorMapEncodeTiled not available in this driver";
+    *out = h;
+    return SEQJ_E_CUDA;
+  }
+  h->encode = reinterpret_cast<EncodeTiledFn>(fn);
+  *out = h;
+  return set_kernel_attrs(h);
+}
+
+void seqj_destroy(seqj_handle* h) {
+  if (!h) return;
+  if (h->st) cudaStreamDestroy(h->st);
+  delete h;
+}
+
+const char* seqj_last_error(const seqj_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
+  if (!h) return SEQJ_E_BADARG;
+  h->ws_limit = bytes;
+  return SEQJ_OK;
+}
+
+static int check_ready(seqj_handle* h) {
+  if (!h) return SEQJ_E_BADARG;
+  if (!h->encode || !h->st) return fail(h, SEQJ_E_CUDA, "handle has no usable sm_100 device (no CPU fallback): " + h->err);
+  if (cudaSetDevice(h->dev) != cudaSuccess) return fail(h, SEQJ_E_CUDA, "cudaSetDevice failed");
+  return SEQJ_OK;
+}
+
+int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t N64, const int32_t* metric_ids,
+                      int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                      const uint8_t* group_mask, seqj_result** out) {
+  ST_TRY(check_ready(h));
+  if (!A_dev || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M64 < 1 || N64 < 2 ||
+      M64 > (1 << 30) || N64 > (1 << 30))
+    return fail(h, SEQJ_E_BADARG, "bad argument (need M >= 1, N >= 2, at least one metric and one scale)");
+  const int M = (int)M64, N = (int)N64;
+  for (int k = 0; k < nmetrics; ++k)
+    if (metric_ids[k] < 0 || metric_ids[k] > 3) return fail(h, SEQJ_E_BADARG, "unknown metric id");
+  for (int l = 0; l < nscales; ++l)
+    if (scales[l] < 1 || scales[l] > M)
+      return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scales[l]) +
+                                        ") cannot be larger than the number of data elements (" + std::to_string(M) + ").");
+  *out = nullptr;
+  Ctx c(h);
+  const int G = nmetrics * nscales;
+  bool needP = false, needLog = false, needUc = false;
+  for (int k = 0; k < nmetrics; ++k) {
+    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD;
+    needLog |= metric_ids[k] == SEQJ_KLD;
+    needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;
+  }
+  std::vector<ScaleLayout> layouts;
+  int64_t max_ldX = 0;
+  int max_chunks = 0;
+  for (int l = 0; l < nscales; ++l) {
+    layouts.push_back(make_layout(M, scales[l]));
+    max_ldX = std::max(max_ldX, layouts.back().ldX);
+    max_chunks = std::max(max_chunks, layouts.back().nchunks);
+  }
+  auto mask = [&](int k, int l) { return !group_mask || group_mask[k * nscales + l]; };
+  const bool do_final = (group_mask == nullptr);
+
+  int tt = c.timer.begin(SEQJ_T_TOTAL);
+
+  PrepBufs pb;
+  ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false));
+  FixBufs fb;
+  ST_TRY(alloc_fix(c, fb, 1u << 22));
+  std::vector<int2> tiles = make_tiles(N, true);
+  int2* tiles_dev;
+  CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
+  CU_TRY(cudaMemcpyAsync(tiles_dev, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c.st));
+
+  // result arrays on device
+  std::vector<int> chunk_off(G, 0);
+  int total_chunks = 0;
+  for (int k = 0; k < nmetrics; ++k)
+    for (int l = 0; l < nscales; ++l) {
+      chunk_off[k * nscales + l] = total_chunks;
+      if (mask(k, l)) total_chunks += layouts[l].nchunks;
+    }
+  const int64_t ldp = N;
+  double *eta_c, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
+  int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f;
+  CU_TRY(c.pool.alloc(&eta_c, (size_t)total_chunks)); CU_TRY(c.pool.alloc(&root_c, (size_t)total_chunks));
+  CU_TRY(c.pool.alloc(&par_c, (size_t)total_chunks * ldp));
+  CU_TRY(c.pool.alloc(&eta_g, (size_t)G)); CU_TRY(c.pool.alloc(&root_g, (size_t)G));
+  CU_TRY(c.pool.alloc(&par_g, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&msti_g, (size_t)G * ldp));
+  CU_TRY(c.pool.alloc(&mstj_g, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&mstw_g, (size_t)G * ldp));
+  CU_TRY(c.pool.alloc(&eta_f, 1)); CU_TRY(c.pool.alloc(&root_f, 1)); CU_TRY(c.pool.alloc(&par_f, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&fmst_i, (size_t)ldp)); CU_TRY(c.pool.alloc(&fmst_j, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp));
+
+  // chunk-matrix workspace: S + B chunk matrices
+  const int64_t ldD = round_up(N, 16);
+  const size_t mat_elems = (size_t)N * ldD;
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = free_b > (size_t(2) << 30) ? free_b - (size_t(2) << 30) : free_b / 2;
+  if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
+  int B = (int)std::min<size_t>(std::min(max_chunks, 32), budget / (mat_elems * 8) > 1 ? budget / (mat_elems * 8) - 1 : 0);
+  if (B < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for one N x N chunk matrix plus the accumulator");
+  double *Sbuf, *Dbuf;
+  CU_TRY(c.pool.alloc(&Sbuf, mat_elems));
+  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * B));
+  GraphWS gws;
+  ST_TRY(graphws_alloc(c, gws, B, N));
+
+  for (int l = 0; l < nscales; ++l) {
+    const ScaleLayout& L = layouts[l];
+    bool any = false;
+    for (int k = 0; k < nmetrics; ++k) any |= mask(k, l);
+    if (!any) continue;
+    ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
+    for (int k = 0; k < nmetrics; ++k) {
+      if (!mask(k, l)) continue;
+      const int g = k * nscales + l;
+      const int coff = chunk_off[g];
+      for (int c0 = 0; c0 < L.nchunks; c0 += B) {
+        const int nb = std::min(B, L.nchunks - c0);
+        ST_TRY(run_distance(c, metric_ids[k], L, pb, tiles_dev, (int)tiles.size(), N, Dbuf, ldD, (int64_t)mat_elems, c0,
+                            nb, eps_floor, l2_thresh, 0, fb));
+        ST_TRY(run_measure(c, gws, Dbuf, ldD, (int64_t)mat_elems, nb, eps_floor, eta_c + coff + c0, root_c + coff + c0,
+                           par_c + (int64_t)(coff + c0) * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
+        int t = c.timer.begin(SEQJ_T_COMBINE);
+        combine_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, Dbuf, (int64_t)mat_elems, nb, eta_c + coff + c0, c0 == 0,
+                                                         c0 + nb >= L.nchunks, eta_c + coff, L.nchunks,
+                                                         (int64_t)mat_elems);
+        c.timer.end(t); c.launches++;
+        CU_TRY(cudaGetLastError());
+      }
+      ST_TRY(run_measure(c, gws, Sbuf, ldD, 0, 1, eps_floor, eta_g + g, root_g + g, par_g + (int64_t)g * ldp, ldp,
+                         msti_g + (int64_t)g * ldp, mstj_g + (int64_t)g * ldp, mstw_g + (int64_t)g * ldp, nullptr));
+    }
+  }
+  if (do_final)
+    ST_TRY(run_fuse(c, gws, Sbuf, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
+                    fmst_j, fmst_w, order_f, edge_val));
+
+  // ---- copy-out ----
+  seqj_result* r = new seqj_result();
+  r->N = N;
+  r->groups.resize(G);
+  int td = c.timer.begin(SEQJ_T_D2H);
+  std::vector<double> h_eta_c(total_chunks), h_eta_g(G), h_mstw((size_t)G * ldp), h_val;
+  std::vector<int> h_root_c(total_chunks), h_par_c((size_t)total_chunks * ldp), h_root_g(G), h_par_g((size_t)G * ldp),
+      h_msti((size_t)G * ldp), h_mstj((size_t)G * ldp);
+  cudaError_t e = cudaSuccess;
+  auto d2h = [&](void* dst, const void* src, size_t bytes) {
+    if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c.st);
+  };
+  d2h(h_eta_c.data(), eta_c, sizeof(double) * total_chunks);
+  d2h(h_root_c.data(), root_c, sizeof(int) * total_chunks);
+  d2h(h_par_c.data(), par_c, sizeof(int) * (size_t)total_chunks * ldp);
+  d2h(h_eta_g.data(), eta_g, sizeof(double) * G);
+  d2h(h_root_g.data(), root_g, sizeof(int) * G);
+  d2h(h_par_g.data(), par_g, sizeof(int) * (size_t)G * ldp);
+  d2h(h_msti.data(), msti_g, sizeof(int) * (size_t)G * ldp);
+  d2h(h_mstj.data(), mstj_g, sizeof(int) * (size_t)G * ldp);
+  d2h(h_mstw.data(), mstw_g, sizeof(double) * (size_t)G * ldp);
+  if (do_final) {
+    r->has_final = 1;
+    r->order.resize(N); r->parents.resize(N); r->mst_i.resize(N - 1); r->mst_j.resize(N - 1); r->mst_w.resize(N - 1);
+    h_val.resize((size_t)G * ldp);
+    d2h(&r->eta, eta_f, sizeof(double));
+    d2h(&r->root, root_f, sizeof(int));
+    d2h(r->order.data(), order_f, sizeof(int) * N);
+    d2h(r->parents.data(), par_f, sizeof(int) * N);
+    d2h(r->mst_i.data(), fmst_i, sizeof(int) * (N - 1));
+    d2h(r->mst_j.data(), fmst_j, sizeof(int) * (N - 1));
+    d2h(r->mst_w.data(), fmst_w, sizeof(double) * (N - 1));
+    d2h(h_val.data(), edge_val, sizeof(double) * (size_t)G * ldp);
+  }
+  c.timer.end(td);
+  c.timer.end(tt);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+  if (e != cudaSuccess) {
+    delete r;
+    return fail(h, SEQJ_E_CUDA, std::string("sequence failed: ") + cudaGetErrorString(e));
+  }
+  for (int k = 0; k < nmetrics; ++k)
+    for (int l = 0; l < nscales; ++l) {
+      const int g = k * nscales + l;
+      GroupRes& gr = r->groups[g];
+      gr.metric = metric_ids[k]; gr.scale = scales[l]; gr.nchunks = layouts[l].nchunks; gr.computed = mask(k, l);
+      if (!gr.computed) continue;
+      const int coff = chunk_off[g];
+      gr.eta_chunk.assign(h_eta_c.begin() + coff, h_eta_c.begin() + coff + gr.nchunks);
+      gr.root_chunk.assign(h_root_c.begin() + coff, h_root_c.begin() + coff + gr.nchunks);
+      gr.parents_chunk.assign(h_par_c.begin() + (size_t)coff * ldp, h_par_c.begin() + (size_t)(coff + gr.nchunks) * ldp);
+      gr.eta = h_eta_g[g]; gr.root = h_root_g[g];
+      gr.parents.assign(h_par_g.begin() + (size_t)g * ldp, h_par_g.begin() + (size_t)g * ldp + N);
+      gr.mst_i.assign(h_msti.begin() + (size_t)g * ldp, h_msti.begin() + (size_t)g * ldp + N - 1);
+      gr.mst_j.assign(h_mstj.begin() + (size_t)g * ldp, h_mstj.begin() + (size_t)g * ldp + N - 1);
+      gr.mst_w.assign(h_mstw.begin() + (size_t)g * ldp, h_mstw.begin() + (size_t)g * ldp + N - 1);
+    }
+  if (do_final) dedup_triplets(r, G, N, ldp, h_msti, h_mstj, h_val);
+  c.timer.collect(r->timers);
+  r->launches = c.launches;
+  *out = r;
+  return SEQJ_OK;
+}
+
+int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
+                  const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
+                  seqj_result** out) {
+  ST_TRY(check_ready(h));
+  if (!A || M < 1 || N < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
+  DevPool pool;
+  double* A_dev;
+  CU_TRY(pool.alloc(&A_dev, (size_t)M * N));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  cudaEventRecord(e0, h->st);
+  cudaError_t e = cudaMemcpyAsync(A_dev, A, (size_t)M * N * 8, cudaMemcpyHostToDevice, h->st);
+  cudaEventRecord(e1, h->st);
+  if (e != cudaSuccess) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return fail(h, SEQJ_E_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e));
+  }
+  int s = seqj_sequence_dev(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
+  if (s == SEQJ_OK) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    (*out)->timers[SEQJ_T_H2D] = ms;
+    (*out)->timers[SEQJ_T_TOTAL] += ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return s;
+}
+
+int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
+              const int32_t* mst_j, const double* mst_w, double eps_floor, seqj_result** out) {
+  ST_TRY(check_ready(h));
+  if (!eta_group || !mst_i || !mst_j || !mst_w || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const int N = (int)N64, G = ngroups;
+  Ctx c(h);
+  const int64_t ldp = N, ldD = round_up(N, 16);
+  int tt = c.timer.begin(SEQJ_T_TOTAL);
+  double *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val, *Sbuf;
+  int *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f;
+  CU_TRY(c.pool.alloc(&eta_g, (size_t)G)); CU_TRY(c.pool.alloc(&msti_g, (size_t)G * ldp));
+  CU_TRY(c.pool.alloc(&mstj_g, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&mstw_g, (size_t)G * ldp));
+  CU_TRY(c.pool.alloc(&eta_f, 1)); CU_TRY(c.pool.alloc(&root_f, 1)); CU_TRY(c.pool.alloc(&par_f, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&fmst_i, (size_t)ldp)); CU_TRY(c.pool.alloc(&fmst_j, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&Sbuf, (size_t)N * ldD));
+  CU_TRY(cudaMemcpyAsync(eta_g, eta_group, sizeof(double) * G, cudaMemcpyHostToDevice, c.st));
+  for (int g = 0; g < G; ++g) {
+    CU_TRY(cudaMemcpyAsync(msti_g + (size_t)g * ldp, mst_i + (size_t)g * (N - 1), sizeof(int) * (N - 1), cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(mstj_g + (size_t)g * ldp, mst_j + (size_t)g * (N - 1), sizeof(int) * (N - 1), cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(mstw_g + (size_t)g * ldp, mst_w + (size_t)g * (N - 1), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, c.st));
+  }
+  GraphWS gws;
+  ST_TRY(graphws_alloc(c, gws, 1, N));
+  ST_TRY(run_fuse(c, gws, Sbuf, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
+                  fmst_j, fmst_w, order_f, edge_val));
+  seqj_result* r = new seqj_result();
+  r->N = N; r->has_final = 1;
+  r->order.resize(N); r->parents.resize(N); r->mst_i.resize(N - 1); r->mst_j.resize(N - 1); r->mst_w.resize(N - 1);
+  std::vector<double> h_val((size_t)G * ldp);
+  std::vector<int> h_mi((size_t)G * ldp), h_mj((size_t)G * ldp);
+  cudaMemcpyAsync(&r->eta, eta_f, sizeof(double), cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(&r->root, root_f, sizeof(int), cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(r->order.data(), order_f, sizeof(int) * N, cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(r->parents.data(), par_f, sizeof(int) * N, cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(r->mst_i.data(), fmst_i, sizeof(int) * (N - 1), cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(r->mst_j.data(), fmst_j, sizeof(int) * (N - 1), cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(r->mst_w.data(), fmst_w, sizeof(double) * (N - 1), cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(h_val.data(), edge_val, sizeof(double) * (size_t)G * ldp, cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(h_mi.data(), msti_g, sizeof(int) * (size_t)G * ldp, cudaMemcpyDeviceToHost, c.st);
+  cudaMemcpyAsync(h_mj.data(), mstj_g, sizeof(int) * (size_t)G * ldp, cudaMemcpyDeviceToHost, c.st);
+  c.timer.end(tt);
+  cudaError_t e = cudaStreamSynchronize(c.st);
+  if (e != cudaSuccess) {
+    delete r;
+    return fail(h, SEQJ_E_CUDA, std::string("fuse failed: ") + cudaGetErrorString(e));
+  }
+  dedup_triplets(r, G, N, ldp, h_mi, h_mj, h_val);
+  c.timer.collect(r->timers);
+  r->launches = c.launches;
+  *out = r;
+  return SEQJ_OK;
+}
+
+// ---- result accessors -------------------------------------------------------------------------
+int seqj_result_dims(const seqj_result* r, int64_t* N, int* ngroups) {
+  if (!r) return SEQJ_E_BADARG;
+  if (N) *N = r->N;
+  if (ngroups) *ngroups = (int)r->groups.size();
+  return SEQJ_OK;
+}
+int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale, int* nchunks, int* computed) {
+  if (!r || g < 0 || g >= (int)r->groups.size()) return SEQJ_E_BADARG;
+  const GroupRes& gr = r->groups[g];
+  if (metric) *metric = gr.metric;
+  if (scale) *scale = gr.scale;
+  if (nchunks) *nchunks = gr.nchunks;
+  if (computed) *computed = gr.computed;
+  return SEQJ_OK;
+}
+int seqj_result_group_chunks(const seqj_result* r, int g, double* eta_chunk, int32_t* root_chunk, int32_t* parents_chunk) {
+  if (!r || g < 0 || g >= (int)r->groups.size() || !r->groups[g].computed) return SEQJ_E_BADARG;
+  const GroupRes& gr = r->groups[g];
+  copy_out(eta_chunk, gr.eta_chunk); copy_out(root_chunk, gr.root_chunk); copy_out(parents_chunk, gr.parents_chunk);
+  return SEQJ_OK;
+}
+int seqj_result_group(const seqj_result* r, int g, double* eta, int32_t* root, int32_t* parents, int32_t* mst_i,
+                      int32_t* mst_j, double* mst_w) {
+  if (!r || g < 0 || g >= (int)r->groups.size() || !r->groups[g].computed) return SEQJ_E_BADARG;
+  const GroupRes& gr = r->groups[g];
+  if (eta) *eta = gr.eta;
+  if (root) *root = gr.root;
+  copy_out(parents, gr.parents); copy_out(mst_i, gr.mst_i); copy_out(mst_j, gr.mst_j); copy_out(mst_w, gr.mst_w);
+  return SEQJ_OK;
+}
+int seqj_result_final(const seqj_result* r, double* eta, int32_t* root, int32_t* order, int32_t* parents,
+                      int32_t* mst_i, int32_t* mst_j, double* mst_w) {
+  if (!r || !r->has_final) return SEQJ_E_BADARG;
+  if (eta) *eta = r->eta;
+  if (root) *root = r->root;
+  copy_out(order, r->order); copy_out(parents, r->parents); copy_out(mst_i, r->mst_i); copy_out(mst_j, r->mst_j);
+  copy_out(mst_w, r->mst_w);
+  return SEQJ_OK;
+}
+int seqj_result_D_nnz(const seqj_result* r, int64_t* nnz) {
+  if (!r || !nnz) return SEQJ_E_BADARG;
+  *nnz = (int64_t)r->Dv.size();
+  return SEQJ_OK;
+}
+int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double* val) {
+  if (!r) return SEQJ_E_BADARG;
+  copy_out(i, r->Di); copy_out(j, r->Dj); copy_out(val, r->Dv);
+  return SEQJ_OK;
+}
+int seqj_result_timings(const seqj_result* r, double* ms) {
+  if (!r || !ms) return SEQJ_E_BADARG;
+  std::memcpy(ms, r->timers, sizeof(r->timers));
+  return SEQJ_OK;
+}
+int seqj_result_launches(const seqj_result* r, int64_t* launches) {
+  if (!r || !launches) return SEQJ_E_BADARG;
+  *launches = r->launches;
+  return SEQJ_OK;
+}
+void seqj_result_free(seqj_result* r) { delete r; }
+
+// ---- unit-level entry points ------------------------------------------------------------------
+int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, int32_t scale, double* P_out,
+                   double* U_out, int32_t* nchunks_out) {
+  ST_TRY(check_ready(h));
+  if (!A || M64 < 1 || N64 < 1 || scale < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (scale > M64)
+    return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scale) + ") cannot be larger than the number of data elements (" +
+                                      std::to_string(M64) + ").");
+  const int M = (int)M64, N = (int)N64;
+  Ctx c(h);
+  ScaleLayout L = make_layout(M, scale);
+  PrepBufs pb;
+  ST_TRY(alloc_prep(c, pb, N, L.ldX, L.nchunks, true, false, false, true));
+  double *A_dev, *out_dev;
+  CU_TRY(c.pool.alloc(&A_dev, (size_t)M * N)); CU_TRY(c.pool.alloc(&out_dev, (size_t)M * N));
+  CU_TRY(cudaMemcpyAsync(A_dev, A, (size_t)M * N * 8, cudaMemcpyHostToDevice, c.st));
+  ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
+  const int64_t tot = (int64_t)M * N;
+  if (P_out) {
+    unpad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(pb.P, L.ldX, L.cl, L.cl_pad, M, N, out_dev);
+    CU_TRY(cudaMemcpyAsync(P_out, out_dev, tot * 8, cudaMemcpyDeviceToHost, c.st));
+  }
+  if (U_out) {
+    unpad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(pb.U, L.ldX, L.cl, L.cl_pad, M, N, out_dev);
+    CU_TRY(cudaMemcpyAsync(U_out, out_dev, tot * 8, cudaMemcpyDeviceToHost, c.st));
+  }
+  CU_TRY(cudaStreamSynchronize(c.st));
+  if (nchunks_out) *nchunks_out = L.nchunks;
+  return SEQJ_OK;
+}
+
+int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m64, int64_t N64, int normalize,
+                  int kl_full, double eps_floor, double l2_thresh, double* D_out) {
+  ST_TRY(check_ready(h));
+  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > 3) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const int m = (int)m64, N = (int)N64;
+  Ctx c(h);
+  ScaleLayout L = make_layout(m, 1);
+  PrepBufs pb;
+  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD, metric == SEQJ_KLD,
+                    metric == SEQJ_EMD || metric == SEQJ_ENERGY, false));
+  FixBufs fb;
+  ST_TRY(alloc_fix(c, fb, 1u << 20));
+  const bool full = (metric == SEQJ_KLD) && kl_full;
+  std::vector<int2> tiles = make_tiles(N, !full);
+  int2* tiles_dev;
+  CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
+  CU_TRY(cudaMemcpyAsync(tiles_dev, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c.st));
+  const int64_t ldD = round_up(N, 16);
+  double *A_dev, *D_dev;
+  CU_TRY(c.pool.alloc(&A_dev, (size_t)m * N)); CU_TRY(c.pool.alloc(&D_dev, (size_t)N * ldD));
+  CU_TRY(cudaMemcpyAsync(A_dev, chunk, (size_t)m * N * 8, cudaMemcpyHostToDevice, c.st));
+  ST_TRY(run_prep(c, A_dev, m, m, N, L, pb, normalize));
+  ST_TRY(run_distance(c, metric, L, pb, tiles_dev, (int)tiles.size(), N, D_dev, ldD, 0, 0, 1, eps_floor, l2_thresh,
+                      full ? 1 : 0, fb));
+  CU_TRY(cudaMemcpy2DAsync(D_out, (size_t)N * 8, D_dev, (size_t)ldD * 8, (size_t)N * 8, N, cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaStreamSynchronize(c.st));
+  return SEQJ_OK;
+}
+
+int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N64, double eps_floor, double* eta, int32_t* root,
+                    int32_t* parents, int32_t* mst_i, int32_t* mst_j, double* mst_w, int32_t* order) {
+  ST_TRY(check_ready(h));
+  if (!D || N64 < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const int N = (int)N64;
+  Ctx c(h);
+  const int64_t ldD = round_up(N, 16), ldp = N;
+  double *up, *Dsym, *eta_d, *w_d;
+  int *root_d, *par_d, *mi_d, *mj_d, *ord_d;
+  CU_TRY(c.pool.alloc(&up, (size_t)N * N)); CU_TRY(c.pool.alloc(&Dsym, (size_t)N * ldD));
+  CU_TRY(c.pool.alloc(&eta_d, 1)); CU_TRY(c.pool.alloc(&root_d, 1)); CU_TRY(c.pool.alloc(&par_d, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&mi_d, (size_t)ldp)); CU_TRY(c.pool.alloc(&mj_d, (size_t)ldp)); CU_TRY(c.pool.alloc(&w_d, (size_t)ldp));
+  CU_TRY(c.pool.alloc(&ord_d, (size_t)ldp));
+  CU_TRY(cudaMemcpyAsync(up, D, (size_t)N * N * 8, cudaMemcpyHostToDevice, c.st));
+  const int64_t tot = (int64_t)N * N;
+  symmetrize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(up, N, Dsym, ldD, eps_floor);
+  GraphWS gws;
+  ST_TRY(graphws_alloc(c, gws, 1, N));
+  ST_TRY(run_measure(c, gws, Dsym, ldD, 0, 1, eps_floor, eta_d, root_d, par_d, ldp, mi_d, mj_d, w_d, order ? ord_d : nullptr));
+  if (eta) CU_TRY(cudaMemcpyAsync(eta, eta_d, 8, cudaMemcpyDeviceToHost, c.st));
+  if (root) CU_TRY(cudaMemcpyAsync(root, root_d, 4, cudaMemcpyDeviceToHost, c.st));
+  if (parents) CU_TRY(cudaMemcpyAsync(parents, par_d, 4 * (size_t)N, cudaMemcpyDeviceToHost, c.st));
+  if (mst_i) CU_TRY(cudaMemcpyAsync(mst_i, mi_d, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+  if (mst_j) CU_TRY(cudaMemcpyAsync(mst_j, mj_d, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+  if (mst_w) CU_TRY(cudaMemcpyAsync(mst_w, w_d, 8 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+  if (order) CU_TRY(cudaMemcpyAsync(order, ord_d, 4 * (size_t)N, cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaStreamSynchronize(c.st));
+  return SEQJ_OK;
+}
+
+int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, int n, int64_t N64, double* Dkl_out) {
+  ST_TRY(check_ready(h));
+  if (!Dchunks || !etas || !Dkl_out || n < 1 || N64 < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const int N = (int)N64;
+  Ctx c(h);
+  const size_t mat = (size_t)N * N;
+  double *D_dev, *S_dev, *eta_dev;
+  const int B = std::min(n, 32);
+  CU_TRY(c.pool.alloc(&D_dev, mat * B)); CU_TRY(c.pool.alloc(&S_dev, mat)); CU_TRY(c.pool.alloc(&eta_dev, (size_t)n));
+  CU_TRY(cudaMemcpyAsync(eta_dev, etas, sizeof(double) * n, cudaMemcpyHostToDevice, c.st));
+  for (int c0 = 0; c0 < n; c0 += B) {
+    const int nb = std::min(B, n - c0);
+    CU_TRY(cudaMemcpyAsync(D_dev, Dchunks + (size_t)c0 * mat, mat * nb * 8, cudaMemcpyHostToDevice, c.st));
+    combine_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(S_dev, D_dev, (int64_t)mat, nb, eta_dev + c0, c0 == 0, c0 + nb >= n,
+                                                     eta_dev, n, (int64_t)mat);
+    CU_TRY(cudaGetLastError());
+  }
+  CU_TRY(cudaMemcpyAsync(Dkl_out, S_dev, mat * 8, cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaStreamSynchronize(c.st));
+  return SEQJ_OK;
+}
+
+}  // extern "C"

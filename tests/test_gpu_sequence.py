@@ -1,0 +1,131 @@
+"""End-to-end parity of seqj_sequence (through the C ABI) against the oracle's `_sequence` restatement."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import rel_close
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _compare(seqj, oracle, A, scales, metrics_ids):
+    metrics = tuple(seqj.ALL_METRICS[i] for i in metrics_ids)
+    r = seqj.sequence(A.copy(), scales=scales, metrics=metrics)
+    ref = oracle.sequence_oracle(A, scales, metrics_ids)
+    assert len(r.EOAlgScale) == len(ref.groups)
+    for g in ref.groups:
+        key = (seqj.ALL_METRICS[g.metric], g.scale)
+        etas, trees = r.EOSeg[key]
+        rel_close(etas, g.eta_chunk, 1e-9)
+        for t, par, root in zip(trees, g.parents_chunk, g.root_chunk):
+            assert t.root == root and np.array_equal(t.parents, par)
+        eta, tree = r.EOAlgScale[key]
+        rel_close([eta], [g.eta], 1e-9)
+        assert tree.root == g.root and np.array_equal(tree.parents, g.parents)
+        mst = r.group_msts[key]
+        assert set(zip(mst.src.tolist(), mst.dst.tolist())) == set(zip(g.mst[0].tolist(), g.mst[1].tolist()))
+    rel_close([r.eta], [ref.eta], 1e-9)
+    assert r.root == ref.root
+    assert np.array_equal(r.order, ref.order)
+    ti, tj, tv = r.D_triplets
+    got = {(int(a), int(b)): v for a, b, v in zip(ti, tj, tv)}
+    assert got.keys() == ref.D_edges.keys()
+    rel_close([got[k] for k in sorted(got)], [ref.D_edges[k] for k in sorted(got)], 1e-9)
+    return r, ref
+
+
+def test_config1_readme_example(seqj, oracle, handle):
+    """BASELINE config 1: rand(50,100), ALL_METRICS, scales (1,2,4) (reference README.md:16-24)."""
+    A = np.random.default_rng(2732).random((50, 100))
+    r, ref = _compare(seqj, oracle, A, (1, 2, 4), (0, 1, 2, 3))
+    assert sorted(r.order.tolist()) == list(range(100))
+    assert len(r.EOSeg[(seqj.WASS1D, 4)][0]) == 4
+
+
+def test_ragged_chunks_and_scale_not_dividing(seqj, oracle, handle):
+    A = np.random.default_rng(5).random((53, 70))
+    _compare(seqj, oracle, A, (3, 6, 7), (0, 1, 2, 3))
+
+
+def test_midsize_all_metrics(seqj, oracle, handle):
+    A = np.random.default_rng(2733).random((300, 600))
+    _compare(seqj, oracle, A, (1, 2, 4, 8), (0, 1, 2, 3))
+
+
+def test_config2_shape_reduced(seqj, oracle, handle):
+    """BASELINE config 2 metrics/scales (EMD+Energy, scales 1,2,4,8) at a size the oracle finishes quickly."""
+    A = np.random.default_rng(2734).random((1000, 500))
+    _compare(seqj, oracle, A, (1, 2, 4, 8), (1, 3))
+
+
+def test_zero_entries_are_clamped_like_reference(seqj, oracle, handle):
+    A = np.random.default_rng(8).random((40, 50))
+    A[A < 0.2] = 0.0
+    B = A.copy()
+    r = seqj.sequence(B, scales=(1, 2), metrics=seqj.ALL_METRICS)
+    assert B.min() == 2.220446049250313e-16          # clamp! is caller-visible (sequencer.jl:130)
+    ref = oracle.sequence_oracle(A, (1, 2))
+    assert np.array_equal(r.order, ref.order)
+
+
+def test_input_validation(seqj, handle):
+    with pytest.raises(AssertionError):
+        seqj.sequence(-np.ones((10, 10)), scales=(1,))
+    with pytest.raises(AssertionError):
+        seqj.sequence(np.full((10, 10), np.nan), scales=(1,))
+    with pytest.raises(AssertionError):
+        seqj.sequence(np.ones((10, 10)), scales=(11,))
+
+
+def test_scales_int_and_single_metric(seqj, oracle, handle):
+    """scales=(1) is an Int in Julia and is tuplified (reference test/runtests.jl:75)."""
+    A = np.random.default_rng(4).random((30, 40))
+    r = seqj.sequence(A.copy(), scales=1, metrics=seqj.KLD)
+    ref = oracle.sequence_oracle(A, (1,), (2,))
+    assert np.array_equal(r.order, ref.order)
+    assert "Sequencer Result" in repr(r)
+
+
+def test_hummingbird_exact_recovery(seqj, handle):
+    """The reference's only exact end-to-end test (test/runtests.jl:167-175): shuffled columns of the
+    transposed Hummingbird image are recovered exactly with (L2, KLD), scales (1,2,4)."""
+    img = np.load(os.path.join(GOLDEN, "hummingbird_gray_u8.npy"))          # 427 x 640 uint8
+    BIG = (img.astype(np.float32) / np.float32(255)).T.astype(np.float64)   # 640 x 427
+    for seed in (0, 1):
+        idx = np.random.default_rng(seed).permutation(BIG.shape[1])
+        sh = BIG[:, idx]
+        r = seqj.sequence(sh.copy(), scales=(1, 2, 4), metrics=(seqj.L2, seqj.KLD))
+        res = sh[:, r.order]
+        assert np.array_equal(res, BIG)            # loss == 0, un-mirrored
+        assert r.eta == 427.0
+
+
+def test_autoscale_returns_fibonacci(seqj, handle):
+    A = np.random.default_rng(1).random((100, 100))
+    s = seqj.autoscale(A, rng=0)
+    assert s in seqj.FIB
+    with pytest.raises(AssertionError):
+        seqj.autoscale(np.random.default_rng(1).random((5, 100)))
+    with pytest.raises(AssertionError):
+        seqj.autoscale(np.random.default_rng(1).random((100, 5)))
+
+
+def test_group_mask_plus_fuse_equals_full_run(seqj, handle):
+    """Sharding contract: groups computed separately and fused equal the single call."""
+    A = np.random.default_rng(12).random((64, 90))
+    At = np.ascontiguousarray(A.T)
+    metrics, scales = seqj.ALL_METRICS, (1, 2, 4)
+    full = seqj.sequence(A.copy(), scales=scales, metrics=metrics)
+    from sequencerj_b200 import api
+    mask_a = np.zeros((4, 3), dtype=np.uint8); mask_a[:2] = 1
+    ra = api._sequence(At, scales, metrics, group_mask=mask_a)
+    rb = api._sequence(At, scales, metrics, group_mask=1 - mask_a)
+    etas, msts = [], []
+    for m in metrics:
+        for l in scales:
+            src = ra if (m, l) in ra.EOAlgScale else rb
+            etas.append(src.EOAlgScale[(m, l)][0]); msts.append(src.group_msts[(m, l)])
+    fz = seqj.fuse(90, etas, msts)
+    assert fz.eta == full.eta and np.array_equal(fz.order, full.order)

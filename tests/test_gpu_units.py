@@ -1,0 +1,169 @@
+"""GPU parity tests of each layer through the C ABI (libseqj_b200.so) against the CPU oracle.
+
+Tolerances (north_star): distance matrices and eta within 1e-9 relative; MST / root / order
+identical (the seeded inputs below have no ties).  CDF-based metrics add an absolute floor of
+64*m*2^-53 for the inherent prefix-sum rounding noise (the reference's own sequential cumsum has
+the same order of noise)."""
+import numpy as np
+import pytest
+
+from conftest import rel_close
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(M, N, seed):
+    return np.random.default_rng(seed).random((M, N))
+
+
+@pytest.mark.parametrize("M,N,scale", [(50, 100, 1), (50, 100, 2), (50, 100, 4), (10, 7, 6), (137, 33, 5),
+                                       (1000, 64, 8), (4096, 16, 16)])
+def test_splitnorm_matches_oracle(seqj, oracle, handle, M, N, scale):
+    A = oracle.clamp_input(_rand(M, N, 1))
+    P, U, nch = seqj.splitnorm(A, scale)
+    chunks = oracle.splitnorm(A, scale)
+    assert nch == len(chunks) == len(oracle.chunk_bounds(M, scale))
+    Pref = np.vstack(chunks)
+    Uref = np.vstack([oracle.chunk_cdf(c) for c in chunks])
+    rel_close(P, Pref, 1e-13)
+    rel_close(U, Uref, 1e-13, atol=1e-15)
+    for (r0, r1) in oracle.chunk_bounds(M, scale):
+        assert np.all(U[r1 - 1] == 1.0)          # last CDF entry is exactly 1 (StatsBase ecdf)
+
+
+def test_splitnorm_scale_too_large(seqj, handle):
+    with pytest.raises(AssertionError):
+        seqj.splitnorm(np.ones((5, 4)), 6)
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+@pytest.mark.parametrize("m,N", [(50, 100), (13, 100), (11, 37), (137, 300), (256, 1000), (1000, 513)])
+def test_pairwise_matches_oracle(seqj, oracle, handle, metric, m, N):
+    A = oracle.clamp_input(_rand(m, N, 7 + metric))
+    P = oracle.splitnorm(A, 1)[0]
+    ref = oracle.chunk_distance(metric, P)
+    got = seqj.pairwise(metric, A, normalize=True, kl_full=True)
+    rel_close(got, ref, 1e-9, atol=64 * m * 2.0 ** -53)
+    if metric != oracle.KLD:
+        assert np.array_equal(got, got.T)
+    assert np.all(np.diag(got) == 1e-6)
+
+
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_pairwise_faithful_small(seqj, oracle, handle, metric):
+    """Per-pair evaluation exactly as the reference's functors (ECDF objects, sorts) at small N."""
+    A = oracle.clamp_input(_rand(25, 40, 3))
+    P = oracle.splitnorm(A, 1)[0]
+    ref = oracle.chunk_distance(metric, P, faithful=True)
+    got = seqj.pairwise(metric, A, normalize=True, kl_full=True)
+    rel_close(got, ref, 1e-9, atol=64 * 25 * 2.0 ** -53)
+
+
+def test_kl_mirrored_upper(seqj, oracle, handle):
+    A = oracle.clamp_input(_rand(64, 150, 5))
+    full = seqj.pairwise(2, A, kl_full=True)
+    sym = seqj.pairwise(2, A, kl_full=False)
+    iu = np.triu_indices(150, 1)
+    rel_close(sym[iu], full[iu], 1e-12)
+    assert np.array_equal(sym, sym.T)        # Symmetric(dm): upper triangle wins (sequencer.jl:365)
+    assert not np.allclose(full, full.T)
+
+
+@pytest.mark.parametrize("metric", [0, 2, 3])
+def test_near_duplicate_columns_take_fixup_path(seqj, oracle, handle, metric):
+    """Gram-form cancellation regime: columns that differ by ~1e-7 relative must still match the
+    direct formulas of the reference (recomputed by the fix-up kernel)."""
+    rng = np.random.default_rng(11)
+    base = rng.random((200, 1)) + 0.1
+    A = base * (1.0 + 1e-7 * rng.standard_normal((200, 90)))
+    A[:, 10] = A[:, 3]                        # exact duplicate -> distance exactly 0 (+eps)
+    A = oracle.clamp_input(A)
+    P = oracle.splitnorm(A, 1)[0]
+    if metric == 0:                           # direct formula (what Distances recomputes below thresh)
+        ref = np.sqrt(((P[:, :, None] - P[:, None, :]) ** 2).sum(axis=0)) + 1e-6
+    else:
+        ref = oracle.chunk_distance(metric, P)
+    got = seqj.pairwise(metric, A, kl_full=True)
+    # Energy: each CDF entry carries a few ulp(1) of prefix-sum rounding noise in BOTH implementations
+    # (sequential cumsum vs warp scan), which dominates when |U_i - U_j| ~ 1e-8: absolute floor 4*m*2^-53.
+    rel_close(got, ref, 1e-9, atol=(4 * 200 * 2.0 ** -53) if metric == 3 else 1e-16)
+    assert got[10, 3] == 1e-6 and got[3, 10] == 1e-6
+
+
+def test_pairwise_algotests_known_answers(seqj, handle):
+    """reference test/algotests.jl:6-25 (Euclidean sqrt(14); KL 0.5108256237659907)."""
+    A = np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 4.0]])
+    Dm = seqj.pairwise(0, A, normalize=False, eps_floor=0.0)
+    assert abs(Dm[0, 1] - np.sqrt(14.0)) < 1e-14 and Dm[0, 0] == 0.0
+    K = seqj.pairwise(2, np.array([[0.5, 0.9], [0.5, 0.1]]), normalize=False, eps_floor=0.0, kl_full=True)
+    assert abs(K[0, 1] - 0.5108256237659907) < 1e-15
+
+
+def test_emd_energy_pair_functions(seqj, oracle, handle):
+    """EMD()(u,v) / Energy()(u,v) on the default unit grid (distancemetrics.jl:46-50,158-162)
+    against the faithful ECDF restatement and SciPy."""
+    from scipy.stats import energy_distance, wasserstein_distance
+    rng = np.random.default_rng(5)
+    u, v = rng.random(37), rng.random(37)
+    g = np.arange(1, 38, dtype=float)
+    assert abs(seqj.emd(u, v) - oracle.emd(u, v)) < 1e-12
+    assert abs(seqj.energy(u, v) - oracle.energy(u, v)) < 1e-12
+    assert abs(seqj.emd(u, v) - wasserstein_distance(g, g, u, v)) < 1e-12
+    assert abs(seqj.energy(u, v) - energy_distance(g, g, u, v)) < 1e-12
+    assert seqj.EMD()(u, v) == seqj.emd(u, v) and seqj.Energy()(u, v) == seqj.energy(u, v)
+
+
+def _random_dist(N, seed):
+    rng = np.random.default_rng(seed)
+    X = rng.random((N, 3))
+    Dm = np.sqrt(((X[:, None, :] - X[None, :, :]) ** 2).sum(-1)) + 1e-6
+    return Dm
+
+
+def _edge_set(t):
+    return set(zip(np.minimum(t.src, t.dst).tolist(), np.maximum(t.src, t.dst).tolist()))
+
+
+@pytest.mark.parametrize("N", [2, 3, 17, 100, 1000, 2500])
+def test_measure_dm_matches_oracle(seqj, oracle, handle, N):
+    Dm = _random_dist(N, N)
+    ref = oracle.measure_dm(Dm)
+    got = seqj.measure_dm(Dm, want_order=True)
+    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+    rel_close(np.sort(got.mst.weight), np.sort(ref.mst_w), 1e-15)
+    assert got.root == ref.root
+    assert got.eta == ref.eta                      # pure function of integers -> bit-identical
+    assert np.array_equal(got.bfs.parents, ref.parents)
+    assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
+
+
+def test_measure_dm_upper_triangle_wins_and_inf_nonedges(seqj, oracle, handle):
+    rng = np.random.default_rng(3)
+    N = 60
+    Dm = rng.random((N, N)) + 0.01                 # asymmetric: Symmetric(dm) keeps the upper triangle
+    got = seqj.measure_dm(Dm)
+    sym = np.triu(Dm) + np.triu(Dm, 1).T
+    ref = oracle.measure_dm(sym)
+    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+    assert got.root == ref.root and got.eta == ref.eta
+    # a path graph with Inf non-edges: the MST must be the path itself, eta = N
+    P = np.full((N, N), np.inf); np.fill_diagonal(P, 0.0)
+    for i in range(N - 1):
+        P[i, i + 1] = P[i + 1, i] = 1.0 + 0.001 * i
+    got = seqj.measure_dm(P, want_order=True)
+    assert _edge_set(got.mst) == {(i, i + 1) for i in range(N - 1)}
+    assert got.eta == float(N)
+    assert got.order.tolist() in (list(range(N)), list(range(N))[::-1])
+
+
+def test_accumulate_matches_reference_formula(seqj, handle):
+    rng = np.random.default_rng(9)
+    Ds = rng.random((5, 40, 40)) + 1e-6
+    etas = rng.random(5) * 5 + 1
+    S = np.zeros((40, 40))
+    for c in range(5):
+        S += np.maximum(etas[c] * Ds[c], 2.220446049250313e-16)
+    tot = 0.0
+    for e in etas:
+        tot += e
+    assert np.array_equal(seqj.accumulate(Ds, etas), S / tot)     # same order of operations: bit-exact

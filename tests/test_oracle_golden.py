@@ -1,0 +1,190 @@
+"""Pins the CPU oracle (oracle/seq_oracle.py) against every known answer the reference's own tests
+hold for the hot path (reference test/algotests.jl, test/runtests.jl:167-175) and against
+independent SciPy / NetworkX implementations.  CPU only."""
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+# ---- reference test/algotests.jl known answers ---------------------------------------------------
+def test_euclidean_known_answers(oracle):
+    # algotests.jl:6-17
+    assert math.isclose(oracle.euclidean([1, 1, 1], [2, 3, 4]), math.sqrt(14), rel_tol=1e-15)
+    A = np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 4.0]])
+    Dm = oracle.pairwise_vec(oracle.L2, A)
+    assert np.allclose(Dm, [[0, math.sqrt(14)], [math.sqrt(14), 0]], rtol=1e-15)
+
+
+def test_kl_known_answer(oracle):
+    # algotests.jl:21-25 ("same as scipy.stats.entropy")
+    assert math.isclose(oracle.kl_divergence([0.5, 0.5], [0.9, 0.1]), 0.5108256237659907, rel_tol=1e-15)
+
+
+def test_emd_known_answers(oracle):
+    # algotests.jl:36-41, 50-57 (explicit, different grids)
+    got = oracle.emd([3.4, 3.9, 7.5, 7.8], [4.5, 1.4], [1.4, 0.9, 3.1, 7.2], [3.2, 3.5])
+    assert math.isclose(got, 4.0781331438047861, rel_tol=1e-14)
+    assert oracle.emd([1, 1, 1], [2, 3, 4]) is not None                 # :30-33
+    g = [0.5, 1.0, 1.5, 2.0]
+    assert oracle.emd(g, g, [3.4, 3.9, 7.5, 7.8], [1.4, 0.9, 3.1, 7.2]) is not None   # :43-48
+
+
+def test_energy_known_answers(oracle):
+    # algotests.jl:74-107
+    assert math.isclose(oracle.energy([0, 8], [0, 8], [3, 1], [2, 2]), 1.0, rel_tol=1e-15)
+    assert math.isclose(oracle.energy([3.4, 3.9, 7.5, 7.8], [4.5, 1.4], [1.4, 0.9, 3.1, 7.2], [3.2, 3.5]),
+                        2.3674181638546394, rel_tol=1e-14)
+    assert math.isclose(oracle.energy([0.7, 7.4, 2.4, 6.8], [1.4, 8.0], [2.1, 4.2, 7.4, 8.0], [7.6, 8.8]),
+                        0.8800334097615822, rel_tol=1e-14)
+    assert oracle.energy([1, 1, 1], [2, 3, 4]) is not None              # :61-64
+
+
+def test_unit_grid_metrics_match_scipy(oracle):
+    from scipy.stats import energy_distance, entropy, wasserstein_distance
+    rng = np.random.default_rng(0)
+    for m in (5, 13, 50):
+        u, v = rng.random(m), rng.random(m)
+        g = np.arange(1, m + 1, dtype=float)
+        assert math.isclose(oracle.emd(u, v), wasserstein_distance(g, g, u, v), rel_tol=1e-12)
+        assert math.isclose(oracle.energy(u, v), energy_distance(g, g, u, v), rel_tol=1e-12)
+        p, q = u / u.sum(), v / v.sum()
+        assert math.isclose(oracle.kl_divergence(p, q), entropy(p, q), rel_tol=1e-12)
+
+
+# ---- _splitnorm quirks ----------------------------------------------------------
+def test_chunk_bounds_quirks(oracle):
+    assert [b - a for a, b in oracle.chunk_bounds(50, 4)] == [13, 13, 13, 11]
+    assert [b - a for a, b in oracle.chunk_bounds(100, 3)] == [34, 34, 32]
+    assert len(oracle.chunk_bounds(10, 6)) == 5           # fewer chunks than the scale
+    assert [b - a for a, b in oracle.chunk_bounds(4096, 16)] == [256] * 16
+    with pytest.raises(AssertionError):
+        oracle.chunk_bounds(5, 6)
+
+
+def test_splitnorm_and_cdf(oracle):
+    A = oracle.clamp_input(np.random.default_rng(1).random((50, 20)))
+    for P in oracle.splitnorm(A, 4):
+        assert np.allclose(P.sum(axis=0), 1.0, rtol=1e-14)
+        U = oracle.chunk_cdf(P)
+        assert np.all(U[-1] == 1.0) and np.all(np.diff(U, axis=0) > 0)
+
+
+def test_clamp_input(oracle):
+    A = np.zeros((3, 3))
+    assert oracle.clamp_input(A).min() == 2.220446049250313e-16
+    with pytest.raises(AssertionError):
+        oracle.clamp_input(-np.ones((2, 2)))
+    with pytest.raises(AssertionError):
+        oracle.clamp_input(np.array([[np.inf, 1.0]]))
+
+
+# ---- faithful (per-pair functors) vs vectorised restatement ---------------------------------------
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_faithful_equals_vectorised(oracle, metric):
+    A = oracle.clamp_input(np.random.default_rng(2).random((23, 30)))
+    P = oracle.splitnorm(A, 1)[0]
+    a = oracle.chunk_distance(metric, P, faithful=True)
+    b = oracle.chunk_distance(metric, P, faithful=False)
+    assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
+    assert np.all(np.diag(a) == 1e-6)
+    if metric == oracle.KLD:
+        assert not np.allclose(a, a.T)
+
+
+# ---- graph layer against independent implementations ----------------------------------------------
+def _random_dist(N, seed):
+    X = np.random.default_rng(seed).random((N, 3))
+    return np.sqrt(((X[:, None] - X[None]) ** 2).sum(-1)) + 1e-6
+
+
+@pytest.mark.parametrize("N", [5, 60, 400])
+def test_kruskal_matches_scipy_and_networkx(oracle, N):
+    import networkx as nx
+    from scipy.sparse.csgraph import minimum_spanning_tree
+    Dm = _random_dist(N, N)
+    ei, ej, ew = oracle.kruskal_mst(Dm)
+    assert len(ei) == N - 1 and np.all(ei < ej)
+    T = minimum_spanning_tree(np.triu(Dm, 1)).tocoo()
+    assert set(zip(ei.tolist(), ej.tolist())) == set(zip(np.minimum(T.row, T.col).tolist(),
+                                                          np.maximum(T.row, T.col).tolist()))
+    G = nx.from_numpy_array(Dm - np.diag(np.diag(Dm)))
+    Tn = nx.minimum_spanning_tree(G, algorithm="kruskal")
+    assert set(zip(ei.tolist(), ej.tolist())) == {(min(a, b), max(a, b)) for a, b in Tn.edges()}
+    assert math.isclose(ew.sum(), T.data.sum(), rel_tol=1e-12)
+
+
+def test_root_elongation_against_networkx(oracle):
+    import networkx as nx
+    N = 80
+    Dm = _random_dist(N, 9)
+    ms = oracle.measure_dm(Dm)
+    T = nx.Graph()
+    T.add_weighted_edges_from(zip(ms.mst_i.tolist(), ms.mst_j.tolist(), ms.mst_w.tolist()))
+    cc = nx.closeness_centrality(T, distance="weight")
+    assert ms.root == min(range(N), key=lambda u: (cc[u], u))      # least central point
+    h = nx.single_source_shortest_path_length(T, ms.root)
+    hs = np.array([h[v] for v in range(N)])
+    levels, counts = np.unique(hs, return_counts=True)
+    eta = hs.mean() / (counts.mean() / 2) + 1                        # sequencer.jl:334-354
+    assert math.isclose(ms.eta, eta, rel_tol=1e-14)
+    assert np.array_equal(ms.depth, hs)
+    # rerooting shortcut agrees with the faithful N-Dijkstra sums
+    a = oracle.tree_distance_sums(N, ms.mst_i, ms.mst_j, ms.mst_w, faithful=True)
+    b = oracle.tree_distance_sums(N, ms.mst_i, ms.mst_j, ms.mst_w, faithful=False)
+    assert np.allclose(a, b, rtol=1e-12)
+
+
+def test_unroll_is_reversed_preorder(oracle):
+    #       0
+    #      / \
+    #     2   1
+    #     |
+    #     3
+    parents = np.array([0, 0, 0, 2])
+    assert oracle.unroll(parents, 0).tolist() == [3, 2, 1, 0]       # reverse of preorder 0,1,2,3
+    path = np.array([1, 2, 3, 3])                                    # 3 -> 2 -> 1 -> 0
+    assert oracle.unroll(path, 3).tolist() == [0, 1, 2, 3]
+
+
+def test_path_graph_elongation_is_N(oracle):
+    N = 25
+    P = np.full((N, N), np.inf); np.fill_diagonal(P, 0.0)
+    for i in range(N - 1):
+        P[i, i + 1] = P[i + 1, i] = 1.0 + 0.01 * i
+    ms = oracle.measure_dm(P)
+    assert ms.eta == float(N) and ms.root in (0, N - 1)
+
+
+# ---- end to end -----------------------------------------------------------------------------------
+def test_sequence_config1_golden_fixture(oracle):
+    """The committed golden vector (tests/golden/make_golden.py) still matches the oracle."""
+    g = np.load(os.path.join(GOLDEN, "config1_oracle.npz"))
+    r = oracle.sequence_oracle(g["A"], (1, 2, 4))
+    assert np.array_equal(r.order, g["order"])
+    assert r.eta == float(g["eta"])
+    assert np.allclose([x.eta for x in r.groups], g["eta_groups"], rtol=1e-12)
+    assert 1.0 < r.eta < 50.0
+    assert sorted(r.order.tolist()) == list(range(100))
+
+
+def test_sequence_faithful_equals_vectorised(oracle):
+    A = np.random.default_rng(2732).random((20, 24))
+    a = oracle.sequence_oracle(A, (1, 2), faithful=True)
+    b = oracle.sequence_oracle(A, (1, 2), faithful=False)
+    assert np.array_equal(a.order, b.order) and a.eta == b.eta
+
+
+def test_hummingbird_exact_recovery_oracle(oracle):
+    """reference test/runtests.jl:167-175: loss == 0, i.e. the shuffled columns come back in the original,
+    un-mirrored order. Pins root choice + unroll + the whole pipeline jointly."""
+    img = np.load(os.path.join(GOLDEN, "hummingbird_gray_u8.npy"))
+    BIG = (img.astype(np.float32) / np.float32(255)).T.astype(np.float64)
+    idx = np.random.default_rng(0).permutation(BIG.shape[1])
+    sh = BIG[:, idx]
+    r = oracle.sequence_oracle(sh, (1, 2, 4), metrics=(oracle.L2, oracle.KLD))
+    assert np.array_equal(sh[:, r.order], BIG)
+    assert r.eta == 427.0
