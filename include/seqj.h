@@ -72,6 +72,10 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev);
 void seqj_destroy(seqj_handle* h);
 const char* seqj_last_error(const seqj_handle* h);
 
+/* The handle keeps its device workspace between calls (repeated calls of one shape reuse it);
+ * this frees it without destroying the handle. */
+int seqj_release_workspace(seqj_handle* h);
+
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
 

@@ -451,44 +451,42 @@ def dense_from_edges(N, edges):
     return D
 
 
-def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_root=True,
-                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR) -> OracleResult:
-    """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects)."""
-    A = clamp_input(A)
+def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=False,
+                  eps_floor=EPS_FLOOR, l2_thresh=L2THR):
+    """One (metric k, scale l) iteration of the double loop in _sequence (sequencer.jl:196-258).
+    A is already clamped. Returns (GroupResult, min root-score gap)."""
     M, N = A.shape
-    if isinstance(scales, (int, np.integer)):
-        scales = (int(scales),)
-    if isinstance(metrics, (int, np.integer)):
-        metrics = (int(metrics),)
-    groups, msts, etas = [], [], []
     min_gap = float("inf")
-    for k in metrics:
-        for l in scales:
-            S = np.zeros((N, N))
-            eta_c, par_c, root_c, Dcs = [], [], [], []
-            for P in splitnorm(A, l):
-                Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh)
-                if k == KLD:                     # Symmetric(dm): only the upper triangle is ever read
-                    Dsym = np.triu(Dc) + np.triu(Dc, 1).T
-                else:
-                    Dsym = Dc
-                ms = measure_dm(Dsym, faithful_root)
-                min_gap = min(min_gap, ms.root_score_gap)
-                S += np.maximum(ms.eta * Dc, JULIA_EPS)          # sequencer.jl:231-235
-                eta_c.append(ms.eta); par_c.append(ms.parents); root_c.append(ms.root)
-                if keep_matrices:
-                    Dcs.append(Dc)
-            tot = 0.0
-            for e in eta_c:
-                tot += e
-            Dkl = S / tot                                        # :247
-            Dsym = np.triu(Dkl) + np.triu(Dkl, 1).T if k == KLD else Dkl
-            ms = measure_dm(Dsym, faithful_root)
-            min_gap = min(min_gap, ms.root_score_gap)
-            mst = (ms.mst_i, ms.mst_j, ms.mst_w)
-            groups.append(GroupResult(k, l, eta_c, par_c, root_c, ms.eta, ms.parents, ms.root, mst,
-                                      Dkl if keep_matrices else None, Dcs if keep_matrices else None))
-            msts.append(mst); etas.append(ms.eta)
+    S = np.zeros((N, N))
+    eta_c, par_c, root_c, Dcs = [], [], [], []
+    for P in splitnorm(A, l):
+        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh)
+        if k == KLD:                     # Symmetric(dm): only the upper triangle is ever read
+            Dsym = np.triu(Dc) + np.triu(Dc, 1).T
+        else:
+            Dsym = Dc
+        ms = measure_dm(Dsym, faithful_root)
+        min_gap = min(min_gap, ms.root_score_gap)
+        S += np.maximum(ms.eta * Dc, JULIA_EPS)          # sequencer.jl:231-235
+        eta_c.append(ms.eta); par_c.append(ms.parents); root_c.append(ms.root)
+        if keep_matrices:
+            Dcs.append(Dc)
+    tot = 0.0
+    for e in eta_c:
+        tot += e
+    Dkl = S / tot                                        # :247
+    Dsym = np.triu(Dkl) + np.triu(Dkl, 1).T if k == KLD else Dkl
+    ms = measure_dm(Dsym, faithful_root)
+    min_gap = min(min_gap, ms.root_score_gap)
+    mst = (ms.mst_i, ms.mst_j, ms.mst_w)
+    return GroupResult(k, l, eta_c, par_c, root_c, ms.eta, ms.parents, ms.root, mst,
+                       Dkl if keep_matrices else None, Dcs if keep_matrices else None), min_gap
+
+
+def fuse_groups(N, groups, faithful_root=True, min_gap=float("inf")) -> OracleResult:
+    """sequencer.jl:266-275: proximity fuse, final _measure_dm, unroll."""
+    msts = [g.mst for g in groups]
+    etas = [g.eta for g in groups]
     edges = weighted_p_edges(N, msts, etas)
     D = dense_from_edges(N, edges)
     ms = measure_dm(D, faithful_root)
@@ -496,3 +494,58 @@ def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_roo
     order = unroll(ms.parents, ms.root)
     return OracleResult(groups, ms.eta, ms.root, order, ms.parents, (ms.mst_i, ms.mst_j, ms.mst_w),
                         edges, min_gap)
+
+
+def _norm_args(scales, metrics):
+    if isinstance(scales, (int, np.integer)):
+        scales = (int(scales),)
+    if isinstance(metrics, (int, np.integer)):
+        metrics = (int(metrics),)
+    return tuple(scales), tuple(metrics)
+
+
+def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_root=True,
+                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR) -> OracleResult:
+    """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects)."""
+    A = clamp_input(A)
+    M, N = A.shape
+    scales, metrics = _norm_args(scales, metrics)
+    groups = []
+    min_gap = float("inf")
+    for k in metrics:
+        for l in scales:
+            g, gap = compute_group(A, k, l, faithful, faithful_root, keep_matrices, eps_floor, l2_thresh)
+            groups.append(g)
+            min_gap = min(min_gap, gap)
+    return fuse_groups(N, groups, faithful_root, min_gap)
+
+
+_PAR_A = None
+
+
+def _par_group(args):
+    k, l, faithful_root = args
+    return compute_group(_PAR_A, k, l, False, faithful_root)[0]
+
+
+def sequence_oracle_parallel(A, scales, metrics=ALL_METRICS, procs=None, faithful_root=True) -> OracleResult:
+    """Same result as sequence_oracle, with the independent (metric, scale) groups spread over host
+    processes (fork). Used only as the CPU baseline of bench.py: the reference itself is single-threaded."""
+    import multiprocessing as mp
+    import os
+    global _PAR_A
+    A = clamp_input(A)
+    M, N = A.shape
+    scales, metrics = _norm_args(scales, metrics)
+    tasks = [(k, l, faithful_root) for k in metrics for l in scales]
+    procs = procs or os.cpu_count() or 1
+    _PAR_A = A
+    try:
+        if procs <= 1 or len(tasks) == 1:
+            groups = [_par_group(t) for t in tasks]
+        else:
+            with mp.get_context("fork").Pool(min(procs, len(tasks))) as pool:
+                groups = pool.map(_par_group, tasks, chunksize=1)
+    finally:
+        _PAR_A = None
+    return fuse_groups(N, groups, faithful_root)

@@ -9,6 +9,7 @@ from .api import (ALL_METRICS, EMD, ENERGY, FIB, KLD, L2, WASS1D, BFSTree, Energ
                   energy, ensuregrid, fuse, measure_dm, mst, order, pairwise, prettyp, sequence, splitnorm)
 from ._lib import Handle, SeqjError, load
 from . import build as _build
+from . import sharding
 
 __all__ = ["ALL_METRICS", "EMD", "ENERGY", "FIB", "KLD", "L2", "WASS1D", "BFSTree", "Energy", "MeasureResult",
            "Metric", "SequencerResult", "WeightedTree", "D", "accumulate", "autoscale", "default_handle", "elong",

@@ -182,10 +182,12 @@ def _prepare_input(A):
         A = A.reshape(1, -1)
     if A.ndim != 2:
         raise ValueError("A must be a vector or an M x N matrix")
-    if not (np.all(np.isfinite(A)) and np.all(A >= 0)):
+    mn, mx = (A.min(), A.max()) if A.size else (0.0, 0.0)      # two streaming passes; NaN propagates into both
+    if not (mn >= 0 and np.isfinite(mx)):
         raise AssertionError("Input data cannot contain negative, NaN or infinite values.")
     if A.dtype == np.float64 and A.flags.writeable:
-        np.maximum(A, JULIA_EPS, out=A)                                         # clamp!(A, eps(), typemax)
+        if mn < JULIA_EPS:
+            np.maximum(A, JULIA_EPS, out=A)                                     # clamp!(A, eps(), typemax)
         Af = A
     else:
         Af = np.maximum(A.astype(np.float64), JULIA_EPS)

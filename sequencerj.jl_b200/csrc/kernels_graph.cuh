@@ -15,13 +15,14 @@
 namespace seqj {
 
 constexpr int kPrimThreads = 1024;
-constexpr int kPrimUnroll = 8;
+constexpr int kPrimUnroll = 8;      // 8 x 16 B loads per thread in flight: one batch covers N <= 16384
 constexpr double kJuliaEps = 2.220446049250313e-16;       // eps(Float64)
 constexpr double kFloatMax32 = 3.4028234663852886e38;     // floatmax(Float32)
 
 struct PrimParams {
-  const double* D;      // batch of dense symmetric N x N matrices (row r at D + r*ldD)
+  const double* D;      // pool of dense symmetric N x N matrices (row r of matrix s at D + s*strideD + r*ldD)
   int64_t ldD, strideD;
+  const int* mat_slot;  // optional: graph g reads matrix mat_slot[g] (else matrix g)
   int N;
   double eps_floor;     // _mst clamps to [eps, Inf] (src/sequencer.jl:360)
   int* parent;          // [graph][ldv]  Prim parent (start vertex 0 -> itself)
@@ -37,20 +38,30 @@ __device__ __forceinline__ void argmin_combine(double& k, int& v, double ok, int
   if (ok < k || (ok == k && ov < v)) { k = ok; v = ov; }
 }
 
-// HBM-bound: each of the N-1 steps streams one 8N-byte row; 8*N^2 bytes per graph in total.
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+
+// Dense Prim, one CTA per graph.  HBM-bound by construction: each of the N-1 steps streams one
+// 8N-byte row exactly once (8*N^2 bytes per graph); the keys live in shared memory.  Thread t owns
+// the vertex pairs {2t, 2t+1} + 2048 r, so a row is fetched with 16-byte loads, all in flight at once.
 __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   extern __shared__ double prim_sm[];
   __shared__ double rk[2][32];
   __shared__ int rv[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
+  const int Npad = (N + 1) & ~1;
   const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
-  const double* __restrict__ D = p.D + (int64_t)blockIdx.x * p.strideD;
+  const int slot = p.mat_slot ? p.mat_slot[blockIdx.x] : (int)blockIdx.x;
+  const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
   double* key;
   int* from;
   if (p.use_smem) {
     key = prim_sm;
-    from = reinterpret_cast<int*>(prim_sm + ((N + 1) & ~1));
+    from = reinterpret_cast<int*>(prim_sm + Npad);
   } else {
     key = p.key_g + gofs;
     from = p.from_g + gofs;
@@ -59,7 +70,8 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   double* weight = p.weight + gofs;
   int* order = p.order + gofs;
 
-  for (int v = tid; v < N; v += kPrimThreads) { key[v] = CUDART_INF; from[v] = 0; }
+  // keys: +Inf = not reached yet, -1 = in the tree (or padding)
+  for (int v = tid; v < Npad; v += kPrimThreads) { key[v] = (v < N) ? CUDART_INF : -1.0; from[v] = 0; }
   __syncthreads();
   if (tid == 0) { key[0] = -1.0; parent[0] = 0; weight[0] = 0.0; order[0] = 0; }
   __syncthreads();
@@ -69,23 +81,30 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
     const double* __restrict__ row = D + (int64_t)u * p.ldD;
     double bk = CUDART_INF;
     int bv = 0x7fffffff;
-    for (int base = tid; base < N; base += kPrimThreads * kPrimUnroll) {
-      double dv[kPrimUnroll];
+    for (int base = 2 * tid; base < N; base += 2 * kPrimThreads * kPrimUnroll) {
+      double2 dv[kPrimUnroll];
 #pragma unroll
       for (int r = 0; r < kPrimUnroll; ++r) {
-        const int v = base + r * kPrimThreads;
-        dv[r] = (v < N) ? __ldg(row + v) : CUDART_INF;
+        const int v = base + r * 2 * kPrimThreads;
+        if (v < N) dv[r] = ldg_stream_f64x2(row + v);      // v even, ldD % 16 == 0: 16 B aligned; v+1 < ldD
       }
 #pragma unroll
       for (int r = 0; r < kPrimUnroll; ++r) {
-        const int v = base + r * kPrimThreads;
+        const int v = base + r * 2 * kPrimThreads;
         if (v < N) {
-          double k = key[v];
-          if (k >= 0.0) {                       // not yet in the tree
-            const double d = fmax(dv[r], p.eps_floor);
-            if (d < k) { k = d; key[v] = d; from[v] = u; }
-            if (k < bk || bv == 0x7fffffff) { bk = k; bv = v; }
+          double2 k2 = *reinterpret_cast<double2*>(key + v);
+          bool upd = false;
+          if (k2.x >= 0.0) {                       // not yet in the tree
+            const double d = fmax(dv[r].x, p.eps_floor);
+            if (d < k2.x) { k2.x = d; from[v] = u; upd = true; }
+            if (k2.x < bk || bv == 0x7fffffff) { bk = k2.x; bv = v; }
           }
+          if (k2.y >= 0.0) {
+            const double d = fmax(dv[r].y, p.eps_floor);
+            if (d < k2.y) { k2.y = d; from[v + 1] = u; upd = true; }
+            if (k2.y < bk || bv == 0x7fffffff) { bk = k2.y; bv = v + 1; }
+          }
+          if (upd) *reinterpret_cast<double2*>(key + v) = k2;
         }
       }
     }
@@ -106,7 +125,7 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
       argmin_combine(bk, bv, ok, ov);
     }
     u = bv;
-    if ((u % kPrimThreads) == tid) {            // the owner of key[u] retires it
+    if (((u >> 1) % kPrimThreads) == tid) {       // the owner of key[u] retires it
       order[step] = u;
       parent[u] = from[u];
       weight[u] = bk;
@@ -315,25 +334,41 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
 
 // ---- eta-weighted combine ---------------------------------------------------------------------
 // S = (first ? 0 : S) + sum_c clamp(eta_c * D_c, eps(), Inf)  in chunk order; if last: S /= sum(eta_all)
-// HBM-bound: 8*(nb+1..2) bytes per entry.
+// (reference src/sequencer.jl:231-235,247; the sequential order keeps the rounding of the reference).
+// HBM-bound: 8*(nb + 1 [+1]) bytes per entry.  One double2 per thread, nb independent loads in flight.
+constexpr int kCombineMax = 32;
 __global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ S, const double* __restrict__ Db,
                                                       int64_t strideD, int nb, const double* __restrict__ eta_b,
                                                       int first, int last, const double* __restrict__ eta_all,
-                                                      int n_all, int64_t total) {
-  double e[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) e[c] = (c < nb) ? eta_b[c] : 0.0;
-  double tot = 0.0;
-  if (last)
-    for (int c = 0; c < n_all; ++c) tot += eta_all[c];
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+                                                      int n_all, int64_t total2 /* number of double2 */) {
+  __shared__ double e[kCombineMax];
+  __shared__ double s_tot;
+  if (threadIdx.x < kCombineMax) e[threadIdx.x] = (threadIdx.x < nb) ? eta_b[threadIdx.x] : 0.0;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    if (last)
+      for (int c = 0; c < n_all; ++c) tot += eta_all[c];
+    s_tot = tot;
+  }
+  __syncthreads();
+  const double tot = s_tot;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total2;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    double s = first ? 0.0 : S[idx];
+    double2 s = first ? make_double2(0.0, 0.0) : reinterpret_cast<const double2*>(S)[idx];
+    for (int c0 = 0; c0 < nb; c0 += 8) {
+      double2 d[8];
 #pragma unroll
-    for (int c = 0; c < 32; ++c)
-      if (c < nb) s += fmax(e[c] * Db[(int64_t)c * strideD + idx], kJuliaEps);
-    if (last) s /= tot;
-    S[idx] = s;
+      for (int c = 0; c < 8; ++c)
+        if (c0 + c < nb) d[c] = ldg_stream_f64x2(Db + (int64_t)(c0 + c) * strideD + 2 * idx);
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+        if (c0 + c < nb) {
+          s.x += fmax(e[c0 + c] * d[c].x, kJuliaEps);
+          s.y += fmax(e[c0 + c] * d[c].y, kJuliaEps);
+        }
+    }
+    if (last) { s.x /= tot; s.y /= tot; }
+    reinterpret_cast<double2*>(S)[idx] = s;
   }
 }
 
@@ -354,9 +389,9 @@ __global__ void fuse_scatter_kernel(double* __restrict__ P, int64_t ldD, const i
 // D = inv.(P / sum(eta)) with +Inf diagonal proximity (=> 0 -> clamped to eps by _mst); non-edges stay +Inf
 // (src/sequencer.jl:324-326,269,360).
 __global__ void fuse_finalize_kernel(double* __restrict__ P, int64_t ldD, int N, const double* __restrict__ eta_g,
-                                     int ngroups, double eps_floor) {
-  double tot = 0.0;
-  for (int g = 0; g < ngroups; ++g) tot += eta_g[g];
+                                     const int* __restrict__ perm, int ngroups, double eps_floor) {
+  double tot = 0.0;      // sum(eta_all) in the reference's (metric-major) group order
+  for (int g = 0; g < ngroups; ++g) tot += eta_g[perm ? perm[g] : g];
   const int64_t total = (int64_t)N * ldD;
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {

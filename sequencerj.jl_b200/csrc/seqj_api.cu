@@ -32,6 +32,10 @@ struct seqj_handle {
   EncodeTiledFn encode = nullptr;
   int sm_count = 0;
   size_t max_smem = 0;
+  // Device blocks kept between calls (exact-size reuse): repeated sequence() calls of the same shape do not
+  // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
+  std::multimap<size_t, void*> cache;
+  size_t cached_bytes = 0;
 };
 
 struct GroupRes {
@@ -80,19 +84,44 @@ int fail(seqj_handle* h, int code, const std::string& msg) {
 
 inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
 
-// RAII device allocations, freed when the owning call returns.
+void release_cache(seqj_handle* h) {
+  for (auto& kv : h->cache) cudaFree(kv.second);
+  h->cache.clear();
+  h->cached_bytes = 0;
+}
+
+// RAII device allocations; blocks go back to the handle's cache when the owning call returns.
 struct DevPool {
-  std::vector<void*> ptrs;
+  seqj_handle* h;
+  std::vector<std::pair<size_t, void*>> blocks;
+  explicit DevPool(seqj_handle* hh) : h(hh) {}
   ~DevPool() {
-    for (void* p : ptrs) cudaFree(p);
+    for (auto& b : blocks) {
+      h->cache.emplace(b.first, b.second);
+      h->cached_bytes += b.first;
+    }
   }
   template <typename T>
   cudaError_t alloc(T** out, size_t count) {
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~size_t(255);
     void* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
-    if (e == cudaSuccess) ptrs.push_back(p);
+    auto it = h->cache.find(bytes);
+    if (it != h->cache.end()) {
+      p = it->second;
+      h->cache.erase(it);
+      h->cached_bytes -= bytes;
+    } else {
+      cudaError_t e = cudaMalloc(&p, bytes);
+      if (e == cudaErrorMemoryAllocation && !h->cache.empty()) {
+        cudaGetLastError();
+        release_cache(h);
+        e = cudaMalloc(&p, bytes);
+      }
+      if (e != cudaSuccess) { *out = nullptr; return e; }
+    }
+    blocks.emplace_back(bytes, p);
     *out = static_cast<T*>(p);
-    return e;
+    return cudaSuccess;
   }
 };
 
@@ -176,7 +205,7 @@ struct Ctx {
   DevPool pool;
   PhaseTimer timer;
   int64_t launches = 0;
-  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), timer(hh->st) {}
+  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), pool(hh), timer(hh->st) {}
 };
 
 int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
@@ -200,10 +229,11 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
 // _measure_dm for `nb` dense matrices: Prim + tree kernels.  Outputs go to device arrays.
 int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t strideD, int nb, double eps_floor,
                 double* eta_out, int* root_out, int* parents_out, int64_t ldp, int* mst_i, int* mst_j, double* mst_w,
-                int* dfs_order) {
+                int* dfs_order, const int* mat_slot = nullptr) {
   seqj_handle* h = c.h;
+  if (nb > g.cap) return fail(h, SEQJ_E_INTERNAL, "graph workspace too small");
   PrimParams pp;
-  pp.D = D; pp.ldD = ldD; pp.strideD = strideD; pp.N = g.N; pp.eps_floor = eps_floor;
+  pp.D = D; pp.ldD = ldD; pp.strideD = strideD; pp.N = g.N; pp.eps_floor = eps_floor; pp.mat_slot = mat_slot;
   pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
   int t = c.timer.begin(SEQJ_T_PRIM);
@@ -355,19 +385,23 @@ int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap) {
 }
 
 // final fuse on device: group MSTs (device arrays, [G][ldp]) -> D (in Sbuf) -> final measure
+// `perm[g]` = index (in the device arrays) of the g-th group in the reference's metric-major order;
+// the scatter and the eta sum follow that order so the rounding matches the reference's loop.
 int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, const double* eta_g, const int* mst_i,
              const int* mst_j, const double* mst_w, int64_t ldp, double eps_floor, double* eta_f, int* root_f,
-             int* parents_f, int* fmst_i, int* fmst_j, double* fmst_w, int* order_f, double* edge_val) {
+             int* parents_f, int* fmst_i, int* fmst_j, double* fmst_w, int* order_f, double* edge_val,
+             const std::vector<int>& perm, const int* perm_dev) {
   seqj_handle* h = c.h;
   int t = c.timer.begin(SEQJ_T_FUSE);
   CU_TRY(cudaMemsetAsync(Sbuf, 0, (size_t)N * ldD * 8, c.st));
   const int ne = N - 1;
-  for (int g = 0; g < G; ++g) {
+  for (int gg = 0; gg < G; ++gg) {
+    const int g = perm[gg];
     fuse_scatter_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
                                                           mst_w + (int64_t)g * ldp, eta_g + g, ne);
     c.launches++;
   }
-  fuse_finalize_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, ldD, N, eta_g, G, eps_floor);
+  fuse_finalize_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, ldD, N, eta_g, perm_dev, G, eps_floor);
   c.launches++;
   for (int g = 0; g < G; ++g) {
     gather_edges_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
@@ -449,11 +483,20 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev) {
 
 void seqj_destroy(seqj_handle* h) {
   if (!h) return;
+  if (h->st) cudaStreamSynchronize(h->st);
+  release_cache(h);
   if (h->st) cudaStreamDestroy(h->st);
   delete h;
 }
 
 const char* seqj_last_error(const seqj_handle* h) { return h ? h->err.c_str() : "null handle"; }
+
+int seqj_release_workspace(seqj_handle* h) {
+  if (!h) return SEQJ_E_BADARG;
+  if (h->st) cudaStreamSynchronize(h->st);
+  release_cache(h);
+  return SEQJ_OK;
+}
 
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
   if (!h) return SEQJ_E_BADARG;
@@ -513,17 +556,63 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
   CU_TRY(cudaMemcpyAsync(tiles_dev, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c.st));
 
-  // result arrays on device
-  std::vector<int> chunk_off(G, 0);
-  int total_chunks = 0;
-  for (int k = 0; k < nmetrics; ++k)
-    for (int l = 0; l < nscales; ++l) {
-      chunk_off[k * nscales + l] = total_chunks;
-      if (mask(k, l)) total_chunks += layouts[l].nchunks;
-    }
+  // ---- static schedule --------------------------------------------------------------------
+  // Processing order is scale-major (one prep per scale), metric inside, chunk innermost.  Chunk
+  // tasks are packed into waves: as many N x N chunk matrices as fit in HBM are produced first and
+  // measured by ONE batched Prim launch (one CTA per graph), which is what makes Prim HBM-bound
+  // instead of latency-bound.  Groups that finish in a wave are combined and measured together.
+  struct Seg { int gp, l, k, c0, c1, slot0, sslot, first, last, out0; };
+  struct Wave { std::vector<Seg> segs; int ntasks = 0, out0 = 0, gp_done0 = -1, gp_done1 = -1; };
   const int64_t ldp = N;
+  const int64_t ldD = round_up(N, 16);
+  const size_t mat_elems = (size_t)N * ldD;
+  size_t free_b = 0, total_b = 0;
+  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  free_b += h->cached_bytes;                    // blocks cached from the previous call are reusable
+  size_t budget = free_b > (size_t(4) << 30) ? free_b - (size_t(4) << 30) : free_b / 2;
+  if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
+  std::vector<int> gp_of(G, -1), g_of_gp;       // g = k*nscales + l (reference order)  <->  gp (processing order)
+  int total_chunks = 0, ngp = 0;
+  for (int l = 0; l < nscales; ++l)
+    for (int k = 0; k < nmetrics; ++k)
+      if (mask(k, l)) { gp_of[k * nscales + l] = ngp++; g_of_gp.push_back(k * nscales + l); total_chunks += layouts[l].nchunks; }
+  const int64_t mats = (int64_t)(budget / (mat_elems * 8));
+  int nS = (int)std::min<int64_t>(std::max(1, ngp), std::max<int64_t>(1, mats / 6));
+  int nD = (int)std::min<int64_t>(mats - nS, total_chunks);
+  if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for one N x N chunk matrix plus the accumulator");
+  std::vector<Wave> waves;
+  std::vector<int> chunk_off(G, 0);             // first output slot of each group's chunks
+  {
+    Wave w;
+    int out = 0, open_groups = 0;
+    auto close = [&]() { if (w.ntasks) { waves.push_back(w); } w = Wave(); w.out0 = out; open_groups = 0; };
+    w.out0 = 0;
+    for (int l = 0; l < nscales; ++l)
+      for (int k = 0; k < nmetrics; ++k) {
+        if (!mask(k, l)) continue;
+        const int g = k * nscales + l, gp = gp_of[g], nch = layouts[l].nchunks;
+        chunk_off[g] = out;
+        int c0 = 0;
+        while (c0 < nch) {
+          if (w.ntasks >= nD || open_groups >= nS) close();
+          const int take = std::min(nch - c0, nD - w.ntasks);
+          Seg sg;
+          sg.gp = gp; sg.l = l; sg.k = k; sg.c0 = c0; sg.c1 = c0 + take; sg.slot0 = w.ntasks; sg.sslot = gp % nS;
+          sg.first = (c0 == 0); sg.last = (c0 + take == nch); sg.out0 = out;
+          w.segs.push_back(sg);
+          w.ntasks += take; out += take; c0 += take; open_groups++;
+          if (sg.last) { if (w.gp_done0 < 0) w.gp_done0 = gp; w.gp_done1 = gp + 1; }
+        }
+      }
+    close();
+  }
+  // A group's accumulator slot (gp % nS) stays live from its first wave to the wave it finishes in; a wave
+  // never touches more than nS groups, and groups finish in order, so slots never collide.
+  int max_wave = 1, max_done = 1;
+  for (auto& w : waves) { max_wave = std::max(max_wave, w.ntasks); max_done = std::max(max_done, w.gp_done1 - w.gp_done0); }
+
   double *eta_c, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
-  int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f;
+  int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f, *sslot_dev, *perm_dev;
   CU_TRY(c.pool.alloc(&eta_c, (size_t)total_chunks)); CU_TRY(c.pool.alloc(&root_c, (size_t)total_chunks));
   CU_TRY(c.pool.alloc(&par_c, (size_t)total_chunks * ldp));
   CU_TRY(c.pool.alloc(&eta_g, (size_t)G)); CU_TRY(c.pool.alloc(&root_g, (size_t)G));
@@ -533,52 +622,53 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   CU_TRY(c.pool.alloc(&fmst_i, (size_t)ldp)); CU_TRY(c.pool.alloc(&fmst_j, (size_t)ldp));
   CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
   CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp));
+  CU_TRY(c.pool.alloc(&sslot_dev, (size_t)G)); CU_TRY(c.pool.alloc(&perm_dev, (size_t)G));
+  std::vector<int> sslot_host(G, 0), perm_host;
+  for (int gp = 0; gp < ngp; ++gp) sslot_host[gp] = gp % nS;
+  for (int g = 0; g < G; ++g) if (gp_of[g] >= 0) perm_host.push_back(gp_of[g]);
+  CU_TRY(cudaMemcpyAsync(sslot_dev, sslot_host.data(), sizeof(int) * G, cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(perm_dev, perm_host.data(), sizeof(int) * perm_host.size(), cudaMemcpyHostToDevice, c.st));
 
-  // chunk-matrix workspace: S + B chunk matrices
-  const int64_t ldD = round_up(N, 16);
-  const size_t mat_elems = (size_t)N * ldD;
-  size_t free_b = 0, total_b = 0;
-  CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = free_b > (size_t(2) << 30) ? free_b - (size_t(2) << 30) : free_b / 2;
-  if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
-  int B = (int)std::min<size_t>(std::min(max_chunks, 32), budget / (mat_elems * 8) > 1 ? budget / (mat_elems * 8) - 1 : 0);
-  if (B < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for one N x N chunk matrix plus the accumulator");
-  double *Sbuf, *Dbuf;
-  CU_TRY(c.pool.alloc(&Sbuf, mat_elems));
-  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * B));
+  double *Spool, *Dbuf;
+  CU_TRY(c.pool.alloc(&Spool, mat_elems * nS));
+  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * (size_t)max_wave));
   GraphWS gws;
-  ST_TRY(graphws_alloc(c, gws, B, N));
+  ST_TRY(graphws_alloc(c, gws, std::max(max_wave, max_done), N));
 
-  for (int l = 0; l < nscales; ++l) {
-    const ScaleLayout& L = layouts[l];
-    bool any = false;
-    for (int k = 0; k < nmetrics; ++k) any |= mask(k, l);
-    if (!any) continue;
-    ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
-    for (int k = 0; k < nmetrics; ++k) {
-      if (!mask(k, l)) continue;
-      const int g = k * nscales + l;
-      const int coff = chunk_off[g];
-      for (int c0 = 0; c0 < L.nchunks; c0 += B) {
-        const int nb = std::min(B, L.nchunks - c0);
-        ST_TRY(run_distance(c, metric_ids[k], L, pb, tiles_dev, (int)tiles.size(), N, Dbuf, ldD, (int64_t)mat_elems, c0,
-                            nb, eps_floor, l2_thresh, 0, fb));
-        ST_TRY(run_measure(c, gws, Dbuf, ldD, (int64_t)mat_elems, nb, eps_floor, eta_c + coff + c0, root_c + coff + c0,
-                           par_c + (int64_t)(coff + c0) * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
-        int t = c.timer.begin(SEQJ_T_COMBINE);
-        combine_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, Dbuf, (int64_t)mat_elems, nb, eta_c + coff + c0, c0 == 0,
-                                                         c0 + nb >= L.nchunks, eta_c + coff, L.nchunks,
-                                                         (int64_t)mat_elems);
-        c.timer.end(t); c.launches++;
-        CU_TRY(cudaGetLastError());
+  int cur_scale = -1;
+  for (auto& w : waves) {
+    for (auto& sg : w.segs) {
+      const ScaleLayout& L = layouts[sg.l];
+      if (sg.l != cur_scale) { ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1)); cur_scale = sg.l; }
+      ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dbuf + (size_t)sg.slot0 * mat_elems, ldD,
+                          (int64_t)mat_elems, sg.c0, sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
+    }
+    ST_TRY(run_measure(c, gws, Dbuf, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
+                       par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
+    int t = c.timer.begin(SEQJ_T_COMBINE);
+    for (auto& sg : w.segs) {
+      const int g = g_of_gp[sg.gp];
+      const int nch = layouts[sg.l].nchunks;
+      for (int b0 = sg.c0; b0 < sg.c1; b0 += kCombineMax) {
+        const int nb = std::min(kCombineMax, sg.c1 - b0);
+        combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(
+            Spool + (size_t)sg.sslot * mat_elems, Dbuf + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
+            eta_c + sg.out0 + (b0 - sg.c0), b0 == 0, b0 + nb >= nch, eta_c + chunk_off[g], nch, (int64_t)(mat_elems / 2));
+        c.launches++;
       }
-      ST_TRY(run_measure(c, gws, Sbuf, ldD, 0, 1, eps_floor, eta_g + g, root_g + g, par_g + (int64_t)g * ldp, ldp,
-                         msti_g + (int64_t)g * ldp, mstj_g + (int64_t)g * ldp, mstw_g + (int64_t)g * ldp, nullptr));
+    }
+    c.timer.end(t);
+    CU_TRY(cudaGetLastError());
+    if (w.gp_done1 > w.gp_done0) {
+      const int a = w.gp_done0, nd = w.gp_done1 - w.gp_done0;
+      ST_TRY(run_measure(c, gws, Spool, ldD, (int64_t)mat_elems, nd, eps_floor, eta_g + a, root_g + a, par_g + (int64_t)a * ldp,
+                         ldp, msti_g + (int64_t)a * ldp, mstj_g + (int64_t)a * ldp, mstw_g + (int64_t)a * ldp, nullptr,
+                         sslot_dev + a));
     }
   }
   if (do_final)
-    ST_TRY(run_fuse(c, gws, Sbuf, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
-                    fmst_j, fmst_w, order_f, edge_val));
+    ST_TRY(run_fuse(c, gws, Spool, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
+                    fmst_j, fmst_w, order_f, edge_val, perm_host, perm_dev));
 
   // ---- copy-out ----
   seqj_result* r = new seqj_result();
@@ -628,14 +718,15 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
       gr.metric = metric_ids[k]; gr.scale = scales[l]; gr.nchunks = layouts[l].nchunks; gr.computed = mask(k, l);
       if (!gr.computed) continue;
       const int coff = chunk_off[g];
+      const size_t gp = (size_t)gp_of[g];        // row of this group in the device arrays (processing order)
       gr.eta_chunk.assign(h_eta_c.begin() + coff, h_eta_c.begin() + coff + gr.nchunks);
       gr.root_chunk.assign(h_root_c.begin() + coff, h_root_c.begin() + coff + gr.nchunks);
       gr.parents_chunk.assign(h_par_c.begin() + (size_t)coff * ldp, h_par_c.begin() + (size_t)(coff + gr.nchunks) * ldp);
-      gr.eta = h_eta_g[g]; gr.root = h_root_g[g];
-      gr.parents.assign(h_par_g.begin() + (size_t)g * ldp, h_par_g.begin() + (size_t)g * ldp + N);
-      gr.mst_i.assign(h_msti.begin() + (size_t)g * ldp, h_msti.begin() + (size_t)g * ldp + N - 1);
-      gr.mst_j.assign(h_mstj.begin() + (size_t)g * ldp, h_mstj.begin() + (size_t)g * ldp + N - 1);
-      gr.mst_w.assign(h_mstw.begin() + (size_t)g * ldp, h_mstw.begin() + (size_t)g * ldp + N - 1);
+      gr.eta = h_eta_g[gp]; gr.root = h_root_g[gp];
+      gr.parents.assign(h_par_g.begin() + gp * ldp, h_par_g.begin() + gp * ldp + N);
+      gr.mst_i.assign(h_msti.begin() + gp * ldp, h_msti.begin() + gp * ldp + N - 1);
+      gr.mst_j.assign(h_mstj.begin() + gp * ldp, h_mstj.begin() + gp * ldp + N - 1);
+      gr.mst_w.assign(h_mstw.begin() + gp * ldp, h_mstw.begin() + gp * ldp + N - 1);
     }
   if (do_final) dedup_triplets(r, G, N, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
@@ -649,7 +740,7 @@ int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const i
                   seqj_result** out) {
   ST_TRY(check_ready(h));
   if (!A || M < 1 || N < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
-  DevPool pool;
+  DevPool pool(h);
   double* A_dev;
   CU_TRY(pool.alloc(&A_dev, (size_t)M * N));
   cudaEvent_t e0, e1;
@@ -696,8 +787,10 @@ int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group,
   }
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, 1, N));
+  std::vector<int> perm(G);
+  for (int g = 0; g < G; ++g) perm[g] = g;
   ST_TRY(run_fuse(c, gws, Sbuf, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
-                  fmst_j, fmst_w, order_f, edge_val));
+                  fmst_j, fmst_w, order_f, edge_val, perm, nullptr));
   seqj_result* r = new seqj_result();
   r->N = N; r->has_final = 1;
   r->order.resize(N); r->parents.resize(N); r->mst_i.resize(N - 1); r->mst_j.resize(N - 1); r->mst_w.resize(N - 1);
@@ -883,16 +976,18 @@ int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, i
   if (!Dchunks || !etas || !Dkl_out || n < 1 || N64 < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   const int N = (int)N64;
   Ctx c(h);
-  const size_t mat = (size_t)N * N;
+  const size_t mat = (size_t)N * N, matp = (mat + 1) & ~size_t(1);     // 16 B aligned matrices for double2 access
   double *D_dev, *S_dev, *eta_dev;
-  const int B = std::min(n, 32);
-  CU_TRY(c.pool.alloc(&D_dev, mat * B)); CU_TRY(c.pool.alloc(&S_dev, mat)); CU_TRY(c.pool.alloc(&eta_dev, (size_t)n));
+  const int B = std::min(n, kCombineMax);
+  CU_TRY(c.pool.alloc(&D_dev, matp * B)); CU_TRY(c.pool.alloc(&S_dev, matp)); CU_TRY(c.pool.alloc(&eta_dev, (size_t)n));
+  CU_TRY(cudaMemsetAsync(D_dev, 0, matp * B * 8, c.st));
   CU_TRY(cudaMemcpyAsync(eta_dev, etas, sizeof(double) * n, cudaMemcpyHostToDevice, c.st));
   for (int c0 = 0; c0 < n; c0 += B) {
     const int nb = std::min(B, n - c0);
-    CU_TRY(cudaMemcpyAsync(D_dev, Dchunks + (size_t)c0 * mat, mat * nb * 8, cudaMemcpyHostToDevice, c.st));
-    combine_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(S_dev, D_dev, (int64_t)mat, nb, eta_dev + c0, c0 == 0, c0 + nb >= n,
-                                                     eta_dev, n, (int64_t)mat);
+    for (int q = 0; q < nb; ++q)
+      CU_TRY(cudaMemcpyAsync(D_dev + (size_t)q * matp, Dchunks + (size_t)(c0 + q) * mat, mat * 8, cudaMemcpyHostToDevice, c.st));
+    combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(S_dev, D_dev, (int64_t)matp, nb, eta_dev + c0, c0 == 0, c0 + nb >= n,
+                                                      eta_dev, n, (int64_t)(matp / 2));
     CU_TRY(cudaGetLastError());
   }
   CU_TRY(cudaMemcpyAsync(Dkl_out, S_dev, mat * 8, cudaMemcpyDeviceToHost, c.st));

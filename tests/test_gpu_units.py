@@ -84,9 +84,11 @@ def test_near_duplicate_columns_take_fixup_path(seqj, oracle, handle, metric):
     else:
         ref = oracle.chunk_distance(metric, P)
     got = seqj.pairwise(metric, A, kl_full=True)
-    # Energy: each CDF entry carries a few ulp(1) of prefix-sum rounding noise in BOTH implementations
-    # (sequential cumsum vs warp scan), which dominates when |U_i - U_j| ~ 1e-8: absolute floor 4*m*2^-53.
-    rel_close(got, ref, 1e-9, atol=(4 * 200 * 2.0 ** -53) if metric == 3 else 1e-16)
+    # Absolute floor 4*m*2^-53 for Energy and KL: when two objects differ by ~1e-7 the result is dominated by
+    # rounding that BOTH implementations carry in their inputs -- a few ulp(1) per CDF entry from the prefix sum
+    # (sequential cumsum vs warp scan), and the column normalisation sum(p) = 1 +- few ulp, to which KL is not
+    # invariant (KL(s*p || t*q) ~ KL + log(s/t)).  The reference's own values carry the same noise.
+    rel_close(got, ref, 1e-9, atol=(4 * 200 * 2.0 ** -53) if metric in (2, 3) else 1e-16)
     assert got[10, 3] == 1e-6 and got[3, 10] == 1e-6
 
 
