@@ -43,13 +43,36 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
   return v;
 }
+__device__ __forceinline__ ulonglong2 ldg_stream_u64x2(const double* p) {
+  ulonglong2 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+  return v;
+}
 
-// Dense Prim, one CTA per graph.  HBM-bound by construction: each of the N-1 steps streams one
-// 8N-byte row exactly once (8*N^2 bytes per graph); the keys live in shared memory.  Thread t owns
-// the vertex pairs {2t, 2t+1} + 2048 r, so a row is fetched with 16-byte loads, all in flight at once.
+// Lexicographic warp argmin of (64-bit key, 32-bit index) with three REDUX.MIN.U32 instead of
+// fifteen shuffles and FP64 compares.
+__device__ __forceinline__ void warp_argmin_u64(unsigned long long& k, int& v) {
+  const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+  const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
+  const bool win = (hi == mhi) && (lo == mlo);
+  const unsigned mv = __reduce_min_sync(0xffffffffu, win ? (unsigned)v : 0x7fffffffu);
+  k = ((unsigned long long)mhi << 32) | mlo;
+  v = (int)mv;
+}
+
+// Dense Prim, one CTA per graph (reference _mst, src/sequencer.jl:358-374).
+// HBM-bound by construction: each of the N-1 steps streams one 8N-byte row exactly once (8*N^2 bytes
+// per graph).  Keys live in shared memory as the bit patterns of non-negative doubles, which order
+// like unsigned integers: the inner loop and both argmin levels are integer-only (no FP64-pipe
+// compares).  key == 0 marks a vertex already in the tree: no weight (>= eps > 0) is smaller, so it is
+// never relaxed, and (key - 1) wraps to the largest value, so it never wins the argmin.
+// Thread t owns the vertex pairs {2t, 2t+1} + 2048 r: rows are fetched with 16-byte streaming loads,
+// all R of them in flight at once.  R = 0 selects the generic path (any N, batches of 8 loads).
+template <int R>
 __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
-  extern __shared__ double prim_sm[];
-  __shared__ double rk[2][32];
+  extern __shared__ unsigned long long prim_sm[];
+  __shared__ unsigned long long rk[2][32];
   __shared__ int rv[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
@@ -57,79 +80,68 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
   const int slot = p.mat_slot ? p.mat_slot[blockIdx.x] : (int)blockIdx.x;
   const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
-  double* key;
+  unsigned long long* key;
   int* from;
   if (p.use_smem) {
     key = prim_sm;
     from = reinterpret_cast<int*>(prim_sm + Npad);
   } else {
-    key = p.key_g + gofs;
+    key = reinterpret_cast<unsigned long long*>(p.key_g + gofs);
     from = p.from_g + gofs;
   }
   int* parent = p.parent + gofs;
   double* weight = p.weight + gofs;
   int* order = p.order + gofs;
+  const unsigned long long kInf = 0x7ff0000000000000ull;
+  const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
 
-  // keys: +Inf = not reached yet, -1 = in the tree (or padding)
-  for (int v = tid; v < Npad; v += kPrimThreads) { key[v] = (v < N) ? CUDART_INF : -1.0; from[v] = 0; }
+  for (int v = tid; v < Npad; v += kPrimThreads) { key[v] = (v < N) ? kInf : 0ull; from[v] = 0; }
   __syncthreads();
-  if (tid == 0) { key[0] = -1.0; parent[0] = 0; weight[0] = 0.0; order[0] = 0; }
+  if (tid == 0) { key[0] = 0ull; parent[0] = 0; weight[0] = 0.0; order[0] = 0; }
   __syncthreads();
 
+  constexpr int U = (R > 0) ? R : kPrimUnroll;
   int u = 0, par = 0;
   for (int step = 1; step < N; ++step) {
     const double* __restrict__ row = D + (int64_t)u * p.ldD;
-    double bk = CUDART_INF;
+    unsigned long long bk = ~0ull;
     int bv = 0x7fffffff;
-    for (int base = 2 * tid; base < N; base += 2 * kPrimThreads * kPrimUnroll) {
-      double2 dv[kPrimUnroll];
+    for (int base = 2 * tid; base < N; base += 2 * kPrimThreads * U) {
+      ulonglong2 dv[U];
 #pragma unroll
-      for (int r = 0; r < kPrimUnroll; ++r) {
+      for (int r = 0; r < U; ++r) {
         const int v = base + r * 2 * kPrimThreads;
-        if (v < N) dv[r] = ldg_stream_f64x2(row + v);      // v even, ldD % 16 == 0: 16 B aligned; v+1 < ldD
+        if (v < N) dv[r] = ldg_stream_u64x2(row + v);      // v even, ldD % 16 == 0: 16 B aligned; v+1 < ldD
       }
 #pragma unroll
-      for (int r = 0; r < kPrimUnroll; ++r) {
+      for (int r = 0; r < U; ++r) {
         const int v = base + r * 2 * kPrimThreads;
         if (v < N) {
-          double2 k2 = *reinterpret_cast<double2*>(key + v);
-          bool upd = false;
-          if (k2.x >= 0.0) {                       // not yet in the tree
-            const double d = fmax(dv[r].x, p.eps_floor);
-            if (d < k2.x) { k2.x = d; from[v] = u; upd = true; }
-            if (k2.x < bk || bv == 0x7fffffff) { bk = k2.x; bv = v; }
-          }
-          if (k2.y >= 0.0) {
-            const double d = fmax(dv[r].y, p.eps_floor);
-            if (d < k2.y) { k2.y = d; from[v + 1] = u; upd = true; }
-            if (k2.y < bk || bv == 0x7fffffff) { bk = k2.y; bv = v + 1; }
-          }
-          if (upd) *reinterpret_cast<double2*>(key + v) = k2;
+          ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
+          const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
+          const bool u0 = d0 < k2.x, u1 = d1 < k2.y;
+          if (u0) { k2.x = d0; from[v] = u; }
+          if (u1) { k2.y = d1; from[v + 1] = u; }
+          if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
+          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;
+          if (c0 < bk) { bk = c0; bv = v; }
+          if (c1 < bk) { bk = c1; bv = v + 1; }
         }
       }
+      if (R > 0) break;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      argmin_combine(bk, bv, ok, ov);
-    }
+    warp_argmin_u64(bk, bv);
     if (lane == 0) { rk[par][warp] = bk; rv[par][warp] = bv; }
     __syncthreads();
     bk = rk[par][lane];
     bv = rv[par][lane];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ok = __shfl_xor_sync(0xffffffffu, bk, o);
-      const int ov = __shfl_xor_sync(0xffffffffu, bv, o);
-      argmin_combine(bk, bv, ok, ov);
-    }
+    warp_argmin_u64(bk, bv);
     u = bv;
-    if (((u >> 1) % kPrimThreads) == tid) {       // the owner of key[u] retires it
+    if (((u >> 1) & (kPrimThreads - 1)) == tid) {       // the owner of key[u] retires it
       order[step] = u;
       parent[u] = from[u];
-      weight[u] = bk;
-      key[u] = -1.0;
+      weight[u] = __longlong_as_double((long long)(bk + 1ull));
+      key[u] = 0ull;
     }
     par ^= 1;
   }
@@ -144,12 +156,15 @@ struct TreeParams {
   const int* order;
   // scratch, each [graph][ldv]
   int* size;
-  double* wd;
+  double* wd;             // wd / wd2 and S / S2: ping-pong buffers of the pointer-jumping passes
+  double* wd2;
   double* S;
+  double* S2;
   int* anc0;
   int* anc1;
   int* dep0;
   int* dep1;
+  int use_smem;           // parent + size fit in dynamic shared memory (8N bytes)
   // outputs (per graph g: index out0 + g)
   double* eta;            // [ngraphs]
   int* root;              // [ngraphs]
@@ -163,11 +178,19 @@ struct TreeParams {
 
 constexpr int kTreeThreads = 1024;
 
+// One CTA per tree.  Replaces _leastcentralpt (N Dijkstra runs in the reference, src/sequencer.jl:331)
+// by the O(N) rerooting identity  S(v) = S(parent) + w(v,parent) * (N - 2*size(v))  for the sums of
+// weighted tree distances S(v) = sum_x d_w(v, x); closeness(v) = (N-1)/S(v).
+//   1. subtree sizes: one thread, reverse Prim order (children after parents), arrays in shared memory;
+//   2. wd(v) (weighted depth from the Prim start) and T(v) = S(v) - S(start): pointer jumping, log2 N rounds;
+//   3. root = first argmin closeness; re-root; hop depths by pointer jumping; eta; optional DFS order.
 __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
+  extern __shared__ int tree_sm[];
   __shared__ double sred_d[32];
   __shared__ int sred_i[32];
   __shared__ long long sred_l[32];
   __shared__ int s_root;
+  __shared__ double s_tot;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
@@ -176,12 +199,17 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   const double* __restrict__ weight = p.weight + gofs;
   const int* __restrict__ order = p.order + gofs;
   int* size = p.size + gofs;
-  double* wd = p.wd + gofs;
-  double* S = p.S + gofs;
   int* newparent = p.newparent + oofs;
   const int r0 = 0;   // Prim start vertex
 
-  for (int v = tid; v < N; v += kTreeThreads) { size[v] = 1; newparent[v] = parent[v]; }
+  int* par_s = p.use_smem ? tree_sm : const_cast<int*>(parent);
+  int* size_s = p.use_smem ? tree_sm + N : size;
+  for (int v = tid; v < N; v += kTreeThreads) {
+    const int q = parent[v];
+    if (p.use_smem) par_s[v] = q;
+    size_s[v] = 1;
+    newparent[v] = q;
+  }
   if (p.mst_i) {
     for (int t = 1 + tid; t < N; t += kTreeThreads) {
       const int v = order[t], q = parent[v];
@@ -192,34 +220,67 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   }
   __syncthreads();
 
-  // Sequential O(N) passes in Prim insertion order (parents always precede children).
+  // 1. subtree sizes, sequential in reverse insertion order
   if (tid == 0) {
-    for (int t = N - 1; t >= 1; --t) {          // subtree sizes
-      const int v = order[t];
-      size[parent[v]] += size[v];
+    int t = N - 1;
+    for (; t >= 4; t -= 4) {                      // order[] is read 4 ahead of the dependent chain
+      const int v0 = order[t], v1 = order[t - 1], v2 = order[t - 2], v3 = order[t - 3];
+      size_s[par_s[v0]] += size_s[v0];
+      size_s[par_s[v1]] += size_s[v1];
+      size_s[par_s[v2]] += size_s[v2];
+      size_s[par_s[v3]] += size_s[v3];
     }
-    double tot = 0.0;                            // weighted depth from r0 and its sum
-    wd[r0] = 0.0;
-    for (int t = 1; t < N; ++t) {
+    for (; t >= 1; --t) {
       const int v = order[t];
-      const double x = wd[parent[v]] + weight[v];
-      wd[v] = x;
-      tot += x;
-    }
-    S[r0] = tot;                                 // rerooting: S(v) = S(parent) + w * (N - 2 size(v))
-    for (int t = 1; t < N; ++t) {
-      const int v = order[t];
-      S[v] = S[parent[v]] + weight[v] * (double)(N - 2 * size[v]);
+      size_s[par_s[v]] += size_s[v];
     }
   }
   __syncthreads();
+
+  // 2. wd and T by pointer jumping: after round j, (a, b)[v] hold the sums over the first 2^j path edges
+  double *wa = p.wd + gofs, *wb = p.wd2 + gofs, *ta = p.S + gofs, *tb = p.S2 + gofs;
+  int *anc_a = p.anc0 + gofs, *anc_b = p.anc1 + gofs;
+  for (int v = tid; v < N; v += kTreeThreads) {
+    const double w = (v == r0) ? 0.0 : weight[v];
+    wa[v] = w;
+    ta[v] = (v == r0) ? 0.0 : w * (double)(N - 2 * size_s[v]);
+    anc_a[v] = par_s[v];
+  }
+  __syncthreads();
+  for (int span = 1; span < N; span <<= 1) {
+    for (int v = tid; v < N; v += kTreeThreads) {
+      const int a = anc_a[v];
+      wb[v] = wa[v] + wa[a];
+      tb[v] = ta[v] + ta[a];
+      anc_b[v] = anc_a[a];
+    }
+    __syncthreads();
+    double* td = wa; wa = wb; wb = td;
+    td = ta; ta = tb; tb = td;
+    int* ti = anc_a; anc_a = anc_b; anc_b = ti;
+  }
+  {                                                // S(r0) = sum_v wd(v)
+    double acc = 0.0;
+    for (int v = tid; v < N; v += kTreeThreads) acc += wa[v];
+    acc = warp_sum(acc);
+    if (lane == 0) sred_d[warp] = acc;
+    __syncthreads();
+    if (tid == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < kTreeThreads / 32; ++w) tot += sred_d[w];
+      s_tot = tot;
+    }
+    __syncthreads();
+  }
+  const double S0 = s_tot;
+  const double* __restrict__ T = ta;
 
   // root = first argmin of closeness (N-1)/S(v)   (LightGraphs.closeness_centrality + findmin)
   {
     double bk = CUDART_INF;
     int bv = 0x7fffffff;
     for (int v = tid; v < N; v += kTreeThreads) {
-      const double c = (N > 1) ? (double)(N - 1) / S[v] : 0.0;
+      const double c = (N > 1) ? (double)(N - 1) / (S0 + T[v]) : 0.0;
       if (c < bk || bv == 0x7fffffff) { bk = c; bv = v; }
     }
 #pragma unroll
@@ -259,8 +320,8 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   __syncthreads();
 
   // hop depths from the new root by pointer jumping (ceil(log2 N) rounds)
-  int* anc_a = p.anc0 + gofs;
-  int* anc_b = p.anc1 + gofs;
+  anc_a = p.anc0 + gofs;
+  anc_b = p.anc1 + gofs;
   int* dep_a = p.dep0 + gofs;
   int* dep_b = p.dep1 + gofs;
   for (int v = tid; v < N; v += kTreeThreads) {

@@ -196,8 +196,26 @@ struct GraphWS {
   size_t prim_smem = 0;
   int *parent = nullptr, *order = nullptr, *size = nullptr, *anc0 = nullptr, *anc1 = nullptr, *dep0 = nullptr,
       *dep1 = nullptr, *from_g = nullptr;
-  double *weight = nullptr, *wd = nullptr, *S = nullptr, *key_g = nullptr;
+  double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
+  int prim_R = 0;
+  int tree_use_smem = 1;
+  size_t tree_smem = 0;
 };
+
+typedef void (*PrimFn)(PrimParams);
+PrimFn prim_fn(int R) {
+  switch (R) {
+    case 1: return prim_kernel<1>;
+    case 2: return prim_kernel<2>;
+    case 3: return prim_kernel<3>;
+    case 4: return prim_kernel<4>;
+    case 5: return prim_kernel<5>;
+    case 6: return prim_kernel<6>;
+    case 7: return prim_kernel<7>;
+    case 8: return prim_kernel<8>;
+    default: return prim_kernel<0>;
+  }
+}
 
 struct Ctx {
   seqj_handle* h;
@@ -215,14 +233,20 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   CU_TRY(c.pool.alloc(&g.parent, n)); CU_TRY(c.pool.alloc(&g.order, n)); CU_TRY(c.pool.alloc(&g.size, n));
   CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
   CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
-  CU_TRY(c.pool.alloc(&g.S, n));
+  CU_TRY(c.pool.alloc(&g.S, n)); CU_TRY(c.pool.alloc(&g.wd2, n)); CU_TRY(c.pool.alloc(&g.S2, n));
   g.prim_smem = (size_t)((N + 1) & ~1) * 8 + (size_t)N * 4;
   g.use_smem = g.prim_smem + 1024 <= h->max_smem;
   if (!g.use_smem) {
     g.prim_smem = 0;
     CU_TRY(c.pool.alloc(&g.key_g, n)); CU_TRY(c.pool.alloc(&g.from_g, n));
   }
-  CU_TRY(cudaFuncSetAttribute(prim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
+  const int R = (N + 2 * kPrimThreads - 1) / (2 * kPrimThreads);
+  g.prim_R = (g.use_smem && R <= 8) ? R : 0;
+  CU_TRY(cudaFuncSetAttribute(prim_fn(g.prim_R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
+  g.tree_smem = (size_t)N * 8;
+  g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
+  if (!g.tree_use_smem) g.tree_smem = 0;
+  CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.tree_smem));
   return SEQJ_OK;
 }
 
@@ -237,16 +261,16 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
   int t = c.timer.begin(SEQJ_T_PRIM);
-  prim_kernel<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
+  prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
   c.timer.end(t); c.launches++;
   CU_TRY(cudaGetLastError());
   TreeParams tp;
   tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
-  tp.size = g.size; tp.wd = g.wd; tp.S = g.S; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
+  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
   tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
   tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
   t = c.timer.begin(SEQJ_T_TREE);
-  tree_kernel<<<nb, kTreeThreads, 0, c.st>>>(tp);
+  tree_kernel<<<nb, kTreeThreads, g.tree_smem, c.st>>>(tp);
   c.timer.end(t); c.launches++;
   CU_TRY(cudaGetLastError());
   return SEQJ_OK;
