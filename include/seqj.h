@@ -37,6 +37,7 @@ extern "C" {
 #define SEQJ_E_NCCL (-3)
 #define SEQJ_E_OOM (-4)
 #define SEQJ_E_INTERNAL (-5)
+#define SEQJ_E_DOMAIN (-6) /* input has negative, NaN or infinite values (AssertionError in the reference) */
 
 /* metric ids, in the order of the reference's ALL_METRICS (src/distancemetrics.jl:234-257) */
 #define SEQJ_L2 0     /* L2 = Distances.Euclidean(1e-7)   src/distancemetrics.jl:234 */
@@ -87,8 +88,11 @@ int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
  * fuse `_weighted_p_matrix` (:310-328), `inv.(Pw)` (:269), the final `_measure_dm` (:271) and
  * `unroll` (src/utils.jl:15-24).
  *
- * A          host pointer, M x N column-major, read-only.  The caller (Julia wrapper) has already
- *            validated it and applied `clamp!(A, eps(), Inf)` (src/sequencer.jl:111,130).
+ * A          host pointer, M x N column-major, read-only.  The input conditioning of `sequence`
+ *            (src/sequencer.jl:111,130) happens on the device copy: negative / NaN / infinite
+ *            values return SEQJ_E_DOMAIN (the reference's AssertionError), and values below
+ *            eps() = 2.22e-16 are clamped on load.  seqj_result_input_range reports min/max so the
+ *            wrapper can apply the caller-visible `clamp!` to the host array only when needed.
  * metric_ids caller order is kept (it fixes the order of groups, src/sequencer.jl:253-254).
  * scales     number of chunks per column for each scale (src/sequencer.jl:389).
  * eps_floor  the reference's `const eps = 1e-6` (src/distancemetrics.jl:3).
@@ -136,6 +140,8 @@ int seqj_result_final(const seqj_result* r, double* eta, int32_t* root, int32_t*
 int seqj_result_D_nnz(const seqj_result* r, int64_t* nnz);
 int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double* val);
 int seqj_result_timings(const seqj_result* r, double* ms /* SEQJ_NTIMERS */);
+/* min / max of the input as seen by the device-side check (min < 2.22e-16 => values were clamped) */
+int seqj_result_input_range(const seqj_result* r, double* minv, double* maxv);
 /* number of kernels the library launched for this result */
 int seqj_result_launches(const seqj_result* r, int64_t* launches);
 void seqj_result_free(seqj_result* r);

@@ -41,6 +41,7 @@ SIGNATURES = {
     "seqj_result_D_triplets": (C.c_int, [vp, c_ip, c_ip, c_dp]),
     "seqj_result_timings": (C.c_int, [vp, c_dp]),
     "seqj_result_launches": (C.c_int, [vp, C.POINTER(C.c_int64)]),
+    "seqj_result_input_range": (C.c_int, [vp, c_dp, c_dp]),
     "seqj_result_free": (None, [vp]),
     "seqj_splitnorm": (C.c_int, [vp, c_dp, C.c_int64, C.c_int64, C.c_int32, c_dp, c_dp, c_ip]),
     "seqj_pairwise": (C.c_int, [vp, C.c_int32, c_dp, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_double,
@@ -100,6 +101,8 @@ class Handle:
             raise SeqjError(st, msg)
 
     def check(self, st):
+        if st == -6:      # SEQJ_E_DOMAIN: the reference raises AssertionError (src/sequencer.jl:111)
+            raise AssertionError(self.lib.seqj_last_error(self.h).decode())
         if st != 0:
             raise SeqjError(st, self.lib.seqj_last_error(self.h).decode())
 

@@ -194,6 +194,21 @@ def _prepare_input(A):
     return np.ascontiguousarray(Af.T)                                           # object-major (N, M)
 
 
+def _layout_input(A):
+    """Layout-only conditioning for the hot call: no pass over the data on the host.  The value checks of
+    `sequence` (src/sequencer.jl:111) and the clamp (:130) run on the device copy inside seqj_sequence;
+    `orig` is the caller's array when the reference's in-place `clamp!` can be made visible on it."""
+    if isinstance(A, (list, tuple)):
+        A = np.stack([np.asarray(c, dtype=np.float64) for c in A], axis=1)     # hcat(A...)
+    A = np.asarray(A)
+    if A.ndim == 1:
+        A = A.reshape(1, -1)
+    if A.ndim != 2:
+        raise ValueError("A must be a vector or an M x N matrix")
+    orig = A if (A.dtype == np.float64 and A.flags.writeable) else None
+    return np.ascontiguousarray(A.T, dtype=np.float64), orig      # no copy for a Fortran-ordered float64 A
+
+
 def _collect(handle, res, N, metrics, scales, want_final=True):
     lib = handle.lib
     ngroups = C.c_int()
@@ -223,6 +238,9 @@ def _collect(handle, res, N, metrics, scales, want_final=True):
     launches = C.c_int64()
     handle.check(lib.seqj_result_launches(res, C.byref(launches)))
     timings = dict(zip(_lib.TIMER_NAMES, tm.tolist()))
+    lo, hi = C.c_double(), C.c_double()
+    handle.check(lib.seqj_result_input_range(res, C.byref(lo), C.byref(hi)))
+    timings["input_min"] = lo.value
     if not want_final:
         return SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
                                group_msts)
@@ -270,7 +288,7 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
 
     A: M x N (rows = samples, columns = objects), non-negative and finite.
     """
-    At = _prepare_input(A)
+    At, orig = _layout_input(A)
     N, M = At.shape
     logger.info("Sequencing data with\n    shape: (%d, %d)\n    metric(s): %s\n    scale(s): %s", M, N, metrics, scales)
     ensuregrid(At.T, grid)
@@ -285,6 +303,8 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
     for s in scales:
         assert 1 <= s <= M, f"Scale ({s}) cannot be larger than the number of data elements ({M})."
     r = _sequence(At, scales, metrics, handle)
+    if orig is not None and r.timings.get("input_min", 1.0) < JULIA_EPS:
+        np.maximum(orig, JULIA_EPS, out=orig)            # clamp!(A, eps(), typemax): caller-visible (sequencer.jl:130)
     for (m, l), (eta, _) in r.EOAlgScale.items():
         logger.info("%s at scale %d: η = %.4g", m, l, eta)
     logger.info("Final: η = %.4g sequence = %s", r.eta, prettyp(r.order, 5))

@@ -147,6 +147,135 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   }
 }
 
+// ---- cluster Prim: one thread-block CLUSTER per graph ------------------------------------------
+// The single-CTA kernel above is bound by what one SM can pull from HBM plus the per-step argmin.
+// Here a cluster of C CTAs shares one graph: CTA r owns the vertex slice [r*W, (r+1)*W), streams only
+// its 8W-byte part of the row, and keeps its keys in ~12 KB of shared memory, so (a) a step costs one
+// DRAM latency plus one DSMEM exchange, and (b) the CTAs are small enough (256 threads) to stay
+// resident next to the FP64 distance tiles.  The cluster-wide argmin uses no barrier: every CTA sends
+// its 16-byte candidate to all peers with st.async (distributed shared memory) that completes a
+// transaction on the receiver's mbarrier; each CTA waits on its own mbarrier and reduces the C
+// candidates locally.  Buffers and mbarriers are double-buffered by step parity.
+constexpr int kPrimClThreads = 256;
+constexpr int kPrimClUnroll = 4;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_async_u64x2(uint32_t dst, unsigned long long a, unsigned long long b, uint32_t mbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+               ::"r"(dst), "l"(a), "l"(b), "r"(mbar) : "memory");
+}
+
+template <int C>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 5) prim_cluster_kernel(PrimParams p, int W) {
+  extern __shared__ unsigned long long primc_sm[];
+  __shared__ __align__(16) ulonglong2 cand[2][C];
+  __shared__ __align__(8) uint64_t mbar[2];
+  __shared__ unsigned long long wk[kPrimClThreads / 32];
+  __shared__ int wv[kPrimClThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = p.N;
+  const int graph = blockIdx.x / C;
+  const uint32_t rank = cluster_ctarank();
+  const int v0 = (int)rank * W;                       // first vertex of this CTA's slice (W is even)
+  const int Wn = max(0, min(W, N - v0));              // vertices in the slice
+  const int Wp = (Wn + 1) & ~1;
+  const int64_t gofs = (int64_t)graph * p.ldv;
+  const int slot = p.mat_slot ? p.mat_slot[graph] : graph;
+  const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
+  unsigned long long* key = primc_sm;
+  int* from = reinterpret_cast<int*>(primc_sm + ((W + 1) & ~1));
+  int* parent = p.parent + gofs;
+  double* weight = p.weight + gofs;
+  int* order = p.order + gofs;
+  const unsigned long long kInf = 0x7ff0000000000000ull;
+  const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
+
+  for (int v = tid; v < Wp; v += kPrimClThreads) { key[v] = (v < Wn) ? kInf : 0ull; from[v] = 0; }
+  if (tid == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_barrier_init();
+    if (rank == 0) { key[0] = 0ull; parent[0] = 0; weight[0] = 0.0; order[0] = 0; }
+  }
+  __syncthreads();
+  cluster_sync_all();                                  // peers' mbarriers are initialised before any st.async
+
+  const uint32_t cand_u32 = smem_u32(&cand[0][0]);
+  const uint32_t mbar_u32 = smem_u32(&mbar[0]);
+  int u = 0;
+  for (int step = 1; step < N; ++step) {
+    const int par = step & 1;
+    const double* __restrict__ row = D + (int64_t)u * p.ldD + v0;
+    unsigned long long bk = ~0ull;
+    int bv = 0x7fffffff;
+    for (int base = 2 * tid; base < Wn; base += 2 * kPrimClThreads * kPrimClUnroll) {
+      ulonglong2 dv[kPrimClUnroll];
+#pragma unroll
+      for (int r = 0; r < kPrimClUnroll; ++r) {
+        const int v = base + r * 2 * kPrimClThreads;
+        if (v < Wn) dv[r] = ldg_stream_u64x2(row + v);
+      }
+#pragma unroll
+      for (int r = 0; r < kPrimClUnroll; ++r) {
+        const int v = base + r * 2 * kPrimClThreads;
+        if (v < Wn) {
+          ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
+          const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
+          const bool u0 = d0 < k2.x, u1 = d1 < k2.y;
+          if (u0) { k2.x = d0; from[v] = u; }
+          if (u1) { k2.y = d1; from[v + 1] = u; }
+          if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
+          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;
+          if (c0 < bk) { bk = c0; bv = v0 + v; }
+          if (c1 < bk) { bk = c1; bv = v0 + v + 1; }
+        }
+      }
+    }
+    warp_argmin_u64(bk, bv);
+    if (lane == 0) { wk[warp] = bk; wv[warp] = bv; }
+    __syncthreads();
+    if (warp == 0) {
+      bk = (lane < kPrimClThreads / 32) ? wk[lane] : ~0ull;
+      bv = (lane < kPrimClThreads / 32) ? wv[lane] : 0x7fffffff;
+      warp_argmin_u64(bk, bv);
+      if (lane == 0) mbar_expect_tx(&mbar[par], C * 16);
+      if (lane < C) {                                  // lane j delivers this CTA's candidate to CTA j
+        const uint32_t dst = mapa_u32(cand_u32 + (uint32_t)((par * C + (int)rank) * 16), (uint32_t)lane);
+        const uint32_t mb = mapa_u32(mbar_u32 + (uint32_t)(par * 8), (uint32_t)lane);
+        st_async_u64x2(dst, bk, (unsigned long long)(unsigned)bv, mb);
+      }
+    }
+    mbar_wait(&mbar[par], (uint32_t)(((step - 1) >> 1) & 1));   // k-th use of this barrier -> phase parity k & 1
+    {
+      const ulonglong2 cnd = (lane < C) ? cand[par][lane] : make_ulonglong2(~0ull, 0x7fffffffull);
+      bk = cnd.x;
+      bv = (int)cnd.y;
+      warp_argmin_u64(bk, bv);
+    }
+    u = bv;
+    const int ul = u - v0;
+    if (ul >= 0 && ul < Wn && ((ul >> 1) & (kPrimClThreads - 1)) == tid) {   // the owner of key[u] retires it
+      order[step] = u;
+      parent[u] = from[ul];
+      weight[u] = __longlong_as_double((long long)(bk + 1ull));
+      key[ul] = 0ull;
+    }
+  }
+  cluster_sync_all();                                  // no CTA exits while a peer may still write to it
+}
+
 // ---- tree measurement -------------------------------------------------------------------------
 struct TreeParams {
   int N;

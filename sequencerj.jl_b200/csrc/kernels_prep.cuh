@@ -14,9 +14,45 @@
 // and per-chunk vectors [nchunks][ldn]:  sP = sum P^2, sU = sum Uc^2, H = sum P log P.
 // HBM-bound: 8*M*N bytes read, up to 3 * 8*M*N written per scale.
 #pragma once
+#include <math_constants.h>
 #include "common.cuh"
 
 namespace seqj {
+
+// clamp!(A, eps(), typemax) of the reference's `sequence` (src/sequencer.jl:130) is applied on load, so the
+// device results equal those of the clamped input whether or not the host copy has been clamped yet.
+constexpr double kClampEps = 2.220446049250313e-16;
+
+struct InputStats {
+  double minv, maxv;
+  int has_nan;
+  int pad;
+};
+
+// Input conditioning check of `sequence` (src/sequencer.jl:111): min / max / NaN over the whole input.
+__global__ void __launch_bounds__(256) input_stats_kernel(const double* __restrict__ A, int64_t n, InputStats* out) {
+  double mn = CUDART_INF, mx = -CUDART_INF;
+  int nan = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double a = A[i];
+    nan |= (a != a);
+    mn = fmin(mn, a);
+    mx = fmax(mx, a);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    nan |= __shfl_xor_sync(0xffffffffu, nan, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative finite doubles order like their bit patterns; negatives / NaN are caught by the flags
+    if (nan) atomicOr(&out->has_nan, 1);
+    if (mn < 0.0) atomicOr(&out->pad, 1);
+    atomicMin(reinterpret_cast<unsigned long long*>(&out->minv), (unsigned long long)__double_as_longlong(fmax(mn, 0.0)));
+    atomicMax(reinterpret_cast<unsigned long long*>(&out->maxv), (unsigned long long)__double_as_longlong(fmax(mx, 0.0)));
+  }
+}
 
 struct PrepParams {
   const double* A;
@@ -47,7 +83,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
 
   // pass 1: chunk mass
   double s = 0.0;
-  for (int k = lane; k < m; k += 32) s += src[k];
+  for (int k = lane; k < m; k += 32) s += fmax(src[k], kClampEps);
   s = warp_sum(s);
 
   // pass 2: PDF, log PDF, moments
@@ -55,7 +91,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
   for (int k = lane; k < p.cl_pad; k += 32) {
     double pv = 0.0, lp = 0.0;
     if (k < m) {
-      const double a = src[k];
+      const double a = fmax(src[k], kClampEps);
       pv = p.normalize ? a / s : a;
       lp = log(pv);
       w += pv;
@@ -77,7 +113,7 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
       const int k = base + lane;
       double x = 0.0;
       if (k < m) {
-        const double a = src[k];
+        const double a = fmax(src[k], kClampEps);
         x = p.normalize ? a / s : a;
       }
 #pragma unroll

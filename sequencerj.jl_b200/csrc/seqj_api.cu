@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -58,6 +59,7 @@ struct seqj_result {
   std::vector<double> mst_w, Dv;
   double timers[SEQJ_NTIMERS] = {0};
   int64_t launches = 0;
+  double in_min = 0, in_max = 0;
 };
 
 // --------------------------------------------------------------------------------------------
@@ -198,6 +200,8 @@ struct GraphWS {
       *dep1 = nullptr, *from_g = nullptr;
   double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
   int prim_R = 0;
+  int cluster = 0, cl_W = 0;      // cluster Prim: CTAs per graph (0 = single-CTA kernel), slice width
+  size_t cl_smem = 0;
   int tree_use_smem = 1;
   size_t tree_smem = 0;
 };
@@ -243,6 +247,17 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   const int R = (N + 2 * kPrimThreads - 1) / (2 * kPrimThreads);
   g.prim_R = (g.use_smem && R <= 8) ? R : 0;
   CU_TRY(cudaFuncSetAttribute(prim_fn(g.prim_R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
+  // cluster Prim for graphs large enough that one SM's load rate / argmin latency is the limit
+  const char* force = getenv("SEQJ_PRIM");
+  g.cluster = (N >= 1024) ? 8 : 0;
+  if (force && !strcmp(force, "single")) g.cluster = 0;
+  if (force && !strcmp(force, "cluster")) g.cluster = 8;
+  if (g.cluster) {
+    g.cl_W = (int)round_up((N + g.cluster - 1) / g.cluster, 2);
+    g.cl_smem = (size_t)((g.cl_W + 1) & ~1) * 8 + (size_t)g.cl_W * 4 + 16;
+    if (g.cl_smem + 4096 > h->max_smem) g.cluster = 0;
+    else CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.cl_smem));
+  }
   g.tree_smem = (size_t)N * 8;
   g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
   if (!g.tree_use_smem) g.tree_smem = 0;
@@ -261,7 +276,10 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
   int t = c.timer.begin(SEQJ_T_PRIM);
-  prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
+  if (g.cluster)
+    prim_cluster_kernel<8><<<nb * g.cluster, kPrimClThreads, g.cl_smem, c.st>>>(pp, g.cl_W);
+  else
+    prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
   c.timer.end(t); c.launches++;
   CU_TRY(cudaGetLastError());
   TreeParams tp;
@@ -571,6 +589,19 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
 
   int tt = c.timer.begin(SEQJ_T_TOTAL);
 
+  // `@assert all(A .>= 0) && no NaN/Inf` (src/sequencer.jl:111), checked on the device copy
+  InputStats* stats_dev;
+  CU_TRY(c.pool.alloc(&stats_dev, 1));
+  InputStats st0;
+  st0.minv = INFINITY; st0.maxv = 0.0; st0.has_nan = 0; st0.pad = 0;
+  CU_TRY(cudaMemcpyAsync(stats_dev, &st0, sizeof(st0), cudaMemcpyHostToDevice, c.st));
+  input_stats_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(A_dev, (int64_t)M * N, stats_dev);
+  c.launches++;
+  CU_TRY(cudaMemcpyAsync(&st0, stats_dev, sizeof(st0), cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaStreamSynchronize(c.st));
+  if (st0.has_nan || st0.pad || !std::isfinite(st0.maxv))
+    return fail(h, SEQJ_E_DOMAIN, "Input data cannot contain negative, NaN or infinite values.");
+
   PrepBufs pb;
   ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false));
   FixBufs fb;
@@ -755,6 +786,7 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   if (do_final) dedup_triplets(r, G, N, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
   r->launches = c.launches;
+  r->in_min = st0.minv; r->in_max = st0.maxv;
   *out = r;
   return SEQJ_OK;
 }
@@ -901,6 +933,12 @@ int seqj_result_timings(const seqj_result* r, double* ms) {
 int seqj_result_launches(const seqj_result* r, int64_t* launches) {
   if (!r || !launches) return SEQJ_E_BADARG;
   *launches = r->launches;
+  return SEQJ_OK;
+}
+int seqj_result_input_range(const seqj_result* r, double* minv, double* maxv) {
+  if (!r) return SEQJ_E_BADARG;
+  if (minv) *minv = r->in_min;
+  if (maxv) *maxv = r->in_max;
   return SEQJ_OK;
 }
 void seqj_result_free(seqj_result* r) { delete r; }

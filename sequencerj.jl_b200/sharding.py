@@ -65,6 +65,8 @@ def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, al
     final SequencerResult; per-group details are kept for the groups it owns."""
     N, M = At.shape
     scales = tuple(int(s) for s in scales)
+    if world == 1:
+        return api._sequence(At, scales, metrics, handle, device_ptr=device_ptr)
     owner = assign_groups(group_costs(M, metrics, scales), world)
     mask = (owner == rank).astype(np.uint8)
     mine = {}

@@ -126,7 +126,7 @@ def _edge_set(t):
     return set(zip(np.minimum(t.src, t.dst).tolist(), np.maximum(t.src, t.dst).tolist()))
 
 
-@pytest.mark.parametrize("N", [2, 3, 17, 100, 1000, 2500])
+@pytest.mark.parametrize("N", [2, 3, 17, 100, 1000, 1024, 1031, 2500, 4099])
 def test_measure_dm_matches_oracle(seqj, oracle, handle, N):
     Dm = _random_dist(N, N)
     ref = oracle.measure_dm(Dm)
