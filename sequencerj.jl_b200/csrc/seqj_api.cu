@@ -27,7 +27,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 
 struct seqj_handle {
   int dev = 0;
-  cudaStream_t st = nullptr;
+  cudaStream_t st = nullptr;     // compute stream: prep + distance tiles
+  cudaStream_t st2 = nullptr;    // graph stream (higher priority): Prim, tree, combine, fuse
   std::string err;
   uint64_t ws_limit = 0;
   EncodeTiledFn encode = nullptr;
@@ -130,20 +131,19 @@ struct DevPool {
 struct PhaseTimer {
   struct Span { int phase; cudaEvent_t a, b; };
   std::vector<Span> spans;
-  cudaStream_t st;
-  bool enabled = true;
-  explicit PhaseTimer(cudaStream_t s) : st(s) {}
+  cudaStream_t* cur;             // the context's current stream
+  explicit PhaseTimer(cudaStream_t* s) : cur(s) {}
   ~PhaseTimer() {
     for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   }
   int begin(int phase) {
     Span s; s.phase = phase;
     cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-    cudaEventRecord(s.a, st);
+    cudaEventRecord(s.a, *cur);
     spans.push_back(s);
     return (int)spans.size() - 1;
   }
-  void end(int id) { cudaEventRecord(spans[id].b, st); }
+  void end(int id) { cudaEventRecord(spans[id].b, *cur); }
   void collect(double* timers) {
     for (auto& s : spans) {
       float ms = 0;
@@ -223,11 +223,32 @@ PrimFn prim_fn(int R) {
 
 struct Ctx {
   seqj_handle* h;
-  cudaStream_t st;
+  cudaStream_t st;               // current stream: every run_* helper enqueues on it
+  cudaStream_t st_compute, st_graph;
   DevPool pool;
   PhaseTimer timer;
   int64_t launches = 0;
-  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), pool(hh), timer(hh->st) {}
+  bool overlap = false;
+  std::vector<cudaEvent_t> events;
+  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), st_compute(hh->st), st_graph(hh->st2), pool(hh), timer(&st) {
+    // Default: one stream.  SEQJ_OVERLAP=1 runs the graph layer on a second stream so that it overlaps the
+    // distance tiles of the next wave; measured on B200 (profiles/r01_overlap_experiments.md) the
+    // interference costs more than it hides at config 3, so it is off until the graph kernels shrink.
+    const char* ov = getenv("SEQJ_OVERLAP");
+    overlap = ov && atoi(ov) != 0;
+    if (!overlap) st_graph = st_compute;
+  }
+  ~Ctx() {
+    for (auto e : events) cudaEventDestroy(e);
+  }
+  void on_compute() { st = st_compute; }
+  void on_graph() { st = st_graph; }
+  cudaEvent_t new_event() {
+    cudaEvent_t e;
+    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    events.push_back(e);
+    return e;
+  }
 };
 
 int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
@@ -510,7 +531,12 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev) {
   }
   h->sm_count = prop.multiProcessorCount;
   h->max_smem = prop.sharedMemPerBlockOptin;
-  cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking);
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char* pr = getenv("SEQJ_PRIO");
+  const bool use_prio = pr ? atoi(pr) != 0 : false;
+  cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
+  cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
@@ -526,8 +552,10 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev) {
 void seqj_destroy(seqj_handle* h) {
   if (!h) return;
   if (h->st) cudaStreamSynchronize(h->st);
+  if (h->st2) cudaStreamSynchronize(h->st2);
   release_cache(h);
   if (h->st) cudaStreamDestroy(h->st);
+  if (h->st2) cudaStreamDestroy(h->st2);
   delete h;
 }
 
@@ -548,7 +576,7 @@ int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
 
 static int check_ready(seqj_handle* h) {
   if (!h) return SEQJ_E_BADARG;
-  if (!h->encode || !h->st) return fail(h, SEQJ_E_CUDA, "handle has no usable sm_100 device (no CPU fallback): " + h->err);
+  if (!h->encode || !h->st || !h->st2) return fail(h, SEQJ_E_CUDA, "handle has no usable sm_100 device (no CPU fallback): " + h->err);
   if (cudaSetDevice(h->dev) != cudaSuccess) return fail(h, SEQJ_E_CUDA, "cudaSetDevice failed");
   return SEQJ_OK;
 }
@@ -626,15 +654,26 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   free_b += h->cached_bytes;                    // blocks cached from the previous call are reusable
   size_t budget = free_b > (size_t(4) << 30) ? free_b - (size_t(4) << 30) : free_b / 2;
   if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
+  // scales with many chunks first: the graph work of the last (smallest) wave is the only part that cannot
+  // hide behind distance tiles of a following wave
+  std::vector<int> scale_order(nscales);
+  for (int l = 0; l < nscales; ++l) scale_order[l] = l;
+  std::stable_sort(scale_order.begin(), scale_order.end(),
+                   [&](int a, int b) { return layouts[a].nchunks > layouts[b].nchunks; });
   std::vector<int> gp_of(G, -1), g_of_gp;       // g = k*nscales + l (reference order)  <->  gp (processing order)
   int total_chunks = 0, ngp = 0;
-  for (int l = 0; l < nscales; ++l)
+  for (int l : scale_order)
     for (int k = 0; k < nmetrics; ++k)
       if (mask(k, l)) { gp_of[k * nscales + l] = ngp++; g_of_gp.push_back(k * nscales + l); total_chunks += layouts[l].nchunks; }
   const int64_t mats = (int64_t)(budget / (mat_elems * 8));
   int nS = (int)std::min<int64_t>(std::max(1, ngp), std::max<int64_t>(1, mats / 6));
-  int nD = (int)std::min<int64_t>(mats - nS, total_chunks);
-  if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for one N x N chunk matrix plus the accumulator");
+  // overlap mode: two D buffers (double buffering between the compute and the graph stream), each nD matrices
+  const int nbuf = c.overlap ? 2 : 1;
+  int nD = (int)std::min<int64_t>((mats - nS) / nbuf, total_chunks);
+  if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for two N x N chunk matrices plus the accumulator");
+  const char* wenv = getenv("SEQJ_WAVES");
+  const int nwaves_target = std::max(1, wenv ? atoi(wenv) : (c.overlap ? 2 : 1));
+  const int wave_target = (total_chunks + nwaves_target - 1) / nwaves_target;
   std::vector<Wave> waves;
   std::vector<int> chunk_off(G, 0);             // first output slot of each group's chunks
   {
@@ -642,7 +681,11 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
     int out = 0, open_groups = 0;
     auto close = [&]() { if (w.ntasks) { waves.push_back(w); } w = Wave(); w.out0 = out; open_groups = 0; };
     w.out0 = 0;
-    for (int l = 0; l < nscales; ++l)
+    for (int l : scale_order) {
+      // Waves end at scale boundaries once they hold about a third of all chunk graphs: every Prim launch is
+      // latency-bound (N dependent steps of ~1.2 us whatever the batch size), so few large launches win; three
+      // waves leave only the smallest one's graph work exposed after the last distance tile.
+      if (w.ntasks >= wave_target) close();
       for (int k = 0; k < nmetrics; ++k) {
         if (!mask(k, l)) continue;
         const int g = k * nscales + l, gp = gp_of[g], nch = layouts[l].nchunks;
@@ -659,6 +702,7 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
           if (sg.last) { if (w.gp_done0 < 0) w.gp_done0 = gp; w.gp_done1 = gp + 1; }
         }
       }
+    }
     close();
   }
   // A group's accumulator slot (gp % nS) stays live from its first wave to the wave it finishes in; a wave
@@ -686,19 +730,33 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
 
   double *Spool, *Dbuf;
   CU_TRY(c.pool.alloc(&Spool, mat_elems * nS));
-  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * (size_t)max_wave));
+  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * (size_t)max_wave * nbuf));
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, std::max(max_wave, max_done), N));
 
+  // Two streams: distance tiles of wave w+1 (FP64-bound) run while the graph stream measures wave w
+  // (latency/HBM-bound, small CTAs that fit next to the tiles).  D buffers alternate between waves.
+  std::vector<cudaEvent_t> ev_dist(waves.size()), ev_graph(waves.size());
+  cudaEvent_t ev_setup = c.new_event();
+  CU_TRY(cudaEventRecord(ev_setup, c.st_compute));              // index arrays / tiles uploaded on the compute stream
+  CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_setup, 0));
   int cur_scale = -1;
-  for (auto& w : waves) {
+  for (size_t wi = 0; wi < waves.size(); ++wi) {
+    Wave& w = waves[wi];
+    double* Dw = Dbuf + (wi % nbuf) * (size_t)max_wave * mat_elems;
+    c.on_compute();
+    if (c.overlap && wi >= 2) CU_TRY(cudaStreamWaitEvent(c.st_compute, ev_graph[wi - 2], 0));   // buffer free again
     for (auto& sg : w.segs) {
       const ScaleLayout& L = layouts[sg.l];
       if (sg.l != cur_scale) { ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1)); cur_scale = sg.l; }
-      ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dbuf + (size_t)sg.slot0 * mat_elems, ldD,
+      ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dw + (size_t)sg.slot0 * mat_elems, ldD,
                           (int64_t)mat_elems, sg.c0, sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
     }
-    ST_TRY(run_measure(c, gws, Dbuf, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
+    ev_dist[wi] = c.new_event();
+    CU_TRY(cudaEventRecord(ev_dist[wi], c.st_compute));
+    c.on_graph();
+    CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_dist[wi], 0));
+    ST_TRY(run_measure(c, gws, Dw, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
                        par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
     int t = c.timer.begin(SEQJ_T_COMBINE);
     for (auto& sg : w.segs) {
@@ -707,13 +765,15 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
       for (int b0 = sg.c0; b0 < sg.c1; b0 += kCombineMax) {
         const int nb = std::min(kCombineMax, sg.c1 - b0);
         combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(
-            Spool + (size_t)sg.sslot * mat_elems, Dbuf + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
+            Spool + (size_t)sg.sslot * mat_elems, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
             eta_c + sg.out0 + (b0 - sg.c0), b0 == 0, b0 + nb >= nch, eta_c + chunk_off[g], nch, (int64_t)(mat_elems / 2));
         c.launches++;
       }
     }
     c.timer.end(t);
     CU_TRY(cudaGetLastError());
+    ev_graph[wi] = c.new_event();
+    CU_TRY(cudaEventRecord(ev_graph[wi], c.st_graph));          // D buffer of this wave is no longer read
     if (w.gp_done1 > w.gp_done0) {
       const int a = w.gp_done0, nd = w.gp_done1 - w.gp_done0;
       ST_TRY(run_measure(c, gws, Spool, ldD, (int64_t)mat_elems, nd, eps_floor, eta_g + a, root_g + a, par_g + (int64_t)a * ldp,
@@ -721,6 +781,7 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
                          sslot_dev + a));
     }
   }
+  c.on_graph();
   if (do_final)
     ST_TRY(run_fuse(c, gws, Spool, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
                     fmst_j, fmst_w, order_f, edge_val, perm_host, perm_dev));
@@ -761,8 +822,11 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   }
   c.timer.end(td);
   c.timer.end(tt);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st_graph);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st_compute);
   if (e != cudaSuccess) {
+    cudaStreamSynchronize(c.st_graph);
+    cudaStreamSynchronize(c.st_compute);
     delete r;
     return fail(h, SEQJ_E_CUDA, std::string("sequence failed: ") + cudaGetErrorString(e));
   }
