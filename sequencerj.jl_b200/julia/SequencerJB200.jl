@@ -1,0 +1,220 @@
+# SequencerJB200.jl -- Julia host side of the B200-native Sequencer hot path.
+#
+# Drop-in for the data-parallel core of SequencerJ.jl: same exported names and keyword arguments
+# (`sequence(A; scales, metrics, grid)`, `SequencerResult`, `D`, `mst`, `elong`, `order`, `L2`,
+# `WASS1D`, `KLD`, `ENERGY`, `ALL_METRICS`), with `_sequence` (reference src/sequencer.jl:184-276)
+# replaced by ONE `ccall` into libseqj_b200.so (C ABI in include/seqj.h).  Julia is not installed in the
+# build image, so this file is syntax-reviewed only; the identical call sequence is exercised through
+# the Python ctypes mirror (sequencerj.jl_b200/api.py) by tests/test_gpu_*.py.
+#
+# Usage:  ENV["SEQJ_B200_LIB"] = "/path/to/libseqj_b200.so";  using SequencerJB200;  r = sequence(A; scales=(1,2,4))
+module SequencerJB200
+
+using Printf: @sprintf
+using Logging
+using LightGraphs
+using SimpleWeightedGraphs
+using SparseArrays: sparse
+
+export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!
+export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS
+
+const libseqj = get(ENV, "SEQJ_B200_LIB", joinpath(@__DIR__, "..", "libseqj_b200.so"))
+
+"Smallest allowed graph weight (reference src/distancemetrics.jl:3)."
+const ϵ = 1e-6
+"Euclidean recompute threshold (reference src/distancemetrics.jl:6)."
+const L2THR = 1e-7
+
+# Metric instances: ids follow include/seqj.h (SEQJ_L2 .. SEQJ_ENERGY), names print like the reference's.
+struct B200Metric
+    id::Int32
+    name::String
+end
+Base.show(io::IO, m::B200Metric) = write(io, m.name)
+const L2 = B200Metric(0, "Euclidean(1.0e-7)")      # reference src/distancemetrics.jl:234
+const WASS1D = B200Metric(1, "EMD(nothing)")       # :247
+const KLD = B200Metric(2, "KLDivergence()")        # :239
+const ENERGY = B200Metric(3, "Energy(nothing)")    # :254
+const ALL_METRICS = (L2, WASS1D, KLD, ENERGY)      # :257
+
+"Scales used in the autoscale option (reference src/sequencer.jl:148)."
+const FIB = [1,2,3,5,8,13,21,34,55,89,144,233,377,610,987,1597,2584,5168]
+
+struct SequencerResult                                # reference src/sequencer.jl:13-20
+    EOSeg::Dict{Tuple,Any}
+    EOAlgScale::Dict{Tuple,Any}
+    D::AbstractMatrix
+    mst::LightGraphs.AbstractGraph
+    η::Real
+    order::AbstractVector
+end
+D(r::SequencerResult) = r.D
+mst(r::SequencerResult) = r.mst
+elong(r::SequencerResult) = r.η
+order(r::SequencerResult) = r.order
+Base.show(io::IO, s::SequencerResult) =
+    write(io, "Sequencer Result: η = $(@sprintf("%.4g", elong(s))), order = $(prettyp(order(s),5))")
+
+function prettyp(v::AbstractVector, len::Int = 3)    # reference src/utils.jl:48-53
+    length(v) < 7 && return join(string.(v), ",")
+    head = join(string.(v[1:len]), ",")
+    tail = join(string.(v[(end-(len-1)):end]), ",")
+    return join([head, tail], "...")
+end
+
+function ensuregrid!(A, grid = nothing)::AbstractVector     # reference src/sequencer.jl:296-304
+    if isnothing(grid)
+        grid = float(collect(axes(A, 1)))
+    end
+    @assert length(grid) == size(A, 1) "Grid length must match dims 1 (row count) of A. Got grid:$(length(grid)) and A:$(size(A, 1))"
+    grid
+end
+
+# ---- thin ccall layer -------------------------------------------------------------------------
+mutable struct Handle
+    ptr::Ptr{Cvoid}
+    function Handle(device::Integer = -1)
+        ref = Ref{Ptr{Cvoid}}(C_NULL)
+        st = device < 0 ?
+            ccall((:seqj_create, libseqj), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), ref, C_NULL, 0) :
+            ccall((:seqj_create, libseqj), Cint, (Ref{Ptr{Cvoid}}, Ref{Cint}, Cint), ref, Ref{Cint}(device), 1)
+        h = new(ref[])
+        st == 0 || error("seqj_create failed ($st): " * lasterror(h))   # no CPU fallback
+        finalizer(x -> ccall((:seqj_destroy, libseqj), Cvoid, (Ptr{Cvoid},), x.ptr), h)
+        h
+    end
+end
+lasterror(h::Handle) = unsafe_string(ccall((:seqj_last_error, libseqj), Cstring, (Ptr{Cvoid},), h.ptr))
+const _handle = Ref{Union{Nothing,Handle}}(nothing)
+handle() = (_handle[] === nothing && (_handle[] = Handle()); _handle[])
+
+function check(h::Handle, st::Integer)
+    st == 0 && return
+    msg = lasterror(h)
+    st == -6 && throw(AssertionError(msg))            # SEQJ_E_DOMAIN: reference src/sequencer.jl:111
+    st == -1 && throw(AssertionError(msg))            # bad scale etc.: reference src/sequencer.jl:385
+    error("seqj error $st: $msg")
+end
+
+bfs_digraph(parents::Vector{Int32}, root::Integer) = begin   # tree(parents) of LightGraphs.bfs_tree
+    g = SimpleDiGraph(length(parents))
+    for v in eachindex(parents)
+        v == root + 1 && continue
+        add_edge!(g, parents[v] + 1, v)
+    end
+    g
+end
+
+"""
+    sequence(A; scales=nothing, metrics=ALL_METRICS, grid=nothing)
+
+Same contract as the reference's `sequence` (src/sequencer.jl:105-145); the whole of `_sequence`
+runs on the GPU behind one `ccall`.
+"""
+function sequence(A::VecOrMat{T}; scales = nothing, metrics = ALL_METRICS, grid = nothing) where {T <: Real}
+    A = A isa Vector ? hcat(A...) : A
+    @info "Sequencing data with\n    shape: $(size(A))\n    metric(s): $(metrics)\n    scale(s): $(scales)"
+    tuplify(x::B200Metric) = tuple(x)
+    tuplify(x) = tuple(x...)
+    G = ensuregrid!(A, grid)
+    metrics = (metrics !== nothing) ? tuplify(metrics) : ALL_METRICS
+    A64 = A isa Matrix{Float64} ? A : convert(Matrix{Float64}, A)    # Q2: FP64 throughout
+    if scales === nothing
+        with_logger(NullLogger()) do
+            scales = autoscale(A64, metrics = metrics, grid = G)
+        end
+        @info "After autoscaling, best scale = $(scales)"
+    end
+    scales = tuplify(scales)
+    r, inmin = _sequence(A64, scales, metrics)
+    # the reference clamps the caller's array in place (src/sequencer.jl:130); the device already
+    # computed on clamped values, so touch host memory only when something was below eps()
+    inmin < eps() && A isa Matrix{Float64} && clamp!(A, eps(), typemax(Float64))
+    return r
+end
+
+function _sequence(A::Matrix{Float64}, scales, metrics)
+    h = handle()
+    M, N = size(A)
+    mids = Int32[m.id for m in metrics]
+    scs = Int32[s for s in scales]
+    res = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:seqj_sequence, libseqj), Cint,
+               (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Float64, Float64,
+                Ptr{UInt8}, Ref{Ptr{Cvoid}}),
+               h.ptr, A, M, N, mids, length(mids), scs, length(scs), ϵ, L2THR, C_NULL, res)
+    check(h, st)
+    r = res[]
+    try
+        EOSeg = Dict{Tuple,Any}()
+        EOAlgScale = Dict{Tuple,Any}()
+        g = 0
+        for k in metrics, l in scales                                     # metric-major, as the reference loops
+            met = Ref{Cint}(0); sc = Ref{Cint}(0); nch = Ref{Cint}(0); comp = Ref{Cint}(0)
+            check(h, ccall((:seqj_result_group_info, libseqj), Cint,
+                           (Ptr{Cvoid}, Cint, Ref{Cint}, Ref{Cint}, Ref{Cint}, Ref{Cint}), r, g, met, sc, nch, comp))
+            etas = Vector{Float64}(undef, nch[]); roots = Vector{Int32}(undef, nch[])
+            pars = Matrix{Int32}(undef, N, nch[])
+            check(h, ccall((:seqj_result_group_chunks, libseqj), Cint,
+                           (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}), r, g, etas, roots, pars))
+            EOSeg[(k, l)] = (Any[etas...], Any[bfs_digraph(pars[:, c], roots[c]) for c in 1:nch[]])
+            eta = Ref{Float64}(0); root = Ref{Int32}(0); par = Vector{Int32}(undef, N)
+            check(h, ccall((:seqj_result_group, libseqj), Cint,
+                           (Ptr{Cvoid}, Cint, Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                           r, g, eta, root, par, C_NULL, C_NULL, C_NULL))
+            EOAlgScale[(k, l)] = (eta[], bfs_digraph(par, root[]))
+            @info "$(k) at scale $(l): η = $(@sprintf("%.4g", eta[]))"
+            g += 1
+        end
+        eta = Ref{Float64}(0); root = Ref{Int32}(0)
+        ord = Vector{Int32}(undef, N); par = Vector{Int32}(undef, N)
+        mi = Vector{Int32}(undef, N - 1); mj = Vector{Int32}(undef, N - 1); mw = Vector{Float64}(undef, N - 1)
+        check(h, ccall((:seqj_result_final, libseqj), Cint,
+                       (Ptr{Cvoid}, Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+                       r, eta, root, ord, par, mi, mj, mw))
+        nnz = Ref{Int64}(0)
+        check(h, ccall((:seqj_result_D_nnz, libseqj), Cint, (Ptr{Cvoid}, Ref{Int64}), r, nnz))
+        ti = Vector{Int32}(undef, nnz[]); tj = Vector{Int32}(undef, nnz[]); tv = Vector{Float64}(undef, nnz[])
+        check(h, ccall((:seqj_result_D_triplets, libseqj), Cint,
+                       (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}), r, ti, tj, tv))
+        lo = Ref{Float64}(0); hi = Ref{Float64}(0)
+        check(h, ccall((:seqj_result_input_range, libseqj), Cint, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}), r, lo, hi))
+        # D = inv.(Pw): +Inf off the edge union, ϵ on the diagonal after _mst's clamp (reference :269,360)
+        Dm = fill(Inf, N, N)
+        for i in 1:N; Dm[i, i] = ϵ; end
+        for e in 1:nnz[]
+            Dm[ti[e] + 1, tj[e] + 1] = tv[e]; Dm[tj[e] + 1, ti[e] + 1] = tv[e]
+        end
+        S = sparse(Int.(mi) .+ 1, Int.(mj) .+ 1, mw, N, N)
+        mstD = SimpleWeightedGraph(S + S')
+        ordr = Int.(ord) .+ 1                                             # 1-based column indices
+        @info "Final: η = $(@sprintf("%.4g", eta[])) sequence = $(prettyp(ordr, 5))"
+        return SequencerResult(EOSeg, EOAlgScale, Dm, mstD, eta[], ordr), lo[]
+    finally
+        ccall((:seqj_result_free, libseqj), Cvoid, (Ptr{Cvoid},), r)
+    end
+end
+
+"Reference src/sequencer.jl:158-179; the column sample uses Julia's RNG (seed it for reproducibility)."
+function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid = nothing, p = 0.1)
+    M, N = size(A)
+    Ŋ = round(Int, N * p, RoundDown)
+    @assert Ŋ > 1 "Matrix A contains too few columns ($(N)) to sample with p = $(p). Use a larger p."
+    sampidx = sort(randperm(N)[1:Ŋ])
+    Asamp = convert(Matrix{Float64}, A[:, sampidx])
+    maxscale = M ÷ 10
+    @assert maxscale > 0 "Matrix A contains too few rows ($(M)) for autoscale. The minimum is 10 rows. It is recommended to set scale=(1,)."
+    bestscale, max_η = 1, 0.0
+    mets = metrics isa B200Metric ? (metrics,) : tuple(metrics...)
+    for s in filter(i -> i < maxscale, FIB)
+        r, _ = _sequence(Asamp, (s,), mets)
+        if elong(r) > max_η
+            max_η = elong(r); bestscale = s
+        end
+    end
+    return bestscale
+end
+using Random: randperm
+
+end # module

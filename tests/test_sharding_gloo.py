@@ -1,0 +1,50 @@
+"""Host logic of the multi-GPU path on CPU: assignment properties and a world_size-2 gloo run."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_assignment_covers_every_group_once_and_balances(seqj):
+    from sequencerj_b200 import sharding
+    metrics, scales = seqj.ALL_METRICS, (1, 2, 4, 8, 16)
+    costs = sharding.group_costs(4096, metrics, scales)
+    assert costs.shape == (4, 5) and np.all(costs > 0)
+    assert costs[1, 0] > costs[0, 0]                       # EMD costs twice the FP64 issue slots of a contraction
+    for world in (1, 2, 4, 8):
+        owner = sharding.assign_groups(costs, world)
+        assert owner.shape == costs.shape and owner.min() >= 0 and owner.max() < world
+        load = np.array([costs[owner == r].sum() for r in range(world)])
+        assert load.min() > 0
+        assert load.max() <= costs.sum() / world + costs.max()          # LPT bound
+    assert sharding.nchunks(10, 6) == 5 and sharding.nchunks(4096, 16) == 16 and sharding.nchunks(50, 4) == 4
+
+
+def test_merge_is_metric_major(seqj):
+    from sequencerj_b200 import sharding
+    metrics, scales = (seqj.L2, seqj.KLD), (1, 2)
+    parts = [{(0, 2): (2.0, [0], [1], [0.5]), (2, 1): (3.0, [0], [1], [0.7])},
+             {(0, 1): (1.0, [0], [1], [0.4]), (2, 2): (4.0, [0], [1], [0.9])}]
+    etas, msts = sharding.merge_group_results(parts, metrics, scales)
+    assert etas == [1.0, 2.0, 3.0, 4.0]                    # (L2,1), (L2,2), (KLD,1), (KLD,2): sequencer.jl:194-196
+    assert [t.weight[0] for t in msts] == [0.4, 0.5, 0.7, 0.9]
+
+
+def test_world_size_2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "result.txt"
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   SEQJ_TEST_OUT=str(out), OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tests", "_gloo_worker.py")], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT))
+    outs = [p.communicate(timeout=300)[0].decode() for p in procs]
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    assert out.read_text() == "OK"
