@@ -603,6 +603,151 @@ __global__ void gather_edges_kernel(const double* __restrict__ D, int64_t ldD, c
   val[e] = D[(int64_t)mi[e] * ldD + mj[e]];
 }
 
+// ---- sparse MST for the final graph ---------------------------------------------------------------
+// The final distance matrix D = inv.(Pw) (reference src/sequencer.jl:269) is +Inf outside the union of the
+// group MSTs, i.e. a sparse graph with at most G*(N-1) edges.  Kruskal over the dense N x N matrix (reference)
+// or a dense Prim (N latency-bound steps) is wasteful here: Boruvka on the edge list needs O(log N) fully
+// parallel rounds.  Edges are totally ordered by (weight, edge index), so the result is the unique MST and
+// the only hooking cycles are mutual pairs, broken by component id.
+// One CTA; edge e = (g, k) lives at mi/mj/val[g*ldp + k].
+struct BoruvkaParams {
+  int N, G;
+  int64_t ldp;
+  const int* mi;
+  const int* mj;
+  const double* val;        // D[i][j] per edge (duplicates carry identical values)
+  double eps_floor;
+  int* comp;                // scratch [N]
+  unsigned long long* best; // scratch [N]
+  int* besti;               // scratch [N]
+  int* out_i;               // MST edges [N-1]
+  int* out_j;
+  double* out_w;
+  int* out_count;           // scratch [1]
+};
+
+constexpr int kBoruvkaThreads = 1024;
+
+__global__ void __launch_bounds__(kBoruvkaThreads, 1) boruvka_sparse_kernel(BoruvkaParams p) {
+  __shared__ int s_ncomp;
+  const int tid = threadIdx.x;
+  const int N = p.N, ne = N - 1;
+  const long long E = (long long)p.G * ne;
+  const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
+  for (int v = tid; v < N; v += kBoruvkaThreads) p.comp[v] = v;
+  if (tid == 0) { *p.out_count = 0; s_ncomp = N; }
+  __syncthreads();
+  for (int round = 0; round < 64 && s_ncomp > 1; ++round) {
+    for (int v = tid; v < N; v += kBoruvkaThreads) { p.best[v] = ~0ull; p.besti[v] = 0x7fffffff; }
+    __syncthreads();
+    // 1. lightest crossing edge weight of every component
+    for (long long e = tid; e < E; e += kBoruvkaThreads) {
+      const int64_t a = (e / ne) * p.ldp + (e % ne);
+      const int ci = p.comp[p.mi[a]], cj = p.comp[p.mj[a]];
+      if (ci != cj) {
+        const unsigned long long w = max((unsigned long long)__double_as_longlong(p.val[a]), eps_bits);
+        atomicMin(&p.best[ci], w);
+        atomicMin(&p.best[cj], w);
+      }
+    }
+    __syncthreads();
+    // 2. among those, the smallest edge index
+    for (long long e = tid; e < E; e += kBoruvkaThreads) {
+      const int64_t a = (e / ne) * p.ldp + (e % ne);
+      const int ci = p.comp[p.mi[a]], cj = p.comp[p.mj[a]];
+      if (ci != cj) {
+        const unsigned long long w = max((unsigned long long)__double_as_longlong(p.val[a]), eps_bits);
+        if (w == p.best[ci]) atomicMin(&p.besti[ci], (int)e);
+        if (w == p.best[cj]) atomicMin(&p.besti[cj], (int)e);
+      }
+    }
+    __syncthreads();
+    // 3. hook every component root onto the other side of its edge; a mutual pair keeps the smaller id as root
+    for (int c = tid; c < N; c += kBoruvkaThreads) {
+      if (p.comp[c] != c) continue;
+      const int e = p.besti[c];
+      if (e == 0x7fffffff) continue;                      // isolated component (disconnected input)
+      const int64_t a = ((long long)e / ne) * p.ldp + ((long long)e % ne);
+      const int i = p.mi[a], j = p.mj[a];
+      const int ci = p.comp[i], cj = p.comp[j];
+      const int other = (ci == c) ? cj : ci;
+      const bool mutual = (p.besti[other] == e);
+      if (mutual && c < other) continue;                  // `other` hooks onto c and records the edge
+      const int k = atomicAdd(p.out_count, 1);
+      p.out_i[k] = min(i, j);
+      p.out_j[k] = max(i, j);
+      p.out_w[k] = __longlong_as_double((long long)p.best[c]);
+      // besti[] is read by other components' mutual test in this step, so only this component's own best[c] is
+      // reused: bit 63 (never set in a finite weight) marks "hooked", the low word is the hook target
+      p.best[c] = (1ull << 63) | (unsigned long long)(unsigned)other;
+    }
+    __syncthreads();
+    for (int c = tid; c < N; c += kBoruvkaThreads)
+      if (p.comp[c] == c && p.besti[c] != 0x7fffffff && (p.best[c] >> 63)) p.comp[c] = (int)(p.best[c] & 0xffffffffull);
+    __syncthreads();
+    // 4. pointer jumping until every vertex points at its root
+    for (int it = 0; it < 32; ++it) {
+      int changed = 0;
+      for (int v = tid; v < N; v += kBoruvkaThreads) {
+        const int c = p.comp[v], cc = p.comp[c];
+        if (c != cc) { p.comp[v] = cc; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+    if (tid == 0) s_ncomp = N - *p.out_count;
+    __syncthreads();
+  }
+}
+
+// Root the MST edge list at vertex 0: produce the (parent, weight, order) arrays that tree_kernel consumes
+// (the same contract as Prim's output: parents precede children in `order`).  CSR adjacency is built in
+// parallel, the BFS itself is one thread (the final tree is path-like, depth ~ N).
+struct RootTreeParams {
+  int N;
+  const int* ei;
+  const int* ej;
+  const double* ew;
+  int* deg;      // scratch [N+1]
+  int* adj;      // scratch [2(N-1)]
+  int* adje;     // scratch [2(N-1)]  edge index of each adjacency entry
+  int* fill;     // scratch [N]
+  int* parent;   // out [N]
+  double* weight;
+  int* order;
+};
+
+__global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
+  const int tid = threadIdx.x, N = p.N, ne = N - 1;
+  for (int v = tid; v <= N; v += 1024) p.deg[v] = 0;
+  for (int v = tid; v < N; v += 1024) p.parent[v] = -1;
+  __syncthreads();
+  for (int e = tid; e < ne; e += 1024) { atomicAdd(&p.deg[p.ei[e]], 1); atomicAdd(&p.deg[p.ej[e]], 1); }
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int v = 0; v < N; ++v) { const int d = p.deg[v]; p.deg[v] = run; p.fill[v] = run; run += d; }
+    p.deg[N] = run;
+  }
+  __syncthreads();
+  for (int e = tid; e < ne; e += 1024) {
+    const int i = p.ei[e], j = p.ej[e];
+    int k = atomicAdd(&p.fill[i], 1); p.adj[k] = j; p.adje[k] = e;
+    k = atomicAdd(&p.fill[j], 1); p.adj[k] = i; p.adje[k] = e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int head = 0, tail = 0;
+    p.order[tail++] = 0; p.parent[0] = 0; p.weight[0] = 0.0;
+    while (head < tail) {
+      const int u = p.order[head++];
+      for (int k = p.deg[u]; k < p.deg[u + 1]; ++k) {
+        const int v = p.adj[k];
+        if (p.parent[v] < 0) { p.parent[v] = u; p.weight[v] = p.ew[p.adje[k]]; p.order[tail++] = v; }
+      }
+    }
+  }
+}
+
 // Unit-level: Symmetric(dm) view of a column-major upload (upper triangle wins), clamped to eps.
 __global__ void symmetrize_kernel(const double* __restrict__ up, int N, double* __restrict__ out, int64_t ldD,
                                   double eps_floor) {

@@ -145,9 +145,13 @@ struct PhaseTimer {
   }
   void end(int id) { cudaEventRecord(spans[id].b, *cur); }
   void collect(double* timers) {
+    const bool trace = getenv("SEQJ_TRACE") != nullptr;      // per-span listing on stderr (debugging)
     for (auto& s : spans) {
       float ms = 0;
-      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) timers[s.phase] += ms;
+      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
+        timers[s.phase] += ms;
+        if (trace) fprintf(stderr, "[seqj] phase %2d  %9.3f ms\n", s.phase, ms);
+      }
     }
   }
 };
@@ -200,6 +204,7 @@ struct GraphWS {
       *dep1 = nullptr, *from_g = nullptr;
   double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
   int prim_R = 0;
+  int *fuse_i0 = nullptr, *fuse_i1 = nullptr;   // scratch of the sparse final MST (root_tree_kernel)
   int cluster = 0, cl_W = 0;      // cluster Prim: CTAs per graph (0 = single-CTA kernel), slice width
   size_t cl_smem = 0;
   int tree_use_smem = 1;
@@ -259,6 +264,7 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
   CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
   CU_TRY(c.pool.alloc(&g.S, n)); CU_TRY(c.pool.alloc(&g.wd2, n)); CU_TRY(c.pool.alloc(&g.S2, n));
+  CU_TRY(c.pool.alloc(&g.fuse_i0, (size_t)2 * N + 64)); CU_TRY(c.pool.alloc(&g.fuse_i1, (size_t)4 * N + 64));
   g.prim_smem = (size_t)((N + 1) & ~1) * 8 + (size_t)N * 4;
   g.use_smem = g.prim_smem + 1024 <= h->max_smem;
   if (!g.use_smem) {
@@ -297,7 +303,11 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
   int t = c.timer.begin(SEQJ_T_PRIM);
-  if (g.cluster)
+  // Measured on B200 at N = 10k (profiles/r01_prim_variants.md): with >= ~50 graphs in flight the single-CTA
+  // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
+  // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.
+  const bool force_cluster = getenv("SEQJ_PRIM") && !strcmp(getenv("SEQJ_PRIM"), "cluster");
+  if (g.cluster && (force_cluster || nb * 3 <= h->sm_count))
     prim_cluster_kernel<8><<<nb * g.cluster, kPrimClThreads, g.cl_smem, c.st>>>(pp, g.cl_W);
   else
     prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
@@ -472,24 +482,56 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     c.launches++;
   }
   CU_TRY(cudaGetLastError());
-  ST_TRY(run_measure(c, gws, Sbuf, ldD, 0, 1, eps_floor, eta_f, root_f, parents_f, ldp, fmst_i, fmst_j, fmst_w, order_f));
+  // final MST on the sparse edge union (Boruvka), rooted at vertex 0, then the usual tree measurement
+  {
+    BoruvkaParams bp;
+    bp.N = N; bp.G = G; bp.ldp = ldp; bp.mi = mst_i; bp.mj = mst_j; bp.val = edge_val; bp.eps_floor = eps_floor;
+    bp.comp = gws.anc0; bp.best = reinterpret_cast<unsigned long long*>(gws.wd); bp.besti = gws.anc1;
+    bp.out_i = gws.dep0; bp.out_j = gws.dep1; bp.out_w = gws.S; bp.out_count = gws.size;
+    boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
+    RootTreeParams rp;
+    rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
+    rp.deg = gws.fuse_i0; rp.adj = gws.fuse_i1; rp.adje = gws.fuse_i1 + 2 * (size_t)N; rp.fill = gws.fuse_i0 + (N + 8);
+    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
+    root_tree_kernel<<<1, 1024, 0, c.st>>>(rp);
+    c.launches += 2;
+    CU_TRY(cudaGetLastError());
+    TreeParams tp;
+    tp.N = N; tp.ldv = gws.ldv; tp.parent = gws.parent; tp.weight = gws.weight; tp.order = gws.order;
+    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem;
+    tp.anc0 = gws.anc0; tp.anc1 = gws.anc1; tp.dep0 = gws.dep0; tp.dep1 = gws.dep1;
+    tp.eta = eta_f; tp.root = root_f; tp.newparent = parents_f; tp.ldp = ldp;
+    tp.mst_i = fmst_i; tp.mst_j = fmst_j; tp.mst_w = fmst_w; tp.dfs_order = order_f;
+    tree_kernel<<<1, kTreeThreads, gws.tree_smem, c.st>>>(tp);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+  }
   c.timer.end(t);
   return SEQJ_OK;
 }
 
 void dedup_triplets(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
                     const std::vector<double>& val) {
-  std::map<std::pair<int, int>, double> m;
+  // first occurrence of every (i, j) in group-major edge order, via an open-addressing table
+  const size_t total = (size_t)G * (N - 1);
+  size_t cap = 16;
+  while (cap < 2 * total) cap <<= 1;
+  std::vector<uint64_t> table(cap, ~uint64_t(0));
+  r->Di.reserve(total); r->Dj.reserve(total); r->Dv.reserve(total);
   for (int g = 0; g < G; ++g)
     for (int e = 0; e < N - 1; ++e) {
       const int64_t k = (int64_t)g * ldp + e;
-      m[std::make_pair(mi[k], mj[k])] = val[k];
+      const uint64_t key = (uint64_t)mi[k] * (uint64_t)N + (uint64_t)mj[k];
+      size_t hpos = (key * 0x9E3779B97F4A7C15ull) & (cap - 1);
+      bool seen = false;
+      while (table[hpos] != ~uint64_t(0)) {
+        if (table[hpos] == key) { seen = true; break; }
+        hpos = (hpos + 1) & (cap - 1);
+      }
+      if (seen) continue;
+      table[hpos] = key;
+      r->Di.push_back(mi[k]); r->Dj.push_back(mj[k]); r->Dv.push_back(val[k]);
     }
-  for (auto& kv : m) {
-    r->Di.push_back(kv.first.first);
-    r->Dj.push_back(kv.first.second);
-    r->Dv.push_back(kv.second);
-  }
 }
 
 template <typename T>
