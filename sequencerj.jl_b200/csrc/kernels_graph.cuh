@@ -294,6 +294,7 @@ struct TreeParams {
   int* dep0;
   int* dep1;
   int use_smem;           // parent + size fit in dynamic shared memory (8N bytes)
+  int dfs_smem;           // the DFS scratch (16N + 16 bytes) fits in dynamic shared memory
   // outputs (per graph g: index out0 + g)
   double* eta;            // [ngraphs]
   int* root;              // [ngraphs]
@@ -497,28 +498,32 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24)
   if (p.dfs_order) {
     __syncthreads();
+    // children CSR + explicit stack; in shared memory when the launch provided 16N+16 bytes (dfs_smem)
+    int* cstart = p.dfs_smem ? tree_sm : size;
+    int* clist = p.dfs_smem ? tree_sm + (N + 1) : anc_a;
+    int* stack = p.dfs_smem ? tree_sm + (2 * N + 1) : anc_b;
+    int* fill = p.dfs_smem ? tree_sm + (3 * N + 1) : dep_a;
+    int* pre = dep_b;                                   // global: written once, read by the parallel reverse copy
+    for (int v = tid; v <= N; v += kTreeThreads) cstart[v] = 0;
+    __syncthreads();
+    for (int v = tid; v < N; v += kTreeThreads)
+      if (v != root) atomicAdd(&cstart[newparent[v]], 1);
+    __syncthreads();
     if (tid == 0) {
-      int* cstart = size;          // reuse scratch: children CSR
-      int* clist = anc_a;
-      int* stack = anc_b;
-      int* pre = dep_b;
-      for (int v = 0; v <= N; ++v) if (v < N) cstart[v] = 0;
-      for (int v = 0; v < N; ++v) if (v != root) cstart[newparent[v]]++;
       int run = 0;
-      for (int v = 0; v < N; ++v) { const int c = cstart[v]; cstart[v] = run; run += c; }
-      int* fill = dep_a;           // next free slot per vertex
-      for (int v = 0; v < N; ++v) fill[v] = cstart[v];
-      for (int v = 0; v < N; ++v) if (v != root) clist[fill[newparent[v]]++] = v;   // ascending v
+      for (int v = 0; v < N; ++v) { const int c = cstart[v]; cstart[v] = run; fill[v] = run; run += c; }
+      cstart[N] = run;
+      for (int v = 0; v < N; ++v) if (v != root) clist[fill[newparent[v]]++] = v;   // ascending v per parent
       int sp = 0, np = 0;
       stack[sp++] = root;
       while (sp > 0) {
         const int x = stack[--sp];
         pre[np++] = x;
-        const int b = cstart[x], e = fill[x];
-        for (int q = e - 1; q >= b; --q) stack[sp++] = clist[q];
+        for (int q = cstart[x + 1] - 1; q >= cstart[x]; --q) stack[sp++] = clist[q];
       }
-      for (int k = 0; k < N; ++k) p.dfs_order[oofs + k] = pre[N - 1 - k];
     }
+    __syncthreads();
+    for (int k = tid; k < N; k += kTreeThreads) p.dfs_order[oofs + k] = pre[N - 1 - k];
   }
 }
 
@@ -707,44 +712,64 @@ struct RootTreeParams {
   const int* ei;
   const int* ej;
   const double* ew;
-  int* deg;      // scratch [N+1]
-  int* adj;      // scratch [2(N-1)]
-  int* adje;     // scratch [2(N-1)]  edge index of each adjacency entry
-  int* fill;     // scratch [N]
+  int* deg;      // global scratch [N+1]      (used when the CSR does not fit in shared memory)
+  int* adj;      // global scratch [2(N-1)]
+  int* queue;    // global scratch [N]
+  int use_smem;  // dynamic smem holds deg (N+1) + adj (2N) + queue (N) + visited bitmap (N/32 + 1) ints
   int* parent;   // out [N]
   double* weight;
   int* order;
 };
 
 __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
+  extern __shared__ int rt_sm[];
   const int tid = threadIdx.x, N = p.N, ne = N - 1;
-  for (int v = tid; v <= N; v += 1024) p.deg[v] = 0;
-  for (int v = tid; v < N; v += 1024) p.parent[v] = -1;
+  int* deg = p.use_smem ? rt_sm : p.deg;
+  int* adj = p.use_smem ? rt_sm + (N + 1) : p.adj;
+  int* queue = p.use_smem ? rt_sm + (3 * N + 1) : p.queue;
+  unsigned* visited = reinterpret_cast<unsigned*>(p.use_smem ? rt_sm + (4 * N + 1) : p.queue + N);
+  int* fill = p.parent;                         // parent[] doubles as the CSR fill cursor before the BFS
+  for (int v = tid; v <= N; v += 1024) deg[v] = 0;
+  for (int v = tid; v < (N + 31) / 32; v += 1024) visited[v] = 0u;
   __syncthreads();
-  for (int e = tid; e < ne; e += 1024) { atomicAdd(&p.deg[p.ei[e]], 1); atomicAdd(&p.deg[p.ej[e]], 1); }
+  for (int e = tid; e < ne; e += 1024) { atomicAdd(&deg[p.ei[e]], 1); atomicAdd(&deg[p.ej[e]], 1); }
   __syncthreads();
   if (tid == 0) {
     int run = 0;
-    for (int v = 0; v < N; ++v) { const int d = p.deg[v]; p.deg[v] = run; p.fill[v] = run; run += d; }
-    p.deg[N] = run;
+    for (int v = 0; v < N; ++v) { const int d = deg[v]; deg[v] = run; fill[v] = run; run += d; }
+    deg[N] = run;
   }
   __syncthreads();
   for (int e = tid; e < ne; e += 1024) {
     const int i = p.ei[e], j = p.ej[e];
-    int k = atomicAdd(&p.fill[i], 1); p.adj[k] = j; p.adje[k] = e;
-    k = atomicAdd(&p.fill[j], 1); p.adj[k] = i; p.adje[k] = e;
+    adj[atomicAdd(&fill[i], 1)] = j;
+    adj[atomicAdd(&fill[j], 1)] = i;
   }
   __syncthreads();
-  if (tid == 0) {
+  if (tid == 0) {                               // BFS from vertex 0; the final tree is path-like (depth ~ N)
     int head = 0, tail = 0;
-    p.order[tail++] = 0; p.parent[0] = 0; p.weight[0] = 0.0;
+    queue[tail++] = 0;
+    visited[0] |= 1u;
+    p.parent[0] = 0;
     while (head < tail) {
-      const int u = p.order[head++];
-      for (int k = p.deg[u]; k < p.deg[u + 1]; ++k) {
-        const int v = p.adj[k];
-        if (p.parent[v] < 0) { p.parent[v] = u; p.weight[v] = p.ew[p.adje[k]]; p.order[tail++] = v; }
+      const int u = queue[head++];
+      for (int k = deg[u]; k < deg[u + 1]; ++k) {
+        const int v = adj[k];
+        if (!((visited[v >> 5] >> (v & 31)) & 1u)) {
+          visited[v >> 5] |= 1u << (v & 31);
+          p.parent[v] = u;
+          queue[tail++] = v;
+        }
       }
     }
+  }
+  __syncthreads();
+  for (int k = tid; k < N; k += 1024) p.order[k] = queue[k];
+  if (tid == 0) p.weight[0] = 0.0;
+  for (int e = tid; e < ne; e += 1024) {        // every tree edge joins a vertex to its parent
+    const int i = p.ei[e], j = p.ej[e];
+    if (p.parent[j] == i) p.weight[j] = p.ew[e];
+    else p.weight[i] = p.ew[e];
   }
 }
 

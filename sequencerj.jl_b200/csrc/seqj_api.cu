@@ -259,7 +259,7 @@ struct Ctx {
 int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   seqj_handle* h = c.h;
   g.cap = cap; g.N = N; g.ldv = round_up(N, 32);
-  const size_t n = (size_t)cap * g.ldv;
+  const size_t n = (size_t)cap * g.ldv + 64;
   CU_TRY(c.pool.alloc(&g.parent, n)); CU_TRY(c.pool.alloc(&g.order, n)); CU_TRY(c.pool.alloc(&g.size, n));
   CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
   CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
@@ -316,6 +316,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   TreeParams tp;
   tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
   tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
+  tp.dfs_smem = 0;
   tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
   tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
   t = c.timer.begin(SEQJ_T_TREE);
@@ -491,9 +492,12 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
     RootTreeParams rp;
     rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
-    rp.deg = gws.fuse_i0; rp.adj = gws.fuse_i1; rp.adje = gws.fuse_i1 + 2 * (size_t)N; rp.fill = gws.fuse_i0 + (N + 8);
+    rp.deg = gws.fuse_i0; rp.adj = gws.fuse_i1; rp.queue = gws.fuse_i1 + 2 * (size_t)N;
     rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
-    root_tree_kernel<<<1, 1024, 0, c.st>>>(rp);
+    const size_t rt_smem = ((size_t)4 * N + 1 + (N + 31) / 32 + 1) * 4;
+    rp.use_smem = rt_smem + 2048 <= h->max_smem;
+    CU_TRY(cudaFuncSetAttribute(root_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rp.use_smem ? rt_smem : 0)));
+    root_tree_kernel<<<1, 1024, rp.use_smem ? rt_smem : 0, c.st>>>(rp);
     c.launches += 2;
     CU_TRY(cudaGetLastError());
     TreeParams tp;
@@ -502,7 +506,12 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     tp.anc0 = gws.anc0; tp.anc1 = gws.anc1; tp.dep0 = gws.dep0; tp.dep1 = gws.dep1;
     tp.eta = eta_f; tp.root = root_f; tp.newparent = parents_f; tp.ldp = ldp;
     tp.mst_i = fmst_i; tp.mst_j = fmst_j; tp.mst_w = fmst_w; tp.dfs_order = order_f;
-    tree_kernel<<<1, kTreeThreads, gws.tree_smem, c.st>>>(tp);
+    const size_t dfs_smem = ((size_t)4 * N + 8) * 4;
+    tp.dfs_smem = gws.tree_use_smem && dfs_smem + 2048 <= h->max_smem;
+    const size_t tsm = tp.dfs_smem ? dfs_smem : gws.tree_smem;
+    CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
+    tree_kernel<<<1, kTreeThreads, tsm, c.st>>>(tp);
+    CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gws.tree_smem));
     c.launches++;
     CU_TRY(cudaGetLastError());
   }
@@ -715,7 +724,8 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for two N x N chunk matrices plus the accumulator");
   const char* wenv = getenv("SEQJ_WAVES");
   const int nwaves_target = std::max(1, wenv ? atoi(wenv) : (c.overlap ? 2 : 1));
-  const int wave_target = (total_chunks + nwaves_target - 1) / nwaves_target;
+  int wave_target = (total_chunks + nwaves_target - 1) / nwaves_target;
+  if (const char* wf = getenv("SEQJ_WAVE_FRAC")) wave_target = std::max(1, (int)(atof(wf) * total_chunks));
   std::vector<Wave> waves;
   std::vector<int> chunk_off(G, 0);             // first output slot of each group's chunks
   {
