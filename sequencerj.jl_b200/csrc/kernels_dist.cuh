@@ -51,6 +51,21 @@ struct DistParams {
 // read by one quarter-warp differ in bit 2 (=> their SWIZZLE_128B chunks never collide).
 __device__ __forceinline__ int rho(int g) { return (g >> 1) + ((g & 1) << 2); }
 
+// sqrt(v) for the epilogue.  The FP64 units are shared between DMMA and scalar FP64 math
+// (profiles/r01_fp64_mix.json), so every epilogue instruction is taken from the tile main loops; the CUDA
+// library sqrt costs ~30 FP64-pipe instructions, this one ~13: MUFU.RSQ64H seed (2^-22), two Newton steps
+// on 1/sqrt, one residual correction.  Result within 1 ulp; v <= 0 gives 0.
+__device__ __forceinline__ double fast_sqrt(double v) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+  const double hv = 0.5 * v;
+  y = y * fma(-hv * y, y, 1.5);
+  y = y * fma(-hv * y, y, 1.5);
+  double sq = v * y;
+  sq = fma(fma(-sq, sq, v), 0.5 * y, sq);
+  return v > 0.0 ? sq : 0.0;
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, 2)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DistParams p) {
@@ -155,7 +170,7 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const double selfterms = ni + nj[b][e];
             const double v = selfterms - 2.0 * c;
             flag = v < p.tau * selfterms;
-            d = sqrt(fmax(v, 0.0));
+            d = fast_sqrt(v);
             if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;   // sqrt(2) * sqrt(sum)
           }
           out = fabs(d) + p.eps_floor;

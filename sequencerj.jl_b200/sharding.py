@@ -7,6 +7,8 @@ combination stay on the GPU that owns it.  The only exchange is the per-group re
 """
 from __future__ import annotations
 
+import time
+
 import numpy as np
 
 from . import api
@@ -59,10 +61,46 @@ def merge_group_results(parts, metrics, scales):
     return etas, msts
 
 
-def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, allgather=None, device_ptr=None):
-    """`_sequence` over `world` ranks. `allgather(obj) -> list of obj` is the only communication
-    (torch.distributed.all_gather_object over NCCL/gloo in practice).  Every rank returns the same
-    final SequencerResult; per-group details are kept for the groups it owns."""
+def torch_allgather_groups(mine, owner, metrics, scales, N, rank, world, dist, device):
+    """All-gather of the per-group (eta, MST edges) as fixed-shape tensors over torch.distributed
+    (NCCL on GPUs): every rank contributes `cap` group slots (cap = max groups per rank), so no pickling
+    and no size negotiation.  Returns the merged dict {(metric_id, scale): (eta, src, dst, w)}."""
+    import torch
+    cap = int(max(int((owner == r).sum()) for r in range(world)))
+    ne = N - 1
+    ints = torch.zeros((cap, 2 + 2 * ne), dtype=torch.int32)          # metric id, scale, src[ne], dst[ne]
+    flts = torch.zeros((cap, 1 + ne), dtype=torch.float64)            # eta, w[ne]
+    ints[:, 0] = -1
+    for slot, ((mid, sc), (eta, src, dst, w)) in enumerate(sorted(mine.items())):
+        ints[slot, 0], ints[slot, 1] = mid, sc
+        ints[slot, 2:2 + ne] = torch.from_numpy(np.ascontiguousarray(src, dtype=np.int32))
+        ints[slot, 2 + ne:] = torch.from_numpy(np.ascontiguousarray(dst, dtype=np.int32))
+        flts[slot, 0] = eta
+        flts[slot, 1:] = torch.from_numpy(np.ascontiguousarray(w, dtype=np.float64))
+    ints_d, flts_d = ints.to(device), flts.to(device)
+    all_i = torch.empty((world,) + tuple(ints.shape), dtype=torch.int32, device=device)
+    all_f = torch.empty((world,) + tuple(flts.shape), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(all_i, ints_d)
+    dist.all_gather_into_tensor(all_f, flts_d)
+    all_i, all_f = all_i.cpu().numpy(), all_f.cpu().numpy()
+    merged = {}
+    for r in range(world):
+        for slot in range(cap):
+            mid = int(all_i[r, slot, 0])
+            if mid < 0:
+                continue
+            merged[(mid, int(all_i[r, slot, 1]))] = (float(all_f[r, slot, 0]), all_i[r, slot, 2:2 + ne],
+                                                     all_i[r, slot, 2 + ne:], all_f[r, slot, 1:])
+    return merged
+
+
+def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, allgather=None, device_ptr=None,
+                     gather_groups=None):
+    """`_sequence` over `world` ranks.  The only communication is the gather of per-group results:
+    `gather_groups(mine, owner) -> merged dict` (tensor all-gather, see torch_allgather_groups) or, as a
+    generic fallback, `allgather(obj) -> list of obj` (all_gather_object).  Every rank returns the same final
+    SequencerResult; per-group details are kept for the groups it owns.  `timings` gains host-side
+    wall-clock entries (host_local_ms, host_gather_ms, host_fuse_ms)."""
     N, M = At.shape
     scales = tuple(int(s) for s in scales)
     if world == 1:
@@ -71,17 +109,27 @@ def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, al
     mask = (owner == rank).astype(np.uint8)
     mine = {}
     local = None
+    t0 = time.perf_counter()
     if mask.any():
         local = api._sequence(At, scales, metrics, handle, group_mask=mask, device_ptr=device_ptr)
         for (m, s), (eta, _) in local.EOAlgScale.items():
             t = local.group_msts[(m, s)]
             mine[(m.id, s)] = (eta, t.src, t.dst, t.weight)
-    parts = allgather(mine) if world > 1 else [mine]
-    etas, msts = merge_group_results(parts, metrics, scales)
+    t1 = time.perf_counter()
+    if gather_groups is not None:
+        merged = gather_groups(mine, owner)
+        etas, msts = merge_group_results([merged], metrics, scales)
+    else:
+        etas, msts = merge_group_results(allgather(mine), metrics, scales)
+    t2 = time.perf_counter()
     final = api.fuse(N, etas, msts, handle=handle)
+    t3 = time.perf_counter()
     if local is not None:
         final.EOSeg, final.EOAlgScale, final.group_msts = local.EOSeg, local.EOAlgScale, local.group_msts
         for k, v in local.timings.items():
             final.timings[k] = final.timings.get(k, 0.0) + v
         final.launches += local.launches
+    final.timings["host_local_ms"] = (t1 - t0) * 1e3
+    final.timings["host_gather_ms"] = (t2 - t1) * 1e3
+    final.timings["host_fuse_ms"] = (t3 - t2) * 1e3
     return final
