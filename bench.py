@@ -165,6 +165,8 @@ def main():
     ap.add_argument("--sample-objects", type=int, default=320, help="objects in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sharding", default="group", choices=["group", "chunk"],
+                    help="multi-GPU split: whole (metric, scale) groups, or equal-cost chunk ranges + NCCL reduce")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.objects:
@@ -219,6 +221,9 @@ def main():
                                                    torch.device("cuda", local))
 
     def step_dev():
+        if world > 1 and args.sharding == "chunk":
+            return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist,
+                                                    torch.device("cuda", local), dev.data_ptr())
         return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, allgather, device_ptr=dev.data_ptr(),
                                          gather_groups=gather_groups)
 
@@ -254,6 +259,10 @@ def main():
         def step_e2e():
             if world == 1:
                 return s.sequence(A_pub, scales=scales, metrics=metrics, handle=handle)
+            if args.sharding == "chunk":
+                d = host.to(torch.device("cuda", local), non_blocking=True)      # H2D of A inside the timed region
+                return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist,
+                                                        torch.device("cuda", local), d.data_ptr())
             return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, allgather, gather_groups=gather_groups)
         rr = step_e2e()
         barrier()
@@ -329,7 +338,7 @@ def main():
            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": cfg["name"], "pairs_per_step": pairs,
                       "cache": "inputs (8*N*L bytes) and every N x N chunk matrix are larger than the 126 MB L2; no flush needed",
-                      "parallelism": f"group-major over {world} GPU(s)"},
+                      "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
            "sequence_wall_s": elapsed / args.steps, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
            "roofline_emd": roof_emd, "roofline_prim": roof_prim, "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},

@@ -112,6 +112,28 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M, int64_t N,
                       double eps_floor, double l2_thresh, const uint8_t* group_mask,
                       seqj_result** out);
 
+/* Chunk-major sharding (needed when one (metric, scale) group does not fit one GPU or
+ * when there are fewer groups than GPUs): this rank computes only the chunks [chunk_lo[g], chunk_hi[g]) of
+ * every group g = k*nscales + l (empty range = group not touched), i.e. the per-chunk part of the loop
+ * src/sequencer.jl:210-236, and leaves the eta-weighted partial sums  sum_c clamp(eta_c * D_c)  (:231-235, no
+ * division) in the caller's device buffer: the i-th touched group (metric-major) at S_out_dev + i*S_stride,
+ * as an N x roundup(N,16) row-major matrix.  The caller all-gathers the chunk etas, reduces the partial sums
+ * to one owner per group (NCCL over NVLink) and calls seqj_groups_finish there. */
+int seqj_sequence_partial(seqj_handle* h, const double* A_dev, int64_t M, int64_t N,
+                          const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
+                          double eps_floor, double l2_thresh, const int32_t* chunk_lo,
+                          const int32_t* chunk_hi, double* S_out_dev, int64_t S_stride,
+                          seqj_result** out);
+
+/* Owner side of the chunk-major path: `Dkl = Dklms / sum(etas)` (src/sequencer.jl:247) and the group-level
+ * `_measure_dm` (:251) for `ngroups` reduced accumulators S_dev + slots[g]*S_stride (slots == NULL: g).
+ * eta_sum[g] = sum of ALL chunk etas of the group in chunk order (host array).  Outputs are host arrays:
+ * eta[ngroups], root[ngroups], parents[ngroups*N], mst_*[ngroups*(N-1)]. */
+int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngroups,
+                       const int32_t* slots, int64_t N, const double* eta_sum, double eps_floor,
+                       double* eta, int32_t* root, int32_t* parents, int32_t* mst_i,
+                       int32_t* mst_j, double* mst_w);
+
 /* Final fuse from per-group MSTs gathered by the caller: `_weighted_p_matrix` + `inv.` + final
  * `_measure_dm` + `unroll` (src/sequencer.jl:266-273).  mst_* hold ngroups*(N-1) entries. */
 int seqj_fuse(seqj_handle* h, int64_t N, int ngroups, const double* eta_group,
@@ -124,6 +146,8 @@ int seqj_fuse(seqj_handle* h, int64_t N, int ngroups, const double* eta_group,
 int seqj_result_dims(const seqj_result* r, int64_t* N, int* ngroups);
 int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale, int* nchunks,
                            int* computed);
+/* chunks of group g held by this result: [0, nchunks) except after seqj_sequence_partial */
+int seqj_result_group_range(const seqj_result* r, int g, int* chunk_lo, int* chunk_hi);
 /* eta_chunk[nchunks], root_chunk[nchunks], parents_chunk[nchunks*N] (BFS-tree parent of each
  * vertex, root -> itself): EOSeg[(alg, l)] = (etas, bfs trees)   (src/sequencer.jl:257) */
 int seqj_result_group_chunks(const seqj_result* r, int g, double* eta_chunk, int32_t* root_chunk,

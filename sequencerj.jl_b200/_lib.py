@@ -30,10 +30,15 @@ SIGNATURES = {
                                 C.c_double, c_u8p, C.POINTER(vp)]),
     "seqj_sequence_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
                                     C.c_double, c_u8p, C.POINTER(vp)]),
+    "seqj_sequence_partial": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
+                                        C.c_double, c_ip, c_ip, vp, C.c_int64, C.POINTER(vp)]),
+    "seqj_groups_finish": (C.c_int, [vp, vp, C.c_int64, C.c_int, c_ip, C.c_int64, c_dp, C.c_double, c_dp, c_ip, c_ip,
+                                     c_ip, c_ip, c_dp]),
     "seqj_fuse": (C.c_int, [vp, C.c_int64, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_double, C.POINTER(vp)]),
     "seqj_result_dims": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "seqj_result_group_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int)]),
+    "seqj_result_group_range": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "seqj_result_group_chunks": (C.c_int, [vp, C.c_int, c_dp, c_ip, c_ip]),
     "seqj_result_group": (C.c_int, [vp, C.c_int, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp]),
     "seqj_result_final": (C.c_int, [vp, c_dp, c_ip, c_ip, c_ip, c_ip, c_ip, c_dp]),

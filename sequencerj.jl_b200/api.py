@@ -209,8 +209,9 @@ def _layout_input(A):
     return np.ascontiguousarray(A.T, dtype=np.float64), orig      # no copy for a Fortran-ordered float64 A
 
 
-def _collect(handle, res, N, metrics, scales, want_final=True):
+def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     lib = handle.lib
+    chunk_ranges = {}
     ngroups = C.c_int()
     n64 = C.c_int64()
     handle.check(lib.seqj_result_dims(res, C.byref(n64), C.byref(ngroups)))
@@ -221,11 +222,17 @@ def _collect(handle, res, N, metrics, scales, want_final=True):
         if not comp.value:
             continue
         key = (_BY_ID[met.value], sc.value)
-        etas = np.empty(nch.value)
-        roots = np.empty(nch.value, dtype=np.int32)
-        pars = np.empty((nch.value, N), dtype=np.int32)
+        lo, hi = C.c_int(), C.c_int()
+        handle.check(lib.seqj_result_group_range(res, g, C.byref(lo), C.byref(hi)))
+        nloc = hi.value - lo.value
+        etas = np.empty(nloc)
+        roots = np.empty(nloc, dtype=np.int32)
+        pars = np.empty((nloc, N), dtype=np.int32)
         handle.check(lib.seqj_result_group_chunks(res, g, _lib.dptr(etas), _lib.iptr(roots), _lib.iptr(pars)))
-        EOSeg[key] = (etas.tolist(), [BFSTree(int(roots[c]), pars[c]) for c in range(nch.value)])
+        EOSeg[key] = (etas.tolist(), [BFSTree(int(roots[c]), pars[c]) for c in range(nloc)])
+        chunk_ranges[key] = (lo.value, hi.value)
+        if partial:
+            continue
         eta = C.c_double(); root = C.c_int32()
         par = np.empty(N, dtype=np.int32)
         mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
@@ -242,8 +249,10 @@ def _collect(handle, res, N, metrics, scales, want_final=True):
     handle.check(lib.seqj_result_input_range(res, C.byref(lo), C.byref(hi)))
     timings["input_min"] = lo.value
     if not want_final:
-        return SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
-                               group_msts)
+        r = SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
+                            group_msts)
+        r.chunk_ranges = chunk_ranges
+        return r
     eta = C.c_double(); root = C.c_int32()
     order_ = np.empty(N, dtype=np.int32); par = np.empty(N, dtype=np.int32)
     mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
@@ -281,6 +290,41 @@ def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None
         return _collect(handle, res, N, metrics, scales, want_final=group_mask is None)
     finally:
         handle.lib.seqj_result_free(res)
+
+
+def _sequence_partial(shape, scales, metrics, chunk_lo, chunk_hi, S_out_ptr, S_stride, device_ptr, handle=None):
+    """Chunk-major shard of `_sequence` (seqj_sequence_partial): chunks [lo, hi) of every group, eta-weighted
+    partial sums left in the caller's device buffer.  Returns a result holding the chunk-level outputs."""
+    handle = handle or default_handle()
+    N, M = shape
+    mids = np.array([m.id for m in metrics], dtype=np.int32)
+    scs = np.array(scales, dtype=np.int32)
+    lo = np.ascontiguousarray(chunk_lo, dtype=np.int32).reshape(-1)
+    hi = np.ascontiguousarray(chunk_hi, dtype=np.int32).reshape(-1)
+    assert lo.size == hi.size == len(mids) * len(scs)
+    res = C.c_void_p()
+    handle.check(handle.lib.seqj_sequence_partial(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
+                                                  _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, _lib.iptr(lo),
+                                                  _lib.iptr(hi), C.c_void_p(S_out_ptr), int(S_stride), C.byref(res)))
+    try:
+        return _collect(handle, res, N, metrics, scales, want_final=False, partial=True)
+    finally:
+        handle.lib.seqj_result_free(res)
+
+
+def groups_finish(S_ptr, S_stride, slots, N, eta_sums, eps_floor=EPS_FLOOR, handle=None):
+    """Owner side of the chunk-major path (seqj_groups_finish): divide the reduced accumulators by sum(etas)
+    and measure them.  Returns [(eta, BFSTree, WeightedTree)] per slot."""
+    handle = handle or default_handle()
+    ng = len(slots)
+    slots_a = np.ascontiguousarray(slots, dtype=np.int32)
+    sums = np.ascontiguousarray(eta_sums, dtype=np.float64)
+    eta = np.empty(ng); root = np.empty(ng, dtype=np.int32); par = np.empty((ng, N), dtype=np.int32)
+    mi = np.empty((ng, N - 1), dtype=np.int32); mj = np.empty((ng, N - 1), dtype=np.int32); mw = np.empty((ng, N - 1))
+    handle.check(handle.lib.seqj_groups_finish(handle.h, C.c_void_p(S_ptr), int(S_stride), ng, _lib.iptr(slots_a), N,
+                                               _lib.dptr(sums), eps_floor, _lib.dptr(eta), _lib.iptr(root),
+                                               _lib.iptr(par), _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw)))
+    return [(float(eta[g]), BFSTree(int(root[g]), par[g]), WeightedTree(N, mi[g], mj[g], mw[g])) for g in range(ng)]
 
 
 def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=None) -> SequencerResult:

@@ -567,6 +567,13 @@ __global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ S, co
   }
 }
 
+// S /= tot, applied by the owner of a group after the partial sums have been reduced (chunk-major sharding)
+__global__ void __launch_bounds__(256) scale_div_kernel(double* __restrict__ S, double tot, int64_t total) {
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    S[idx] = S[idx] / tot;
+}
+
 // ---- proximity fuse ---------------------------------------------------------------------------
 // P[i,j] = P[j,i] += eta * inv(w) for every MST edge of one group (src/sequencer.jl:313-322).
 __global__ void fuse_scatter_kernel(double* __restrict__ P, int64_t ldD, const int* __restrict__ mi,

@@ -42,6 +42,7 @@ struct seqj_handle {
 
 struct GroupRes {
   int metric = 0, scale = 0, nchunks = 0, computed = 0;
+  int chunk_lo = 0, chunk_hi = 0;     // chunks of this group held by this result (partial / sharded runs)
   std::vector<double> eta_chunk;
   std::vector<int32_t> root_chunk, parents_chunk;
   double eta = 0;
@@ -363,8 +364,13 @@ struct FixBufs {
   unsigned int cap = 0;
 };
 
-constexpr double kTauGram = 1e-3;   // relative fix-up threshold for the Gram forms (see kernels_dist.cuh)
-constexpr double kTauKL = 1e-3;
+// Relative fix-up thresholds (see kernels_dist.cuh).  Rounding in the DMMA accumulation over m terms behaves like
+// a random walk: |dv| ~ sqrt(m/4) * 2^-53 * (s_i + s_j) ~ 4e-15 * selfterms at m = 4096 (worst case m/4 times
+// that).  A distance is within 1e-9 relative when dv / v <= 2e-9, i.e. v >= 2e-6 * selfterms typically;
+// 1e-4 leaves a 50x margin and keeps the flagged set small on smooth data (neighbouring objects that differ
+// by < 1 %).  KL: |d(H - C)| ~ 3e-14 against results compared as d + 1e-6, flagged below 1e-4 * |H|.
+constexpr double kTauGram = 1e-4;
+constexpr double kTauKL = 1e-4;
 
 // distance matrices of chunks [chunk0, chunk0+nb) of one scale into D (stride strideD)
 int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const int2* tiles_dev, int ntiles,
@@ -632,9 +638,13 @@ static int check_ready(seqj_handle* h) {
   return SEQJ_OK;
 }
 
-int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t N64, const int32_t* metric_ids,
-                      int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
-                      const uint8_t* group_mask, seqj_result** out) {
+// Shared implementation of seqj_sequence_dev (whole groups, optional group mask) and seqj_sequence_partial
+// (chunk-major sharding: this rank computes chunks [chunk_lo[g], chunk_hi[g]) of every group g and leaves the
+// eta-weighted partial sums  sum_c eta_c * D_c  in S_out; no division, no group-level measure, no fuse).
+static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64_t N64, const int32_t* metric_ids,
+                         int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                         const uint8_t* group_mask, const int32_t* chunk_lo, const int32_t* chunk_hi, double* S_out,
+                         int64_t S_stride, seqj_result** out) {
   ST_TRY(check_ready(h));
   if (!A_dev || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M64 < 1 || N64 < 2 ||
       M64 > (1 << 30) || N64 > (1 << 30))
@@ -663,8 +673,19 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
     max_ldX = std::max(max_ldX, layouts.back().ldX);
     max_chunks = std::max(max_chunks, layouts.back().nchunks);
   }
-  auto mask = [&](int k, int l) { return !group_mask || group_mask[k * nscales + l]; };
-  const bool do_final = (group_mask == nullptr);
+  const bool partial = (chunk_lo != nullptr);
+  if (partial && (!chunk_hi || !S_out)) return fail(h, SEQJ_E_BADARG, "partial mode needs chunk_hi and S_out");
+  auto c_lo = [&](int k, int l) { return partial ? std::max(0, (int)chunk_lo[k * nscales + l]) : 0; };
+  auto c_hi = [&](int k, int l) { return partial ? std::min(layouts[l].nchunks, (int)chunk_hi[k * nscales + l]) : layouts[l].nchunks; };
+  auto mask = [&](int k, int l) {
+    if (partial) return c_lo(k, l) < c_hi(k, l);
+    return !group_mask || group_mask[k * nscales + l] != 0;
+  };
+  const bool do_final = (group_mask == nullptr) && !partial;
+  if (partial) {                                   // S_out slot = rank of the group among the active ones (metric-major)
+    const size_t need = (size_t)N64 * round_up(N64, 16);
+    if (S_stride < (int64_t)need || (S_stride & 1)) return fail(h, SEQJ_E_BADARG, "S_stride too small (need N*roundup(N,16), even)");
+  }
 
   int tt = c.timer.begin(SEQJ_T_TOTAL);
 
@@ -684,7 +705,7 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   PrepBufs pb;
   ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false));
   FixBufs fb;
-  ST_TRY(alloc_fix(c, fb, 1u << 22));
+  ST_TRY(alloc_fix(c, fb, 1u << 24));     // 16M flagged entries (256 MB) before the dense fallback kicks in
   std::vector<int2> tiles = make_tiles(N, true);
   int2* tiles_dev;
   CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
@@ -715,9 +736,10 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   int total_chunks = 0, ngp = 0;
   for (int l : scale_order)
     for (int k = 0; k < nmetrics; ++k)
-      if (mask(k, l)) { gp_of[k * nscales + l] = ngp++; g_of_gp.push_back(k * nscales + l); total_chunks += layouts[l].nchunks; }
+      if (mask(k, l)) { gp_of[k * nscales + l] = ngp++; g_of_gp.push_back(k * nscales + l); total_chunks += c_hi(k, l) - c_lo(k, l); }
   const int64_t mats = (int64_t)(budget / (mat_elems * 8));
   int nS = (int)std::min<int64_t>(std::max(1, ngp), std::max<int64_t>(1, mats / 6));
+  if (partial) nS = std::max(1, ngp);            // accumulators live in the caller's S_out, one slot per active group
   // overlap mode: two D buffers (double buffering between the compute and the graph stream), each nD matrices
   const int nbuf = c.overlap ? 2 : 1;
   int nD = (int)std::min<int64_t>((mats - nS) / nbuf, total_chunks);
@@ -740,18 +762,18 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
       if (w.ntasks >= wave_target) close();
       for (int k = 0; k < nmetrics; ++k) {
         if (!mask(k, l)) continue;
-        const int g = k * nscales + l, gp = gp_of[g], nch = layouts[l].nchunks;
+        const int g = k * nscales + l, gp = gp_of[g], nch = c_hi(k, l);
         chunk_off[g] = out;
-        int c0 = 0;
+        int c0 = c_lo(k, l);
         while (c0 < nch) {
           if (w.ntasks >= nD || open_groups >= nS) close();
           const int take = std::min(nch - c0, nD - w.ntasks);
           Seg sg;
           sg.gp = gp; sg.l = l; sg.k = k; sg.c0 = c0; sg.c1 = c0 + take; sg.slot0 = w.ntasks; sg.sslot = gp % nS;
-          sg.first = (c0 == 0); sg.last = (c0 + take == nch); sg.out0 = out;
+          sg.first = (c0 == c_lo(k, l)); sg.last = (c0 + take == nch); sg.out0 = out;
           w.segs.push_back(sg);
           w.ntasks += take; out += take; c0 += take; open_groups++;
-          if (sg.last) { if (w.gp_done0 < 0) w.gp_done0 = gp; w.gp_done1 = gp + 1; }
+          if (sg.last && !partial) { if (w.gp_done0 < 0) w.gp_done0 = gp; w.gp_done1 = gp + 1; }
         }
       }
     }
@@ -780,8 +802,14 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   CU_TRY(cudaMemcpyAsync(sslot_dev, sslot_host.data(), sizeof(int) * G, cudaMemcpyHostToDevice, c.st));
   CU_TRY(cudaMemcpyAsync(perm_dev, perm_host.data(), sizeof(int) * perm_host.size(), cudaMemcpyHostToDevice, c.st));
 
-  double *Spool, *Dbuf;
-  CU_TRY(c.pool.alloc(&Spool, mat_elems * nS));
+  // active groups in metric-major order -> slot in S_out (partial mode)
+  std::vector<int> out_slot(G, -1);
+  {
+    int sidx = 0;
+    for (int g = 0; g < G; ++g) if (gp_of[g] >= 0) out_slot[g] = sidx++;
+  }
+  double *Spool = nullptr, *Dbuf;
+  if (!partial) CU_TRY(c.pool.alloc(&Spool, mat_elems * nS));
   CU_TRY(c.pool.alloc(&Dbuf, mat_elems * (size_t)max_wave * nbuf));
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, std::max(max_wave, max_done), N));
@@ -814,11 +842,14 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
     for (auto& sg : w.segs) {
       const int g = g_of_gp[sg.gp];
       const int nch = layouts[sg.l].nchunks;
+      const int lo = c_lo(sg.k, sg.l);
+      double* Sg = partial ? S_out + (size_t)out_slot[g] * (size_t)S_stride : Spool + (size_t)sg.sslot * mat_elems;
       for (int b0 = sg.c0; b0 < sg.c1; b0 += kCombineMax) {
         const int nb = std::min(kCombineMax, sg.c1 - b0);
         combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(
-            Spool + (size_t)sg.sslot * mat_elems, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
-            eta_c + sg.out0 + (b0 - sg.c0), b0 == 0, b0 + nb >= nch, eta_c + chunk_off[g], nch, (int64_t)(mat_elems / 2));
+            Sg, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
+            eta_c + sg.out0 + (b0 - sg.c0), b0 == lo, !partial && b0 + nb >= nch, eta_c + chunk_off[g], nch,
+            (int64_t)(mat_elems / 2));
         c.launches++;
       }
     }
@@ -888,11 +919,14 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
       GroupRes& gr = r->groups[g];
       gr.metric = metric_ids[k]; gr.scale = scales[l]; gr.nchunks = layouts[l].nchunks; gr.computed = mask(k, l);
       if (!gr.computed) continue;
+      gr.chunk_lo = c_lo(k, l); gr.chunk_hi = c_hi(k, l);
+      const int nloc = gr.chunk_hi - gr.chunk_lo;
       const int coff = chunk_off[g];
       const size_t gp = (size_t)gp_of[g];        // row of this group in the device arrays (processing order)
-      gr.eta_chunk.assign(h_eta_c.begin() + coff, h_eta_c.begin() + coff + gr.nchunks);
-      gr.root_chunk.assign(h_root_c.begin() + coff, h_root_c.begin() + coff + gr.nchunks);
-      gr.parents_chunk.assign(h_par_c.begin() + (size_t)coff * ldp, h_par_c.begin() + (size_t)(coff + gr.nchunks) * ldp);
+      gr.eta_chunk.assign(h_eta_c.begin() + coff, h_eta_c.begin() + coff + nloc);
+      gr.root_chunk.assign(h_root_c.begin() + coff, h_root_c.begin() + coff + nloc);
+      gr.parents_chunk.assign(h_par_c.begin() + (size_t)coff * ldp, h_par_c.begin() + (size_t)(coff + nloc) * ldp);
+      if (partial) continue;                     // group-level results come from seqj_groups_finish on the owner rank
       gr.eta = h_eta_g[gp]; gr.root = h_root_g[gp];
       gr.parents.assign(h_par_g.begin() + gp * ldp, h_par_g.begin() + gp * ldp + N);
       gr.mst_i.assign(h_msti.begin() + gp * ldp, h_msti.begin() + gp * ldp + N - 1);
@@ -904,6 +938,60 @@ int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M64, int64_t 
   r->launches = c.launches;
   r->in_min = st0.minv; r->in_max = st0.maxv;
   *out = r;
+  return SEQJ_OK;
+}
+
+int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M, int64_t N, const int32_t* metric_ids,
+                      int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                      const uint8_t* group_mask, seqj_result** out) {
+  return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, nullptr,
+                       nullptr, nullptr, 0, out);
+}
+
+int seqj_sequence_partial(seqj_handle* h, const double* A_dev, int64_t M, int64_t N, const int32_t* metric_ids,
+                          int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                          const int32_t* chunk_lo, const int32_t* chunk_hi, double* S_out_dev, int64_t S_stride,
+                          seqj_result** out) {
+  if (!chunk_lo || !chunk_hi || !S_out_dev) return fail(h, SEQJ_E_BADARG, "bad argument");
+  return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, nullptr, chunk_lo,
+                       chunk_hi, S_out_dev, S_stride, out);
+}
+
+int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngroups, const int32_t* slots, int64_t N64,
+                       const double* eta_sum, double eps_floor, double* eta, int32_t* root, int32_t* parents,
+                       int32_t* mst_i, int32_t* mst_j, double* mst_w) {
+  ST_TRY(check_ready(h));
+  if (!S_dev || !eta_sum || ngroups < 1 || N64 < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const int N = (int)N64, ng = ngroups;
+  Ctx c(h);
+  const int64_t ldD = round_up(N, 16), ldp = N;
+  double *eta_d, *w_d;
+  int *root_d, *par_d, *mi_d, *mj_d, *slot_d;
+  CU_TRY(c.pool.alloc(&eta_d, (size_t)ng)); CU_TRY(c.pool.alloc(&root_d, (size_t)ng));
+  CU_TRY(c.pool.alloc(&par_d, (size_t)ng * ldp)); CU_TRY(c.pool.alloc(&mi_d, (size_t)ng * ldp));
+  CU_TRY(c.pool.alloc(&mj_d, (size_t)ng * ldp)); CU_TRY(c.pool.alloc(&w_d, (size_t)ng * ldp));
+  CU_TRY(c.pool.alloc(&slot_d, (size_t)ng));
+  std::vector<int> slot_h(ng);
+  for (int g = 0; g < ng; ++g) slot_h[g] = slots ? slots[g] : g;
+  CU_TRY(cudaMemcpyAsync(slot_d, slot_h.data(), sizeof(int) * ng, cudaMemcpyHostToDevice, c.st));
+  for (int g = 0; g < ng; ++g) {                  // Dkl = Dklms / sum(etas)  (reference src/sequencer.jl:247)
+    scale_div_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(S_dev + (size_t)slot_h[g] * (size_t)S_stride, eta_sum[g],
+                                                       (int64_t)N * ldD);
+    c.launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  GraphWS gws;
+  ST_TRY(graphws_alloc(c, gws, ng, N));
+  ST_TRY(run_measure(c, gws, S_dev, ldD, S_stride, ng, eps_floor, eta_d, root_d, par_d, ldp, mi_d, mj_d, w_d, nullptr, slot_d));
+  if (eta) CU_TRY(cudaMemcpyAsync(eta, eta_d, 8 * (size_t)ng, cudaMemcpyDeviceToHost, c.st));
+  if (root) CU_TRY(cudaMemcpyAsync(root, root_d, 4 * (size_t)ng, cudaMemcpyDeviceToHost, c.st));
+  if (parents) CU_TRY(cudaMemcpyAsync(parents, par_d, 4 * (size_t)ng * N, cudaMemcpyDeviceToHost, c.st));
+  for (int g = 0; g < ng; ++g) {
+    if (mst_i) CU_TRY(cudaMemcpyAsync(mst_i + (size_t)g * (N - 1), mi_d + (size_t)g * ldp, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+    if (mst_j) CU_TRY(cudaMemcpyAsync(mst_j + (size_t)g * (N - 1), mj_d + (size_t)g * ldp, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+    if (mst_w) CU_TRY(cudaMemcpyAsync(mst_w + (size_t)g * (N - 1), w_d + (size_t)g * ldp, 8 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
+  }
+  CU_TRY(cudaStreamSynchronize(c.st));
   return SEQJ_OK;
 }
 
@@ -1005,6 +1093,12 @@ int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale,
   if (scale) *scale = gr.scale;
   if (nchunks) *nchunks = gr.nchunks;
   if (computed) *computed = gr.computed;
+  return SEQJ_OK;
+}
+int seqj_result_group_range(const seqj_result* r, int g, int* chunk_lo, int* chunk_hi) {
+  if (!r || g < 0 || g >= (int)r->groups.size()) return SEQJ_E_BADARG;
+  if (chunk_lo) *chunk_lo = r->groups[g].chunk_lo;
+  if (chunk_hi) *chunk_hi = r->groups[g].chunk_hi;
   return SEQJ_OK;
 }
 int seqj_result_group_chunks(const seqj_result* r, int g, double* eta_chunk, int32_t* root_chunk, int32_t* parents_chunk) {

@@ -133,3 +133,114 @@ def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, al
     final.timings["host_gather_ms"] = (t2 - t1) * 1e3
     final.timings["host_fuse_ms"] = (t3 - t2) * 1e3
     return final
+
+
+# ---- chunk-major sharding: all-gather of chunk etas + reduce of N x N partials ----
+def chunk_lengths(M: int, scale: int):
+    cl = -(-M // scale)
+    return [min(cl, M - r0) for r0 in range(0, M, cl)]
+
+
+def chunk_partition(M: int, metrics, scales, world: int):
+    """Contiguous equal-cost split of the metric-major list of (metric, scale, chunk) tasks over `world` ranks.
+    Returns (lo, hi): int arrays [world, G], rank r computes chunks [lo[r,g], hi[r,g]) of group g."""
+    G = len(metrics) * len(scales)
+    tasks = []
+    for k, m in enumerate(metrics):
+        for l, s in enumerate(scales):
+            for c, mc in enumerate(chunk_lengths(M, s)):
+                # Prim is one latency-bound launch per rank whatever the number of graphs, so a chunk's cost is its
+                # distance work plus a small per-graph term
+                tasks.append((k * len(scales) + l, c, METRIC_COST[m.id] * mc + 32.0))
+    total = sum(t[2] for t in tasks)
+    lo = np.zeros((world, G), dtype=np.int32)
+    hi = np.zeros((world, G), dtype=np.int32)
+    seen = np.zeros((world, G), dtype=bool)
+    cum = 0.0
+    for g, c, cost in tasks:
+        r = min(world - 1, int((cum + 0.5 * cost) * world / total))
+        if not seen[r, g]:
+            lo[r, g] = c
+            seen[r, g] = True
+        hi[r, g] = c + 1
+        cum += cost
+    return lo, hi
+
+
+def sequence_sharded_chunks(shape, scales, metrics, rank: int, world: int, handle, dist, device, device_ptr):
+    """`_sequence` with the chunk tasks split evenly over the ranks.  Communication (torch.distributed, NCCL over
+    NVLink): (1) all-gather of the chunk etas (a [G, max_chunks] table, all-reduce of disjoint entries), (2) for
+    every group computed by more than one rank, a reduce (sum) of the eta-weighted N x N partials to the group's
+    owner, in rank = chunk order, (3) the all-gather of per-group (eta, MST) before the fuse.  The summation
+    order of step (2) differs from the reference's sequential loop by rounding only."""
+    import torch
+    N, M = shape
+    scales = tuple(int(s) for s in scales)
+    G = len(metrics) * len(scales)
+    lo, hi = chunk_partition(M, metrics, scales, world)
+    nch = [nchunks(M, s) for _ in metrics for s in scales]
+    active = [g for g in range(G) if lo[rank, g] < hi[rank, g]]
+    slot_of = {g: i for i, g in enumerate(active)}
+    ldD = -(-N // 16) * 16
+    stride = N * ldD
+    t0 = time.perf_counter()
+    S = torch.empty((max(1, len(active)), stride), dtype=torch.float64, device=device)
+    local = api._sequence_partial((N, M), scales, metrics, lo[rank], hi[rank], S.data_ptr(), stride, device_ptr, handle)
+    t1 = time.perf_counter()
+    # (1) chunk etas
+    eta = torch.zeros((G, max(nch)), dtype=torch.float64, device=device)
+    for (m, s), (etas, _) in local.EOSeg.items():
+        g = metrics.index(m) * len(scales) + scales.index(s)
+        a, b = local.chunk_ranges[(m, s)]
+        eta[g, a:b] = torch.tensor(etas, dtype=torch.float64)
+    dist.all_reduce(eta)
+    eta_h = eta.cpu().numpy()
+    # (2) reduce the partial sums to the owners
+    owned = []
+    tmp = None
+    for g in range(G):
+        parts = [r for r in range(world) if lo[r, g] < hi[r, g]]
+        owner = parts[0]
+        if rank == owner:
+            for r in parts[1:]:
+                if tmp is None:
+                    tmp = torch.empty(stride, dtype=torch.float64, device=device)
+                dist.recv(tmp, src=r)
+                S[slot_of[g]].add_(tmp)
+            owned.append(g)
+        elif rank in parts:
+            dist.send(S[slot_of[g]], dst=owner)
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    # owners: Dkl = sum / sum(etas); group-level _measure_dm
+    mine = {}
+    if owned:
+        sums = []
+        for g in owned:
+            tot = 0.0
+            for c in range(nch[g]):
+                tot += float(eta_h[g, c])
+            sums.append(tot)
+        res = api.groups_finish(S.data_ptr(), stride, [slot_of[g] for g in owned], N, sums, handle=handle)
+        for g, (e, tree, mst) in zip(owned, res):
+            m, s = metrics[g // len(scales)], scales[g % len(scales)]
+            mine[(m.id, s)] = (e, mst.src, mst.dst, mst.weight)
+            local.EOAlgScale[(m, s)] = (e, tree)
+            local.group_msts[(m, s)] = mst
+    t3 = time.perf_counter()
+    owner_tbl = np.zeros((len(metrics), len(scales)), dtype=np.int64)
+    for g in range(G):
+        owner_tbl[g // len(scales), g % len(scales)] = [r for r in range(world) if lo[r, g] < hi[r, g]][0]
+    merged = torch_allgather_groups(mine, owner_tbl, metrics, scales, N, rank, world, dist, device)
+    etas, msts = merge_group_results([merged], metrics, scales)
+    t4 = time.perf_counter()
+    final = api.fuse(N, etas, msts, handle=handle)
+    t5 = time.perf_counter()
+    final.EOSeg, final.EOAlgScale, final.group_msts = local.EOSeg, local.EOAlgScale, local.group_msts
+    final.chunk_ranges = local.chunk_ranges
+    for k, v in local.timings.items():
+        final.timings[k] = final.timings.get(k, 0.0) + v
+    final.launches += local.launches
+    final.timings.update(host_local_ms=(t1 - t0) * 1e3, host_reduce_ms=(t2 - t1) * 1e3, host_finish_ms=(t3 - t2) * 1e3,
+                         host_gather_ms=(t4 - t3) * 1e3, host_fuse_ms=(t5 - t4) * 1e3)
+    return final

@@ -92,6 +92,25 @@ def test_near_duplicate_columns_take_fixup_path(seqj, oracle, handle, metric):
     assert got[10, 3] == 1e-6 and got[3, 10] == 1e-6
 
 
+@pytest.mark.parametrize("metric", [0, 1, 2, 3])
+def test_pairwise_smooth_ordered_family(seqj, oracle, handle, metric):
+    """Smooth 1-parameter family (a bump moving across the grid, the Sequencer paper's toy data): neighbouring
+    objects differ by ~1 %, i.e. the regime between the Gram form and the direct fix-up.  Checked against the
+    oracle's direct formulas."""
+    N, m = 400, 96
+    x = np.arange(m)[:, None]
+    mu = np.linspace(0.2 * m, 0.8 * m, N)[None, :]
+    A = np.exp(-0.5 * ((x - mu) / (0.08 * m)) ** 2) + 1e-3
+    A = A[:, np.random.default_rng(3).permutation(N)]
+    P = oracle.splitnorm(oracle.clamp_input(A), 1)[0]
+    if metric == 0:
+        ref = np.sqrt(((P[:, :, None] - P[:, None, :]) ** 2).sum(axis=0)) + 1e-6       # direct, no Gram form
+    else:
+        ref = oracle.chunk_distance(metric, P)
+    got = seqj.pairwise(metric, A, kl_full=True)
+    rel_close(got, ref, 1e-9, atol=4 * m * 2.0 ** -53)
+
+
 def test_pairwise_algotests_known_answers(seqj, handle):
     """reference test/algotests.jl:6-25 (Euclidean sqrt(14); KL 0.5108256237659907)."""
     A = np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 4.0]])
