@@ -306,10 +306,19 @@ def main():
     if os.path.exists(mp):
         hbm = json.load(open(mp)).get("hbm_gbs", hbm)
     roof = None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_ncu_config3_metrics.json")
+    if args.config == 3 and not (args.objects or args.length) and world == 1 and os.path.exists(tpath):
+        tt = json.load(open(tpath))["per_sequence_totals"]["gemm_dist"]
+        # dram__bytes_read.sum + dram__bytes_write.sum of the 15 DMMA launches of one sequence(), per launch
+        traffic = (tt["rd"] + tt["wr"]) * 1e9 / tt["n"]
     if gemm_ms > 0:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = {"kernel": "gemm_dist_kernel<L2|KL|Energy> (+ fix-up)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": None,
+                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
+                "traffic_note": "bytes per launch averaged over the 15 launches of one sequence(), ncu capture in "
+                                "profiles/r01_ncu_config3_metrics.json; algorithmic output is 4.96e9 bytes per launch",
+                "launches_per_step": len(scales) * ngemm,
                 "peak_source": "FP64 DMMA.8x8x4 rate measured on this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.json); "
                                "MEASURED_PEAKS.json has no FP64 figure"}
     roof_emd = None
