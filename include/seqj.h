@@ -44,6 +44,10 @@ extern "C" {
 #define SEQJ_EMD 1    /* WASS1D = EMD()                   src/distancemetrics.jl:247 */
 #define SEQJ_KLD 2    /* KLD = Distances.KLDivergence()   src/distancemetrics.jl:239 */
 #define SEQJ_ENERGY 3 /* ENERGY = Energy()                src/distancemetrics.jl:254 */
+/* the TYPES EMD / Energy passed as metrics: the reference then builds EMD((lgrid, lgrid)) / Energy((lgrid, lgrid))
+ * from the chunk-local slice of `grid` (src/sequencer.jl:217-219), i.e. delta-weighted CDF distances */
+#define SEQJ_EMD_GRID 4
+#define SEQJ_ENERGY_GRID 5
 
 /* phase timers returned by seqj_result_timings (milliseconds, CUDA events on the library's streams) */
 #define SEQJ_T_TOTAL 0    /* whole seqj_sequence call, device side (H2D .. results ready) */
@@ -76,6 +80,10 @@ const char* seqj_last_error(const seqj_handle* h);
 /* The handle keeps its device workspace between calls (repeated calls of one shape reuse it);
  * this frees it without destroying the handle. */
 int seqj_release_workspace(seqj_handle* h);
+
+/* Grid used by SEQJ_EMD_GRID / SEQJ_ENERGY_GRID: M finite, positive, strictly increasing values (the `grid`
+ * keyword of `sequence`, src/sequencer.jl:105-109,296-304).  NULL clears it. */
+int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M);
 
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);

@@ -46,6 +46,7 @@ FLOATMAX32 = 3.4028234663852886e38  # floatmax(Float32), sequencer.jl:351-352
 
 # metric ids shared with the C ABI (include/seqj.h)
 L2, EMD, KLD, ENERGY = 0, 1, 2, 3
+EMD_GRID, ENERGY_GRID = 4, 5                   # the TYPES EMD / Energy + explicit grid (sequencer.jl:217-219)
 ALL_METRICS = (L2, EMD, KLD, ENERGY)           # distancemetrics.jl:257 (order matters)
 METRIC_NAMES = {L2: "Euclidean", EMD: "EMD", KLD: "KLDivergence", ENERGY: "Energy"}
 FIB = [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 5168]  # sequencer.jl:148
@@ -253,8 +254,34 @@ def pairwise_vec(metric: int, P: np.ndarray, l2_thresh: float = L2THR, block: in
     return r
 
 
+def pairwise_grid(metric: int, P: np.ndarray, lgrid: np.ndarray, faithful: bool = False, block: int = 64) -> np.ndarray:
+    """EMD((lgrid, lgrid)) / Energy((lgrid, lgrid)) as the reference builds them from the chunk-local grid slice
+    (sequencer.jl:217-219): same-grid branch of _cdf_distance with deltas g_k - g_{k-1}, g_0 = 0
+    (distancemetrics.jl:199-209,217-219)."""
+    m, N = P.shape
+    r = np.zeros((N, N))
+    if faithful:
+        fn = emd if metric == EMD_GRID else energy
+        for j in range(N):
+            for i in range(j + 1, N):
+                r[i, j] = r[j, i] = fn(lgrid, lgrid, P[:, i], P[:, j])
+        return r
+    dx = np.diff(np.concatenate(([0.0], lgrid)))
+    UT = np.ascontiguousarray(chunk_cdf(P).T)
+    for i0 in range(0, N, block):
+        d = UT[i0:i0 + block, None, :] - UT[None, :, :]
+        if metric == EMD_GRID:
+            r[i0:i0 + block, :] = np.sum(np.abs(d) * dx, axis=2)
+        else:
+            r[i0:i0 + block, :] = math.sqrt(2.0) * np.sqrt(np.sum(d * d * dx, axis=2))
+    np.fill_diagonal(r, 0.0)
+    return r
+
+
 def chunk_distance(metric: int, P: np.ndarray, faithful: bool = False,
-                   eps_floor: float = EPS_FLOOR, l2_thresh: float = L2THR) -> np.ndarray:
+                   eps_floor: float = EPS_FLOOR, l2_thresh: float = L2THR, lgrid=None) -> np.ndarray:
+    if metric in (EMD_GRID, ENERGY_GRID):
+        return np.abs(pairwise_grid(metric, P, np.asarray(lgrid, dtype=np.float64), faithful)) + eps_floor
     f = pairwise_faithful if faithful else pairwise_vec
     return np.abs(f(metric, P, l2_thresh)) + eps_floor
 
@@ -452,15 +479,17 @@ def dense_from_edges(N, edges):
 
 
 def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=False,
-                  eps_floor=EPS_FLOOR, l2_thresh=L2THR):
+                  eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None):
     """One (metric k, scale l) iteration of the double loop in _sequence (sequencer.jl:196-258).
     A is already clamped. Returns (GroupResult, min root-score gap)."""
     M, N = A.shape
     min_gap = float("inf")
     S = np.zeros((N, N))
     eta_c, par_c, root_c, Dcs = [], [], [], []
-    for P in splitnorm(A, l):
-        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh)
+    if grid is None:
+        grid = np.arange(1, M + 1, dtype=np.float64)          # ensuregrid! default (sequencer.jl:298)
+    for P, (r0, r1) in zip(splitnorm(A, l), chunk_bounds(M, l)):
+        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh, lgrid=grid[r0:r1])
         if k == KLD:                     # Symmetric(dm): only the upper triangle is ever read
             Dsym = np.triu(Dc) + np.triu(Dc, 1).T
         else:
@@ -505,7 +534,7 @@ def _norm_args(scales, metrics):
 
 
 def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_root=True,
-                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR) -> OracleResult:
+                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None) -> OracleResult:
     """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects)."""
     A = clamp_input(A)
     M, N = A.shape
@@ -514,7 +543,8 @@ def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_roo
     min_gap = float("inf")
     for k in metrics:
         for l in scales:
-            g, gap = compute_group(A, k, l, faithful, faithful_root, keep_matrices, eps_floor, l2_thresh)
+            g, gap = compute_group(A, k, l, faithful, faithful_root, keep_matrices, eps_floor, l2_thresh,
+                                   None if grid is None else np.asarray(grid, dtype=np.float64))
             groups.append(g)
             min_gap = min(min_gap, gap)
     return fuse_groups(N, groups, faithful_root, min_gap)

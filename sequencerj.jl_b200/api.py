@@ -45,7 +45,11 @@ WASS1D = Metric(1, "EMD(nothing)")         # EMD()                        distan
 KLD = Metric(2, "KLDivergence()")          # Distances.KLDivergence()     distancemetrics.jl:239
 ENERGY = Metric(3, "Energy(nothing)")      # Energy()                     distancemetrics.jl:254
 ALL_METRICS = (L2, WASS1D, KLD, ENERGY)    # distancemetrics.jl:257
-_BY_ID = {m.id: m for m in ALL_METRICS}
+# what the reference builds when the TYPES EMD / Energy are passed as metrics: EMD((lgrid, lgrid)) with the
+# chunk-local slice of `grid` (sequencer.jl:217-219) -- delta-weighted CDF distances on the explicit grid
+EMD_GRID = Metric(4, "EMD(grid)")
+ENERGY_GRID = Metric(5, "Energy(grid)")
+_BY_ID = {m.id: m for m in ALL_METRICS + (EMD_GRID, ENERGY_GRID)}
 
 _default_handle = None
 
@@ -163,6 +167,27 @@ def ensuregrid(A, grid=None):
     grid = np.asarray(grid, dtype=np.float64)
     assert len(grid) == M, f"Grid length must match dims 1 (row count) of A. Got grid:{len(grid)} and A:{M}"
     return grid
+
+
+def _normalize_metrics(metrics):
+    """Instances (L2, WASS1D, KLD, ENERGY) stay; the TYPES EMD / Energy select the explicit-grid variants, as the
+    reference's `k in (EMD, Energy)` test does (sequencer.jl:217)."""
+    if metrics is None:
+        return ALL_METRICS
+    if isinstance(metrics, (Metric, type)):
+        metrics = (metrics,)
+    out = []
+    for m in metrics:
+        if isinstance(m, Metric):
+            out.append(m)
+        elif m is EMD:
+            out.append(EMD_GRID)
+        elif m is Energy:
+            out.append(ENERGY_GRID)
+        else:
+            raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY and the "
+                            "EMD / Energy types with an explicit grid")
+    return tuple(out)
 
 
 def _tuplify(x):
@@ -336,10 +361,11 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
     N, M = At.shape
     logger.info("Sequencing data with\n    shape: (%d, %d)\n    metric(s): %s\n    scale(s): %s", M, N, metrics, scales)
     ensuregrid(At.T, grid)
-    metrics = _tuplify(metrics) if metrics is not None else ALL_METRICS
-    for m in metrics:
-        if not isinstance(m, Metric):
-            raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY")
+    metrics = _normalize_metrics(metrics)
+    if any(m.id >= 4 for m in metrics):
+        h_ = handle or default_handle()
+        g = np.ascontiguousarray(ensuregrid(At.T, grid), dtype=np.float64)
+        h_.check(h_.lib.seqj_set_grid(h_.h, _lib.dptr(g), len(g)))
     if scales is None:
         scales = autoscale(At.T, metrics=metrics, grid=grid, handle=handle, rng=rng, _At=At)
         logger.info("After autoscaling, best scale = %s", scales)
@@ -369,7 +395,7 @@ def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None,
     gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
     idx = np.sort(gen.choice(N, size=nsamp, replace=False))                   # sample(..., ordered=true)
     Asamp = np.ascontiguousarray(At[idx])
-    metrics = _tuplify(metrics)
+    metrics = _normalize_metrics(metrics)
     best, max_eta = 1, 0.0
     for s in [f for f in FIB if f < maxscale]:
         r = _sequence(Asamp, (s,), metrics, handle)

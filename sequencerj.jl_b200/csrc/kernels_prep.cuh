@@ -68,6 +68,14 @@ struct PrepParams {
   double* sU;
   double* H;
   int normalize;
+  // explicit grid (reference: metrics passed as the TYPES EMD / Energy, src/sequencer.jl:217-219): per-row
+  // deltas g_k - g_{k-1} of the chunk-local grid with g_0 = 0 (src/distancemetrics.jl:199-209).  Since the
+  // deltas are positive, |U-V|*d = |d*U - d*V| and (U-V)^2*d = (sqrt(d)*U - sqrt(d)*V)^2: the grid only scales
+  // the operands.
+  const double* grid;     // [M] grid values, or nullptr
+  double* UwE;            // Uc * delta        (EMD on the grid)
+  double* UwG;            // Uc * sqrt(delta)  (Energy on the grid)
+  double* sUG;            // sum (Uc*sqrt(delta))^2
 };
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
@@ -106,8 +114,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
   h = warp_sum(h);
 
   // pass 3: CDF by warp-shuffle inclusive scan with a running carry
-  double su = 0.0;
-  if (p.Uc || p.U || p.sU) {
+  double su = 0.0, sug = 0.0;
+  if (p.Uc || p.U || p.sU || p.UwE || p.UwG) {
     double carry = 0.0;
     for (int base = 0; base < p.cl_pad; base += 32) {
       const int k = base + lane;
@@ -129,18 +137,29 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
         uc = u - (double)(k + 1) / (double)m;
         su += uc * uc;
       }
+      double ue = 0.0, ug = 0.0;
+      if (p.grid && k < m) {
+        const double dlt = p.grid[r0 + k] - (k == 0 ? 0.0 : p.grid[r0 + k - 1]);
+        ue = uc * dlt;
+        ug = uc * sqrt(dlt);
+        sug += ug * ug;
+      }
       if (k < p.cl_pad) {            // cl_pad is a multiple of 16, not of the 32-wide scan step
         if (p.Uc) p.Uc[dst + k] = uc;
         if (p.U) p.U[dst + k] = u;
+        if (p.UwE) p.UwE[dst + k] = ue;
+        if (p.UwG) p.UwG[dst + k] = ug;
       }
     }
     su = warp_sum(su);
+    sug = warp_sum(sug);
   }
   if (lane == 0) {
     const int64_t o = (int64_t)c * p.ldn + j;
     if (p.sP) p.sP[o] = sq;
     if (p.sU) p.sU[o] = su;
     if (p.H) p.H[o] = h;
+    if (p.sUG) p.sUG[o] = sug;
   }
 }
 

@@ -36,6 +36,7 @@ struct seqj_handle {
   size_t max_smem = 0;
   // Device blocks kept between calls (exact-size reuse): repeated sequence() calls of the same shape do not
   // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
+  std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
   std::multimap<size_t, void*> cache;
   size_t cached_bytes = 0;
 };
@@ -329,6 +330,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
 
 struct PrepBufs {
   double *P = nullptr, *logP = nullptr, *Uc = nullptr, *U = nullptr, *sP = nullptr, *sU = nullptr, *H = nullptr;
+  double *UwE = nullptr, *UwG = nullptr, *sUG = nullptr, *grid = nullptr;
   int64_t ldn = 0, rows_pad = 0;
   int* m_of_chunk = nullptr;
 };
@@ -340,6 +342,7 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
   pp.A = A_dev; pp.ldA = ldA; pp.M = M; pp.N = N; pp.cl = L.cl; pp.cl_pad = L.cl_pad; pp.nchunks = L.nchunks;
   pp.ldX = L.ldX; pp.ldn = b.ldn; pp.P = b.P; pp.logP = b.logP; pp.Uc = b.Uc; pp.U = b.U;
   pp.sP = b.sP; pp.sU = b.sU; pp.H = b.H; pp.normalize = normalize;
+  pp.grid = b.grid; pp.UwE = b.UwE; pp.UwG = b.UwG; pp.sUG = b.sUG;
   int t = c.timer.begin(SEQJ_T_PREP);
   // rows [N, rows_pad) are read by TMA boxes of the last tiles: keep them zero
   const size_t tail = (size_t)(b.rows_pad - N) * L.ldX * 8;
@@ -347,6 +350,8 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
     if (b.P) CU_TRY(cudaMemsetAsync(b.P + (size_t)N * L.ldX, 0, tail, c.st));
     if (b.logP) CU_TRY(cudaMemsetAsync(b.logP + (size_t)N * L.ldX, 0, tail, c.st));
     if (b.Uc) CU_TRY(cudaMemsetAsync(b.Uc + (size_t)N * L.ldX, 0, tail, c.st));
+    if (b.UwE) CU_TRY(cudaMemsetAsync(b.UwE + (size_t)N * L.ldX, 0, tail, c.st));
+    if (b.UwG) CU_TRY(cudaMemsetAsync(b.UwG + (size_t)N * L.ldX, 0, tail, c.st));
   }
   CU_TRY(cudaMemcpyAsync(b.m_of_chunk, L.m_of_chunk.data(), sizeof(int) * L.nchunks, cudaMemcpyHostToDevice, c.st));
   const int64_t warps = (int64_t)N * L.nchunks;
@@ -382,12 +387,14 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   dp.chunk0 = chunk0; dp.ldn = pb.ldn; dp.tiles = tiles_dev; dp.eps_floor = eps_floor;
   dp.mirror = 1; dp.kl_swap = 0;
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  const bool on_grid = metric >= SEQJ_EMD_GRID;        // EMD / Energy on the explicit grid: pre-scaled operands
+  if (on_grid) metric = (metric == SEQJ_EMD_GRID) ? SEQJ_EMD : SEQJ_ENERGY;
   const int phase = SEQJ_T_DIST_L2 + metric;
   int t = c.timer.begin(phase);
   dim3 grid(ntiles, nb);
   if (metric == SEQJ_EMD) {
     CUtensorMap tmU;
-    ST_TRY(make_tmap(h, &tmU, pb.Uc, L.ldX, pb.rows_pad));
+    ST_TRY(make_tmap(h, &tmU, on_grid ? pb.UwE : pb.Uc, L.ldX, pb.rows_pad));
     dp.normA = nullptr; dp.tau = 0;
     emd_dist_kernel<<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmU, dp);
     c.launches++;
@@ -407,8 +414,8 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
     dp.normA = pb.sP; dp.tau = std::max(kTauGram, l2_thresh); fp.X = pb.P;
     gemm_dist_kernel<MODE_L2><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
   } else if (metric == SEQJ_ENERGY) {
-    ST_TRY(make_tmap(h, &tmA, pb.Uc, L.ldX, pb.rows_pad));
-    dp.normA = pb.sU; dp.tau = kTauGram; fp.X = pb.Uc;
+    ST_TRY(make_tmap(h, &tmA, on_grid ? pb.UwG : pb.Uc, L.ldX, pb.rows_pad));
+    dp.normA = on_grid ? pb.sUG : pb.sU; dp.tau = kTauGram; fp.X = on_grid ? pb.UwG : pb.Uc;
     gemm_dist_kernel<MODE_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
   } else {  // KL
     ST_TRY(make_tmap(h, &tmA, pb.P, L.ldX, pb.rows_pad));
@@ -440,7 +447,7 @@ int set_kernel_attrs(seqj_handle* h) {
 }
 
 int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, bool needP, bool needLog, bool needUc,
-               bool needU) {
+               bool needU, bool needWE = false, bool needWG = false) {
   seqj_handle* h = c.h;
   pb.rows_pad = round_up(N, kTileN);
   pb.ldn = round_up(N, 8);
@@ -449,8 +456,11 @@ int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, boo
   if (needLog) CU_TRY(c.pool.alloc(&pb.logP, n));
   if (needUc) CU_TRY(c.pool.alloc(&pb.Uc, n));
   if (needU) CU_TRY(c.pool.alloc(&pb.U, n));
+  if (needWE) CU_TRY(c.pool.alloc(&pb.UwE, n));
+  if (needWG) CU_TRY(c.pool.alloc(&pb.UwG, n));
   const size_t nn = (size_t)max_chunks * pb.ldn;
   CU_TRY(c.pool.alloc(&pb.sP, nn)); CU_TRY(c.pool.alloc(&pb.sU, nn)); CU_TRY(c.pool.alloc(&pb.H, nn));
+  CU_TRY(c.pool.alloc(&pb.sUG, nn));
   CU_TRY(c.pool.alloc(&pb.m_of_chunk, (size_t)max_chunks));
   return SEQJ_OK;
 }
@@ -625,6 +635,21 @@ int seqj_release_workspace(seqj_handle* h) {
   return SEQJ_OK;
 }
 
+int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M) {
+  if (!h) return SEQJ_E_BADARG;
+  h->grid.clear();
+  if (!grid || M <= 0) return SEQJ_OK;
+  double prev = 0.0;
+  for (int64_t i = 0; i < M; ++i) {
+    if (!(grid[i] > prev) || !std::isfinite(grid[i]))
+      return fail(h, SEQJ_E_BADARG, "grid must be finite, positive and strictly increasing (the same-grid shortcut of "
+                                    "_cdf_distance, src/distancemetrics.jl:206-209, needs non-zero deltas)");
+    prev = grid[i];
+  }
+  h->grid.assign(grid, grid + M);
+  return SEQJ_OK;
+}
+
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
   if (!h) return SEQJ_E_BADARG;
   h->ws_limit = bytes;
@@ -651,7 +676,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     return fail(h, SEQJ_E_BADARG, "bad argument (need M >= 1, N >= 2, at least one metric and one scale)");
   const int M = (int)M64, N = (int)N64;
   for (int k = 0; k < nmetrics; ++k)
-    if (metric_ids[k] < 0 || metric_ids[k] > 3) return fail(h, SEQJ_E_BADARG, "unknown metric id");
+    if (metric_ids[k] < 0 || metric_ids[k] > SEQJ_ENERGY_GRID) return fail(h, SEQJ_E_BADARG, "unknown metric id");
   for (int l = 0; l < nscales; ++l)
     if (scales[l] < 1 || scales[l] > M)
       return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scales[l]) +
@@ -659,12 +684,17 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   *out = nullptr;
   Ctx c(h);
   const int G = nmetrics * nscales;
-  bool needP = false, needLog = false, needUc = false;
+  bool needP = false, needLog = false, needUc = false, needWE = false, needWG = false;
   for (int k = 0; k < nmetrics; ++k) {
     needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD;
     needLog |= metric_ids[k] == SEQJ_KLD;
     needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;
+    needWE |= metric_ids[k] == SEQJ_EMD_GRID;
+    needWG |= metric_ids[k] == SEQJ_ENERGY_GRID;
   }
+  if ((needWE || needWG) && (int64_t)h->grid.size() != M64)
+    return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of A. Got grid:" +
+                                      std::to_string(h->grid.size()) + " and A:" + std::to_string(M64));
   std::vector<ScaleLayout> layouts;
   int64_t max_ldX = 0;
   int max_chunks = 0;
@@ -703,7 +733,11 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     return fail(h, SEQJ_E_DOMAIN, "Input data cannot contain negative, NaN or infinite values.");
 
   PrepBufs pb;
-  ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false));
+  ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false, needWE, needWG));
+  if (needWE || needWG) {
+    CU_TRY(c.pool.alloc(&pb.grid, (size_t)M));
+    CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c.st));
+  }
   FixBufs fb;
   ST_TRY(alloc_fix(c, fb, 1u << 24));     // 16M flagged entries (256 MB) before the dense fallback kicks in
   std::vector<int2> tiles = make_tiles(N, true);
@@ -1187,13 +1221,19 @@ int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, in
 int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m64, int64_t N64, int normalize,
                   int kl_full, double eps_floor, double l2_thresh, double* D_out) {
   ST_TRY(check_ready(h));
-  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > 3) return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_ENERGY_GRID) return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (metric >= SEQJ_EMD_GRID && (int64_t)h->grid.size() != m64)
+    return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of the chunk");
   const int m = (int)m64, N = (int)N64;
   Ctx c(h);
   ScaleLayout L = make_layout(m, 1);
   PrepBufs pb;
   ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD, metric == SEQJ_KLD,
-                    metric == SEQJ_EMD || metric == SEQJ_ENERGY, false));
+                    metric == SEQJ_EMD || metric == SEQJ_ENERGY, false, metric == SEQJ_EMD_GRID, metric == SEQJ_ENERGY_GRID));
+  if (metric >= SEQJ_EMD_GRID) {
+    CU_TRY(c.pool.alloc(&pb.grid, (size_t)m));
+    CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * m, cudaMemcpyHostToDevice, c.st));
+  }
   FixBufs fb;
   ST_TRY(alloc_fix(c, fb, 1u << 20));
   const bool full = (metric == SEQJ_KLD) && kl_full;

@@ -129,3 +129,37 @@ def test_group_mask_plus_fuse_equals_full_run(seqj, handle):
             etas.append(src.EOAlgScale[(m, l)][0]); msts.append(src.group_msts[(m, l)])
     fz = seqj.fuse(90, etas, msts)
     assert fz.eta == full.eta and np.array_equal(fz.order, full.order)
+
+
+def test_explicit_grid_types(seqj, oracle, handle):
+    """metrics = the TYPES (EMD, Energy) + grid: delta-weighted CDF distances on the chunk-local grid slices
+    (reference src/sequencer.jl:217-219; docs example `sequence(A; metrics=(WASS1D,L2), grid=collect(0.5:0.5:...))`)."""
+    rng = np.random.default_rng(21)
+    A = rng.random((48, 80))
+    g = np.cumsum(rng.random(48) * 0.5 + 0.25)
+    r = seqj.sequence(A.copy(), scales=(1, 2, 3), metrics=(seqj.EMD, seqj.Energy, seqj.L2), grid=g)
+    ref = oracle.sequence_oracle(A, (1, 2, 3), metrics=(oracle.EMD_GRID, oracle.ENERGY_GRID, oracle.L2), grid=g)
+    for gr in ref.groups:
+        key = ({4: seqj.EMD_GRID, 5: seqj.ENERGY_GRID, 0: seqj.L2}[gr.metric], gr.scale)
+        rel_close(r.EOSeg[key][0], gr.eta_chunk, 1e-9)
+        rel_close([r.EOAlgScale[key][0]], [gr.eta], 1e-9)
+        assert np.array_equal(r.EOAlgScale[key][1].parents, gr.parents)
+    assert np.array_equal(r.order, ref.order) and abs(r.eta - ref.eta) <= 1e-9 * ref.eta
+    # on the default grid 1:M the types differ from the instances only through the first delta of later chunks
+    r1 = seqj.sequence(A.copy(), scales=(1,), metrics=(seqj.EMD,))
+    r2 = seqj.sequence(A.copy(), scales=(1,), metrics=(seqj.WASS1D,))
+    assert np.array_equal(r1.order, r2.order) and abs(r1.eta - r2.eta) < 1e-12
+    with pytest.raises(AssertionError):
+        seqj.sequence(A.copy(), scales=(1,), metrics=(seqj.EMD,), grid=g[:-1])
+
+
+def test_pairwise_on_grid(seqj, oracle, handle):
+    rng = np.random.default_rng(22)
+    A = oracle.clamp_input(rng.random((37, 50)))
+    g = np.cumsum(rng.random(37) + 0.1)
+    P = oracle.splitnorm(A, 1)[0]
+    h = seqj.default_handle()
+    from sequencerj_b200 import _lib
+    h.check(h.lib.seqj_set_grid(h.h, _lib.dptr(np.ascontiguousarray(g)), len(g)))
+    for met in (4, 5):
+        rel_close(seqj.pairwise(met, A), oracle.chunk_distance(met, P, lgrid=g), 1e-9, atol=64 * 37 * 2.0 ** -53 * g[-1])

@@ -188,3 +188,20 @@ def test_hummingbird_exact_recovery_oracle(oracle):
     r = oracle.sequence_oracle(sh, (1, 2, 4), metrics=(oracle.L2, oracle.KLD))
     assert np.array_equal(sh[:, r.order], BIG)
     assert r.eta == 427.0
+
+
+def test_explicit_grid_same_grid_branch(oracle):
+    """EMD((g,g)) / Energy((g,g)) as `sequence` builds them from types + grid (sequencer.jl:217-219): the
+    vectorised delta-weighted formulas equal the faithful ECDF evaluation; on the unit grid they reduce to the
+    default functors."""
+    rng = np.random.default_rng(4)
+    A = oracle.clamp_input(rng.random((15, 8)))
+    P = oracle.splitnorm(A, 1)[0]
+    g = np.cumsum(rng.random(15) + 0.05)
+    for met in (oracle.EMD_GRID, oracle.ENERGY_GRID):
+        a = oracle.chunk_distance(met, P, faithful=True, lgrid=g)
+        b = oracle.chunk_distance(met, P, faithful=False, lgrid=g)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-15)
+    unit = np.arange(1, 16, dtype=float)
+    assert np.allclose(oracle.chunk_distance(oracle.EMD_GRID, P, lgrid=unit), oracle.chunk_distance(oracle.EMD, P), rtol=1e-13)
+    assert np.allclose(oracle.chunk_distance(oracle.ENERGY_GRID, P, lgrid=unit), oracle.chunk_distance(oracle.ENERGY, P), rtol=1e-13)
