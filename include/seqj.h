@@ -72,7 +72,9 @@ typedef struct seqj_result seqj_result;
 int seqj_version(void);
 
 /* Create a handle driving `ndev` CUDA devices (devices == NULL or ndev <= 0: current device).
- * Round 1 drives devices[0]; multi-GPU sharding is done one process per GPU above this ABI. */
+ * With ndev > 1, seqj_sequence (host input, no group mask) shards the (metric, scale) groups over the devices
+ * from this ONE process (one host thread per device; devices[0] runs the final fuse).  The one-process-per-GPU
+ * layout (torch.distributed above this ABI) uses single-device handles with group masks or chunk ranges. */
 int seqj_create(seqj_handle** out, const int* devices, int ndev);
 void seqj_destroy(seqj_handle* h);
 const char* seqj_last_error(const seqj_handle* h);

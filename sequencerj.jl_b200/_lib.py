@@ -93,14 +93,16 @@ def iptr(a):
 class Handle:
     """Owns a seqj_handle. Creation fails (SeqjError) when no sm_100 device is usable."""
 
-    def __init__(self, device: int | None = None):
+    def __init__(self, device=None):
+        """device: None (current device), an int, or a list of ints (one process drives several GPUs)."""
         self.lib = load()
         self.h = vp()
         if device is None:
             st = self.lib.seqj_create(C.byref(self.h), None, 0)
         else:
-            dev = (C.c_int32 * 1)(device)
-            st = self.lib.seqj_create(C.byref(self.h), dev, 1)
+            devs = [device] if isinstance(device, int) else list(device)
+            dev = (C.c_int32 * len(devs))(*devs)
+            st = self.lib.seqj_create(C.byref(self.h), dev, len(devs))
         if st != 0:
             msg = self.lib.seqj_last_error(self.h).decode() if self.h else "seqj_create failed"
             self.close()

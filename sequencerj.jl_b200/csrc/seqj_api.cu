@@ -11,6 +11,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/seqj.h"
@@ -36,6 +37,7 @@ struct seqj_handle {
   size_t max_smem = 0;
   // Device blocks kept between calls (exact-size reuse): repeated sequence() calls of the same shape do not
   // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
+  std::vector<seqj_handle*> peers;   // additional devices driven by this handle (seqj_create with ndev > 1)
   std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
   std::multimap<size_t, void*> cache;
   size_t cached_bytes = 0;
@@ -571,7 +573,28 @@ extern "C" {
 
 int seqj_version(void) { return SEQJ_VERSION; }
 
+static int create_one(seqj_handle** out, const int* devices, int ndev);
+
 int seqj_create(seqj_handle** out, const int* devices, int ndev) {
+  // devices[0] is the primary device (final fuse, results); devices[1..] become peer handles, each driven by
+  // its own host thread inside seqj_sequence (single-process multi-GPU for the Julia host)
+  int st = create_one(out, devices, ndev);
+  if (st != SEQJ_OK || !devices || ndev <= 1) return st;
+  for (int d = 1; d < ndev; ++d) {
+    seqj_handle* p = nullptr;
+    st = create_one(&p, devices + d, 1);
+    if (st != SEQJ_OK) {
+      (*out)->err = "peer device " + std::to_string(devices[d]) + ": " + (p ? p->err : std::string("create failed"));
+      if (p) seqj_destroy(p);
+      return st;
+    }
+    (*out)->peers.push_back(p);
+  }
+  cudaSetDevice((*out)->dev);
+  return SEQJ_OK;
+}
+
+static int create_one(seqj_handle** out, const int* devices, int ndev) {
   if (!out) return SEQJ_E_BADARG;
   *out = nullptr;
   seqj_handle* h = new seqj_handle();
@@ -618,6 +641,9 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev) {
 
 void seqj_destroy(seqj_handle* h) {
   if (!h) return;
+  for (seqj_handle* p : h->peers) seqj_destroy(p);
+  h->peers.clear();
+  cudaSetDevice(h->dev);
   if (h->st) cudaStreamSynchronize(h->st);
   if (h->st2) cudaStreamSynchronize(h->st2);
   release_cache(h);
@@ -1029,9 +1055,110 @@ int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngro
   return SEQJ_OK;
 }
 
+static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids,
+                             int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                             const uint8_t* group_mask, seqj_result** out);
+
+// Single-process multi-GPU: whole (metric, scale) groups are assigned to the devices of the handle by an LPT
+// greedy on estimated cost, one host thread per device runs the masked sequence, the per-group (eta, MST) are
+// merged on the host (~160 KB per group) and the primary device runs the fuse.  No N x N data leaves a GPU.
+static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
+                          const int32_t* scales, int nscales, double eps_floor, double l2_thresh, seqj_result** out) {
+  const int ndev = 1 + (int)h->peers.size(), G = nmetrics * nscales;
+  std::vector<seqj_handle*> hs;
+  hs.push_back(h);
+  for (auto* p : h->peers) hs.push_back(p);
+  // cost model: distance work ~ L * (2 for EMD, 1 for the contractions) plus a per-chunk graph term
+  std::vector<std::pair<double, int>> order;
+  for (int k = 0; k < nmetrics; ++k)
+    for (int l = 0; l < nscales; ++l) {
+      const int sc = std::max(1, scales[l]);
+      const int64_t cl = (M + sc - 1) / sc, nch = (M + cl - 1) / cl;
+      const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID;
+      order.push_back({(emd ? 2.0 : 1.0) * (double)M + 600.0 * (double)(nch + 1), k * nscales + l});
+    }
+  std::stable_sort(order.begin(), order.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+  std::vector<std::vector<uint8_t>> masks(ndev, std::vector<uint8_t>(G, 0));
+  std::vector<double> load(ndev, 0.0);
+  std::vector<int> owner(G, 0);
+  for (auto& og : order) {
+    const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+    masks[d][og.second] = 1; load[d] += og.first; owner[og.second] = d;
+  }
+  std::vector<seqj_result*> parts(ndev, nullptr);
+  std::vector<int> status(ndev, SEQJ_OK);
+  std::vector<std::thread> threads;
+  for (int d = 0; d < ndev; ++d) {
+    hs[d]->grid = h->grid;
+    threads.emplace_back([&, d]() {
+      bool any = false;
+      for (uint8_t b : masks[d]) any |= b != 0;
+      if (!any) return;
+      status[d] = sequence_host_one(hs[d], A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh,
+                                    masks[d].data(), &parts[d]);
+    });
+  }
+  for (auto& t : threads) t.join();
+  cudaSetDevice(h->dev);
+  for (int d = 0; d < ndev; ++d)
+    if (status[d] != SEQJ_OK) {
+      const int st = status[d];
+      h->err = "device " + std::to_string(hs[d]->dev) + ": " + hs[d]->err;
+      for (auto* r : parts) delete r;
+      return st;
+    }
+  // merge the groups, then fuse on the primary device
+  std::vector<double> etas(G), mw((size_t)G * (N - 1));
+  std::vector<int32_t> mi((size_t)G * (N - 1)), mj((size_t)G * (N - 1));
+  for (int g = 0; g < G; ++g) {
+    const GroupRes& gr = parts[owner[g]]->groups[g];
+    etas[g] = gr.eta;
+    std::copy(gr.mst_i.begin(), gr.mst_i.end(), mi.begin() + (size_t)g * (N - 1));
+    std::copy(gr.mst_j.begin(), gr.mst_j.end(), mj.begin() + (size_t)g * (N - 1));
+    std::copy(gr.mst_w.begin(), gr.mst_w.end(), mw.begin() + (size_t)g * (N - 1));
+  }
+  seqj_result* fin = nullptr;
+  int st = seqj_fuse(h, N, G, etas.data(), mi.data(), mj.data(), mw.data(), eps_floor, &fin);
+  if (st != SEQJ_OK) {
+    for (auto* r : parts) delete r;
+    return st;
+  }
+  fin->groups.resize(G);
+  double fuse_total = fin->timers[SEQJ_T_TOTAL];
+  for (int t = 0; t < SEQJ_NTIMERS; ++t) fin->timers[t] = (t == SEQJ_T_FUSE) ? fuse_total : 0.0;
+  double slowest = 0.0;
+  fin->in_min = INFINITY; fin->in_max = 0.0;
+  for (int d = 0; d < ndev; ++d) {
+    if (!parts[d]) continue;
+    for (int g = 0; g < G; ++g)
+      if (owner[g] == d) fin->groups[g] = std::move(parts[d]->groups[g]);
+    for (int t = 1; t < SEQJ_NTIMERS; ++t)
+      if (t != SEQJ_T_FUSE) fin->timers[t] = std::max(fin->timers[t], parts[d]->timers[t]);   // max over devices
+    slowest = std::max(slowest, parts[d]->timers[SEQJ_T_TOTAL]);
+    fin->launches += parts[d]->launches;
+    fin->in_min = std::min(fin->in_min, parts[d]->in_min);
+    fin->in_max = std::max(fin->in_max, parts[d]->in_max);
+    delete parts[d];
+  }
+  fin->timers[SEQJ_T_TOTAL] = slowest + fuse_total;
+  *out = fin;
+  return SEQJ_OK;
+}
+
 int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
                   const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
                   seqj_result** out) {
+  ST_TRY(check_ready(h));
+  if (!A || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M < 1 || N < 2)
+    return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (!h->peers.empty() && !group_mask && nmetrics * nscales > 1)
+    return sequence_multi(h, A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, out);
+  return sequence_host_one(h, A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
+}
+
+static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids,
+                             int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                             const uint8_t* group_mask, seqj_result** out) {
   ST_TRY(check_ready(h));
   if (!A || M < 1 || N < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
   DevPool pool(h);
