@@ -163,3 +163,48 @@ def test_pairwise_on_grid(seqj, oracle, handle):
     h.check(h.lib.seqj_set_grid(h.h, _lib.dptr(np.ascontiguousarray(g)), len(g)))
     for met in (4, 5):
         rel_close(seqj.pairwise(met, A), oracle.chunk_distance(met, P, lgrid=g), 1e-9, atol=64 * 37 * 2.0 ** -53 * g[-1])
+
+
+def test_streaming_waves_under_workspace_limit(seqj, oracle):
+    """Config-4-style streaming: with the chunk-matrix workspace limited to a few N x N matrices, groups are
+    split over several waves (partial eta-weighted accumulation across waves).  Results must not change."""
+    from sequencerj_b200 import _lib
+    A = np.random.default_rng(31).random((96, 300))
+    scales, mets = (1, 4, 8, 12), seqj.ALL_METRICS
+    full = seqj.sequence(A.copy(), scales=scales, metrics=mets)
+    h = seqj.Handle()
+    mat = 300 * 304 * 8
+    for nmats in (3, 7):
+        h.check(h.lib.seqj_set_workspace_limit(h.h, nmats * mat))
+        r = seqj.sequence(A.copy(), scales=scales, metrics=mets, handle=h)
+        assert np.array_equal(r.order, full.order) and r.eta == full.eta
+        for key in full.EOAlgScale:
+            # a group accumulated over several waves sums in the same chunk order: identical to the one-wave run
+            assert r.EOAlgScale[key][0] == full.EOAlgScale[key][0]
+            assert r.EOSeg[key][0] == full.EOSeg[key][0]
+            assert np.array_equal(r.EOAlgScale[key][1].parents, full.EOAlgScale[key][1].parents)
+    ref = oracle.sequence_oracle(A, scales)
+    assert np.array_equal(full.order, ref.order)
+    h.close()
+
+
+def test_cabi_error_paths(seqj, handle):
+    """Status codes and messages of the C ABI: bad arguments never reach a kernel."""
+    import ctypes as C
+    from sequencerj_b200 import _lib
+    lib, h = handle.lib, handle.h
+    A = np.ascontiguousarray(np.random.default_rng(0).random((20, 30)))
+    res = C.c_void_p()
+    mids = np.array([0], dtype=np.int32); scs = np.array([1], dtype=np.int32)
+    call = lambda M, N, m, s: lib.seqj_sequence(h, A.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(m), len(m), _lib.iptr(s), len(s),
+                                                1e-6, 1e-7, None, C.byref(res))
+    assert call(30, 1, mids, scs) == -1                                   # N < 2
+    assert call(30, 20, np.array([9], dtype=np.int32), scs) == -1         # unknown metric
+    assert call(30, 20, mids, np.array([31], dtype=np.int32)) == -1       # scale > M
+    assert b"cannot be larger than the number of data elements" in lib.seqj_last_error(h)
+    bad = A.copy(); bad[3, 4] = -1.0
+    st = lib.seqj_sequence(h, bad.ctypes.data_as(C.c_void_p), 30, 20, _lib.iptr(mids), 1, _lib.iptr(scs), 1, 1e-6, 1e-7, None,
+                           C.byref(res))
+    assert st == -6 and b"negative, NaN or infinite" in lib.seqj_last_error(h)   # the reference's AssertionError text
+    assert call(30, 20, mids, scs) == 0
+    lib.seqj_result_free(res)
