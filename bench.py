@@ -239,8 +239,9 @@ def main():
         r = step_dev()
         launches += r.launches
         for k, v in r.timings.items():
-            if k != "input_min":
+            if k not in ("input_min", "derived_groups"):
                 phases[k] = phases.get(k, 0.0) + v
+        derived = r.timings.get("derived_groups", 0)
     barrier()
     elapsed = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -295,7 +296,9 @@ def main():
     ngemm = sum(1 for m in cfg["metrics"] if m != 1)
     nemd = sum(1 for m in cfg["metrics"] if m == 1)
     npair1 = N * (N - 1) // 2
-    gemm_flops = 2.0 * L * npair1 * len(scales) * ngemm * args.steps / world       # this rank's share (approx. for N>1)
+    # DMMA flops actually executed: groups whose chunk matrices were derived from the finest scale ran no tiles
+    gemm_groups = len(scales) * ngemm / world - derived                             # this rank's share (approx. for N>1)
+    gemm_flops = 2.0 * L * npair1 * max(gemm_groups, 0) * args.steps
     gemm_ms = phases.get("dist_l2", 0) + phases.get("dist_kld", 0) + phases.get("dist_energy", 0)
     emd_instr = 2.0 * L * npair1 * len(scales) * nemd * args.steps / world
     emd_ms = phases.get("dist_emd", 0)
@@ -318,7 +321,7 @@ def main():
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
                 "traffic_note": "bytes per launch averaged over the 15 launches of one sequence(), ncu capture in "
                                 "profiles/r01_ncu_config3_metrics.json; algorithmic output is 4.96e9 bytes per launch",
-                "launches_per_step": len(scales) * ngemm,
+                "launches_per_step": int(max(gemm_groups, 0)), "derived_groups_per_step": int(derived),
                 "peak_source": "FP64 DMMA.8x8x4 rate measured on this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.json); "
                                "MEASURED_PEAKS.json has no FP64 figure"}
     roof_emd = None

@@ -62,7 +62,8 @@ extern "C" {
 #define SEQJ_T_COMBINE 9  /* eta-weighted accumulation */
 #define SEQJ_T_FUSE 10    /* proximity fuse + final MST / order */
 #define SEQJ_T_D2H 11     /* result copy-out */
-#define SEQJ_NTIMERS 12
+#define SEQJ_T_DERIVE 12  /* coarse-scale chunk matrices derived from the finest scale (no DMMA) */
+#define SEQJ_NTIMERS 13
 
 typedef struct seqj_handle seqj_handle;
 typedef struct seqj_result seqj_result;
@@ -176,6 +177,9 @@ int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double*
 int seqj_result_timings(const seqj_result* r, double* ms /* SEQJ_NTIMERS */);
 /* min / max of the input as seen by the device-side check (min < 2.22e-16 => values were clamped) */
 int seqj_result_input_range(const seqj_result* r, double* minv, double* maxv);
+/* number of (metric, scale) groups whose chunk matrices were derived from the finest scale instead of being
+ * computed by the tile kernels (they are excluded from the DMMA flop count of the roofline) */
+int seqj_result_derived_groups(const seqj_result* r, int* n);
 /* number of kernels the library launched for this result */
 int seqj_result_launches(const seqj_result* r, int64_t* launches);
 void seqj_result_free(seqj_result* r);

@@ -9,9 +9,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libseqj_b200.so")
 
-SEQJ_NTIMERS = 12
+SEQJ_NTIMERS = 13
 TIMER_NAMES = ["total", "h2d", "prep", "dist_l2", "dist_emd", "dist_kld", "dist_energy", "prim", "tree",
-               "combine", "fuse", "d2h"]
+               "combine", "fuse", "d2h", "derive"]
 
 c_dp = C.POINTER(C.c_double)
 c_ip = C.POINTER(C.c_int32)
@@ -46,6 +46,7 @@ SIGNATURES = {
     "seqj_result_D_nnz": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "seqj_result_D_triplets": (C.c_int, [vp, c_ip, c_ip, c_dp]),
     "seqj_result_timings": (C.c_int, [vp, c_dp]),
+    "seqj_result_derived_groups": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "seqj_result_launches": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "seqj_result_input_range": (C.c_int, [vp, c_dp, c_dp]),
     "seqj_result_free": (None, [vp]),

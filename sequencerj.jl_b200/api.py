@@ -273,6 +273,9 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     lo, hi = C.c_double(), C.c_double()
     handle.check(lib.seqj_result_input_range(res, C.byref(lo), C.byref(hi)))
     timings["input_min"] = lo.value
+    nder = C.c_int()
+    handle.check(lib.seqj_result_derived_groups(res, C.byref(nder)))
+    timings["derived_groups"] = nder.value
     if not want_final:
         r = SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
                             group_msts)

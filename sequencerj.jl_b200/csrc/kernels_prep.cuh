@@ -76,6 +76,10 @@ struct PrepParams {
   double* UwE;            // Uc * delta        (EMD on the grid)
   double* UwG;            // Uc * sqrt(delta)  (Energy on the grid)
   double* sUG;            // sum (Uc*sqrt(delta))^2
+  // per-chunk vectors used to derive coarser scales from the finest one (kernels_derive.cuh)
+  double* mass;           // sum a          (the chunk mass the column is normalised by)
+  double* sR;             // sum Uc * (k+1)/m
+  double* sT;             // sum Uc
 };
 
 __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
@@ -114,8 +118,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
   h = warp_sum(h);
 
   // pass 3: CDF by warp-shuffle inclusive scan with a running carry
-  double su = 0.0, sug = 0.0;
-  if (p.Uc || p.U || p.sU || p.UwE || p.UwG) {
+  double su = 0.0, sug = 0.0, sr = 0.0, st = 0.0;
+  if (p.Uc || p.U || p.sU || p.UwE || p.UwG || p.sR) {
     double carry = 0.0;
     for (int base = 0; base < p.cl_pad; base += 32) {
       const int k = base + lane;
@@ -134,8 +138,11 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
       double u = 0.0, uc = 0.0;
       if (k < m) {
         u = (k == m - 1) ? 1.0 : cum / w;
-        uc = u - (double)(k + 1) / (double)m;
+        const double ramp = (double)(k + 1) / (double)m;
+        uc = u - ramp;
         su += uc * uc;
+        sr += uc * ramp;
+        st += uc;
       }
       double ue = 0.0, ug = 0.0;
       if (p.grid && k < m) {
@@ -153,6 +160,8 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
     }
     su = warp_sum(su);
     sug = warp_sum(sug);
+    sr = warp_sum(sr);
+    st = warp_sum(st);
   }
   if (lane == 0) {
     const int64_t o = (int64_t)c * p.ldn + j;
@@ -160,6 +169,9 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
     if (p.sU) p.sU[o] = su;
     if (p.H) p.H[o] = h;
     if (p.sUG) p.sUG[o] = sug;
+    if (p.mass) p.mass[o] = s;
+    if (p.sR) p.sR[o] = sr;
+    if (p.sT) p.sT[o] = st;
   }
 }
 

@@ -17,6 +17,7 @@
 #include "../../include/seqj.h"
 #include "common.cuh"
 #include "kernels_dist.cuh"
+#include "kernels_derive.cuh"
 #include "kernels_graph.cuh"
 #include "kernels_prep.cuh"
 
@@ -65,6 +66,7 @@ struct seqj_result {
   double timers[SEQJ_NTIMERS] = {0};
   int64_t launches = 0;
   double in_min = 0, in_max = 0;
+  int derived_groups = 0;
 };
 
 // --------------------------------------------------------------------------------------------
@@ -333,6 +335,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
 struct PrepBufs {
   double *P = nullptr, *logP = nullptr, *Uc = nullptr, *U = nullptr, *sP = nullptr, *sU = nullptr, *H = nullptr;
   double *UwE = nullptr, *UwG = nullptr, *sUG = nullptr, *grid = nullptr;
+  double *mass = nullptr, *sR = nullptr, *sT = nullptr;
   int64_t ldn = 0, rows_pad = 0;
   int* m_of_chunk = nullptr;
 };
@@ -345,6 +348,7 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
   pp.ldX = L.ldX; pp.ldn = b.ldn; pp.P = b.P; pp.logP = b.logP; pp.Uc = b.Uc; pp.U = b.U;
   pp.sP = b.sP; pp.sU = b.sU; pp.H = b.H; pp.normalize = normalize;
   pp.grid = b.grid; pp.UwE = b.UwE; pp.UwG = b.UwG; pp.sUG = b.sUG;
+  pp.mass = b.mass; pp.sR = b.sR; pp.sT = b.sT;
   int t = c.timer.begin(SEQJ_T_PREP);
   // rows [N, rows_pad) are read by TMA boxes of the last tiles: keep them zero
   const size_t tail = (size_t)(b.rows_pad - N) * L.ldX * 8;
@@ -440,6 +444,52 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   return SEQJ_OK;
 }
 
+// Fine-scale per-chunk vectors kept aside while the prep buffers are reused for the coarser scales.
+struct FineVecs {
+  double *mass = nullptr, *sP = nullptr, *sU = nullptr, *sR = nullptr, *sT = nullptr;
+  int* m_of_chunk = nullptr;
+  int nchunks = 0, cl = 0;
+};
+
+// chunk matrices [c0, c1) of a coarse (metric, scale) group derived from the finished fine matrices
+int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const FineVecs& fv, const double* Dfine,
+               int N, double* D, int64_t ldD, int64_t strideD, int c0, int c1, double eps_floor, double l2_thresh,
+               FixBufs& fb) {
+  seqj_handle* h = c.h;
+  int t = c.timer.begin(SEQJ_T_DERIVE);
+  CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
+  CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
+  const int ratio = L.cl / fv.cl;
+  DeriveParams dp;
+  dp.mode = metric; dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.Dfine = Dfine; dp.ldn = pb.ldn;
+  dp.fmass = fv.mass; dp.fg = (metric == SEQJ_ENERGY) ? fv.sU : fv.sP; dp.fR = fv.sR; dp.fT = fv.sT; dp.fm = fv.m_of_chunk;
+  dp.eps_floor = eps_floor;
+  dp.tau = (metric == SEQJ_L2) ? std::max(kTauGram, l2_thresh) : (metric == SEQJ_KLD ? kTauKL : kTauGram);
+  dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  const int T = (N + 31) / 32;
+  for (int cc = c0; cc < c1; ++cc) {
+    dp.f0 = cc * ratio; dp.nf = std::min(ratio, fv.nchunks - dp.f0);
+    dp.Dout = D + (size_t)(cc - c0) * (size_t)strideD;
+    dp.cmass = pb.mass + (size_t)cc * pb.ldn;
+    dp.cself = ((metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU)) + (size_t)cc * pb.ldn;
+    dp.chunk_local = cc - c0;
+    derive_kernel<<<dim3(T, T), dim3(32, 8), 0, c.st>>>(dp);
+    c.launches++;
+  }
+  CU_TRY(cudaGetLastError());
+  FixParams fp;
+  fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
+  fp.chunk0 = c0; fp.m_of_chunk = pb.m_of_chunk; fp.eps_floor = eps_floor; fp.mirror = 1; fp.kl_swap = 0;
+  fp.fix_list = fb.list; fp.fix_count = fb.count; fp.fix_cap = fb.cap; fp.fix_overflow = fb.overflow;
+  fp.X = (metric == SEQJ_ENERGY) ? pb.Uc : pb.P;
+  fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
+  fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, c1 - c0);
+  c.launches += 2;
+  CU_TRY(cudaGetLastError());
+  c.timer.end(t);
+  return SEQJ_OK;
+}
+
 int set_kernel_attrs(seqj_handle* h) {
   CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
@@ -463,6 +513,7 @@ int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, boo
   const size_t nn = (size_t)max_chunks * pb.ldn;
   CU_TRY(c.pool.alloc(&pb.sP, nn)); CU_TRY(c.pool.alloc(&pb.sU, nn)); CU_TRY(c.pool.alloc(&pb.H, nn));
   CU_TRY(c.pool.alloc(&pb.sUG, nn));
+  CU_TRY(c.pool.alloc(&pb.mass, nn)); CU_TRY(c.pool.alloc(&pb.sR, nn)); CU_TRY(c.pool.alloc(&pb.sT, nn));
   CU_TRY(c.pool.alloc(&pb.m_of_chunk, (size_t)max_chunks));
   return SEQJ_OK;
 }
@@ -844,6 +895,36 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   int max_wave = 1, max_done = 1;
   for (auto& w : waves) { max_wave = std::max(max_wave, w.ntasks); max_done = std::max(max_done, w.gp_done1 - w.gp_done0); }
 
+  // Coarse scales of the contraction metrics are derived from the finest scale when chunk boundaries nest
+  // (kernels_derive.cuh); needs the whole call in one wave so the fine matrices are still resident.
+  const char* henv = getenv("SEQJ_HIER");
+  const bool hier_on = !partial && waves.size() == 1 && !(henv && atoi(henv) == 0) && nscales > 1;
+  const int lf = scale_order[0];                      // finest scale of the call
+  std::vector<uint8_t> derivable(G, 0);
+  int n_derived = 0;
+  if (hier_on)
+    for (int k = 0; k < nmetrics; ++k) {
+      const int mid = metric_ids[k];
+      if (!(mid == SEQJ_L2 || mid == SEQJ_KLD || mid == SEQJ_ENERGY) || !mask(k, lf)) continue;
+      for (int l = 0; l < nscales; ++l) {
+        if (l == lf || !mask(k, l)) continue;
+        const int ratio = layouts[l].cl / layouts[lf].cl;
+        if (layouts[l].cl % layouts[lf].cl == 0 && ratio <= kDeriveMaxFine && layouts[l].nchunks < layouts[lf].nchunks) {
+          derivable[k * nscales + l] = 1;
+          n_derived++;
+        }
+      }
+    }
+  FineVecs fv;
+  if (n_derived) {
+    const size_t nn = (size_t)layouts[lf].nchunks * pb.ldn;
+    CU_TRY(c.pool.alloc(&fv.mass, nn)); CU_TRY(c.pool.alloc(&fv.sP, nn)); CU_TRY(c.pool.alloc(&fv.sU, nn));
+    CU_TRY(c.pool.alloc(&fv.sR, nn)); CU_TRY(c.pool.alloc(&fv.sT, nn));
+    CU_TRY(c.pool.alloc(&fv.m_of_chunk, (size_t)layouts[lf].nchunks));
+    fv.nchunks = layouts[lf].nchunks; fv.cl = layouts[lf].cl;
+  }
+  std::vector<int> fine_slot0(nmetrics, -1);
+
   double *eta_c, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
   int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f, *sslot_dev, *perm_dev;
   CU_TRY(c.pool.alloc(&eta_c, (size_t)total_chunks)); CU_TRY(c.pool.alloc(&root_c, (size_t)total_chunks));
@@ -888,7 +969,26 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     if (c.overlap && wi >= 2) CU_TRY(cudaStreamWaitEvent(c.st_compute, ev_graph[wi - 2], 0));   // buffer free again
     for (auto& sg : w.segs) {
       const ScaleLayout& L = layouts[sg.l];
-      if (sg.l != cur_scale) { ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1)); cur_scale = sg.l; }
+      if (sg.l != cur_scale) {
+        ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
+        cur_scale = sg.l;
+        if (n_derived && sg.l == lf) {               // keep the fine-scale vectors for the derivations
+          const size_t nb8 = (size_t)L.nchunks * pb.ldn * 8;
+          CU_TRY(cudaMemcpyAsync(fv.mass, pb.mass, nb8, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.sP, pb.sP, nb8, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.sU, pb.sU, nb8, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.sR, pb.sR, nb8, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.sT, pb.sT, nb8, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * L.nchunks, cudaMemcpyDeviceToDevice, c.st));
+        }
+      }
+      const int gidx = sg.k * nscales + sg.l;
+      if (derivable[gidx] && fine_slot0[sg.k] >= 0) {
+        ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Dw + (size_t)fine_slot0[sg.k] * mat_elems, N,
+                          Dw + (size_t)sg.slot0 * mat_elems, ldD, (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb));
+        continue;
+      }
+      if (sg.l == lf && sg.c0 == 0 && sg.c1 == L.nchunks) fine_slot0[sg.k] = sg.slot0;
       ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dw + (size_t)sg.slot0 * mat_elems, ldD,
                           (int64_t)mat_elems, sg.c0, sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
     }
@@ -997,6 +1097,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   c.timer.collect(r->timers);
   r->launches = c.launches;
   r->in_min = st0.minv; r->in_max = st0.maxv;
+  for (int g = 0; g < G; ++g) r->derived_groups += (derivable[g] && fine_slot0[g / nscales] >= 0) ? 1 : 0;
   *out = r;
   return SEQJ_OK;
 }
@@ -1299,6 +1400,11 @@ int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double*
 int seqj_result_timings(const seqj_result* r, double* ms) {
   if (!r || !ms) return SEQJ_E_BADARG;
   std::memcpy(ms, r->timers, sizeof(r->timers));
+  return SEQJ_OK;
+}
+int seqj_result_derived_groups(const seqj_result* r, int* n) {
+  if (!r || !n) return SEQJ_E_BADARG;
+  *n = r->derived_groups;
   return SEQJ_OK;
 }
 int seqj_result_launches(const seqj_result* r, int64_t* launches) {

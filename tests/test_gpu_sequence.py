@@ -208,3 +208,42 @@ def test_cabi_error_paths(seqj, handle):
     assert st == -6 and b"negative, NaN or infinite" in lib.seqj_last_error(h)   # the reference's AssertionError text
     assert call(30, 20, mids, scs) == 0
     lib.seqj_result_free(res)
+
+
+def _planted_small(N, L, seed):
+    x = np.arange(L)[:, None]
+    mu = np.linspace(0.15 * L, 0.85 * L, N)[None, :]
+    rng = np.random.default_rng(seed)
+    # the noisy floor keeps chunks that only see the tail of the bump free of exact duplicates (exact ties make
+    # the MST ambiguous: Kruskal and Prim may then legitimately differ), while objects stay near-duplicates
+    A = np.exp(-0.5 * ((x - mu) / (0.05 * L)) ** 2) + 1e-3 * (1.0 + 0.5 * rng.random((L, N)))
+    return A[:, rng.permutation(N)]
+
+
+@pytest.mark.parametrize("kind", ["random", "smooth"])
+def test_nested_scales_derived_from_finest(seqj, oracle, handle, kind):
+    """Scales whose chunk boundaries nest (1,2,4,8,16 on a length-256 grid): the contraction metrics of the
+    coarser scales are derived from the finest scale's matrices instead of running tiles.  Same parity bar."""
+    M, N = 256, 300
+    A = np.random.default_rng(41).random((M, N)) if kind == "random" else _planted_small(N, M, 42)
+    scales = (1, 2, 4, 8, 16)
+    r, ref = _compare(seqj, oracle, A, scales, (0, 1, 2, 3))
+    assert r.timings["derived_groups"] == 12            # L2, KL, Energy at scales 1, 2, 4, 8
+    # ragged nesting: M = 250, scales (1, 2, 5, 10) -> chunk lengths 250, 125, 50, 25 all multiples of 25
+    A2 = np.random.default_rng(43).random((250, 120)) if kind == "random" else _planted_small(120, 250, 44)
+    r2, _ = _compare(seqj, oracle, A2, (1, 2, 5, 10), (0, 2, 3))
+    assert r2.timings["derived_groups"] == 9
+
+
+def test_derived_equals_direct_tiles(seqj, handle, monkeypatch):
+    """A/B: SEQJ_HIER=0 forces the tile kernels for every scale; both paths agree to 1e-9 and give the same trees."""
+    A = np.random.default_rng(45).random((512, 400))
+    scales = (1, 2, 4, 8)
+    a = seqj.sequence(A.copy(), scales=scales, metrics=seqj.ALL_METRICS)
+    monkeypatch.setenv("SEQJ_HIER", "0")
+    b = seqj.sequence(A.copy(), scales=scales, metrics=seqj.ALL_METRICS)
+    assert a.timings["derived_groups"] == 9 and b.timings["derived_groups"] == 0
+    assert np.array_equal(a.order, b.order)
+    for key in a.EOAlgScale:
+        rel_close(a.EOSeg[key][0], b.EOSeg[key][0], 1e-12)
+        assert np.array_equal(a.EOAlgScale[key][1].parents, b.EOAlgScale[key][1].parents)
