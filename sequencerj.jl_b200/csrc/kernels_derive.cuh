@@ -25,7 +25,7 @@
 
 namespace seqj {
 
-constexpr int kDeriveMaxFine = 32;     // 2 x 2 x 32 x 32 doubles of weights = 32 KB of static shared memory
+constexpr int kDeriveMaxFine = 64;     // dynamic shared memory: 2 KB per fine chunk
 
 struct DeriveParams {
   int mode;               // MODE_L2 / MODE_KL / MODE_ENERGY
@@ -33,7 +33,9 @@ struct DeriveParams {
   int64_t ldD, strideD;
   const double* Dfine;    // fine chunk matrices: chunk f at Dfine + (f - 0) * strideD  (f = fine chunk index in the group)
   double* Dout;           // coarse chunk matrix
-  int f0, nf;             // fine chunks [f0, f0 + nf) make up this coarse chunk
+  int ratio, nfine;       // coarse chunk z = blockIdx.z covers fine chunks [z*ratio + f_base, ...) (at most `ratio`, nfine in total)
+  int c_first;            // first coarse chunk of this launch
+  int f0, nf;             // (derived per block)
   int64_t ldn;
   const double* fmass;    // fine-scale vectors [nfine_total][ldn]
   const double* fg;       // sum p^2        (L2)  or  sum Uc^2 (Energy)
@@ -51,77 +53,129 @@ struct DeriveParams {
 };
 
 // 32 x 32 tiles of the upper triangle; block = 32 x 8 threads; result mirrored through shared memory.
+// Per-object factors of the 64 objects of a tile are precomputed once per block in (dynamic) shared memory,
+// 4 doubles per (side, fine chunk, object):  L2: {w, w*g}   KL: {w, log w}   Energy: {w, b, w*(q + 2R), w*T},
+// so the inner loop is 6-14 FP64 operations per (entry, fine chunk) and the pass stays HBM-bound.
 __global__ void __launch_bounds__(256) derive_kernel(DeriveParams p) {
+  extern __shared__ double dsm[];                 // [2][nf][4][32]: consecutive lanes read consecutive doubles
   __shared__ double tile[32][33];
-  __shared__ double s_w[2][kDeriveMaxFine][32];   // w_i^f for the 32 rows (0) and 32 cols (1) of this tile
-  __shared__ double s_b[2][kDeriveMaxFine][32];   // b_i^f
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
   const int tx = threadIdx.x, ty = threadIdx.y;
-  const int N = p.N;
+  {                                   // one launch covers all coarse chunks of the group: z selects the chunk
+    const int z = blockIdx.z, cc = p.c_first + z;
+    p.f0 = cc * p.ratio;
+    p.nf = min(p.ratio, p.nfine - p.f0);
+    p.Dout += (int64_t)z * p.strideD;
+    p.cmass += (int64_t)cc * p.ldn;
+    p.cself += (int64_t)cc * p.ldn;
+    p.chunk_local = z;
+  }
+  const int N = p.N, nf = p.nf;
   const int i0 = bi * 32, j0 = bj * 32;
+  auto fac = [&](int side, int q, int o) -> double* { return dsm + ((size_t)side * nf + q) * 128 + o; };   // + 32 * component
 
-  // per-object weights of the 64 objects touched by this tile
-  for (int t = ty * 32 + tx; t < 64; t += 256) {
-    const int side = t >> 5, o = (side ? j0 : i0) + (t & 31);
-    double run = 0.0;
-    const double cm = (o < N) ? p.cmass[o] : 1.0;
-    for (int q = 0; q < p.nf; ++q) {
-      const double fmv = (o < N) ? p.fmass[(int64_t)(p.f0 + q) * p.ldn + o] : 0.0;
-      s_w[side][q][t & 31] = fmv / cm;
-      s_b[side][q][t & 31] = run / cm;
-      run += fmv;
+  // per-object factors, all 256 threads: item = (side, q, object)
+  for (int t = ty * 32 + tx; t < 64 * nf; t += 256) {
+    const int oo = t & 31, side = (t >> 5) & 1, q = t >> 6;
+    const int o = (side ? j0 : i0) + oo;
+    const int64_t fo = (int64_t)(p.f0 + q) * p.ldn + o;
+    const bool ok = o < N;
+    const double cm = ok ? p.cmass[o] : 1.0;
+    const double fmv = ok ? p.fmass[fo] : 1.0;
+    const double w = fmv / cm;
+    double* d = fac(side, q, oo);
+    d[0] = w;
+    if (p.mode == MODE_L2) {
+      d[32] = ok ? w * p.fg[fo] : 0.0;
+    } else if (p.mode == MODE_KL) {
+      d[32] = log(w);
+    } else {
+      d[32] = fmv;                                   // turned into b = (mass of the preceding fine chunks) / cm below
+      d[64] = ok ? w * (p.fg[fo] + 2.0 * p.fR[fo]) : 0.0;
+      d[96] = ok ? w * p.fT[fo] : 0.0;
     }
   }
   __syncthreads();
+  if (p.mode == MODE_ENERGY) {
+    const int t = ty * 32 + tx;
+    if (t < 64) {
+      const int oo = t & 31, side = t >> 5, o = (side ? j0 : i0) + oo;
+      const double cm = (o < N) ? p.cmass[o] : 1.0;
+      double run = 0.0;
+      for (int q = 0; q < nf; ++q) {
+        double* d = fac(side, q, oo);
+        const double fmv = d[32];
+        d[32] = run / cm;
+        run += fmv;
+      }
+    }
+    __syncthreads();
+  }
 
+  // each thread: column j, rows ty + 8 rr (rr = 0..3): 4 independent loads per fine chunk in flight
   const int j = j0 + tx;
-  for (int r = ty; r < 32; r += 8) {
-    const int i = i0 + r;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  bool live[4], swp[4];
+  const double* src[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int i = i0 + ty + 8 * rr;
+    live[rr] = (i < N) && (j < N) && (i != j);
+    swp[rr] = i > j;                                  // only inside diagonal tiles: stored value is for (lo, hi) = (j, i)
+    src[rr] = p.Dfine + (int64_t)p.f0 * p.strideD + (int64_t)min(i, N - 1) * p.ldD + min(j, N - 1);
+  }
+#pragma unroll 2
+  for (int q = 0; q < nf; ++q) {
+    double dv[4];
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) dv[rr] = __ldg(src[rr] + (int64_t)q * p.strideD) - p.eps_floor;
+    const double* fc = fac(1, q, tx);                 // factors of the column object j
+    const double c0 = fc[0], c1 = fc[32];
+    double c2 = 0.0, c3 = 0.0, m = 0.0, P1 = 0.0, P2 = 0.0;
+    if (p.mode == MODE_ENERGY) {
+      c2 = fc[64]; c3 = fc[96];
+      m = (double)p.fm[p.f0 + q];
+      P1 = 0.5 * (m + 1.0);                                  // sum_{t=1..m} t/m
+      P2 = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);          // sum (t/m)^2
+    }
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const double* fr = fac(0, q, ty + 8 * rr);      // factors of the row object i
+      // (lo, hi) = (row, col) except below the diagonal of a diagonal tile
+      const double l0 = swp[rr] ? c0 : fr[0], h0 = swp[rr] ? fr[0] : c0;
+      const double l1 = swp[rr] ? c1 : fr[32], h1 = swp[rr] ? fr[32] : c1;
+      if (p.mode == MODE_KL) {
+        acc[rr] += l0 * (dv[rr] + l1 - h1);
+      } else if (p.mode == MODE_L2) {
+        acc[rr] += l0 * h0 * (dv[rr] * dv[rr]) + (l0 - h0) * (l1 - h1);
+      } else {
+        const double r2 = fr[64], r3 = fr[96];
+        const double dw = l0 - h0, db = l1 - h1;
+        const double dA = swp[rr] ? (c2 - r2) : (r2 - c2), dB = swp[rr] ? (c3 - r3) : (r3 - c3);
+        acc[rr] += l0 * h0 * (0.5 * dv[rr] * dv[rr]) + dw * dA + 2.0 * db * dB + dw * (dw * P2 + 2.0 * db * P1) + m * db * db;
+      }
+    }
+  }
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = ty + 8 * rr, i = i0 + r;
     double out = 0.0;
     if (i < N && j < N) {
       if (i == j) {
         out = p.eps_floor;
       } else {
-        // (lo, hi) ordering matters for KL only: the stored value is KL(p_lo || p_hi)
-        const bool swap = i > j;           // only inside diagonal tiles
-        const int lo = swap ? j : i, hi = swap ? i : j;
-        const int slo = swap ? 1 : 0, shi = swap ? 0 : 1;
-        const int tlo = swap ? tx : r, thi = swap ? r : tx;
-        double acc = 0.0;
-        for (int q = 0; q < p.nf; ++q) {
-          const int f = p.f0 + q;
-          const double dv = p.Dfine[(int64_t)f * p.strideD + (int64_t)i * p.ldD + j] - p.eps_floor;
-          const double wi = s_w[slo][q][tlo], wj = s_w[shi][q][thi];
-          if (p.mode == MODE_KL) {
-            acc += wi * (dv + log(wi) - log(wj));
-          } else if (p.mode == MODE_L2) {
-            const double gi = p.fg[(int64_t)f * p.ldn + lo], gj = p.fg[(int64_t)f * p.ldn + hi];
-            acc += wi * wj * dv * dv + (wi - wj) * (wi * gi - wj * gj);
-          } else {
-            const double e = 0.5 * dv * dv;
-            const double qi = p.fg[(int64_t)f * p.ldn + lo], qj = p.fg[(int64_t)f * p.ldn + hi];
-            const double Ri = p.fR[(int64_t)f * p.ldn + lo], Rj = p.fR[(int64_t)f * p.ldn + hi];
-            const double Ti = p.fT[(int64_t)f * p.ldn + lo], Tj = p.fT[(int64_t)f * p.ldn + hi];
-            const double bi_ = s_b[slo][q][tlo], bj_ = s_b[shi][q][thi];
-            const double m = (double)p.fm[f];
-            const double P1 = 0.5 * (m + 1.0);                               // sum_{t=1..m} t/m
-            const double P2 = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);       // sum (t/m)^2
-            const double dw = wi - wj, db = bi_ - bj_;
-            acc += wi * wj * e + dw * (wi * qi - wj * qj) + 2.0 * dw * (wi * Ri - wj * Rj) +
-                   2.0 * db * (wi * Ti - wj * Tj) + dw * dw * P2 + 2.0 * dw * db * P1 + m * db * db;
-          }
-        }
+        const int lo = min(i, j), hi = max(i, j);
         double d;
         bool flag;
         if (p.mode == MODE_KL) {
           const double hh = p.cself[lo];
-          d = acc;
+          d = acc[rr];
           flag = d < p.tau * fabs(hh);
         } else {
           const double selfterms = p.cself[lo] + p.cself[hi];
-          flag = acc < p.tau * selfterms;
-          d = fast_sqrt(acc);
+          flag = acc[rr] < p.tau * selfterms;
+          d = fast_sqrt(acc[rr]);
           if (p.mode == MODE_ENERGY) d = 1.4142135623730951 * d;
         }
         out = fabs(d) + p.eps_floor;
@@ -131,8 +185,8 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveParams p) {
           else { *p.fix_overflow = 1; out = -1.0; }
         }
       }
+      p.Dout[(int64_t)i * p.ldD + j] = out;
     }
-    if (i < N && j < N) p.Dout[(int64_t)i * p.ldD + j] = out;
     tile[r][tx] = out;
   }
   if (bi == bj) return;          // diagonal tiles computed both halves directly

@@ -467,15 +467,13 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
   dp.tau = (metric == SEQJ_L2) ? std::max(kTauGram, l2_thresh) : (metric == SEQJ_KLD ? kTauKL : kTauGram);
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
   const int T = (N + 31) / 32;
-  for (int cc = c0; cc < c1; ++cc) {
-    dp.f0 = cc * ratio; dp.nf = std::min(ratio, fv.nchunks - dp.f0);
-    dp.Dout = D + (size_t)(cc - c0) * (size_t)strideD;
-    dp.cmass = pb.mass + (size_t)cc * pb.ldn;
-    dp.cself = ((metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU)) + (size_t)cc * pb.ldn;
-    dp.chunk_local = cc - c0;
-    derive_kernel<<<dim3(T, T), dim3(32, 8), 0, c.st>>>(dp);
-    c.launches++;
-  }
+  CU_TRY(cudaFuncSetAttribute(derive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDeriveMaxFine * 2048));
+  dp.ratio = ratio; dp.nfine = fv.nchunks; dp.c_first = c0; dp.f0 = 0; dp.nf = 0; dp.chunk_local = 0;
+  dp.Dout = D;
+  dp.cmass = pb.mass;
+  dp.cself = (metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU);
+  derive_kernel<<<dim3(T, T, c1 - c0), dim3(32, 8), (size_t)std::min(ratio, fv.nchunks) * 2048, c.st>>>(dp);
+  c.launches++;
   CU_TRY(cudaGetLastError());
   FixParams fp;
   fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
