@@ -898,30 +898,42 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   const char* henv = getenv("SEQJ_HIER");
   const bool hier_on = !partial && waves.size() == 1 && !(henv && atoi(henv) == 0) && nscales > 1;
   const int lf = scale_order[0];                      // finest scale of the call
+  // Chain: every scale is derived from the scale processed just before it (the next finer one) when that one
+  // nests and the metric's group there is part of this call; e.g. 16 -> 8 -> 4 -> 2 -> 1, each step reading
+  // only the matrices of the previous scale (total traffic ~2x the output instead of n_f x per scale).
   std::vector<uint8_t> derivable(G, 0);
+  std::vector<int> src_of(G, -1);
   int n_derived = 0;
-  if (hier_on)
-    for (int k = 0; k < nmetrics; ++k) {
-      const int mid = metric_ids[k];
-      if (!(mid == SEQJ_L2 || mid == SEQJ_KLD || mid == SEQJ_ENERGY) || !mask(k, lf)) continue;
-      for (int l = 0; l < nscales; ++l) {
-        if (l == lf || !mask(k, l)) continue;
-        const int ratio = layouts[l].cl / layouts[lf].cl;
-        if (layouts[l].cl % layouts[lf].cl == 0 && ratio <= kDeriveMaxFine && layouts[l].nchunks < layouts[lf].nchunks) {
-          derivable[k * nscales + l] = 1;
-          n_derived++;
+  if (hier_on) {
+    int l_prev = -1;
+    for (int l : scale_order) {
+      bool any = false;
+      for (int k = 0; k < nmetrics; ++k) any |= mask(k, l);
+      if (!any) continue;
+      if (l_prev >= 0)
+        for (int k = 0; k < nmetrics; ++k) {
+          const int mid = metric_ids[k];
+          if (!(mid == SEQJ_L2 || mid == SEQJ_KLD || mid == SEQJ_ENERGY) || !mask(k, l) || !mask(k, l_prev)) continue;
+          const int ratio = layouts[l].cl / layouts[l_prev].cl;
+          if (layouts[l].cl % layouts[l_prev].cl == 0 && ratio <= kDeriveMaxFine && layouts[l].nchunks < layouts[l_prev].nchunks) {
+            derivable[k * nscales + l] = 1;
+            src_of[k * nscales + l] = l_prev;
+            n_derived++;
+          }
         }
-      }
+      l_prev = l;
     }
+  }
   FineVecs fv;
   if (n_derived) {
     const size_t nn = (size_t)layouts[lf].nchunks * pb.ldn;
     CU_TRY(c.pool.alloc(&fv.mass, nn)); CU_TRY(c.pool.alloc(&fv.sP, nn)); CU_TRY(c.pool.alloc(&fv.sU, nn));
     CU_TRY(c.pool.alloc(&fv.sR, nn)); CU_TRY(c.pool.alloc(&fv.sT, nn));
     CU_TRY(c.pool.alloc(&fv.m_of_chunk, (size_t)layouts[lf].nchunks));
-    fv.nchunks = layouts[lf].nchunks; fv.cl = layouts[lf].cl;
   }
-  std::vector<int> fine_slot0(nmetrics, -1);
+  std::vector<int> last_slot0(nmetrics, -1), last_scale(nmetrics, -1);
+  int fv_scale = -1;                                  // scale whose vectors are currently in fv
+  int n_derived_done = 0;
 
   double *eta_c, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
   int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f, *sslot_dev, *perm_dev;
@@ -968,25 +980,31 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     for (auto& sg : w.segs) {
       const ScaleLayout& L = layouts[sg.l];
       if (sg.l != cur_scale) {
-        ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
-        cur_scale = sg.l;
-        if (n_derived && sg.l == lf) {               // keep the fine-scale vectors for the derivations
-          const size_t nb8 = (size_t)L.nchunks * pb.ldn * 8;
+        if (n_derived && cur_scale >= 0) {           // the vectors of the scale just finished become the source
+          const ScaleLayout& Lp = layouts[cur_scale];
+          const size_t nb8 = (size_t)Lp.nchunks * pb.ldn * 8;
           CU_TRY(cudaMemcpyAsync(fv.mass, pb.mass, nb8, cudaMemcpyDeviceToDevice, c.st));
           CU_TRY(cudaMemcpyAsync(fv.sP, pb.sP, nb8, cudaMemcpyDeviceToDevice, c.st));
           CU_TRY(cudaMemcpyAsync(fv.sU, pb.sU, nb8, cudaMemcpyDeviceToDevice, c.st));
           CU_TRY(cudaMemcpyAsync(fv.sR, pb.sR, nb8, cudaMemcpyDeviceToDevice, c.st));
           CU_TRY(cudaMemcpyAsync(fv.sT, pb.sT, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * L.nchunks, cudaMemcpyDeviceToDevice, c.st));
+          CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * Lp.nchunks, cudaMemcpyDeviceToDevice, c.st));
+          fv.nchunks = Lp.nchunks; fv.cl = Lp.cl; fv_scale = cur_scale;
         }
+        ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
+        cur_scale = sg.l;
       }
       const int gidx = sg.k * nscales + sg.l;
-      if (derivable[gidx] && fine_slot0[sg.k] >= 0) {
-        ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Dw + (size_t)fine_slot0[sg.k] * mat_elems, N,
+      const bool whole = (sg.c0 == 0 && sg.c1 == L.nchunks);
+      if (derivable[gidx] && whole && last_scale[sg.k] == src_of[gidx] && fv_scale == src_of[gidx] && last_slot0[sg.k] >= 0) {
+        ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Dw + (size_t)last_slot0[sg.k] * mat_elems, N,
                           Dw + (size_t)sg.slot0 * mat_elems, ldD, (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb));
+        last_slot0[sg.k] = sg.slot0; last_scale[sg.k] = sg.l;
+        n_derived_done++;
         continue;
       }
-      if (sg.l == lf && sg.c0 == 0 && sg.c1 == L.nchunks) fine_slot0[sg.k] = sg.slot0;
+      if (whole) { last_slot0[sg.k] = sg.slot0; last_scale[sg.k] = sg.l; }
+      else { last_slot0[sg.k] = -1; last_scale[sg.k] = -1; }
       ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dw + (size_t)sg.slot0 * mat_elems, ldD,
                           (int64_t)mat_elems, sg.c0, sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
     }
@@ -1095,7 +1113,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   c.timer.collect(r->timers);
   r->launches = c.launches;
   r->in_min = st0.minv; r->in_max = st0.maxv;
-  for (int g = 0; g < G; ++g) r->derived_groups += (derivable[g] && fine_slot0[g / nscales] >= 0) ? 1 : 0;
+  r->derived_groups = n_derived_done;
   *out = r;
   return SEQJ_OK;
 }

@@ -229,10 +229,11 @@ def test_nested_scales_derived_from_finest(seqj, oracle, handle, kind):
     scales = (1, 2, 4, 8, 16)
     r, ref = _compare(seqj, oracle, A, scales, (0, 1, 2, 3))
     assert r.timings["derived_groups"] == 12            # L2, KL, Energy at scales 1, 2, 4, 8
-    # ragged nesting: M = 250, scales (1, 2, 5, 10) -> chunk lengths 250, 125, 50, 25 all multiples of 25
+    # partial nesting: M = 250, scales (1, 2, 5, 10) -> chunk lengths 250, 125, 50, 25.  Each scale derives from the
+    # next finer one when that nests: 5 from 10 and 1 from 2 do, 2 from 5 does not (125 % 50 != 0) and runs tiles.
     A2 = np.random.default_rng(43).random((250, 120)) if kind == "random" else _planted_small(120, 250, 44)
     r2, _ = _compare(seqj, oracle, A2, (1, 2, 5, 10), (0, 2, 3))
-    assert r2.timings["derived_groups"] == 9
+    assert r2.timings["derived_groups"] == 6
 
 
 def test_derived_equals_direct_tiles(seqj, handle, monkeypatch):
