@@ -1185,22 +1185,40 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   std::vector<seqj_handle*> hs;
   hs.push_back(h);
   for (auto* p : h->peers) hs.push_back(p);
-  // cost model: distance work ~ L * (2 for EMD, 1 for the contractions) plus a per-chunk graph term
-  std::vector<std::pair<double, int>> order;
-  for (int k = 0; k < nmetrics; ++k)
-    for (int l = 0; l < nscales; ++l) {
-      const int sc = std::max(1, scales[l]);
-      const int64_t cl = (M + sc - 1) / sc, nch = (M + cl - 1) / cl;
-      const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID;
-      order.push_back({(emd ? 2.0 : 1.0) * (double)M + 600.0 * (double)(nch + 1), k * nscales + l});
+  // Units of work: every EMD group; every other group -- or, when the scales nest (each chunk length a multiple
+  // of the next finer one), all scales of a contraction metric together, because only the finest scale runs
+  // DMMA tiles and the others are derived from it on the same GPU.  LPT greedy on estimated cost.
+  auto nchunks_of = [&](int l) { const int64_t sc = std::max(1, scales[l]); const int64_t cl = (M + sc - 1) / sc; return (M + cl - 1) / cl; };
+  std::vector<int64_t> cls;
+  for (int l = 0; l < nscales; ++l) { const int64_t sc = std::max(1, scales[l]); cls.push_back((M + sc - 1) / sc); }
+  std::sort(cls.begin(), cls.end());
+  cls.erase(std::unique(cls.begin(), cls.end()), cls.end());
+  bool nested = cls.size() > 1;
+  for (size_t q = 1; q < cls.size(); ++q) nested = nested && (cls[q] % cls[q - 1] == 0);
+  struct Unit { double cost; std::vector<int> groups; };
+  std::vector<Unit> units;
+  for (int k = 0; k < nmetrics; ++k) {
+    const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID;
+    const bool contraction = metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_ENERGY;
+    if (nested && contraction) {
+      Unit u;
+      double graphs = 0;
+      for (int l = 0; l < nscales; ++l) { u.groups.push_back(k * nscales + l); graphs += (double)nchunks_of(l) + 1; }
+      u.cost = 1.45 * (double)M + 0.15 * (double)M * (nscales - 1) + 150.0 * graphs;
+      units.push_back(u);
+    } else {
+      for (int l = 0; l < nscales; ++l)
+        units.push_back({(emd ? 2.0 : 1.0) * (double)M + 600.0 * (double)(nchunks_of(l) + 1), {k * nscales + l}});
     }
-  std::stable_sort(order.begin(), order.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first > b.first; });
+  }
+  std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.cost > b.cost; });
   std::vector<std::vector<uint8_t>> masks(ndev, std::vector<uint8_t>(G, 0));
   std::vector<double> load(ndev, 0.0);
   std::vector<int> owner(G, 0);
-  for (auto& og : order) {
+  for (auto& u : units) {
     const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-    masks[d][og.second] = 1; load[d] += og.first; owner[og.second] = d;
+    for (int g : u.groups) { masks[d][g] = 1; owner[g] = d; }
+    load[d] += u.cost;
   }
   std::vector<seqj_result*> parts(ndev, nullptr);
   std::vector<int> status(ndev, SEQJ_OK);

@@ -32,17 +32,44 @@ def group_costs(M: int, metrics, scales) -> np.ndarray:
     return c
 
 
-def assign_groups(costs: np.ndarray, world: int) -> np.ndarray:
-    """Longest-processing-time greedy assignment of groups to ranks. Returns owner[k, l]."""
+def scales_chain_nested(M: int, scales) -> bool:
+    """True when every scale's chunk length is a multiple of the next finer one's, i.e. the library can derive
+    the contraction metrics of each scale from the previous one (csrc/kernels_derive.cuh)."""
+    cls = sorted({-(-M // int(s)) for s in scales})
+    return len(cls) > 1 and all(b % a == 0 for a, b in zip(cls, cls[1:]))
+
+
+def assign_groups(costs: np.ndarray, world: int, bundles=None) -> np.ndarray:
+    """Longest-processing-time greedy assignment of groups to ranks. Returns owner[k, l].
+    `bundles`: optional list of (cost, [(k, l), ...]) units that must stay on one rank."""
     owner = np.zeros(costs.shape, dtype=np.int64)
     load = np.zeros(world)
-    flat = sorted(((costs[k, l], k, l) for k in range(costs.shape[0]) for l in range(costs.shape[1])),
-                  key=lambda t: (-t[0], t[1], t[2]))
-    for cst, k, l in flat:
+    if bundles is None:
+        bundles = [(costs[k, l], [(k, l)]) for k in range(costs.shape[0]) for l in range(costs.shape[1])]
+    for cst, members in sorted(bundles, key=lambda t: (-t[0], t[1][0])):
         r = int(np.argmin(load))
-        owner[k, l] = r
+        for k, l in members:
+            owner[k, l] = r
         load[r] += cst
     return owner
+
+
+def plan_groups(M: int, metrics, scales, world: int) -> np.ndarray:
+    """Group-major plan.  When the scales nest, all scales of a contraction metric (L2, KL, Energy) form one
+    unit: only its finest scale runs DMMA tiles, the others are derived on the same GPU; EMD groups stay
+    individual units (every EMD scale runs the tile kernel)."""
+    costs = group_costs(M, metrics, scales)
+    if not scales_chain_nested(M, scales):
+        return assign_groups(costs, world)
+    bundles = []
+    for k, m in enumerate(metrics):
+        if m.id in (0, 2, 3):
+            # finest scale: tiles at ~70 % efficiency for short chunks; each derived scale: one HBM-bound pass
+            cst = 1.45 * M + 0.15 * M * (len(scales) - 1) + PRIM_COST_ROWS * sum(nchunks(M, s) + 1 for s in scales) / 4
+            bundles.append((cst, [(k, l) for l in range(len(scales))]))
+        else:
+            bundles += [(costs[k, l], [(k, l)]) for l in range(len(scales))]
+    return assign_groups(costs, world, bundles)
 
 
 def merge_group_results(parts, metrics, scales):
@@ -105,7 +132,7 @@ def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, al
     scales = tuple(int(s) for s in scales)
     if world == 1:
         return api._sequence(At, scales, metrics, handle, device_ptr=device_ptr)
-    owner = assign_groups(group_costs(M, metrics, scales), world)
+    owner = plan_groups(M, metrics, scales, world)
     mask = (owner == rank).astype(np.uint8)
     mine = {}
     local = None

@@ -56,7 +56,7 @@ def main():
 
     r = sharding.sequence_sharded(At, scales, metrics, rank, world, None, allgather)
     ref = O.sequence_oracle(A, scales)
-    owner = sharding.assign_groups(sharding.group_costs(40, metrics, scales), world)
+    owner = sharding.plan_groups(40, metrics, scales, world)
     ok = (np.array_equal(r.order, ref.order) and r.eta == ref.eta and calls["seq"] == 1 and calls["fuse"] == 1
           and np.array_equal(calls["mask"], (owner == rank).astype(np.uint8))
           and len(r.EOAlgScale) == int((owner == rank).sum()))

@@ -22,6 +22,14 @@ def test_assignment_covers_every_group_once_and_balances(seqj):
         assert load.min() > 0
         assert load.max() <= costs.sum() / world + costs.max()          # LPT bound
     assert sharding.nchunks(10, 6) == 5 and sharding.nchunks(4096, 16) == 16 and sharding.nchunks(50, 4) == 4
+    # nested scales: every contraction metric stays on one rank (its coarse scales are derived there)
+    assert sharding.scales_chain_nested(4096, scales) and not sharding.scales_chain_nested(50, (1, 2, 4))
+    for world in (2, 4, 8):
+        owner = sharding.plan_groups(4096, metrics, scales, world)
+        for k, m in enumerate(metrics):
+            if m.id != 1:
+                assert len(set(owner[k].tolist())) == 1
+        assert len(set(owner.reshape(-1).tolist())) == world
 
 
 def test_merge_is_metric_major(seqj):
