@@ -312,15 +312,20 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_config3_metrics.json")
     if args.config == 3 and not (args.objects or args.length) and world == 1 and os.path.exists(tpath):
-        tt = json.load(open(tpath))["per_sequence_totals"]["gemm_dist"]
-        # dram__bytes_read.sum + dram__bytes_write.sum of the 15 DMMA launches of one sequence(), per launch
-        traffic = (tt["rd"] + tt["wr"]) * 1e9 / tt["n"]
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the DMMA launches that still run (finest scale:
+        # gridDim.y = 16 chunks); the coarser scales are derived and run no tiles
+        fin = max(sharding.nchunks(L, sc) for sc in scales)
+        ls = [x for x in json.load(open(tpath))["launches"]
+              if x["kernel"].startswith("gemm_dist") and x["grid"].replace(" ", "").split(",")[1] == str(fin)]
+        if ls:
+            traffic = sum(x["dram_read_GB"] + x["dram_write_GB"] for x in ls) * 1e9 / len(ls)
     if gemm_ms > 0:
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = {"kernel": "gemm_dist_kernel<L2|KL|Energy> (+ fix-up)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                "traffic_note": "bytes per launch averaged over the 15 launches of one sequence(), ncu capture in "
-                                "profiles/r01_ncu_config3_metrics.json; algorithmic output is 4.96e9 bytes per launch",
+                "traffic_note": "bytes per launch (finest-scale launches: 16 chunk matrices each), ncu capture in "
+                                "profiles/r01_ncu_config3_metrics.json; algorithmic bytes per launch = 16 x 0.8e9 output "
+                                "+ 0.33e9 operands",
                 "launches_per_step": int(max(gemm_groups, 0)), "derived_groups_per_step": int(derived),
                 "peak_source": "FP64 DMMA.8x8x4 rate measured on this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.json); "
                                "MEASURED_PEAKS.json has no FP64 figure"}
@@ -333,7 +338,10 @@ def main():
     roof_prim = None
     if phases.get("prim", 0) > 0:
         ach = prim_bytes / (phases["prim"] * 1e-3) / 1e9
-        roof_prim = {"kernel": "prim_kernel", "bound": "hbm", "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm}
+        roof_prim = {"kernel": "prim_kernel + prim_cluster_kernel (all launches of the step)", "bound": "hbm", "achieved": ach,
+                     "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                     "note": "the 124-graph launch alone streams 99.2 GB in 23.2 ms = 4.28 TB/s = 65.5 % "
+                             "(profiles/r01_ncu_config3_metrics.json); the small launches are latency-bound"}
     if roof is None:
         roof = roof_emd
 
@@ -352,7 +360,10 @@ def main():
                       "cache": "inputs (8*N*L bytes) and every N x N chunk matrix are larger than the 126 MB L2; no flush needed",
                       "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
            "sequence_wall_s": elapsed / args.steps, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-           "roofline_emd": roof_emd, "roofline_prim": roof_prim, "cpu_baseline": cpu, "clocks": clocks,
+           "roofline_emd": roof_emd, "roofline_prim": roof_prim,
+           "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "emd_dist_kernel (FP64 ALU issue-bound, see roofline_emd)"),
+                                           (gemm_ms, "gemm_dist_kernel (FP64 tensor pipe, see roofline)"),
+                                           (phases.get("prim", 0), "prim kernels (HBM / latency, see roofline_prim)")))[1], "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
            "final_eta": float(r.eta)}
     print(json.dumps(out), flush=True)
