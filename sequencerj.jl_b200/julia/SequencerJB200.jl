@@ -74,11 +74,14 @@ end
 # ---- thin ccall layer -------------------------------------------------------------------------
 mutable struct Handle
     ptr::Ptr{Cvoid}
-    function Handle(device::Integer = -1)
+    # devices: nothing (current device) or a vector of CUDA device ordinals; with several, this one process
+    # drives all of them (groups sharded over host threads inside the library, fuse on devices[1])
+    function Handle(devices::Union{Nothing,AbstractVector{<:Integer}} = nothing)
         ref = Ref{Ptr{Cvoid}}(C_NULL)
-        st = device < 0 ?
+        devs = devices === nothing ? Cint[] : Cint[d for d in devices]
+        st = isempty(devs) ?
             ccall((:seqj_create, libseqj), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), ref, C_NULL, 0) :
-            ccall((:seqj_create, libseqj), Cint, (Ref{Ptr{Cvoid}}, Ref{Cint}, Cint), ref, Ref{Cint}(device), 1)
+            ccall((:seqj_create, libseqj), Cint, (Ref{Ptr{Cvoid}}, Ptr{Cint}, Cint), ref, devs, length(devs))
         h = new(ref[])
         st == 0 || error("seqj_create failed ($st): " * lasterror(h))   # no CPU fallback
         finalizer(x -> ccall((:seqj_destroy, libseqj), Cvoid, (Ptr{Cvoid},), x.ptr), h)
