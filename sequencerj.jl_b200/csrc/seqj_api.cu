@@ -369,6 +369,7 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
 }
 
 struct FixBufs {
+  int* sm_slots = nullptr;        // per-SM arrival counters for the first-wave stagger of the tile kernels
   int4* list = nullptr;
   unsigned int* count = nullptr;
   int* overflow = nullptr;
@@ -397,6 +398,9 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   if (on_grid) metric = (metric == SEQJ_EMD_GRID) ? SEQJ_EMD : SEQJ_ENERGY;
   const int phase = SEQJ_T_DIST_L2 + metric;
   int t = c.timer.begin(phase);
+  const char* stg = getenv("SEQJ_STAGGER");
+  dp.sm_slots = (stg && atoi(stg) == 0) ? nullptr : fb.sm_slots;
+  if (dp.sm_slots) CU_TRY(cudaMemsetAsync(fb.sm_slots, 0, 256 * sizeof(int), c.st));
   dim3 grid(ntiles, nb);
   if (metric == SEQJ_EMD) {
     CUtensorMap tmU;
@@ -522,6 +526,7 @@ int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap) {
   CU_TRY(c.pool.alloc(&fb.list, (size_t)cap));
   CU_TRY(c.pool.alloc(&fb.count, 1));
   CU_TRY(c.pool.alloc(&fb.overflow, 1));
+  CU_TRY(c.pool.alloc(&fb.sm_slots, 256));
   return SEQJ_OK;
 }
 
