@@ -111,11 +111,36 @@ class SequencerResult:
         self.launches = launches
         self.group_msts = group_msts
         self._D = None
+        self._lazy = None          # (handle, C result pointer) while the D triplets have not been fetched yet
+
+    def _fetch_triplets(self):
+        if self._lazy is not None:
+            handle, res = self._lazy
+            self._lazy = None
+            try:
+                lib = handle.lib
+                nnz = C.c_int64()
+                handle.check(lib.seqj_result_D_nnz(res, C.byref(nnz)))
+                ti = np.empty(nnz.value, dtype=np.int32); tj = np.empty(nnz.value, dtype=np.int32); tv = np.empty(nnz.value)
+                handle.check(lib.seqj_result_D_triplets(res, _lib.iptr(ti), _lib.iptr(tj), _lib.dptr(tv)))
+                self._D_triplets = (ti, tj, tv)
+            finally:
+                handle.lib.seqj_result_free(res)
+
+    def __del__(self):
+        if getattr(self, "_lazy", None) is not None:
+            handle, res = self._lazy
+            self._lazy = None
+            try:
+                handle.lib.seqj_result_free(res)
+            except Exception:
+                pass
 
     @property
     def D(self):
         """Dense final distance matrix: +Inf off the edge union, 1e-6 on the diagonal (sequencer.jl:269,360)."""
         if self._D is None:
+            self._fetch_triplets()
             i, j, v = self._D_triplets
             D = np.full((self.N, self.N), np.inf)
             np.fill_diagonal(D, EPS_FLOOR)
@@ -126,6 +151,9 @@ class SequencerResult:
 
     @property
     def D_triplets(self):
+        """(i, j, value) of the final distance matrix on the edge union, i < j (fetched from the library and
+        deduplicated on first access)."""
+        self._fetch_triplets()
         return self._D_triplets
 
     def __repr__(self):
@@ -286,12 +314,21 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     mi = np.empty(N - 1, dtype=np.int32); mj = np.empty(N - 1, dtype=np.int32); mw = np.empty(N - 1)
     handle.check(lib.seqj_result_final(res, C.byref(eta), C.byref(root), _lib.iptr(order_), _lib.iptr(par),
                                        _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw)))
-    nnz = C.c_int64()
-    handle.check(lib.seqj_result_D_nnz(res, C.byref(nnz)))
-    ti = np.empty(nnz.value, dtype=np.int32); tj = np.empty(nnz.value, dtype=np.int32); tv = np.empty(nnz.value)
-    handle.check(lib.seqj_result_D_triplets(res, _lib.iptr(ti), _lib.iptr(tj), _lib.dptr(tv)))
-    return SequencerResult(N, EOSeg, EOAlgScale, (ti, tj, tv), WeightedTree(N, mi, mj, mw), eta.value, order_,
-                           root.value, par, timings, launches.value, group_msts)
+    r = SequencerResult(N, EOSeg, EOAlgScale, None, WeightedTree(N, mi, mj, mw), eta.value, order_,
+                        root.value, par, timings, launches.value, group_msts)
+    r._lazy = (handle, res)        # the result object now owns the C result until the triplets are fetched
+    return r
+
+
+def _collect_and_release(handle, res, N, metrics, scales, want_final=True, partial=False):
+    """_collect, then free the C result unless the returned object took ownership of it (lazy D triplets)."""
+    r = None
+    try:
+        r = _collect(handle, res, N, metrics, scales, want_final=want_final, partial=partial)
+        return r
+    finally:
+        if r is None or r._lazy is None:
+            handle.lib.seqj_result_free(res)
 
 
 def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None):
@@ -314,10 +351,7 @@ def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None
         st = handle.lib.seqj_sequence(handle.h, At.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(mids), len(mids),
                                       _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
     handle.check(st)
-    try:
-        return _collect(handle, res, N, metrics, scales, want_final=group_mask is None)
-    finally:
-        handle.lib.seqj_result_free(res)
+    return _collect_and_release(handle, res, N, metrics, scales, want_final=group_mask is None)
 
 
 def _sequence_partial(shape, scales, metrics, chunk_lo, chunk_hi, S_out_ptr, S_stride, device_ptr, handle=None):
@@ -334,10 +368,7 @@ def _sequence_partial(shape, scales, metrics, chunk_lo, chunk_hi, S_out_ptr, S_s
     handle.check(handle.lib.seqj_sequence_partial(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
                                                   _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, _lib.iptr(lo),
                                                   _lib.iptr(hi), C.c_void_p(S_out_ptr), int(S_stride), C.byref(res)))
-    try:
-        return _collect(handle, res, N, metrics, scales, want_final=False, partial=True)
-    finally:
-        handle.lib.seqj_result_free(res)
+    return _collect_and_release(handle, res, N, metrics, scales, want_final=False, partial=True)
 
 
 def groups_finish(S_ptr, S_stride, slots, N, eta_sums, eps_floor=EPS_FLOOR, handle=None):
@@ -490,10 +521,7 @@ def fuse(N, etas, msts, eps_floor=EPS_FLOOR, handle=None) -> SequencerResult:
     res = C.c_void_p()
     handle.check(handle.lib.seqj_fuse(handle.h, N, G, _lib.dptr(etas), _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw),
                                       eps_floor, C.byref(res)))
-    try:
-        return _collect(handle, res, N, None, None, want_final=True)
-    finally:
-        handle.lib.seqj_result_free(res)
+    return _collect_and_release(handle, res, N, None, None, want_final=True)
 
 
 class EMD:

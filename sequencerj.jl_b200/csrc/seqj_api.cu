@@ -67,6 +67,12 @@ struct seqj_result {
   int64_t launches = 0;
   double in_min = 0, in_max = 0;
   int derived_groups = 0;
+  // raw group edge lists + D values; the deduplicated triplets (Di, Dj, Dv) are built on first request
+  mutable std::vector<int32_t> raw_i, raw_j;
+  mutable std::vector<double> raw_v;
+  mutable int raw_G = 0;
+  mutable int64_t raw_ldp = 0;
+  mutable bool triplets_ready = false;
 };
 
 // --------------------------------------------------------------------------------------------
@@ -591,8 +597,25 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
   return SEQJ_OK;
 }
 
-void dedup_triplets(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
-                    const std::vector<double>& val) {
+void stash_triplets(seqj_result* r, int G, int64_t ldp, std::vector<int>& mi, std::vector<int>& mj, std::vector<double>& val) {
+  r->raw_i.swap(mi); r->raw_j.swap(mj); r->raw_v.swap(val);
+  r->raw_G = G; r->raw_ldp = ldp; r->triplets_ready = false;
+}
+
+void dedup_triplets_impl(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
+                         const std::vector<double>& val);
+
+// D triplets are rarely read (the wrapper materialises D(r) on demand): deduplicate on first access
+void ensure_triplets(const seqj_result* cr) {
+  if (cr->triplets_ready) return;
+  seqj_result* r = const_cast<seqj_result*>(cr);
+  if (r->raw_G > 0) dedup_triplets_impl(r, r->raw_G, (int)r->N, r->raw_ldp, r->raw_i, r->raw_j, r->raw_v);
+  r->raw_i.clear(); r->raw_i.shrink_to_fit(); r->raw_j.clear(); r->raw_j.shrink_to_fit(); r->raw_v.clear(); r->raw_v.shrink_to_fit();
+  r->triplets_ready = true;
+}
+
+void dedup_triplets_impl(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
+                         const std::vector<double>& val) {
   // first occurrence of every (i, j) in group-major edge order, via an open-addressing table
   const size_t total = (size_t)G * (N - 1);
   size_t cap = 16;
@@ -1114,7 +1137,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       gr.mst_j.assign(h_mstj.begin() + gp * ldp, h_mstj.begin() + gp * ldp + N - 1);
       gr.mst_w.assign(h_mstw.begin() + gp * ldp, h_mstw.begin() + gp * ldp + N - 1);
     }
-  if (do_final) dedup_triplets(r, G, N, ldp, h_msti, h_mstj, h_val);
+  if (do_final) stash_triplets(r, G, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
   r->launches = c.launches;
   r->in_min = st0.minv; r->in_max = st0.maxv;
@@ -1373,7 +1396,7 @@ int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group,
     delete r;
     return fail(h, SEQJ_E_CUDA, std::string("fuse failed: ") + cudaGetErrorString(e));
   }
-  dedup_triplets(r, G, N, ldp, h_mi, h_mj, h_val);
+  stash_triplets(r, G, ldp, h_mi, h_mj, h_val);
   c.timer.collect(r->timers);
   r->launches = c.launches;
   *out = r;
@@ -1428,11 +1451,13 @@ int seqj_result_final(const seqj_result* r, double* eta, int32_t* root, int32_t*
 }
 int seqj_result_D_nnz(const seqj_result* r, int64_t* nnz) {
   if (!r || !nnz) return SEQJ_E_BADARG;
+  ensure_triplets(r);
   *nnz = (int64_t)r->Dv.size();
   return SEQJ_OK;
 }
 int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double* val) {
   if (!r) return SEQJ_E_BADARG;
+  ensure_triplets(r);
   copy_out(i, r->Di); copy_out(j, r->Dj); copy_out(val, r->Dv);
   return SEQJ_OK;
 }
