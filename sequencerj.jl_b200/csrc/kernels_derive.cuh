@@ -50,13 +50,18 @@ struct DeriveParams {
   unsigned int* fix_count;
   unsigned int fix_cap;
   int* fix_overflow;
+  // dense blocks: more than 1/32 of a 32 x 32 block flagged -> flag the enclosing 64 x 128 tile for the direct
+  // tile kernels instead of listing the entries one by one
+  unsigned char* tile_flags;   // [coarse chunks of the launch][tile_flag_stride]; may be nullptr
+  int tile_flag_stride;
+  const int* tile_col_offset;  // index of the first tile of every 128-column block in the tile list
 };
 
 // 32 x 32 tiles of the upper triangle; block = 32 x 8 threads; result mirrored through shared memory.
 // Per-object factors of the 64 objects of a tile are precomputed once per block in (dynamic) shared memory,
 // 4 doubles per (side, fine chunk, object):  L2: {w, w*g}   KL: {w, log w}   Energy: {w, b, w*(q + 2R), w*T},
 // so the inner loop is 6-14 FP64 operations per (entry, fine chunk) and the pass stays HBM-bound.
-__global__ void __launch_bounds__(256) derive_kernel(DeriveParams p) {
+__global__ void __launch_bounds__(256, 4) derive_kernel(DeriveParams p) {
   extern __shared__ double dsm[];                 // [2][nf][4][32]: consecutive lanes read consecutive doubles
   __shared__ double tile[32][33];
   const int bi = blockIdx.y, bj = blockIdx.x;
@@ -157,13 +162,18 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveParams p) {
       }
     }
   }
+  // phase A: results + flags
+  double outv[4];
+  bool flg[4];
+  int nflag = 0;
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
-    const int r = ty + 8 * rr, i = i0 + r;
-    double out = 0.0;
+    const int i = i0 + ty + 8 * rr;
+    outv[rr] = 0.0;
+    flg[rr] = false;
     if (i < N && j < N) {
       if (i == j) {
-        out = p.eps_floor;
+        outv[rr] = p.eps_floor;
       } else {
         const int lo = min(i, j), hi = max(i, j);
         double d;
@@ -178,12 +188,36 @@ __global__ void __launch_bounds__(256) derive_kernel(DeriveParams p) {
           d = fast_sqrt(acc[rr]);
           if (p.mode == MODE_ENERGY) d = 1.4142135623730951 * d;
         }
-        out = fabs(d) + p.eps_floor;
-        if (flag && i < j) {      // (j, i) of a diagonal tile is rewritten by the mirrored store of the fix-up
-          const unsigned int idx = atomicAdd(p.fix_count, 1u);
-          if (idx < p.fix_cap) p.fix_list[idx] = make_int4(p.chunk_local, i, j, 0);
-          else { *p.fix_overflow = 1; out = -1.0; }
-        }
+        outv[rr] = fabs(d) + p.eps_floor;
+        flg[rr] = flag && i < j;      // (j, i) of a diagonal tile is rewritten by the mirrored store of the fix-up
+        nflag += flg[rr] ? 1 : 0;
+      }
+    }
+  }
+  // block-level decision
+  bool dense = false;
+  if (p.tile_flags != nullptr) {
+    __shared__ int s_cnt;
+    if (tx == 0 && ty == 0) s_cnt = 0;
+    __syncthreads();
+    if (nflag) atomicAdd(&s_cnt, nflag);
+    __syncthreads();
+    dense = s_cnt > 32;
+    if (dense && tx == 0 && ty == 0) {
+      const int tidx = p.tile_col_offset[j0 / kTileN] + i0 / kTileM;
+      p.tile_flags[(size_t)p.chunk_local * p.tile_flag_stride + tidx] = 1;
+    }
+  }
+  // phase B: stores (+ per-entry list when the block is not dense)
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int r = ty + 8 * rr, i = i0 + r;
+    double out = outv[rr];
+    if (i < N && j < N) {
+      if (flg[rr] && !dense) {
+        const unsigned int idx = atomicAdd(p.fix_count, 1u);
+        if (idx < p.fix_cap) p.fix_list[idx] = make_int4(p.chunk_local, i, j, 0);
+        else { *p.fix_overflow = 1; out = -1.0; }
       }
       p.Dout[(int64_t)i * p.ldD + j] = out;
     }

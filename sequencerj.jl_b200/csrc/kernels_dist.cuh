@@ -38,6 +38,15 @@ struct DistParams {
   double eps_floor;
   double tau;           // relative fix-up threshold
   int mirror;           // 1: write (i,j) and (j,i) for i<j only;  0: write every (i,j) (KL full)
+  // dense tiles: a tile whose epilogue flags more than `dense_thresh` entries is recomputed as a whole by the
+  // direct tile kernel (direct_dist_kernel / kl_direct_kernel) instead of entry by entry
+  unsigned char* tile_flags;   // [nb][tile_flag_stride], indexed by blockIdx.y, blockIdx.x; may be nullptr
+  int tile_flag_stride;
+  int dense_thresh;
+  // direct kernels: with a dense list, a small persistent grid loops over the listed (chunk_local, tile) entries;
+  // without one (EMD) every CTA computes the tile (blockIdx.x, blockIdx.y)
+  const int2* dense_list;
+  const unsigned int* dense_count;
   int* sm_slots;        // optional [#SMs] counters (zeroed before the launch) for the first-wave stagger
   int kl_swap;          // KL full mode: operand A = log P, B = P, so that D[r][c] = KL(p_c || p_r), i.e. the
                         // row-major buffer is the column-major pairwise matrix of the C ABI
@@ -90,7 +99,7 @@ __device__ __forceinline__ void stagger_first_wave(int* sm_slots, int nk, int cy
 
 template <int MODE, bool INTERIOR>
 __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)[8][4][2], int i0, int j0, int chunk,
-                                              int warp, int rg, int t) {
+                                              int warp, int rg, int t, int* s_cnt) {
   const double* __restrict__ nrm = p.normA + (int64_t)chunk * p.ldn;
   double* __restrict__ D = p.D + (int64_t)blockIdx.y * p.strideD;
   const int N = p.N;
@@ -103,11 +112,50 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
       const int j = jbase + 8 * b + 4 * e;
       nj[b][e] = (INTERIOR || j < N) ? nrm[j] : 0.0;
     }
+  // phase A: distances in place of the accumulators + one flag bit per entry
+  unsigned long long flags = 0ull;
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int i = i0 + 8 * a + rg;
+    const double ni = (INTERIOR || i < N) ? nrm[i] : 0.0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = jbase + 8 * b + 4 * e;
+        const bool live = INTERIOR || (i < N && j < N && i != j && !(p.mirror && i > j));
+        const double c = acc[a][b][e];
+        bool flag;
+        double d;
+        if (MODE == MODE_KL) {
+          const double hh = p.kl_swap ? nj[b][e] : ni;
+          d = hh - c;                                   // H_i - sum_k p_ik log p_jk
+          flag = d < p.tau * fabs(hh);
+        } else {
+          const double selfterms = ni + nj[b][e];
+          const double v = selfterms - 2.0 * c;
+          flag = v < p.tau * selfterms;
+          d = fast_sqrt(v);
+          if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;   // sqrt(2) * sqrt(sum)
+        }
+        acc[a][b][e] = fabs(d) + p.eps_floor;
+        if (live && flag) flags |= 1ull << (a * 8 + b * 2 + e);
+      }
+    }
+  }
+  // tile-level decision: many flagged entries (near-duplicate objects) -> the whole tile goes to the direct kernel
+  bool dense = false;
+  if (p.tile_flags != nullptr) {
+    if (flags) atomicAdd(s_cnt, __popcll(flags));
+    __syncthreads();
+    dense = *s_cnt > p.dense_thresh;
+    if (dense && threadIdx.x == 0) p.tile_flags[(size_t)blockIdx.y * p.tile_flag_stride + blockIdx.x] = 1;
+  }
+  // phase B: stores (+ per-entry fix-up list when the tile is not dense)
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const int i = i0 + 8 * a + rg;
     if (!INTERIOR && i >= N) continue;
-    const double ni = nrm[i];
     double* __restrict__ drow = D + (int64_t)i * p.ldD + jbase;          // direct stores: drow[8b + 4e]
     double* __restrict__ dcol = D + (int64_t)jbase * p.ldD + i;          // mirrored stores: dcol[(8b + 4e) * ldD]
 #pragma unroll
@@ -119,33 +167,14 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
           if (j >= N) continue;
           if (p.mirror && i > j) continue;
         }
-        double out;
-        if (!INTERIOR && i == j) {
-          out = p.eps_floor;     // pairwise sets the diagonal to 0, then .+ eps
-        } else {
-          const double c = acc[a][b][e];
-          bool flag;
-          double d;
-          if (MODE == MODE_KL) {
-            const double hh = p.kl_swap ? nj[b][e] : ni;
-            d = hh - c;                                   // H_i - sum_k p_ik log p_jk
-            flag = d < p.tau * fabs(hh);
+        double out = (!INTERIOR && i == j) ? p.eps_floor : acc[a][b][e];   // pairwise sets the diagonal to 0, then .+ eps
+        if (!dense && ((flags >> (a * 8 + b * 2 + e)) & 1ull)) {
+          const unsigned int idx = atomicAdd(p.fix_count, 1u);
+          if (idx < p.fix_cap) {
+            p.fix_list[idx] = make_int4((int)blockIdx.y, i, j, p.kl_swap);
           } else {
-            const double selfterms = ni + nj[b][e];
-            const double v = selfterms - 2.0 * c;
-            flag = v < p.tau * selfterms;
-            d = fast_sqrt(v);
-            if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;   // sqrt(2) * sqrt(sum)
-          }
-          out = fabs(d) + p.eps_floor;
-          if (flag) {
-            const unsigned int idx = atomicAdd(p.fix_count, 1u);
-            if (idx < p.fix_cap) {
-              p.fix_list[idx] = make_int4((int)blockIdx.y, i, j, p.kl_swap);
-            } else {
-              *p.fix_overflow = 1;
-              out = -1.0;     // marker for the dense fix-up pass
-            }
+            *p.fix_overflow = 1;
+            out = -1.0;     // marker for the dense fix-up pass
           }
         }
         drow[8 * b + 4 * e] = out;
@@ -158,6 +187,7 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
 template <int MODE>
 __global__ void __launch_bounds__(kTileThreads, 2)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DistParams p) {
+  __shared__ int s_cnt;
   extern __shared__ uint8_t smem_raw[];
   const TileSmem s = carve_tile_smem(smem_raw);
   const int warp = threadIdx.x >> 5;
@@ -167,6 +197,7 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int chunk = p.chunk0 + blockIdx.y;
   const int kbase = chunk * p.cl_pad;
 
+  if (threadIdx.x == 0) s_cnt = 0;
   if (threadIdx.x == 0) {
     tile_barriers_init(s);
     tma_prefetch_desc(&tmA);
@@ -225,85 +256,221 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // Interior tiles (entirely above the diagonal and inside the matrix: ~95 % of them) skip every per-entry
   // bounds / triangle test; the general path handles the diagonal band and the ragged edge.
   const bool interior = p.mirror && (i0 + kTileM <= j0) && (j0 + kTileN <= p.N);
-  if (interior) gemm_epilogue<MODE, true>(p, acc, i0, j0, chunk, warp, rg, t);
-  else gemm_epilogue<MODE, false>(p, acc, i0, j0, chunk, warp, rg, t);
+  if (interior) gemm_epilogue<MODE, true>(p, acc, i0, j0, chunk, warp, rg, t, &s_cnt);
+  else gemm_epilogue<MODE, false>(p, acc, i0, j0, chunk, warp, rg, t, &s_cnt);
+}
+
+// flags -> list of (chunk_local, tile) entries for the persistent direct kernels
+__global__ void compact_flags_kernel(const unsigned char* __restrict__ flags, int total, int stride, int2* list,
+                                     unsigned int* count) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < total && flags[q]) list[atomicAdd(count, 1u)] = make_int2(q / stride, q % stride);
 }
 
 // ---- EMD: sum_k |U_ik - U_jk| on CUDA cores -------------------------------------------------
 // thread T of the 128 consumers: ti = T>>4 (rows 8ti..8ti+7), tj = T&15 (cols (tj&7)+8(tj>>3)+16bb).
+// OP_L1: EMD.  OP_SQ / OP_SQ_ENERGY: sum_k (a-b)^2 -> Euclidean / Energy computed WITHOUT the Gram form; used
+// as the fix-up of whole tiles that the DMMA epilogue (or derive_kernel) found full of cancelling entries.
+enum DirectOp { OP_L1 = 0, OP_SQ = 1, OP_SQ_ENERGY = 2 };
+
+template <int OP>
 __global__ void __launch_bounds__(kTileThreads, 2)
-emd_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
+direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
   extern __shared__ uint8_t smem_raw[];
   const TileSmem s = carve_tile_smem(smem_raw);
-  const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int2 tile = p.tiles[blockIdx.x];
-  const int i0 = tile.x, j0 = tile.y;
-  const int chunk = p.chunk0 + blockIdx.y;
-  const int kbase = chunk * p.cl_pad;
-
-  if (threadIdx.x == 0) {
-    tile_barriers_init(s);
-    tma_prefetch_desc(&tmU);
-  }
-  __syncthreads();
-  stagger_first_wave(p.sm_slots, p.nk, 4096);
-
-  if (threadIdx.x == 0)
-    for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmU, &tmU, s, it, kbase, i0, j0);
-
+  const bool listed = p.dense_list != nullptr;
+  const int ntodo = listed ? (int)*p.dense_count : 1;
   const int T = threadIdx.x;
   const int ti = T >> 4, tj = T & 15;
   const int jrow0 = (tj & 7) + 8 * (tj >> 3);   // + 16*bb ; (row & 7) == (tj & 7)
   const int jsw = tj & 7;
-
-  double acc[8][8];
-#pragma unroll
-  for (int a = 0; a < 8; ++a)
-#pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-
   const uint32_t stages_u32 = smem_u32(s.stages);
-  for (int it = 0; it < p.nk; ++it) {
-    const int st = it % kStages;
-    const uint32_t ph = (it / kStages) & 1;
-    if (threadIdx.x == 0) tile_refill(&tmU, &tmU, s, it, p.nk, kbase, i0, j0);
-    mbar_wait(&s.full[st], ph);
-    const uint32_t sa = stages_u32 + st * kStageBytes + (8 * ti) * 128;
-    const uint32_t sb = stages_u32 + st * kStageBytes + kStageBytesA + jrow0 * 128;
+  const int N = p.N;
+
+  for (int e = listed ? (int)blockIdx.x : 0; e < ntodo; e += listed ? (int)gridDim.x : 1) {
+    int tile_idx = blockIdx.x, chunk_local = blockIdx.y;
+    if (listed) { const int2 ent = p.dense_list[e]; chunk_local = ent.x; tile_idx = ent.y; }
+    const int2 tile = p.tiles[tile_idx];
+    const int i0 = tile.x, j0 = tile.y;
+    const int kbase = (p.chunk0 + chunk_local) * p.cl_pad;
+
+    if (threadIdx.x == 0) {
+      tile_barriers_init(s);
+      tma_prefetch_desc(&tmU);
+    }
+    __syncthreads();
+    if (!listed) stagger_first_wave(p.sm_slots, p.nk, 4096);
+    if (threadIdx.x == 0)
+      for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmU, &tmU, s, it, kbase, i0, j0);
+
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+    for (int it = 0; it < p.nk; ++it) {
+      const int st = it % kStages;
+      const uint32_t ph = (it / kStages) & 1;
+      if (threadIdx.x == 0) tile_refill(&tmU, &tmU, s, it, p.nk, kbase, i0, j0);
+      mbar_wait(&s.full[st], ph);
+      const uint32_t sa = stages_u32 + st * kStageBytes + (8 * ti) * 128;
+      const uint32_t sb = stages_u32 + st * kStageBytes + kStageBytesA + jrow0 * 128;
 #pragma unroll 2
-    for (int c = 0; c < 8; ++c) {    // 16 B chunk = 2 consecutive k
-      double2 fb[8];
+      for (int c = 0; c < 8; ++c) {    // 16 B chunk = 2 consecutive k
+        double2 fb[8];
 #pragma unroll
-      for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
+        for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
 #pragma unroll
-      for (int a = 0; a < 8; ++a) {
-        const double2 fa = lds128(sa + a * 128 + ((c ^ a) << 4));
+        for (int a = 0; a < 8; ++a) {
+          const double2 fa = lds128(sa + a * 128 + ((c ^ a) << 4));
 #pragma unroll
-        for (int b = 0; b < 8; ++b) {
-          acc[a][b] += fabs(fa.x - fb[b].x);
-          acc[a][b] += fabs(fa.y - fb[b].y);
+          for (int b = 0; b < 8; ++b) {
+            if (OP == OP_L1) {
+              acc[a][b] += fabs(fa.x - fb[b].x);
+              acc[a][b] += fabs(fa.y - fb[b].y);
+            } else {
+              const double dx = fa.x - fb[b].x, dy = fa.y - fb[b].y;
+              acc[a][b] = fma(dx, dx, acc[a][b]);
+              acc[a][b] = fma(dy, dy, acc[a][b]);
+            }
+          }
         }
       }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s.empty[st]);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.empty[st]);
-  }
 
-  double* __restrict__ D = p.D + (int64_t)blockIdx.y * p.strideD;
-  const int N = p.N;
+    double* __restrict__ D = p.D + (int64_t)chunk_local * p.strideD;
 #pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int i = i0 + 8 * ti + a;
-    if (i >= N) continue;
+    for (int a = 0; a < 8; ++a) {
+      const int i = i0 + 8 * ti + a;
+      if (i >= N) continue;
 #pragma unroll
-    for (int b = 0; b < 8; ++b) {
-      const int j = j0 + jrow0 + 16 * b;
-      if (j >= N || i > j) continue;
-      const double out = (i == j) ? p.eps_floor : fabs(acc[a][b]) + p.eps_floor;
-      D[(int64_t)i * p.ldD + j] = out;
-      if (i != j) D[(int64_t)j * p.ldD + i] = out;
+      for (int b = 0; b < 8; ++b) {
+        const int j = j0 + jrow0 + 16 * b;
+        if (j >= N || i > j) continue;
+        double d = acc[a][b];
+        if (OP != OP_L1) d = fast_sqrt(d);
+        if (OP == OP_SQ_ENERGY) d = 1.4142135623730951 * d;
+        const double out = (i == j) ? p.eps_floor : fabs(d) + p.eps_floor;
+        D[(int64_t)i * p.ldD + j] = out;
+        if (i != j) D[(int64_t)j * p.ldD + i] = out;
+      }
     }
+    if (listed) __syncthreads();      // every warp is done with the pipeline before the barriers are re-initialised
+  }
+}
+
+// ---- KL on whole tiles without the entropy-minus-cross-term form -----------------------------------
+// KL(p_i || p_j) = sum_k p_ik (log p_ik - log p_jk): the per-term difference is small when the objects are close,
+// so there is no cancellation of large sums.  Operands per stage: P and log P for the 64 rows i, log P for the
+// 128 rows j (32 KB, 3 stages, 2 CTAs/SM).  Same 8 x 8 register tile as the EMD kernel; 2 FP64 instructions per
+// element (DADD + DFMA).  Used only for tiles flagged dense by the DMMA epilogue / derive_kernel.
+constexpr int kKlStages = 3;
+constexpr int kKlStageBytes = 2 * kStageBytesA + kStageBytesB;          // P_i, logP_i (8 KB each) + logP_j (16 KB)
+constexpr int kKlSmemBytes = kKlStages * kKlStageBytes + 1024 + 256;
+
+__device__ __forceinline__ void kl_issue(const CUtensorMap* tmP, const CUtensorMap* tmL, uint8_t* stages, uint64_t* full,
+                                         int it, int kbase, int i0, int j0) {
+  const int st = it % kKlStages;
+  mbar_expect_tx(&full[st], kKlStageBytes);
+  uint8_t* base = stages + st * kKlStageBytes;
+  const int k0 = kbase + it * kTileK;
+  tma_load_2d(base, tmP, &full[st], k0, i0);
+  tma_load_2d(base + kStageBytesA, tmL, &full[st], k0, i0);
+  tma_load_2d(base + 2 * kStageBytesA, tmL, &full[st], k0, j0);
+  tma_load_2d(base + 3 * kStageBytesA, tmL, &full[st], k0, j0 + kTileM);
+}
+
+__global__ void __launch_bounds__(kTileThreads, 2)
+kl_direct_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant__ CUtensorMap tmL, DistParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* stages = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full = reinterpret_cast<uint64_t*>(stages + kKlStages * kKlStageBytes);
+  uint64_t* empty = full + kKlStages;
+  const int lane = threadIdx.x & 31;
+  const int ntodo = (int)*p.dense_count;
+  const int T = threadIdx.x;
+  const int ti = T >> 4, tj = T & 15;
+  const int jrow0 = (tj & 7) + 8 * (tj >> 3);
+  const int jsw = tj & 7;
+  const uint32_t stages_u32 = smem_u32(stages);
+  const int N = p.N;
+
+  for (int e = blockIdx.x; e < ntodo; e += gridDim.x) {
+    const int2 ent = p.dense_list[e];
+    const int chunk_local = ent.x;
+    const int2 tile = p.tiles[ent.y];
+    const int i0 = tile.x, j0 = tile.y;
+    const int kbase = (p.chunk0 + chunk_local) * p.cl_pad;
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < kKlStages; ++q) { mbar_init(&full[q], 1); mbar_init(&empty[q], kConsumerWarps); }
+      fence_barrier_init();
+      tma_prefetch_desc(&tmP);
+      tma_prefetch_desc(&tmL);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0)
+      for (int it = 0; it < min(kKlStages, p.nk); ++it) kl_issue(&tmP, &tmL, stages, full, it, kbase, i0, j0);
+
+    double acc[8][8];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+      for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
+
+    for (int it = 0; it < p.nk; ++it) {
+      const int st = it % kKlStages;
+      const uint32_t ph = (it / kKlStages) & 1;
+      if (threadIdx.x == 0) {
+        const int nxt = it - 1 + kKlStages;
+        if (it >= 1 && nxt < p.nk) {
+          mbar_wait(&empty[(it - 1) % kKlStages], ((it - 1) / kKlStages) & 1);
+          kl_issue(&tmP, &tmL, stages, full, nxt, kbase, i0, j0);
+        }
+      }
+      mbar_wait(&full[st], ph);
+      const uint32_t sp = stages_u32 + st * kKlStageBytes + (8 * ti) * 128;       // P rows i
+      const uint32_t sl = sp + kStageBytesA;                                        // log P rows i
+      const uint32_t sb = stages_u32 + st * kKlStageBytes + 2 * kStageBytesA + jrow0 * 128;   // log P rows j
+#pragma unroll 2
+      for (int c = 0; c < 8; ++c) {
+        double2 fb[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
+#pragma unroll
+        for (int a = 0; a < 8; ++a) {
+          const uint32_t off = a * 128 + ((c ^ a) << 4);
+          const double2 pa = lds128(sp + off);
+          const double2 la = lds128(sl + off);
+#pragma unroll
+          for (int b = 0; b < 8; ++b) {
+            acc[a][b] = fma(pa.x, la.x - fb[b].x, acc[a][b]);
+            acc[a][b] = fma(pa.y, la.y - fb[b].y, acc[a][b]);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[st]);
+    }
+
+    double* __restrict__ D = p.D + (int64_t)chunk_local * p.strideD;
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+      const int i = i0 + 8 * ti + a;
+      if (i >= N) continue;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        const int j = j0 + jrow0 + 16 * b;
+        if (j >= N || i > j) continue;           // mirrored storage: the stored value is KL(p_i || p_j), i < j
+        const double out = (i == j) ? p.eps_floor : fabs(acc[a][b]) + p.eps_floor;
+        D[(int64_t)i * p.ldD + j] = out;
+        if (i != j) D[(int64_t)j * p.ldD + i] = out;
+      }
+    }
+    __syncthreads();      // every warp is done with the pipeline before the barriers are re-initialised
   }
 }
 

@@ -375,6 +375,10 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
 }
 
 struct FixBufs {
+  int2* dense_list = nullptr;            // compacted (chunk_local, tile) entries of the flagged tiles
+  unsigned int* dense_count = nullptr;
+  unsigned char* tile_flags = nullptr;   // [max chunks per launch][ntiles] dense-tile flags
+  size_t tile_flags_bytes = 0;
   int* sm_slots = nullptr;        // per-SM arrival counters for the first-wave stagger of the tile kernels
   int4* list = nullptr;
   unsigned int* count = nullptr;
@@ -390,6 +394,24 @@ struct FixBufs {
 constexpr double kTauGram = 1e-4;
 constexpr double kTauKL = 1e-4;
 
+// Dense fix-up: compact the tile flags into a list, then a small persistent grid of the direct tile kernel
+// recomputes the listed tiles from the operands (no Gram form).  With nothing flagged this costs two tiny launches.
+int run_dense_tiles(Ctx& c, int metric, DistParams dd, const CUtensorMap& tm1, const CUtensorMap& tm2, FixBufs& fb,
+                    int ntiles, int nb) {
+  seqj_handle* h = c.h;
+  CU_TRY(cudaMemsetAsync(fb.dense_count, 0, sizeof(unsigned int), c.st));
+  const int total = ntiles * nb;
+  compact_flags_kernel<<<(total + 255) / 256, 256, 0, c.st>>>(fb.tile_flags, total, ntiles, fb.dense_list, fb.dense_count);
+  dd.dense_list = fb.dense_list; dd.dense_count = fb.dense_count; dd.sm_slots = nullptr;
+  const int grid = h->sm_count * 2 * 4;
+  if (metric == SEQJ_L2) direct_dist_kernel<OP_SQ><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
+  else if (metric == SEQJ_ENERGY) direct_dist_kernel<OP_SQ_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
+  else kl_direct_kernel<<<grid, kTileThreads, kKlSmemBytes, c.st>>>(tm1, tm2, dd);
+  c.launches += 2;
+  CU_TRY(cudaGetLastError());
+  return SEQJ_OK;
+}
+
 // distance matrices of chunks [chunk0, chunk0+nb) of one scale into D (stride strideD)
 int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const int2* tiles_dev, int ntiles,
                  int N, double* D, int64_t ldD, int64_t strideD, int chunk0, int nb, double eps_floor,
@@ -399,6 +421,7 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.D = D; dp.nk = L.cl_pad / kTileK; dp.cl_pad = L.cl_pad;
   dp.chunk0 = chunk0; dp.ldn = pb.ldn; dp.tiles = tiles_dev; dp.eps_floor = eps_floor;
   dp.mirror = 1; dp.kl_swap = 0;
+  dp.tile_flags = nullptr; dp.tile_flag_stride = ntiles; dp.dense_thresh = 0x7fffffff; dp.dense_list = nullptr; dp.dense_count = nullptr;
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
   const bool on_grid = metric >= SEQJ_EMD_GRID;        // EMD / Energy on the explicit grid: pre-scaled operands
   if (on_grid) metric = (metric == SEQJ_EMD_GRID) ? SEQJ_EMD : SEQJ_ENERGY;
@@ -411,8 +434,8 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   if (metric == SEQJ_EMD) {
     CUtensorMap tmU;
     ST_TRY(make_tmap(h, &tmU, on_grid ? pb.UwE : pb.Uc, L.ldX, pb.rows_pad));
-    dp.normA = nullptr; dp.tau = 0;
-    emd_dist_kernel<<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmU, dp);
+    dp.normA = nullptr; dp.tau = 0; dp.tile_flags = nullptr; dp.dense_list = nullptr; dp.dense_count = nullptr;
+    direct_dist_kernel<OP_L1><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmU, dp);
     c.launches++;
     CU_TRY(cudaGetLastError());
     c.timer.end(t);
@@ -421,6 +444,13 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
   CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
   CUtensorMap tmA, tmB;
+  // dense-tile path (L2 / Energy with mirrored output): tiles with > 1/32 of their entries flagged
+  const bool dense_ok = (metric == SEQJ_L2 || metric == SEQJ_ENERGY || (metric == SEQJ_KLD && !kl_full)) && fb.tile_flags &&
+                        (size_t)nb * ntiles <= fb.tile_flags_bytes && !(getenv("SEQJ_DENSE_TILES") && atoi(getenv("SEQJ_DENSE_TILES")) == 0);
+  if (dense_ok) {
+    CU_TRY(cudaMemsetAsync(fb.tile_flags, 0, (size_t)nb * ntiles, c.st));
+    dp.tile_flags = fb.tile_flags; dp.dense_thresh = kTileM * kTileN / 32;
+  }
   FixParams fp;
   fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
   fp.chunk0 = chunk0; fp.m_of_chunk = pb.m_of_chunk; fp.eps_floor = eps_floor; fp.mirror = 1; fp.kl_swap = 0;
@@ -449,6 +479,8 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
   fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, nb);
   c.launches += 2;
+  if (dense_ok)              // whole tiles full of cancelling entries: recompute them without the Gram form
+    ST_TRY(run_dense_tiles(c, metric, dp, tmA, metric == SEQJ_KLD ? tmB : tmA, fb, ntiles, nb));
   CU_TRY(cudaGetLastError());
   c.timer.end(t);
   return SEQJ_OK;
@@ -464,7 +496,7 @@ struct FineVecs {
 // chunk matrices [c0, c1) of a coarse (metric, scale) group derived from the finished fine matrices
 int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const FineVecs& fv, const double* Dfine,
                int N, double* D, int64_t ldD, int64_t strideD, int c0, int c1, double eps_floor, double l2_thresh,
-               FixBufs& fb) {
+               FixBufs& fb, const int2* tiles_dev, int ntiles, const int* tile_col_offset) {
   seqj_handle* h = c.h;
   int t = c.timer.begin(SEQJ_T_DERIVE);
   CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
@@ -476,6 +508,10 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
   dp.eps_floor = eps_floor;
   dp.tau = (metric == SEQJ_L2) ? std::max(kTauGram, l2_thresh) : (metric == SEQJ_KLD ? kTauKL : kTauGram);
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  const bool dense_ok = fb.tile_flags && tile_col_offset && (size_t)(c1 - c0) * ntiles <= fb.tile_flags_bytes &&
+                        !(getenv("SEQJ_DENSE_TILES") && atoi(getenv("SEQJ_DENSE_TILES")) == 0);
+  dp.tile_flags = dense_ok ? fb.tile_flags : nullptr; dp.tile_flag_stride = ntiles; dp.tile_col_offset = tile_col_offset;
+  if (dense_ok) CU_TRY(cudaMemsetAsync(fb.tile_flags, 0, (size_t)(c1 - c0) * ntiles, c.st));
   const int T = (N + 31) / 32;
   CU_TRY(cudaFuncSetAttribute(derive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDeriveMaxFine * 2048));
   dp.ratio = ratio; dp.nfine = fv.nchunks; dp.c_first = c0; dp.f0 = 0; dp.nf = 0; dp.chunk_local = 0;
@@ -493,6 +529,24 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
   fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
   fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, c1 - c0);
   c.launches += 2;
+  if (dense_ok) {            // tiles full of near-duplicate pairs: recompute them directly from the coarse operands
+    DistParams dd;
+    dd.N = N; dd.ldD = ldD; dd.strideD = strideD; dd.D = D; dd.nk = L.cl_pad / kTileK; dd.cl_pad = L.cl_pad;
+    dd.chunk0 = c0; dd.normA = nullptr; dd.ldn = pb.ldn; dd.tiles = tiles_dev; dd.eps_floor = eps_floor; dd.tau = 0;
+    dd.mirror = 1; dd.kl_swap = 0; dd.tile_flags = fb.tile_flags; dd.tile_flag_stride = ntiles; dd.dense_thresh = 0;
+    dd.dense_list = nullptr; dd.dense_count = nullptr; dd.sm_slots = nullptr;
+    dd.fix_list = fb.list; dd.fix_count = fb.count; dd.fix_cap = fb.cap; dd.fix_overflow = fb.overflow;
+    CUtensorMap tm1, tm2;
+    if (metric == SEQJ_ENERGY) {
+      ST_TRY(make_tmap(h, &tm1, pb.Uc, L.ldX, pb.rows_pad));
+      tm2 = tm1;
+    } else {
+      ST_TRY(make_tmap(h, &tm1, pb.P, L.ldX, pb.rows_pad));
+      if (metric == SEQJ_KLD) ST_TRY(make_tmap(h, &tm2, pb.logP, L.ldX, pb.rows_pad));
+      else tm2 = tm1;
+    }
+    ST_TRY(run_dense_tiles(c, metric, dd, tm1, tm2, fb, ntiles, c1 - c0));
+  }
   CU_TRY(cudaGetLastError());
   c.timer.end(t);
   return SEQJ_OK;
@@ -502,7 +556,10 @@ int set_kernel_attrs(seqj_handle* h) {
   CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(emd_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(kl_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes));
   return SEQJ_OK;
 }
 
@@ -526,9 +583,15 @@ int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, boo
   return SEQJ_OK;
 }
 
-int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap) {
+int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap, size_t tile_flags_bytes = 0) {
   seqj_handle* h = c.h;
   fb.cap = cap;
+  fb.tile_flags_bytes = tile_flags_bytes;
+  if (tile_flags_bytes) {
+    CU_TRY(c.pool.alloc(&fb.tile_flags, tile_flags_bytes));
+    CU_TRY(c.pool.alloc(&fb.dense_list, tile_flags_bytes));
+    CU_TRY(c.pool.alloc(&fb.dense_count, 1));
+  }
   CU_TRY(c.pool.alloc(&fb.list, (size_t)cap));
   CU_TRY(c.pool.alloc(&fb.count, 1));
   CU_TRY(c.pool.alloc(&fb.overflow, 1));
@@ -842,11 +905,18 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c.st));
   }
   FixBufs fb;
-  ST_TRY(alloc_fix(c, fb, 1u << 24));     // 16M flagged entries (256 MB) before the dense fallback kicks in
   std::vector<int2> tiles = make_tiles(N, true);
+  ST_TRY(alloc_fix(c, fb, 1u << 24, (size_t)max_chunks * tiles.size()));     // 16M flagged entries (256 MB) in the list
   int2* tiles_dev;
   CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
   CU_TRY(cudaMemcpyAsync(tiles_dev, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c.st));
+  // first tile of every 128-column block (the derive kernel maps its 32 x 32 blocks onto the tile list with it)
+  std::vector<int> col_off((N + kTileN - 1) / kTileN + 1, 0);
+  for (size_t q = 0; q < tiles.size(); ++q)
+    if (tiles[q].x == 0) col_off[tiles[q].y / kTileN] = (int)q;
+  int* col_off_dev;
+  CU_TRY(c.pool.alloc(&col_off_dev, col_off.size()));
+  CU_TRY(cudaMemcpyAsync(col_off_dev, col_off.data(), col_off.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
 
   // ---- static schedule --------------------------------------------------------------------
   // Processing order is scale-major (one prep per scale), metric inside, chunk innermost.  Chunk
@@ -1026,7 +1096,8 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       const bool whole = (sg.c0 == 0 && sg.c1 == L.nchunks);
       if (derivable[gidx] && whole && last_scale[sg.k] == src_of[gidx] && fv_scale == src_of[gidx] && last_slot0[sg.k] >= 0) {
         ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Dw + (size_t)last_slot0[sg.k] * mat_elems, N,
-                          Dw + (size_t)sg.slot0 * mat_elems, ldD, (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb));
+                          Dw + (size_t)sg.slot0 * mat_elems, ldD, (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb,
+                          tiles_dev, (int)tiles.size(), col_off_dev));
         last_slot0[sg.k] = sg.slot0; last_scale[sg.k] = sg.l;
         n_derived_done++;
         continue;

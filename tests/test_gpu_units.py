@@ -111,6 +111,27 @@ def test_pairwise_smooth_ordered_family(seqj, oracle, handle, metric):
     rel_close(got, ref, 1e-9, atol=4 * m * 2.0 ** -53)
 
 
+@pytest.mark.parametrize("metric", [0, 2, 3])
+def test_dense_near_duplicate_tiles(seqj, oracle, handle, metric):
+    """Whole tiles of near-duplicate objects (500 perturbed copies of one profile + 200 unrelated objects): the
+    DMMA epilogue flags more than 1/32 of such tiles, which are then recomputed by the direct tile kernels
+    (sum (a-b)^2, sum p (log p - log q)) instead of entry by entry.  Same 1e-9 bar against the direct formulas."""
+    rng = np.random.default_rng(77)
+    m, n_dup, n_rand = 64, 500, 200
+    base = rng.random((m, 1)) + 0.2
+    A = np.concatenate([base * (1.0 + 1e-6 * rng.standard_normal((m, n_dup))), rng.random((m, n_rand)) + 0.05], axis=1)
+    A = oracle.clamp_input(A[:, rng.permutation(n_dup + n_rand)])
+    P = oracle.splitnorm(A, 1)[0]
+    if metric == 0:
+        ref = np.sqrt(((P[:, :, None] - P[:, None, :]) ** 2).sum(axis=0)) + 1e-6
+    else:
+        ref = oracle.chunk_distance(metric, P)
+    got = seqj.pairwise(metric, A, kl_full=False)
+    if metric == 2:
+        ref = np.triu(ref) + np.triu(ref, 1).T           # mirrored upper triangle (what the pipeline consumes)
+    rel_close(got, ref, 1e-9, atol=4 * m * 2.0 ** -53)
+
+
 def test_pairwise_algotests_known_answers(seqj, handle):
     """reference test/algotests.jl:6-25 (Euclidean sqrt(14); KL 0.5108256237659907)."""
     A = np.array([[1.0, 2.0], [1.0, 3.0], [1.0, 4.0]])
