@@ -49,16 +49,44 @@ __device__ __forceinline__ ulonglong2 ldg_stream_u64x2(const double* p) {
   return v;
 }
 
-// Lexicographic warp argmin of (64-bit key, 32-bit index) with three REDUX.MIN.U32 instead of
-// fifteen shuffles and FP64 compares.
-__device__ __forceinline__ void warp_argmin_u64(unsigned long long& k, int& v) {
+// Edge order of the reference's Kruskal: stable sort by weight of the upper-triangle edges enumerated in
+// column-major order (LightGraphs.kruskal_mst over SimpleWeightedGraph), i.e. the strict total order
+// (weight, max(u,v), min(u,v)).  The MST under a strict total order is unique, so Prim with the same order
+// returns exactly Kruskal's tree even when weights tie (duplicate objects, integer data).
+constexpr unsigned long long kPrimNone = ~0ull - 1ull;    // "no candidate": above every real key - 1, below (0 - 1)
+
+__device__ __forceinline__ bool edge_less(int v1, int f1, int v2, int f2) {      // weights equal
+  const int h1 = max(v1, f1), h2 = max(v2, f2);
+  return h1 < h2 || (h1 == h2 && min(v1, f1) < min(v2, f2));
+}
+
+// Warp argmin of candidates (key = weight bits - 1, v = vertex outside the tree) under that order.  The fast path is
+// three REDUX.MIN.U32 (key high word, key low word, vertex) plus a vote that detects weight ties; only then (rare) the
+// tied lanes fetch the tree endpoint of their candidate through `getf` and two more reductions order them by
+// (max, min) of the endpoints.
+struct NoHook { __device__ __forceinline__ void operator()() const {} };
+
+// `pre` / `post` bracket the tie path (the cluster-level reduction fences its remote reads with them).
+template <class F, class Pre = NoHook, class Post = NoHook>
+__device__ __forceinline__ void warp_argmin_edge(unsigned long long& k, int& v, F getf, Pre pre = Pre(), Post post = Post()) {
   const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
   const unsigned mhi = __reduce_min_sync(0xffffffffu, hi);
   const unsigned mlo = __reduce_min_sync(0xffffffffu, hi == mhi ? lo : 0xffffffffu);
   const bool win = (hi == mhi) && (lo == mlo);
-  const unsigned mv = __reduce_min_sync(0xffffffffu, win ? (unsigned)v : 0x7fffffffu);
+  const unsigned m = __ballot_sync(0xffffffffu, win);
+  int mv = (int)__reduce_min_sync(0xffffffffu, win ? (unsigned)v : 0xffffffffu);
+  if (__popc(m) > 1) {
+    pre();
+    const int f = (win && v != 0x7fffffff) ? getf(v) : 0x7fffffff;
+    const unsigned eh = win ? (unsigned)max(v, f) : 0xffffffffu;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, eh);
+    const unsigned el = (win && eh == mh) ? (unsigned)min(v, f) : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, el);
+    mv = __shfl_sync(0xffffffffu, v, __ffs(__ballot_sync(0xffffffffu, win && eh == mh && el == ml)) - 1);
+    post();
+  }
+  v = mv;
   k = ((unsigned long long)mhi << 32) | mlo;
-  v = (int)mv;
 }
 
 // Dense Prim, one CTA per graph (reference _mst, src/sequencer.jl:358-374).
@@ -104,8 +132,8 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   int u = 0, par = 0;
   for (int step = 1; step < N; ++step) {
     const double* __restrict__ row = D + (int64_t)u * p.ldD;
-    unsigned long long bk = ~0ull;
-    int bv = 0x7fffffff;
+    unsigned long long bk = kPrimNone;
+    int bv = 0x7fffffff, bl = 0x7fffffff;
     for (int base = 2 * tid; base < N; base += 2 * kPrimThreads * U) {
       ulonglong2 dv[U];
 #pragma unroll
@@ -118,24 +146,41 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
         const int v = base + r * 2 * kPrimThreads;
         if (v < N) {
           ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
-          const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
-          const bool u0 = d0 < k2.x, u1 = d1 < k2.y;
-          if (u0) { k2.x = d0; from[v] = u; }
-          if (u1) { k2.y = d1; from[v + 1] = u; }
-          if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
-          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;
+          if (dv[r].x <= k2.x || dv[r].y <= k2.y) {
+            // Relaxation candidates: rare after the first steps, so everything careful lives in this branch -- the
+            // eps clamp (keys are clamped values, so a clamped weight can only relax a key if the raw one passes the
+            // test above) and the tie rule: at equal weight the edge that comes first in Kruskal's order wins.
+            const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
+            const bool u0 = k2.x != 0ull && (d0 < k2.x || (d0 == k2.x && edge_less(v, u, v, from[v])));
+            const bool u1 = k2.y != 0ull && (d1 < k2.y || (d1 == k2.y && edge_less(v + 1, u, v + 1, from[v + 1])));
+            if (u0) { k2.x = d0; from[v] = u; }
+            if (u1) { k2.y = d1; from[v + 1] = u; }
+            if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
+          }
+          // bv = first, bl = last of this thread's vertices at its minimum key: bv != bl flags a tie
+          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;   // in-tree: ~0 > kPrimNone, never a candidate
           if (c0 < bk) { bk = c0; bv = v; }
+          if (c0 <= bk) bl = v;
           if (c1 < bk) { bk = c1; bv = v + 1; }
+          if (c1 <= bk) bl = v + 1;
         }
       }
       if (R > 0) break;
     }
-    warp_argmin_u64(bk, bv);
+    if (bl != bv) {                                        // rare: order the tied candidates like Kruskal
+      for (int base = 2 * tid; base < N; base += 2 * kPrimThreads) {
+        const ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + base);
+        if (k2.x - 1ull == bk && base != bv && edge_less(base, from[base], bv, from[bv])) bv = base;
+        if (k2.y - 1ull == bk && base + 1 != bv && edge_less(base + 1, from[base + 1], bv, from[bv])) bv = base + 1;
+      }
+    }
+    auto getf = [&](int v) { return from[v]; };
+    warp_argmin_edge(bk, bv, getf);
     if (lane == 0) { rk[par][warp] = bk; rv[par][warp] = bv; }
     __syncthreads();
     bk = rk[par][lane];
     bv = rv[par][lane];
-    warp_argmin_u64(bk, bv);
+    warp_argmin_edge(bk, bv, getf);
     u = bv;
     if (((u >> 1) & (kPrimThreads - 1)) == tid) {       // the owner of key[u] retires it
       order[step] = u;
@@ -172,13 +217,20 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+__device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_async_u64x2(uint32_t dst, unsigned long long a, unsigned long long b, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
                ::"r"(dst), "l"(a), "l"(b), "r"(mbar) : "memory");
 }
 
 template <int C>
-__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 5) prim_cluster_kernel(PrimParams p, int W) {
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 4)
+prim_cluster_kernel(PrimParams p, int W) {
+  constexpr int kU = kPrimClUnroll;
   extern __shared__ unsigned long long primc_sm[];
   __shared__ __align__(16) ulonglong2 cand[2][C];
   __shared__ __align__(8) uint64_t mbar[2];
@@ -214,42 +266,58 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 5) p
 
   const uint32_t cand_u32 = smem_u32(&cand[0][0]);
   const uint32_t mbar_u32 = smem_u32(&mbar[0]);
+  const uint32_t from_u32 = smem_u32(from);
   int u = 0;
   for (int step = 1; step < N; ++step) {
     const int par = step & 1;
     const double* __restrict__ row = D + (int64_t)u * p.ldD + v0;
-    unsigned long long bk = ~0ull;
-    int bv = 0x7fffffff;
-    for (int base = 2 * tid; base < Wn; base += 2 * kPrimClThreads * kPrimClUnroll) {
-      ulonglong2 dv[kPrimClUnroll];
+    unsigned long long bk = kPrimNone;
+    int bv = 0x7fffffff, bl = 0x7fffffff;
+    for (int base = 2 * tid; base < Wn; base += 2 * kPrimClThreads * kU) {
+      ulonglong2 dv[kU];
 #pragma unroll
-      for (int r = 0; r < kPrimClUnroll; ++r) {
+      for (int r = 0; r < kU; ++r) {
         const int v = base + r * 2 * kPrimClThreads;
         if (v < Wn) dv[r] = ldg_stream_u64x2(row + v);
       }
 #pragma unroll
-      for (int r = 0; r < kPrimClUnroll; ++r) {
+      for (int r = 0; r < kU; ++r) {
         const int v = base + r * 2 * kPrimClThreads;
         if (v < Wn) {
           ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
-          const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
-          const bool u0 = d0 < k2.x, u1 = d1 < k2.y;
-          if (u0) { k2.x = d0; from[v] = u; }
-          if (u1) { k2.y = d1; from[v + 1] = u; }
-          if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
-          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;
-          if (c0 < bk) { bk = c0; bv = v0 + v; }
-          if (c1 < bk) { bk = c1; bv = v0 + v + 1; }
+          const int gv = v0 + v;                                         // global vertex id
+          if (dv[r].x <= k2.x || dv[r].y <= k2.y) {                      // rare: clamp + tie rule as in prim_kernel
+            const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
+            const bool u0 = k2.x != 0ull && (d0 < k2.x || (d0 == k2.x && edge_less(gv, u, gv, from[v])));
+            const bool u1 = k2.y != 0ull && (d1 < k2.y || (d1 == k2.y && edge_less(gv + 1, u, gv + 1, from[v + 1])));
+            if (u0) { k2.x = d0; from[v] = u; }
+            if (u1) { k2.y = d1; from[v + 1] = u; }
+            if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
+          }
+          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;   // in-tree: ~0 > kPrimNone, never a candidate
+          if (c0 < bk) { bk = c0; bv = gv; }
+          if (c0 <= bk) bl = gv;
+          if (c1 < bk) { bk = c1; bv = gv + 1; }
+          if (c1 <= bk) bl = gv + 1;
         }
       }
     }
-    warp_argmin_u64(bk, bv);
+    if (bl != bv) {                                        // rare: two of this thread's candidates tie at its minimum
+      for (int v = 2 * tid; v < Wn; v += 2 * kPrimClThreads) {
+        const ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
+        const int gv = v0 + v;
+        if (k2.x - 1ull == bk && gv != bv && edge_less(gv, from[v], bv, from[bv - v0])) bv = gv;
+        if (k2.y - 1ull == bk && gv + 1 != bv && edge_less(gv + 1, from[v + 1], bv, from[bv - v0])) bv = gv + 1;
+      }
+    }
+    auto getf = [&](int v) { return from[v - v0]; };
+    warp_argmin_edge(bk, bv, getf);
     if (lane == 0) { wk[warp] = bk; wv[warp] = bv; }
     __syncthreads();
     if (warp == 0) {
-      bk = (lane < kPrimClThreads / 32) ? wk[lane] : ~0ull;
+      bk = (lane < kPrimClThreads / 32) ? wk[lane] : kPrimNone;
       bv = (lane < kPrimClThreads / 32) ? wv[lane] : 0x7fffffff;
-      warp_argmin_u64(bk, bv);
+      warp_argmin_edge(bk, bv, getf);
       if (lane == 0) mbar_expect_tx(&mbar[par], C * 16);
       if (lane < C) {                                  // lane j delivers this CTA's candidate to CTA j
         const uint32_t dst = mapa_u32(cand_u32 + (uint32_t)((par * C + (int)rank) * 16), (uint32_t)lane);
@@ -259,10 +327,18 @@ __global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 5) p
     }
     mbar_wait(&mbar[par], (uint32_t)(((step - 1) >> 1) & 1));   // k-th use of this barrier -> phase parity k & 1
     {
-      const ulonglong2 cnd = (lane < C) ? cand[par][lane] : make_ulonglong2(~0ull, 0x7fffffffull);
+      // Every warp of every CTA reduces the same C candidates, so all of them take the tie path together: it may
+      // therefore use cluster barriers.  The tied candidates' tree endpoints live in their owners' shared memory;
+      // the barriers keep every owner from relaxing (rewriting from[]) until all readers are done.
+      const ulonglong2 cnd = (lane < C) ? cand[par][lane] : make_ulonglong2(kPrimNone, 0x7fffffffull);
       bk = cnd.x;
-      bv = (int)cnd.y;
-      warp_argmin_u64(bk, bv);
+      bv = (int)(unsigned)cnd.y;
+      auto getf_remote = [&](int v) {
+        const int owner = v / W;
+        return (int)ld_dsmem_u32(mapa_u32(from_u32 + (uint32_t)((v - owner * W) * 4), (uint32_t)owner));
+      };
+      auto fence = [&]() { cluster_sync_all(); };
+      warp_argmin_edge(bk, bv, getf_remote, fence, fence);
     }
     u = bv;
     const int ul = u - v0;
@@ -619,8 +695,9 @@ __global__ void gather_edges_kernel(const double* __restrict__ D, int64_t ldD, c
 // The final distance matrix D = inv.(Pw) (reference src/sequencer.jl:269) is +Inf outside the union of the
 // group MSTs, i.e. a sparse graph with at most G*(N-1) edges.  Kruskal over the dense N x N matrix (reference)
 // or a dense Prim (N latency-bound steps) is wasteful here: Boruvka on the edge list needs O(log N) fully
-// parallel rounds.  Edges are totally ordered by (weight, edge index), so the result is the unique MST and
-// the only hooking cycles are mutual pairs, broken by component id.
+// parallel rounds.  Edges are totally ordered by (weight, max(i,j), min(i,j)) -- the order Kruskal visits them in
+// the reference -- so the result is the unique MST under that order (= the reference's tree even with tied
+// weights) and the only hooking cycles are mutual pairs, broken by component id.
 // One CTA; edge e = (g, k) lives at mi/mj/val[g*ldp + k].
 struct BoruvkaParams {
   int N, G;
@@ -631,7 +708,7 @@ struct BoruvkaParams {
   double eps_floor;
   int* comp;                // scratch [N]
   unsigned long long* best; // scratch [N]
-  int* besti;               // scratch [N]
+  unsigned long long* bestp; // scratch [N]: (max(i,j) << 32 | min(i,j)) of the chosen edge
   int* out_i;               // MST edges [N-1]
   int* out_j;
   double* out_w;
@@ -650,7 +727,7 @@ __global__ void __launch_bounds__(kBoruvkaThreads, 1) boruvka_sparse_kernel(Boru
   if (tid == 0) { *p.out_count = 0; s_ncomp = N; }
   __syncthreads();
   for (int round = 0; round < 64 && s_ncomp > 1; ++round) {
-    for (int v = tid; v < N; v += kBoruvkaThreads) { p.best[v] = ~0ull; p.besti[v] = 0x7fffffff; }
+    for (int v = tid; v < N; v += kBoruvkaThreads) { p.best[v] = ~0ull; p.bestp[v] = ~0ull; }
     __syncthreads();
     // 1. lightest crossing edge weight of every component
     for (long long e = tid; e < E; e += kBoruvkaThreads) {
@@ -663,39 +740,40 @@ __global__ void __launch_bounds__(kBoruvkaThreads, 1) boruvka_sparse_kernel(Boru
       }
     }
     __syncthreads();
-    // 2. among those, the smallest edge index
+    // 2. among those, the first vertex pair in Kruskal's order
     for (long long e = tid; e < E; e += kBoruvkaThreads) {
       const int64_t a = (e / ne) * p.ldp + (e % ne);
       const int ci = p.comp[p.mi[a]], cj = p.comp[p.mj[a]];
       if (ci != cj) {
         const unsigned long long w = max((unsigned long long)__double_as_longlong(p.val[a]), eps_bits);
-        if (w == p.best[ci]) atomicMin(&p.besti[ci], (int)e);
-        if (w == p.best[cj]) atomicMin(&p.besti[cj], (int)e);
+        const int i = p.mi[a], j = p.mj[a];
+        const unsigned long long pr = ((unsigned long long)(unsigned)max(i, j) << 32) | (unsigned)min(i, j);
+        if (w == p.best[ci]) atomicMin(&p.bestp[ci], pr);
+        if (w == p.best[cj]) atomicMin(&p.bestp[cj], pr);
       }
     }
     __syncthreads();
     // 3. hook every component root onto the other side of its edge; a mutual pair keeps the smaller id as root
     for (int c = tid; c < N; c += kBoruvkaThreads) {
       if (p.comp[c] != c) continue;
-      const int e = p.besti[c];
-      if (e == 0x7fffffff) continue;                      // isolated component (disconnected input)
-      const int64_t a = ((long long)e / ne) * p.ldp + ((long long)e % ne);
-      const int i = p.mi[a], j = p.mj[a];
+      const unsigned long long pr = p.bestp[c];
+      if (pr == ~0ull) continue;                          // isolated component (disconnected input)
+      const int i = (int)(unsigned)(pr & 0xffffffffull), j = (int)(unsigned)(pr >> 32);
       const int ci = p.comp[i], cj = p.comp[j];
       const int other = (ci == c) ? cj : ci;
-      const bool mutual = (p.besti[other] == e);
+      const bool mutual = (p.bestp[other] == pr);
       if (mutual && c < other) continue;                  // `other` hooks onto c and records the edge
       const int k = atomicAdd(p.out_count, 1);
-      p.out_i[k] = min(i, j);
-      p.out_j[k] = max(i, j);
+      p.out_i[k] = i;
+      p.out_j[k] = j;
       p.out_w[k] = __longlong_as_double((long long)p.best[c]);
-      // besti[] is read by other components' mutual test in this step, so only this component's own best[c] is
+      // bestp[] is read by other components' mutual test in this step, so only this component's own best[c] is
       // reused: bit 63 (never set in a finite weight) marks "hooked", the low word is the hook target
       p.best[c] = (1ull << 63) | (unsigned long long)(unsigned)other;
     }
     __syncthreads();
     for (int c = tid; c < N; c += kBoruvkaThreads)
-      if (p.comp[c] == c && p.besti[c] != 0x7fffffff && (p.best[c] >> 63)) p.comp[c] = (int)(p.best[c] & 0xffffffffull);
+      if (p.comp[c] == c && p.bestp[c] != ~0ull && (p.best[c] >> 63)) p.comp[c] = (int)(p.best[c] & 0xffffffffull);
     __syncthreads();
     // 4. pointer jumping until every vertex points at its root
     for (int it = 0; it < 32; ++it) {

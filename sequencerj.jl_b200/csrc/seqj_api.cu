@@ -217,11 +217,19 @@ struct GraphWS {
   double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
   int prim_R = 0;
   int *fuse_i0 = nullptr, *fuse_i1 = nullptr;   // scratch of the sparse final MST (root_tree_kernel)
-  int cluster = 0, cl_W = 0;      // cluster Prim: CTAs per graph (0 = single-CTA kernel), slice width
-  size_t cl_smem = 0;
+  int cluster = 0;                // cluster Prim available (N large enough, slices fit in shared memory)
   int tree_use_smem = 1;
   size_t tree_smem = 0;
 };
+
+constexpr int kPrimCluster = 8;     // CTAs per graph; 2 and 4 measured slower at every graph count (profiles/r01_prim_variants.md)
+
+// Slice width and dynamic shared memory of a C-CTA cluster Prim over N vertices.
+void prim_cluster_geometry(int N, int C, int* W_out, size_t* smem_out) {
+  const int W = (int)round_up((N + C - 1) / C, 2);
+  if (W_out) *W_out = W;
+  if (smem_out) *smem_out = (size_t)((W + 1) & ~1) * 8 + (size_t)W * 4 + 16;
+}
 
 typedef void (*PrimFn)(PrimParams);
 PrimFn prim_fn(int R) {
@@ -288,14 +296,15 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   CU_TRY(cudaFuncSetAttribute(prim_fn(g.prim_R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
   // cluster Prim for graphs large enough that one SM's load rate / argmin latency is the limit
   const char* force = getenv("SEQJ_PRIM");
-  g.cluster = (N >= 1024) ? 8 : 0;
+  g.cluster = (N >= 1024) ? 1 : 0;
   if (force && !strcmp(force, "single")) g.cluster = 0;
-  if (force && !strcmp(force, "cluster")) g.cluster = 8;
   if (g.cluster) {
-    g.cl_W = (int)round_up((N + g.cluster - 1) / g.cluster, 2);
-    g.cl_smem = (size_t)((g.cl_W + 1) & ~1) * 8 + (size_t)g.cl_W * 4 + 16;
-    if (g.cl_smem + 4096 > h->max_smem) g.cluster = 0;
-    else CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.cl_smem));
+    size_t smem2 = 0;
+    prim_cluster_geometry(N, kPrimCluster, nullptr, &smem2);
+    if (smem2 + 4096 > h->max_smem) g.cluster = 0;
+    else {
+      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    }
   }
   g.tree_smem = (size_t)N * 8;
   g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
@@ -319,10 +328,14 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
   // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.
   const bool force_cluster = getenv("SEQJ_PRIM") && !strcmp(getenv("SEQJ_PRIM"), "cluster");
-  if (g.cluster && (force_cluster || nb * 3 <= h->sm_count))
-    prim_cluster_kernel<8><<<nb * g.cluster, kPrimClThreads, g.cl_smem, c.st>>>(pp, g.cl_W);
-  else
+  if (g.cluster && (force_cluster || nb * 3 <= h->sm_count)) {
+    int W = 0;
+    size_t smem = 0;
+    prim_cluster_geometry(g.N, kPrimCluster, &W, &smem);
+    prim_cluster_kernel<kPrimCluster><<<nb * kPrimCluster, kPrimClThreads, smem, c.st>>>(pp, W);
+  } else {
     prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
+  }
   c.timer.end(t); c.launches++;
   CU_TRY(cudaGetLastError());
   TreeParams tp;
@@ -628,7 +641,7 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
   {
     BoruvkaParams bp;
     bp.N = N; bp.G = G; bp.ldp = ldp; bp.mi = mst_i; bp.mj = mst_j; bp.val = edge_val; bp.eps_floor = eps_floor;
-    bp.comp = gws.anc0; bp.best = reinterpret_cast<unsigned long long*>(gws.wd); bp.besti = gws.anc1;
+    bp.comp = gws.anc0; bp.best = reinterpret_cast<unsigned long long*>(gws.wd); bp.bestp = reinterpret_cast<unsigned long long*>(gws.wd2);
     bp.out_i = gws.dep0; bp.out_j = gws.dep1; bp.out_w = gws.S; bp.out_count = gws.size;
     boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
     RootTreeParams rp;

@@ -44,6 +44,40 @@ def test_config1_readme_example(seqj, oracle, handle):
     assert len(r.EOSeg[(seqj.WASS1D, 4)][0]) == 4
 
 
+def _tree_edges(parents, root):
+    return {(min(v, int(p)), max(v, int(p))) for v, p in enumerate(parents) if v != root}
+
+
+def test_duplicate_objects_tie_break_like_kruskal(seqj, oracle, handle):
+    """Exact duplicate objects: their mutual distances collapse to the 1e-6 offset and every distance to a third
+    object ties, in every chunk, every group and the final graph.  The reference's Kruskal resolves ties by the
+    column-major position of the edge; Prim (chunks, groups) and Boruvka (final graph) use the same total order, so
+    every MST is the reference's tree, not merely one of equal weight.  EMD only: its per-pair arithmetic does not
+    depend on where the pair sits in the matrix, on either side of the comparison.
+    Roots are NOT compared: duplicates that hang off the same vertex have mathematically equal closeness, and which
+    one wins the argmin depends on the rounding of the distance sums (Dijkstra order in the reference, rerooting
+    identity here).  The elongation is the same from either of the symmetric roots."""
+    rng = np.random.default_rng(77)
+    base = rng.random((64, 40))
+    A = np.concatenate([base, base, base], axis=1)[:, rng.permutation(120)]
+    r = seqj.sequence(A.copy(), scales=(1, 2, 4), metrics=(seqj.WASS1D,))
+    ref = oracle.sequence_oracle(A, (1, 2, 4), (1,))
+    for g in ref.groups:
+        key = (seqj.WASS1D, g.scale)
+        etas, trees = r.EOSeg[key]
+        rel_close(etas, g.eta_chunk, 1e-9)
+        for t, par, root in zip(trees, g.parents_chunk, g.root_chunk):
+            assert _tree_edges(t.parents, t.root) == _tree_edges(par, root)
+        mst = r.group_msts[key]
+        assert set(zip(mst.src.tolist(), mst.dst.tolist())) == set(zip(g.mst[0].tolist(), g.mst[1].tolist()))
+        rel_close([r.EOAlgScale[key][0]], [g.eta], 1e-9)
+    assert _tree_edges(r.parents, r.root) == _tree_edges(ref.parents, ref.root)
+    rel_close([r.eta], [ref.eta], 1e-9)
+    assert sorted(r.order.tolist()) == list(range(120))
+    r = seqj.sequence(A.copy(), scales=(1, 2), metrics=seqj.ALL_METRICS)   # other metrics: still a valid permutation
+    assert sorted(r.order.tolist()) == list(range(120))
+
+
 def test_ragged_chunks_and_scale_not_dividing(seqj, oracle, handle):
     A = np.random.default_rng(5).random((53, 70))
     _compare(seqj, oracle, A, (3, 6, 7), (0, 1, 2, 3))

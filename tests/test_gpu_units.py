@@ -179,6 +179,34 @@ def test_measure_dm_matches_oracle(seqj, oracle, handle, N):
     assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
 
 
+@pytest.mark.parametrize("N,levels", [(7, 2), (64, 3), (300, 4), (1031, 3), (2500, 5), (4099, 2)])
+def test_measure_dm_tied_weights_follow_kruskal_order(seqj, oracle, handle, N, levels):
+    """Heavily tied weights (a handful of distinct integer values): the reference's Kruskal visits equal-weight
+    edges in column-major order of the upper triangle; the device MST uses the same strict total order, so
+    the tree -- not only its weight -- is the reference's."""
+    rng = np.random.default_rng(N + levels)
+    Dm = rng.integers(1, levels + 1, size=(N, N)).astype(np.float64)
+    Dm = np.triu(Dm, 1); Dm = Dm + Dm.T
+    ref = oracle.measure_dm(Dm)
+    got = seqj.measure_dm(Dm, want_order=True)
+    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+    assert got.root == ref.root
+    assert got.eta == ref.eta
+    assert np.array_equal(got.bfs.parents, ref.parents)
+    assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
+
+
+def test_measure_dm_all_equal_weights(seqj, oracle, handle):
+    """Every edge ties (duplicate objects: all distances collapse to the 1e-6 offset)."""
+    N = 200
+    Dm = np.full((N, N), 1e-6); np.fill_diagonal(Dm, 0.0)
+    ref = oracle.measure_dm(Dm)
+    got = seqj.measure_dm(Dm)
+    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+    assert got.root == ref.root and got.eta == ref.eta
+    assert np.array_equal(got.bfs.parents, ref.parents)
+
+
 def test_measure_dm_upper_triangle_wins_and_inf_nonedges(seqj, oracle, handle):
     rng = np.random.default_rng(3)
     N = 60
