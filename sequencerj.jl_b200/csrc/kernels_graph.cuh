@@ -643,6 +643,70 @@ __global__ void __launch_bounds__(256) combine_kernel(double* __restrict__ S, co
   }
 }
 
+// Same accumulation for the pipeline, where every chunk matrix is symmetric bit for bit (the distance, derive and
+// fix-up kernels store each value and its mirror image): only the upper-triangle 64 x 64 tiles are read and
+// accumulated, the lower ones are written as their transposes through shared memory.  HBM traffic per entry pair
+// drops from 2*8*(nb + 1 [+1]) to 8*(nb + 2 [+1]) bytes, i.e. nearly half.  Grid (T, T), T = ceil(N / 64); the
+// CTAs below the diagonal exit at once.
+constexpr int kCombineTile = 64;
+__global__ void __launch_bounds__(256) combine_sym_kernel(double* __restrict__ S, int64_t ldD, int N,
+                                                          const double* __restrict__ Db, int64_t strideD, int nb,
+                                                          const double* __restrict__ eta_b, int first, int last,
+                                                          const double* __restrict__ eta_all, int n_all) {
+  const int bi = blockIdx.y, bj = blockIdx.x;
+  if (bi > bj) return;
+  __shared__ double e[kCombineMax];
+  __shared__ double s_tot;
+  __shared__ double tile[kCombineTile][kCombineTile + 1];
+  if (threadIdx.x < kCombineMax) e[threadIdx.x] = (threadIdx.x < nb) ? eta_b[threadIdx.x] : 0.0;
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    if (last)
+      for (int c = 0; c < n_all; ++c) tot += eta_all[c];
+    s_tot = tot;
+  }
+  __syncthreads();
+  const double tot = s_tot;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = bj * kCombineTile + 2 * tx;                     // even; j + 1 < ldD (ldD is even and >= N)
+#pragma unroll 1
+  for (int pass = 0; pass < kCombineTile / 8; ++pass) {
+    const int il = pass * 8 + ty, i = bi * kCombineTile + il;
+    if (i < N && j < N) {
+      const int64_t off = (int64_t)i * ldD + j;
+      double2 s = first ? make_double2(0.0, 0.0) : *reinterpret_cast<const double2*>(S + off);
+      for (int c0 = 0; c0 < nb; c0 += 8) {
+        double2 d[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c0 + c < nb) d[c] = ldg_stream_f64x2(Db + (int64_t)(c0 + c) * strideD + off);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (c0 + c < nb) {
+            s.x += fmax(e[c0 + c] * d[c].x, kJuliaEps);
+            s.y += fmax(e[c0 + c] * d[c].y, kJuliaEps);
+          }
+      }
+      if (last) { s.x /= tot; s.y /= tot; }
+      *reinterpret_cast<double2*>(S + off) = s;
+      tile[il][2 * tx] = s.x;
+      tile[il][2 * tx + 1] = s.y;
+    }
+  }
+  if (bi == bj) return;                                         // a diagonal tile holds both halves already
+  __syncthreads();
+  const int ii = bi * kCombineTile + 2 * tx;
+#pragma unroll 1
+  for (int pass = 0; pass < kCombineTile / 8; ++pass) {
+    const int jl = pass * 8 + ty, jj = bj * kCombineTile + jl;
+    if (jj < N && ii < N) {
+      double* dst = S + (int64_t)jj * ldD + ii;
+      if (ii + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(tile[2 * tx][jl], tile[2 * tx + 1][jl]);
+      else *dst = tile[2 * tx][jl];
+    }
+  }
+}
+
 // S /= tot, applied by the owner of a group after the partial sums have been reduced (chunk-major sharding)
 __global__ void __launch_bounds__(256) scale_div_kernel(double* __restrict__ S, double tot, int64_t total) {
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;

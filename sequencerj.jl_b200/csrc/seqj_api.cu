@@ -1134,10 +1134,10 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       double* Sg = partial ? S_out + (size_t)out_slot[g] * (size_t)S_stride : Spool + (size_t)sg.sslot * mat_elems;
       for (int b0 = sg.c0; b0 < sg.c1; b0 += kCombineMax) {
         const int nb = std::min(kCombineMax, sg.c1 - b0);
-        combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(
-            Sg, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
-            eta_c + sg.out0 + (b0 - sg.c0), b0 == lo, !partial && b0 + nb >= nch, eta_c + chunk_off[g], nch,
-            (int64_t)(mat_elems / 2));
+        const unsigned T = (unsigned)((N + kCombineTile - 1) / kCombineTile);
+        combine_sym_kernel<<<dim3(T, T), 256, 0, c.st>>>(
+            Sg, ldD, N, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
+            eta_c + sg.out0 + (b0 - sg.c0), b0 == lo, !partial && b0 + nb >= nch, eta_c + chunk_off[g], nch);
         c.launches++;
       }
     }
