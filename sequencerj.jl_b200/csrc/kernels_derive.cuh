@@ -25,7 +25,7 @@
 
 namespace seqj {
 
-constexpr int kDeriveMaxFine = 64;     // dynamic shared memory: 2 KB per fine chunk
+constexpr int kDeriveMaxFine = 32;     // dynamic shared memory: 2 KB (L2, KL) / 4 KB (Energy) per fine chunk
 
 struct DeriveParams {
   int mode;               // MODE_L2 / MODE_KL / MODE_ENERGY
@@ -57,16 +57,43 @@ struct DeriveParams {
   const int* tile_col_offset;  // index of the first tile of every 128-column block in the tile list
 };
 
-// 32 x 32 tiles of the upper triangle; block = 32 x 8 threads; result mirrored through shared memory.
-// Per-object factors of the 64 objects of a tile are precomputed once per block in (dynamic) shared memory,
-// 4 doubles per (side, fine chunk, object):  L2: {w, w*g}   KL: {w, log w}   Energy: {w, b, w*(q + 2R), w*T},
+// 64 x 64 tiles of the upper triangle; block = 32 x 8 threads, each thread owns 2 adjacent columns (one 16-byte
+// chunk) of 8 rows.  The fine tiles are staged in shared memory with per-thread cp.async (16 bytes each, L2 only):
+// a thread copies exactly the chunks it reads back, so the staging needs no barrier, costs no registers, and all of
+// a CTA's loads (64 KB for two fine chunks) are in flight at once; three CTAs per SM overlap one block's arithmetic
+// with the others' loads.  (The first version loaded into registers, 4 x 16 bytes per thread at a time with 16
+// warps per SM: 49 % of the HBM rate, stalled on the loads.)  Fine chunks are consumed two at a time.
+// Results are written over stage 0, re-read by their owner for the direct store (after the block-level dense
+// decision) and re-read transposed for the mirror image.  Stage rows are XOR-swizzled by 16-byte chunk
+// (slot = chunk ^ (row >> 1)) so that the row-wise and the transposed accesses are both (nearly) conflict-free
+// without padding.
+// Per-object factors of the 128 objects of a tile are precomputed once per block in (dynamic) shared memory,
+// NF doubles per (side, fine chunk, object):  L2: {w, w*g}   KL: {w, log w}   Energy: {w, b, w*(q + 2R), w*T},
 // so the inner loop is 6-14 FP64 operations per (entry, fine chunk) and the pass stays HBM-bound.
-__global__ void __launch_bounds__(256, 4) derive_kernel(DeriveParams p) {
-  extern __shared__ double dsm[];                 // [2][nf][4][32]: consecutive lanes read consecutive doubles
-  __shared__ double tile[32][33];
+constexpr int kDeriveTile = 64;
+constexpr int kDeriveStage = 2;                       // fine chunks staged at a time
+constexpr int kDeriveStageDoubles = kDeriveTile * kDeriveTile;
+__host__ __device__ constexpr int derive_nf(int mode) { return mode == MODE_ENERGY ? 4 : 2; }
+inline size_t derive_smem_bytes(int mode, int nf) {
+  return ((size_t)kDeriveStage * kDeriveStageDoubles + (size_t)2 * nf * derive_nf(mode) * kDeriveTile) * sizeof(double);
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256, 3) derive_kernel(DeriveParams p) {
+  constexpr int NF = derive_nf(MODE);
+  constexpr int TS = kDeriveTile;
+  extern __shared__ __align__(16) double dsm[];   // [kDeriveStage][64][64] staged fine tiles, then [2][nf][NF][64] factors
+  __shared__ int s_cnt;
   const int bi = blockIdx.y, bj = blockIdx.x;
   if (bi > bj) return;
-  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * 32 + tx;
   {                                   // one launch covers all coarse chunks of the group: z selects the chunk
     const int z = blockIdx.z, cc = p.c_first + z;
     p.f0 = cc * p.ratio;
@@ -77,12 +104,32 @@ __global__ void __launch_bounds__(256, 4) derive_kernel(DeriveParams p) {
     p.chunk_local = z;
   }
   const int N = p.N, nf = p.nf;
-  const int i0 = bi * 32, j0 = bj * 32;
-  auto fac = [&](int side, int q, int o) -> double* { return dsm + ((size_t)side * nf + q) * 128 + o; };   // + 32 * component
+  const int i0 = bi * TS, j0 = bj * TS;
+  const bool diag = (bi == bj);
+  double* stage = dsm;
+  double* facs = dsm + kDeriveStage * kDeriveStageDoubles;
+  auto fac = [&](int side, int q, int o) -> double* { return facs + ((size_t)side * nf + q) * (NF * TS) + o; };   // + TS * component
+  // element (r, 2*chunk + e) of stage s
+  auto at = [&](int s_, int r, int chunk) -> double* { return stage + s_ * kDeriveStageDoubles + r * TS + ((chunk ^ ((r >> 1) & 31)) << 1); };
+
+  const int j = j0 + 2 * tx;                          // this thread's columns: j, j + 1 (j even, j + 1 < ldD)
+  const int jc = min(j, (N - 1) & ~1);                // clamped load column (results of columns >= N are dropped)
+  const double* gbase = p.Dfine + (int64_t)p.f0 * p.strideD + jc;
+  auto issue = [&](int qb) {                          // stage fine chunks qb, qb + 1 (this thread's 16 chunks)
+#pragma unroll
+    for (int s_ = 0; s_ < kDeriveStage; ++s_)
+      if (qb + s_ < nf) {
+        const double* g = gbase + (int64_t)(qb + s_) * p.strideD;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          cp_async16(smem_u32(at(s_, ty + 8 * k, tx)), g + (int64_t)min(i0 + ty + 8 * k, N - 1) * p.ldD);
+      }
+  };
+  issue(0);
 
   // per-object factors, all 256 threads: item = (side, q, object)
-  for (int t = ty * 32 + tx; t < 64 * nf; t += 256) {
-    const int oo = t & 31, side = (t >> 5) & 1, q = t >> 6;
+  for (int t = tid; t < 2 * TS * nf; t += 256) {
+    const int oo = t & (TS - 1), side = (t / TS) & 1, q = t / (2 * TS);
     const int o = (side ? j0 : i0) + oo;
     const int64_t fo = (int64_t)(p.f0 + q) * p.ldn + o;
     const bool ok = o < N;
@@ -91,144 +138,167 @@ __global__ void __launch_bounds__(256, 4) derive_kernel(DeriveParams p) {
     const double w = fmv / cm;
     double* d = fac(side, q, oo);
     d[0] = w;
-    if (p.mode == MODE_L2) {
-      d[32] = ok ? w * p.fg[fo] : 0.0;
-    } else if (p.mode == MODE_KL) {
-      d[32] = log(w);
+    if (MODE == MODE_L2) {
+      d[TS] = ok ? w * p.fg[fo] : 0.0;
+    } else if (MODE == MODE_KL) {
+      d[TS] = log(w);
     } else {
-      d[32] = fmv;                                   // turned into b = (mass of the preceding fine chunks) / cm below
-      d[64] = ok ? w * (p.fg[fo] + 2.0 * p.fR[fo]) : 0.0;
-      d[96] = ok ? w * p.fT[fo] : 0.0;
+      d[TS] = fmv;                                   // turned into b = (mass of the preceding fine chunks) / cm below
+      d[2 * TS] = ok ? w * (p.fg[fo] + 2.0 * p.fR[fo]) : 0.0;
+      d[3 * TS] = ok ? w * p.fT[fo] : 0.0;
     }
   }
+  if (tid == 0) s_cnt = 0;
   __syncthreads();
-  if (p.mode == MODE_ENERGY) {
-    const int t = ty * 32 + tx;
-    if (t < 64) {
-      const int oo = t & 31, side = t >> 5, o = (side ? j0 : i0) + oo;
+  if (MODE == MODE_ENERGY) {
+    if (tid < 2 * TS) {
+      const int oo = tid & (TS - 1), side = tid / TS, o = (side ? j0 : i0) + oo;
       const double cm = (o < N) ? p.cmass[o] : 1.0;
       double run = 0.0;
       for (int q = 0; q < nf; ++q) {
         double* d = fac(side, q, oo);
-        const double fmv = d[32];
-        d[32] = run / cm;
+        const double fmv = d[TS];
+        d[TS] = run / cm;
         run += fmv;
       }
     }
     __syncthreads();
   }
 
-  // each thread: column j, rows ty + 8 rr (rr = 0..3): 4 independent loads per fine chunk in flight
-  const int j = j0 + tx;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  bool live[4], swp[4];
-  const double* src[4];
+  double acc[8][2];
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int i = i0 + ty + 8 * rr;
-    live[rr] = (i < N) && (j < N) && (i != j);
-    swp[rr] = i > j;                                  // only inside diagonal tiles: stored value is for (lo, hi) = (j, i)
-    src[rr] = p.Dfine + (int64_t)p.f0 * p.strideD + (int64_t)min(i, N - 1) * p.ldD + min(j, N - 1);
-  }
-#pragma unroll 2
-  for (int q = 0; q < nf; ++q) {
-    double dv[4];
+  for (int k = 0; k < 8; ++k) acc[k][0] = acc[k][1] = 0.0;
+  for (int qb = 0; qb < nf; qb += kDeriveStage) {
+    cp_async_wait_all();
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) dv[rr] = __ldg(src[rr] + (int64_t)q * p.strideD) - p.eps_floor;
-    const double* fc = fac(1, q, tx);                 // factors of the column object j
-    const double c0 = fc[0], c1 = fc[32];
-    double c2 = 0.0, c3 = 0.0, m = 0.0, P1 = 0.0, P2 = 0.0;
-    if (p.mode == MODE_ENERGY) {
-      c2 = fc[64]; c3 = fc[96];
-      m = (double)p.fm[p.f0 + q];
-      P1 = 0.5 * (m + 1.0);                                  // sum_{t=1..m} t/m
-      P2 = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);          // sum (t/m)^2
-    }
+    for (int s_ = 0; s_ < kDeriveStage; ++s_) {
+      const int q = qb + s_;
+      if (q >= nf) break;
+      const double* fc = fac(1, q, 2 * tx);           // factors of the column objects j, j + 1
+      const double2 c0 = *reinterpret_cast<const double2*>(fc), c1 = *reinterpret_cast<const double2*>(fc + TS);
+      double2 c2 = make_double2(0.0, 0.0), c3 = c2;
+      double m = 0.0, P1 = 0.0, P2 = 0.0;
+      if (MODE == MODE_ENERGY) {
+        c2 = *reinterpret_cast<const double2*>(fc + 2 * TS);
+        c3 = *reinterpret_cast<const double2*>(fc + 3 * TS);
+        m = (double)p.fm[p.f0 + q];
+        P1 = 0.5 * (m + 1.0);                                  // sum_{t=1..m} t/m
+        P2 = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);          // sum (t/m)^2
+      }
 #pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const double* fr = fac(0, q, ty + 8 * rr);      // factors of the row object i
-      // (lo, hi) = (row, col) except below the diagonal of a diagonal tile
-      const double l0 = swp[rr] ? c0 : fr[0], h0 = swp[rr] ? fr[0] : c0;
-      const double l1 = swp[rr] ? c1 : fr[32], h1 = swp[rr] ? fr[32] : c1;
-      if (p.mode == MODE_KL) {
-        acc[rr] += l0 * (dv[rr] + l1 - h1);
-      } else if (p.mode == MODE_L2) {
-        acc[rr] += l0 * h0 * (dv[rr] * dv[rr]) + (l0 - h0) * (l1 - h1);
-      } else {
-        const double r2 = fr[64], r3 = fr[96];
-        const double dw = l0 - h0, db = l1 - h1;
-        const double dA = swp[rr] ? (c2 - r2) : (r2 - c2), dB = swp[rr] ? (c3 - r3) : (r3 - c3);
-        acc[rr] += l0 * h0 * (0.5 * dv[rr] * dv[rr]) + dw * dA + 2.0 * db * dB + dw * (dw * P2 + 2.0 * db * P1) + m * db * db;
+      for (int k = 0; k < 8; ++k) {
+        const int r = ty + 8 * k, i = i0 + r;
+        const double* fr = fac(0, q, r);              // factors of the row object i (warp-wide broadcast)
+        const double r0 = fr[0], r1 = fr[TS];
+        double2 dv = *reinterpret_cast<const double2*>(at(s_, r, tx));
+        dv.x -= p.eps_floor;
+        dv.y -= p.eps_floor;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const double cc0 = e ? c0.y : c0.x, cc1 = e ? c1.y : c1.x, d = e ? dv.y : dv.x;
+          if (MODE == MODE_KL) {
+            // (lo, hi) = (row, col) except below the diagonal of a diagonal tile, where the stored value is for (j, i)
+            const bool swp = diag && i > j + e;
+            const double l0 = swp ? cc0 : r0, l1 = swp ? cc1 : r1, h1 = swp ? r1 : cc1;
+            acc[k][e] += l0 * (d + l1 - h1);
+          } else if (MODE == MODE_L2) {               // symmetric in (row, col): no swap needed
+            acc[k][e] += r0 * cc0 * (d * d) + (r0 - cc0) * (r1 - cc1);
+          } else {
+            const double r2 = fr[2 * TS], r3 = fr[3 * TS];
+            const double cc2 = e ? c2.y : c2.x, cc3 = e ? c3.y : c3.x;
+            const double dw = r0 - cc0, db = r1 - cc1;
+            acc[k][e] += r0 * cc0 * (0.5 * d * d) + dw * (r2 - cc2) + 2.0 * db * (r3 - cc3) +
+                         dw * (dw * P2 + 2.0 * db * P1) + m * db * db;
+          }
+        }
       }
     }
+    if (qb + kDeriveStage < nf) issue(qb + kDeriveStage);     // the thread overwrites only chunks it has consumed
   }
-  // phase A: results + flags
-  double outv[4];
-  bool flg[4];
+  // results + flags, written over stage 0 (each thread's own chunks)
+  unsigned flagbits = 0;                              // bit (2k + e) = entry flagged for the fix-up
   int nflag = 0;
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int i = i0 + ty + 8 * rr;
-    outv[rr] = 0.0;
-    flg[rr] = false;
-    if (i < N && j < N) {
-      if (i == j) {
-        outv[rr] = p.eps_floor;
-      } else {
-        const int lo = min(i, j), hi = max(i, j);
-        double d;
-        bool flag;
-        if (p.mode == MODE_KL) {
-          const double hh = p.cself[lo];
-          d = acc[rr];
-          flag = d < p.tau * fabs(hh);
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k, i = i0 + r;
+    double2 o2;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int jj = j + e;
+      double out = 0.0;
+      if (i < N && jj < N) {
+        if (i == jj) {
+          out = p.eps_floor;
         } else {
-          const double selfterms = p.cself[lo] + p.cself[hi];
-          flag = acc[rr] < p.tau * selfterms;
-          d = fast_sqrt(acc[rr]);
-          if (p.mode == MODE_ENERGY) d = 1.4142135623730951 * d;
+          const int lo = min(i, jj), hi = max(i, jj);
+          double d;
+          bool flag;
+          if (MODE == MODE_KL) {
+            d = acc[k][e];
+            flag = d < p.tau * fabs(p.cself[lo]);
+          } else {
+            flag = acc[k][e] < p.tau * (p.cself[lo] + p.cself[hi]);
+            d = fast_sqrt(acc[k][e]);
+            if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;
+          }
+          out = fabs(d) + p.eps_floor;
+          if (flag && i < jj) {       // (j, i) of a diagonal tile is rewritten by the mirrored store of the fix-up
+            flagbits |= 1u << (2 * k + e);
+            ++nflag;
+          }
         }
-        outv[rr] = fabs(d) + p.eps_floor;
-        flg[rr] = flag && i < j;      // (j, i) of a diagonal tile is rewritten by the mirrored store of the fix-up
-        nflag += flg[rr] ? 1 : 0;
       }
+      if (e) o2.y = out; else o2.x = out;
     }
+    *reinterpret_cast<double2*>(at(0, r, tx)) = o2;
   }
-  // block-level decision
+  // block-level decision: more than 1/32 of the block flagged -> the enclosing 64 x 128 tile goes to the direct kernels
   bool dense = false;
   if (p.tile_flags != nullptr) {
-    __shared__ int s_cnt;
-    if (tx == 0 && ty == 0) s_cnt = 0;
-    __syncthreads();
     if (nflag) atomicAdd(&s_cnt, nflag);
     __syncthreads();
-    dense = s_cnt > 32;
-    if (dense && tx == 0 && ty == 0) {
+    dense = s_cnt > TS * TS / 32;
+    if (dense && tid == 0) {
       const int tidx = p.tile_col_offset[j0 / kTileN] + i0 / kTileM;
       p.tile_flags[(size_t)p.chunk_local * p.tile_flag_stride + tidx] = 1;
     }
   }
-  // phase B: stores (+ per-entry list when the block is not dense)
+  // direct stores of the thread's own entries (+ per-entry list when the block is not dense)
 #pragma unroll
-  for (int rr = 0; rr < 4; ++rr) {
-    const int r = ty + 8 * rr, i = i0 + r;
-    double out = outv[rr];
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k, i = i0 + r;
     if (i < N && j < N) {
-      if (flg[rr] && !dense) {
-        const unsigned int idx = atomicAdd(p.fix_count, 1u);
-        if (idx < p.fix_cap) p.fix_list[idx] = make_int4(p.chunk_local, i, j, 0);
-        else { *p.fix_overflow = 1; out = -1.0; }
+      double2* own = reinterpret_cast<double2*>(at(0, r, tx));
+      double2 out = *own;
+      if (!dense && ((flagbits >> (2 * k)) & 3u)) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if ((flagbits >> (2 * k + e)) & 1u) {
+            const unsigned int idx = atomicAdd(p.fix_count, 1u);
+            if (idx < p.fix_cap) p.fix_list[idx] = make_int4(p.chunk_local, i, j + e, 0);
+            else {
+              *p.fix_overflow = 1;
+              if (e) out.y = -1.0; else out.x = -1.0;
+              *own = out;
+            }
+          }
       }
-      p.Dout[(int64_t)i * p.ldD + j] = out;
+      *reinterpret_cast<double2*>(p.Dout + (int64_t)i * p.ldD + j) = out;      // column j + 1 == N lands in the row padding
     }
-    tile[r][tx] = out;
   }
-  if (bi == bj) return;          // diagonal tiles computed both halves directly
+  if (diag) return;              // diagonal tiles computed both halves directly
   __syncthreads();
   // mirror: element (ii, jj) of the tile is also written at (jj, ii), coalesced along ii
-  for (int r = ty; r < 32; r += 8) {
-    const int jj = j0 + r, ii = i0 + tx;
-    if (ii < N && jj < N) p.Dout[(int64_t)jj * p.ldD + ii] = tile[tx][r];
+  const int ii = i0 + 2 * tx;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int r = ty + 8 * k, jj = j0 + r;
+    if (jj < N && ii < N) {
+      const double a = at(0, 2 * tx, r >> 1)[r & 1], b = at(0, 2 * tx + 1, r >> 1)[r & 1];
+      double* dst = p.Dout + (int64_t)jj * p.ldD + ii;
+      if (ii + 1 < N) *reinterpret_cast<double2*>(dst) = make_double2(a, b);
+      else *dst = a;
+    }
   }
 }
 

@@ -525,13 +525,16 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
                         !(getenv("SEQJ_DENSE_TILES") && atoi(getenv("SEQJ_DENSE_TILES")) == 0);
   dp.tile_flags = dense_ok ? fb.tile_flags : nullptr; dp.tile_flag_stride = ntiles; dp.tile_col_offset = tile_col_offset;
   if (dense_ok) CU_TRY(cudaMemsetAsync(fb.tile_flags, 0, (size_t)(c1 - c0) * ntiles, c.st));
-  const int T = (N + 31) / 32;
-  CU_TRY(cudaFuncSetAttribute(derive_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDeriveMaxFine * 2048));
+  const unsigned T = (unsigned)((N + kDeriveTile - 1) / kDeriveTile);
   dp.ratio = ratio; dp.nfine = fv.nchunks; dp.c_first = c0; dp.f0 = 0; dp.nf = 0; dp.chunk_local = 0;
   dp.Dout = D;
   dp.cmass = pb.mass;
   dp.cself = (metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU);
-  derive_kernel<<<dim3(T, T, c1 - c0), dim3(32, 8), (size_t)std::min(ratio, fv.nchunks) * 2048, c.st>>>(dp);
+  const size_t dsmem = derive_smem_bytes(metric, std::min(ratio, fv.nchunks));
+  const dim3 dgrid(T, T, (unsigned)(c1 - c0)), dblock(32, 8);
+  if (metric == SEQJ_L2) derive_kernel<MODE_L2><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  else if (metric == SEQJ_KLD) derive_kernel<MODE_KL><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  else derive_kernel<MODE_ENERGY><<<dgrid, dblock, dsmem, c.st>>>(dp);
   c.launches++;
   CU_TRY(cudaGetLastError());
   FixParams fp;
@@ -573,6 +576,9 @@ int set_kernel_attrs(seqj_handle* h) {
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(kl_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_L2, kDeriveMaxFine)));
+  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_KL, kDeriveMaxFine)));
+  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_ENERGY, kDeriveMaxFine)));
   return SEQJ_OK;
 }
 
