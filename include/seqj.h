@@ -208,6 +208,16 @@ int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N, double eps_floor
                     int32_t* root, int32_t* parents, int32_t* mst_i, int32_t* mst_j,
                     double* mst_w, int32_t* order);
 
+/* `EMD(u, v, uw, vw)` / `Energy(u, v, uw, vw)` (src/distancemetrics.jl:82-87, 143-148): distance between two
+ * weighted empirical CDFs on their OWN grids, `_cdf_distance(ecdf(u; weights = uw), ecdf(v; weights = vw), p)`
+ * (:191-223) with p = 1 for SEQJ_EMD and sqrt(2) * (p = 2) for SEQJ_ENERGY.  u / v are grid values (any order,
+ * any lengths nu / nv), uw / vw their weights.  Identical grids take the reference's shortcut branch (:206-209),
+ * whose non-zero grid steps must number nu or one (SEQJ_E_DOMAIN otherwise, where the reference throws).  This is
+ * the per-pair form of the reference's known-answer tests (test/algotests.jl:36-107); `EMD(grids)(u, v)` and
+ * `emd(u, v)` with vectors of different lengths reduce to it. */
+int seqj_cdf_distance(seqj_handle* h, int32_t metric, const double* u, const double* uw, int64_t nu,
+                      const double* v, const double* vw, int64_t nv, double* out);
+
 /* `Dklms .+= clamp(eta .* Dklm, eps(), Inf)` over chunks, then `/ sum(etas)`
  * (src/sequencer.jl:231-235,247).  Dchunks = n stacked N x N matrices. */
 int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, int n, int64_t N,

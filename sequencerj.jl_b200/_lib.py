@@ -55,6 +55,7 @@ SIGNATURES = {
                                 C.c_double, c_dp]),
     "seqj_measure_dm": (C.c_int, [vp, c_dp, C.c_int64, C.c_double, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp, c_ip]),
     "seqj_accumulate": (C.c_int, [vp, c_dp, c_dp, C.c_int, C.c_int64, c_dp]),
+    "seqj_cdf_distance": (C.c_int, [vp, C.c_int32, c_dp, c_dp, C.c_int64, c_dp, c_dp, C.c_int64, c_dp]),
 }
 
 _lib = None

@@ -212,6 +212,8 @@ def _normalize_metrics(metrics):
             out.append(EMD_GRID)
         elif m is Energy:
             out.append(ENERGY_GRID)
+        elif isinstance(m, (EMD, Energy)) and m.grids is None:      # EMD() / Energy() instances == WASS1D / ENERGY
+            out.append(WASS1D if isinstance(m, EMD) else ENERGY)
         else:
             raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY and the "
                             "EMD / Energy types with an explicit grid")
@@ -524,26 +526,49 @@ def fuse(N, etas, msts, eps_floor=EPS_FLOOR, handle=None) -> SequencerResult:
     return _collect_and_release(handle, res, N, None, None, want_final=True)
 
 
+def cdf_distance(metric, u, v, uw, vw, handle=None) -> float:
+    """`EMD(u, v, uw, vw)` / `Energy(u, v, uw, vw)` (src/distancemetrics.jl:82-87, 143-148): distance between two
+    weighted ECDFs on their own grids `u`, `v` (weights `uw`, `vw`), through `seqj_cdf_distance`."""
+    handle = handle or default_handle()
+    u, v, uw, vw = (np.ascontiguousarray(x, dtype=np.float64) for x in (u, v, uw, vw))
+    if u.ndim != 1 or v.ndim != 1:
+        raise ValueError("Only 1-d data vectors are supported.")
+    if len(u) != len(uw):
+        raise ValueError(f"u and u weights must have same length. Got u {len(u)} and uw {len(uw)}")
+    if len(v) != len(vw):
+        raise ValueError(f"v and v weights must have same length. Got v {len(v)} and vw {len(vw)}")
+    mid = {WASS1D.id: 1, ENERGY.id: 3}[metric.id]
+    out = C.c_double()
+    handle.check(handle.lib.seqj_cdf_distance(handle.h, mid, _lib.dptr(u), _lib.dptr(uw), len(u), _lib.dptr(v),
+                                              _lib.dptr(vw), len(v), C.byref(out)))
+    return float(out.value)
+
+
 class EMD:
-    """`EMD()` functor on the shared unit grid (src/distancemetrics.jl:16-21,46-50,90)."""
+    """`EMD()` / `EMD((gridu, gridv))` functor (src/distancemetrics.jl:16-21, 90-93): `EMD(grids)(u, v)` is
+    `EMD(gridu, gridv, u, v)` with u, v the weights on those grids; without grids, the shared unit grid."""
 
     def __init__(self, grids=None):
-        if grids is not None:
-            raise NotImplementedError("explicit grids are a 'next' row (SURVEY.md §8f)")
+        self.grids = None if grids is None else tuple(np.asarray(g, dtype=np.float64) for g in grids)
 
-    def __call__(self, u, v=None):
-        return emd(u, v)
+    def __call__(self, u, v=None, uw=None, vw=None):
+        if uw is not None:
+            return emd(u, v, uw, vw)
+        v = u if v is None else v
+        return emd(u, v) if self.grids is None else emd(self.grids[0], self.grids[1], u, v)
 
 
 class Energy:
-    """`Energy()` functor on the shared unit grid (src/distancemetrics.jl:121-132,158-162)."""
+    """`Energy()` / `Energy((gridu, gridv))` functor (src/distancemetrics.jl:121-132)."""
 
     def __init__(self, grids=None):
-        if grids is not None:
-            raise NotImplementedError("explicit grids are a 'next' row (SURVEY.md §8f)")
+        self.grids = None if grids is None else tuple(np.asarray(g, dtype=np.float64) for g in grids)
 
-    def __call__(self, u, v=None):
-        return energy(u, v)
+    def __call__(self, u, v=None, uw=None, vw=None):
+        if uw is not None:
+            return energy(u, v, uw, vw)
+        v = u if v is None else v
+        return energy(u, v) if self.grids is None else energy(self.grids[0], self.grids[1], u, v)
 
 
 def _pair(metric, u, v, handle=None):
@@ -551,17 +576,22 @@ def _pair(metric, u, v, handle=None):
     v = u if v is None else np.asarray(v, dtype=np.float64)
     if u.ndim != 1 or v.ndim != 1:
         raise ValueError("Only 1-d data vectors are supported.")
-    if len(u) != len(v):
-        raise ValueError("u and v must have the same length on the shared unit grid")
+    if len(u) != len(v):          # default grids axes(u,1) and axes(v,1) differ: the general branch (:210-214)
+        return cdf_distance(metric, np.arange(1, len(u) + 1.0), np.arange(1, len(v) + 1.0), u, v, handle)
     Dm = pairwise(metric, np.stack([u, v], axis=1), normalize=False, eps_floor=0.0, handle=handle)
     return float(Dm[0, 1])
 
 
-def emd(u, v=None, handle=None):
-    """`emd(u, v)` (src/distancemetrics.jl:101): EMD on the default unit grid."""
+def emd(u, v=None, uw=None, vw=None, handle=None):
+    """`emd(u, v)` (src/distancemetrics.jl:101): EMD of the weights u, v on the default unit grids;
+    `emd(u, v, uw, vw)` (:108): explicit grids u, v with weights uw, vw."""
+    if uw is not None or vw is not None:
+        return cdf_distance(WASS1D, u, v, uw, vw, handle)
     return _pair(WASS1D, u, v, handle)
 
 
-def energy(u, v=None, handle=None):
-    """`energy(u, v)` (src/distancemetrics.jl:172): Energy distance on the default unit grid."""
+def energy(u, v=None, uw=None, vw=None, handle=None):
+    """`energy(u, v)` (src/distancemetrics.jl:172) and `energy(u, v, uw, vw)` (:167)."""
+    if uw is not None or vw is not None:
+        return cdf_distance(ENERGY, u, v, uw, vw, handle)
     return _pair(ENERGY, u, v, handle)

@@ -19,6 +19,7 @@
 #include "kernels_dist.cuh"
 #include "kernels_derive.cuh"
 #include "kernels_graph.cuh"
+#include "kernels_pair.cuh"
 #include "kernels_prep.cuh"
 
 using namespace seqj;
@@ -1691,6 +1692,45 @@ int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, i
   }
   CU_TRY(cudaMemcpyAsync(Dkl_out, S_dev, mat * 8, cudaMemcpyDeviceToHost, c.st));
   CU_TRY(cudaStreamSynchronize(c.st));
+  return SEQJ_OK;
+}
+
+int seqj_cdf_distance(seqj_handle* h, int32_t metric, const double* u, const double* uw, int64_t nu64, const double* v,
+                      const double* vw, int64_t nv64, double* out) {
+  ST_TRY(check_ready(h));
+  if (!u || !uw || !v || !vw || !out || nu64 < 1 || nv64 < 1 || nu64 + nv64 >= (1ll << 26))
+    return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (metric != SEQJ_EMD && metric != SEQJ_ENERGY) return fail(h, SEQJ_E_BADARG, "metric must be SEQJ_EMD or SEQJ_ENERGY");
+  const int nu = (int)nu64, nv = (int)nv64;
+  auto pow2 = [](int n) { int q = 1; while (q < n) q <<= 1; return q; };
+  Ctx c(h);
+  CdfPairParams pp;
+  pp.nu = nu; pp.nv = nv; pp.p = (metric == SEQJ_EMD) ? 1 : 2;
+  pp.pu = pow2(nu); pp.pv = pow2(nv); pp.pa = pow2(nu + nv + 1);
+  double *u_d, *uw_d, *v_d, *vw_d, *out_d;
+  int* status_d;
+  CU_TRY(c.pool.alloc(&u_d, (size_t)nu)); CU_TRY(c.pool.alloc(&uw_d, (size_t)nu));
+  CU_TRY(c.pool.alloc(&v_d, (size_t)nv)); CU_TRY(c.pool.alloc(&vw_d, (size_t)nv));
+  CU_TRY(c.pool.alloc(&pp.su, (size_t)pp.pu)); CU_TRY(c.pool.alloc(&pp.sv, (size_t)pp.pv)); CU_TRY(c.pool.alloc(&pp.A, (size_t)pp.pa));
+  CU_TRY(c.pool.alloc(&pp.iu, (size_t)pp.pu)); CU_TRY(c.pool.alloc(&pp.iv, (size_t)pp.pv));
+  CU_TRY(c.pool.alloc(&pp.cu, (size_t)nu)); CU_TRY(c.pool.alloc(&pp.cv, (size_t)nv));
+  CU_TRY(c.pool.alloc(&pp.dx, (size_t)nu + nv)); CU_TRY(c.pool.alloc(&pp.pos, (size_t)nu + nv + 1));
+  CU_TRY(c.pool.alloc(&out_d, 1)); CU_TRY(c.pool.alloc(&status_d, 1));
+  CU_TRY(cudaMemcpyAsync(u_d, u, 8 * (size_t)nu, cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(uw_d, uw, 8 * (size_t)nu, cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(v_d, v, 8 * (size_t)nv, cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(vw_d, vw, 8 * (size_t)nv, cudaMemcpyHostToDevice, c.st));
+  pp.u = u_d; pp.uw = uw_d; pp.v = v_d; pp.vw = vw_d; pp.out = out_d; pp.status = status_d;
+  cdf_pair_kernel<<<1, kPairThreads, 0, c.st>>>(pp);
+  CU_TRY(cudaGetLastError());
+  double res = 0.0;
+  int status = 0;
+  CU_TRY(cudaMemcpyAsync(&res, out_d, 8, cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaMemcpyAsync(&status, status_d, 4, cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaStreamSynchronize(c.st));
+  if (status == 1) return fail(h, SEQJ_E_DOMAIN, "grid values and weights must be finite");
+  if (status == 2) return fail(h, SEQJ_E_DOMAIN, "identical grids: the non-zero grid steps do not match the grid length (the reference fails with a DimensionMismatch)");
+  *out = (metric == SEQJ_ENERGY) ? 1.4142135623730951 * res : res;
   return SEQJ_OK;
 }
 

@@ -16,7 +16,7 @@ using LightGraphs
 using SimpleWeightedGraphs
 using SparseArrays: sparse
 
-export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!
+export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!, emd, energy
 export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS
 
 const libseqj = get(ENV, "SEQJ_B200_LIB", joinpath(@__DIR__, "..", "libseqj_b200.so"))
@@ -219,5 +219,26 @@ function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid 
     return bestscale
 end
 using Random: randperm
+
+# ---- pair distances on explicit grids (reference src/distancemetrics.jl:82-87, 143-148) -----------
+function _cdf_distance(mid::Integer, u, v, uw, vw)
+    length(u) == length(uw) || error("u and u weights must have same length. Got u $(length(u)) and uw $(length(uw))")
+    length(v) == length(vw) || error("v and v weights must have same length. Got v $(length(v)) and vw $(length(vw))")
+    ndims(u) == 1 && ndims(v) == 1 || error("Only 1-d data vectors are supported.")
+    h = handle()
+    out = Ref{Float64}(0.0)
+    check(h, ccall((:seqj_cdf_distance, libseqj), Cint,
+                   (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int64, Ptr{Float64}, Ptr{Float64}, Int64, Ref{Float64}),
+                   h.ptr, Int32(mid), Vector{Float64}(u), Vector{Float64}(uw), length(u),
+                   Vector{Float64}(v), Vector{Float64}(vw), length(v), out))
+    out[]
+end
+"`emd(u, v, uw, vw)`: EMD between the weighted ECDFs on the grids `u`, `v` (reference :108)."
+emd(u, v, uw, vw) = _cdf_distance(1, u, v, uw, vw)
+"`emd(u, v)`: weights on the default unit grids `axes(u,1)`, `axes(v,1)` (reference :101)."
+emd(u::AbstractVector, v = u) = _cdf_distance(1, collect(1.0:length(u)), collect(1.0:length(v)), u, v)
+"`energy(u, v, uw, vw)` (reference :167) and `energy(u, v)` (:172)."
+energy(u, v, uw, vw) = _cdf_distance(3, u, v, uw, vw)
+energy(u::AbstractVector, v = u) = _cdf_distance(3, collect(1.0:length(u)), collect(1.0:length(v)), u, v)
 
 end # module

@@ -141,6 +141,65 @@ def test_pairwise_algotests_known_answers(seqj, handle):
     assert abs(K[0, 1] - 0.5108256237659907) < 1e-15
 
 
+def test_cdf_distance_algotests_known_answers(seqj, handle):
+    """Reference test/algotests.jl:36-107: explicit, DIFFERENT grids (the merge branch of _cdf_distance), values
+    checked there against scipy.stats.wasserstein_distance / energy_distance."""
+    g1, g2, u, v = [3.4, 3.9, 7.5, 7.8], [4.5, 1.4], [1.4, 0.9, 3.1, 7.2], [3.2, 3.5]
+    rel_close([seqj.emd(g1, g2, u, v)], [4.0781331438047861], 1e-12)                  # :36-41
+    rel_close([seqj.EMD((g1, g2))(u, v)], [4.0781331438047861], 1e-12)                # :50-57
+    rel_close([seqj.Energy()(g1, g2, u, v)], [2.3674181638546394], 1e-12)             # :80-85
+    rel_close([seqj.Energy()([0, 8], [0, 8], [3, 1], [2, 2])], [1.0], 1e-12)          # :74-78
+    h1, h2, a, b = [0.7, 7.4, 2.4, 6.8], [1.4, 8.0], [2.1, 4.2, 7.4, 8.0], [7.6, 8.8]
+    rel_close([seqj.energy(h1, h2, a, b)], [0.8800334097615822], 1e-12)               # :88-92
+    rel_close([seqj.Energy((h1, h2))(a, b)], [0.8800334097615822], 1e-12)             # :100-107
+    g = [0.5, 1.0, 1.5, 2.0]
+    assert np.isfinite(seqj.EMD((g, g))([3.4, 3.9, 7.5, 7.8], [1.4, 0.9, 3.1, 7.2]))  # :43-48
+    assert seqj.EMD()([1, 1, 1], [2, 3, 4]) is not None                               # :30-33
+    assert seqj.Energy()([1, 1, 1], [2, 3, 4]) is not None                            # :62-65
+
+
+@pytest.mark.parametrize("nu,nv", [(1, 1), (2, 5), (17, 17), (100, 37), (1000, 1500), (9000, 9000), (20000, 3)])
+@pytest.mark.parametrize("kind", ["different", "same", "overlap"])
+def test_cdf_distance_matches_oracle(seqj, oracle, handle, nu, nv, kind):
+    rng = np.random.default_rng(nu * 31 + nv)
+    if kind == "same":
+        nv = nu
+        gu = rng.permutation(np.cumsum(rng.random(nu) + 0.01))        # distinct, positive, unsorted
+        gv = gu.copy()
+    elif kind == "overlap":                                            # grids share values and repeat some
+        pool = np.round(rng.random(max(nu, nv)) * 20, 1) + 0.1
+        gu, gv = rng.choice(pool, nu), rng.choice(pool, nv)
+        if nu == nv and np.array_equal(np.sort(gu), np.sort(gv)):
+            gv = gv + 0.05
+    else:
+        gu, gv = rng.random(nu) * 10, rng.random(nv) * 12
+    wu, wv = rng.random(nu) + 1e-3, rng.random(nv) + 1e-3
+    rel_close([seqj.emd(gu, gv, wu, wv)], [oracle.emd(gu, gv, wu, wv)], 1e-11)
+    rel_close([seqj.energy(gu, gv, wu, wv)], [oracle.energy(gu, gv, wu, wv)], 1e-11)
+
+
+def test_cdf_distance_default_grids_of_different_length(seqj, oracle, handle):
+    """`emd(u, v)` with length(u) != length(v): grids axes(u,1), axes(v,1) differ -> general branch."""
+    rng = np.random.default_rng(4)
+    u, v = rng.random(40), rng.random(25)
+    rel_close([seqj.emd(u, v)], [oracle.emd(u, v)], 1e-12)
+    rel_close([seqj.energy(u, v)], [oracle.energy(u, v)], 1e-12)
+    u2 = rng.random(40)
+    rel_close([seqj.emd(u, u2)], [oracle.emd(u, u2)], 1e-12)           # equal lengths: the tile path
+    rel_close([seqj.emd(u, u2)], [seqj.emd(np.arange(1, 41.0), np.arange(1, 41.0), u, u2)], 1e-12)
+
+
+def test_cdf_distance_errors(seqj, handle):
+    with pytest.raises(ValueError):
+        seqj.emd([1.0, 2.0], [1.0], [0.5], [1.0])                      # u and uw lengths differ
+    with pytest.raises(ValueError):
+        seqj.emd(np.ones((2, 2)), [1.0], np.ones((2, 2)), [1.0])
+    with pytest.raises(AssertionError):                                # identical grids with a repeated value:
+        seqj.emd([1.0, 1.0, 2.0], [1.0, 1.0, 2.0], [1, 1, 1], [1, 2, 3])   # the reference throws DimensionMismatch
+    with pytest.raises(AssertionError):
+        seqj.emd([1.0, np.nan], [1.0, 2.0], [1, 1], [1, 1])
+
+
 def test_emd_energy_pair_functions(seqj, oracle, handle):
     """EMD()(u,v) / Energy()(u,v) on the default unit grid (distancemetrics.jl:46-50,158-162)
     against the faithful ECDF restatement and SciPy."""
