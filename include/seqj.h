@@ -48,6 +48,7 @@ extern "C" {
  * from the chunk-local slice of `grid` (src/sequencer.jl:217-219), i.e. delta-weighted CDF distances */
 #define SEQJ_EMD_GRID 4
 #define SEQJ_ENERGY_GRID 5
+#define SEQJ_PERIODIC 6 /* Distances.PeriodicEuclidean(periods), set with seqj_set_periods (test/runtests.jl:189-236) */
 
 /* phase timers returned by seqj_result_timings (milliseconds, CUDA events on the library's streams) */
 #define SEQJ_T_TOTAL 0    /* whole seqj_sequence call, device side (H2D .. results ready) */
@@ -87,6 +88,13 @@ int seqj_release_workspace(seqj_handle* h);
 /* Grid used by SEQJ_EMD_GRID / SEQJ_ENERGY_GRID: M finite, positive, strictly increasing values (the `grid`
  * keyword of `sequence`, src/sequencer.jl:105-109,296-304).  NULL clears it. */
 int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M);
+
+/* Periods of SEQJ_PERIODIC = `Distances.PeriodicEuclidean(periods)`: d(a,b) = sqrt(sum_k s_k^2) with
+ * s = |a_k - b_k| mod p_k, s_k = min(s, p_k - s).  M positive finite values, one per row of a chunk; as in
+ * Distances.jl the metric only applies to vectors of exactly that length, i.e. to scales whose single chunk is
+ * the whole column (the reference's tests use scales = (1,), test/runtests.jl:189-236); other scales are
+ * rejected with SEQJ_E_BADARG where Julia throws a DimensionMismatch.  periods == NULL clears them. */
+int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M);
 
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);

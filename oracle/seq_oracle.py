@@ -47,6 +47,7 @@ FLOATMAX32 = 3.4028234663852886e38  # floatmax(Float32), sequencer.jl:351-352
 # metric ids shared with the C ABI (include/seqj.h)
 L2, EMD, KLD, ENERGY = 0, 1, 2, 3
 EMD_GRID, ENERGY_GRID = 4, 5                   # the TYPES EMD / Energy + explicit grid (sequencer.jl:217-219)
+PERIODIC = 6                                   # Distances.PeriodicEuclidean(periods) (test/runtests.jl:189-236)
 ALL_METRICS = (L2, EMD, KLD, ENERGY)           # distancemetrics.jl:257 (order matters)
 METRIC_NAMES = {L2: "Euclidean", EMD: "EMD", KLD: "KLDivergence", ENERGY: "Energy"}
 FIB = [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 5168]  # sequencer.jl:148
@@ -278,8 +279,41 @@ def pairwise_grid(metric: int, P: np.ndarray, lgrid: np.ndarray, faithful: bool 
     return r
 
 
+def periodic_euclidean(a, b, periods) -> float:
+    """Distances.PeriodicEuclidean(periods)(a, b) (Distances.jl 0.10 metrics.jl, `eval_op`/`eval_end`; un-vendored
+    dependency, Project.toml compat "0.10"):  s1 = |a - b|; s2 = mod(s1, p); s3 = min(s2, p - s2); sqrt(sum s3^2)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    p = np.asarray(periods, dtype=np.float64)
+    if not (len(a) == len(b) == len(p)):
+        raise ValueError("DimensionMismatch: PeriodicEuclidean needs one period per element")
+    s = np.mod(np.abs(a - b), p)
+    s = np.minimum(s, p - s)
+    return float(np.sqrt(np.sum(s * s)))
+
+
+def pairwise_periodic(P: np.ndarray, periods, faithful: bool = False) -> np.ndarray:
+    m, N = P.shape
+    p = np.asarray(periods, dtype=np.float64)
+    if len(p) != m:
+        raise ValueError("DimensionMismatch: PeriodicEuclidean needs one period per row of the chunk")
+    r = np.zeros((N, N))
+    if faithful:
+        for j in range(N):
+            for i in range(j + 1, N):
+                r[i, j] = r[j, i] = periodic_euclidean(P[:, i], P[:, j], p)
+        return r
+    for i in range(N):
+        s = np.mod(np.abs(P[:, i:i + 1] - P), p[:, None])
+        s = np.minimum(s, p[:, None] - s)
+        r[i, :] = np.sqrt(np.sum(s * s, axis=0))
+    np.fill_diagonal(r, 0.0)
+    return r
+
+
 def chunk_distance(metric: int, P: np.ndarray, faithful: bool = False,
-                   eps_floor: float = EPS_FLOOR, l2_thresh: float = L2THR, lgrid=None) -> np.ndarray:
+                   eps_floor: float = EPS_FLOOR, l2_thresh: float = L2THR, lgrid=None, periods=None) -> np.ndarray:
+    if metric == PERIODIC:
+        return np.abs(pairwise_periodic(P, periods, faithful)) + eps_floor
     if metric in (EMD_GRID, ENERGY_GRID):
         return np.abs(pairwise_grid(metric, P, np.asarray(lgrid, dtype=np.float64), faithful)) + eps_floor
     f = pairwise_faithful if faithful else pairwise_vec
@@ -479,7 +513,7 @@ def dense_from_edges(N, edges):
 
 
 def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=False,
-                  eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None):
+                  eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None):
     """One (metric k, scale l) iteration of the double loop in _sequence (sequencer.jl:196-258).
     A is already clamped. Returns (GroupResult, min root-score gap)."""
     M, N = A.shape
@@ -489,7 +523,7 @@ def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=Fal
     if grid is None:
         grid = np.arange(1, M + 1, dtype=np.float64)          # ensuregrid! default (sequencer.jl:298)
     for P, (r0, r1) in zip(splitnorm(A, l), chunk_bounds(M, l)):
-        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh, lgrid=grid[r0:r1])
+        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh, lgrid=grid[r0:r1], periods=periods)
         if k == KLD:                     # Symmetric(dm): only the upper triangle is ever read
             Dsym = np.triu(Dc) + np.triu(Dc, 1).T
         else:
@@ -534,7 +568,7 @@ def _norm_args(scales, metrics):
 
 
 def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_root=True,
-                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None) -> OracleResult:
+                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None) -> OracleResult:
     """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects)."""
     A = clamp_input(A)
     M, N = A.shape
@@ -544,7 +578,7 @@ def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_roo
     for k in metrics:
         for l in scales:
             g, gap = compute_group(A, k, l, faithful, faithful_root, keep_matrices, eps_floor, l2_thresh,
-                                   None if grid is None else np.asarray(grid, dtype=np.float64))
+                                   None if grid is None else np.asarray(grid, dtype=np.float64), periods)
             groups.append(g)
             min_gap = min(min_gap, gap)
     return fuse_groups(N, groups, faithful_root, min_gap)

@@ -27,6 +27,7 @@ SIGNATURES = {
     "seqj_set_workspace_limit": (C.c_int, [vp, C.c_uint64]),
     "seqj_release_workspace": (C.c_int, [vp]),
     "seqj_set_grid": (C.c_int, [vp, c_dp, C.c_int64]),
+    "seqj_set_periods": (C.c_int, [vp, c_dp, C.c_int64]),
     "seqj_sequence": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
                                 C.c_double, c_u8p, C.POINTER(vp)]),
     "seqj_sequence_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,

@@ -51,6 +51,27 @@ EMD_GRID = Metric(4, "EMD(grid)")
 ENERGY_GRID = Metric(5, "Energy(grid)")
 _BY_ID = {m.id: m for m in ALL_METRICS + (EMD_GRID, ENERGY_GRID)}
 
+
+class PeriodicEuclidean(Metric):
+    """`Distances.PeriodicEuclidean(periods)` as a `sequence` metric (reference test/runtests.jl:189-236):
+    d(a, b) = sqrt(sum_k min(s_k, p_k - s_k)^2), s_k = |a_k - b_k| mod p_k.  One period per row; like Distances.jl
+    it only evaluates vectors of exactly that length, i.e. scales whose single chunk is the whole column."""
+
+    def __init__(self, periods):
+        per = np.ascontiguousarray(periods, dtype=np.float64)
+        if per.ndim != 1 or len(per) < 1:
+            raise ValueError("periods must be a non-empty vector")
+        object.__setattr__(self, "periods", per)
+        # the reference's `show`: PeriodicEuclidean(n) [min,max]  (src/distancemetrics.jl:260)
+        object.__setattr__(self, "id", 6)
+        object.__setattr__(self, "name", f"PeriodicEuclidean({len(self.periods)}) [{self.periods.min()},{self.periods.max()}]")
+
+    def __eq__(self, other):
+        return isinstance(other, PeriodicEuclidean) and np.array_equal(self.periods, other.periods)
+
+    def __hash__(self):
+        return hash((6, self.periods.tobytes()))
+
 _default_handle = None
 
 
@@ -271,12 +292,14 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     n64 = C.c_int64()
     handle.check(lib.seqj_result_dims(res, C.byref(n64), C.byref(ngroups)))
     EOSeg, EOAlgScale, group_msts = {}, {}, {}
+    by_id = dict(_BY_ID)
+    by_id.update({m.id: m for m in (metrics or ()) if isinstance(m, PeriodicEuclidean)})
     for g in range(ngroups.value):
         met, sc, nch, comp = C.c_int(), C.c_int(), C.c_int(), C.c_int()
         handle.check(lib.seqj_result_group_info(res, g, C.byref(met), C.byref(sc), C.byref(nch), C.byref(comp)))
         if not comp.value:
             continue
-        key = (_BY_ID[met.value], sc.value)
+        key = (by_id[met.value], sc.value)
         lo, hi = C.c_int(), C.c_int()
         handle.check(lib.seqj_result_group_range(res, g, C.byref(lo), C.byref(hi)))
         nloc = hi.value - lo.value
@@ -388,6 +411,15 @@ def groups_finish(S_ptr, S_stride, slots, N, eta_sums, eps_floor=EPS_FLOOR, hand
     return [(float(eta[g]), BFSTree(int(root[g]), par[g]), WeightedTree(N, mi[g], mj[g], mw[g])) for g in range(ng)]
 
 
+def _set_periods(metrics, handle):
+    per = [m for m in metrics if isinstance(m, PeriodicEuclidean)]
+    if len({m for m in per}) > 1:
+        raise ValueError("one PeriodicEuclidean metric per call")
+    if per:
+        h_ = handle or default_handle()
+        h_.check(h_.lib.seqj_set_periods(h_.h, _lib.dptr(per[0].periods), len(per[0].periods)))
+
+
 def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=None) -> SequencerResult:
     """Drop-in for `sequence(A; scales, metrics, grid)` (src/sequencer.jl:105-145).
 
@@ -398,10 +430,11 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
     logger.info("Sequencing data with\n    shape: (%d, %d)\n    metric(s): %s\n    scale(s): %s", M, N, metrics, scales)
     ensuregrid(At.T, grid)
     metrics = _normalize_metrics(metrics)
-    if any(m.id >= 4 for m in metrics):
+    if any(m.id in (EMD_GRID.id, ENERGY_GRID.id) for m in metrics):
         h_ = handle or default_handle()
         g = np.ascontiguousarray(ensuregrid(At.T, grid), dtype=np.float64)
         h_.check(h_.lib.seqj_set_grid(h_.h, _lib.dptr(g), len(g)))
+    _set_periods(metrics, handle)
     if scales is None:
         scales = autoscale(At.T, metrics=metrics, grid=grid, handle=handle, rng=rng, _At=At)
         logger.info("After autoscaling, best scale = %s", scales)
@@ -460,6 +493,8 @@ def pairwise(metric, chunk, normalize=True, kl_full=True, eps_floor=EPS_FLOOR, l
     """`abs.(pairwise(alg, m; dims=2)) .+ ϵ` (src/sequencer.jl:226) for one m x N chunk."""
     handle = handle or default_handle()
     mid = metric.id if isinstance(metric, Metric) else int(metric)
+    if isinstance(metric, PeriodicEuclidean):
+        _set_periods((metric,), handle)
     chunk = np.asarray(chunk, dtype=np.float64)
     m, N = chunk.shape
     Ct = np.ascontiguousarray(chunk.T)

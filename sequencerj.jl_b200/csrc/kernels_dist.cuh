@@ -55,6 +55,7 @@ struct DistParams {
   unsigned int* fix_count;
   unsigned int fix_cap;
   int* fix_overflow;
+  const double* period; // OP_PERIODIC: period of every row of the (single) chunk, padded to cl_pad with 1.0
 };
 
 // rho: logical fragment row g -> physical row inside an 8-row group, chosen so that the two rows
@@ -271,7 +272,16 @@ __global__ void compact_flags_kernel(const unsigned char* __restrict__ flags, in
 // thread T of the 128 consumers: ti = T>>4 (rows 8ti..8ti+7), tj = T&15 (cols (tj&7)+8(tj>>3)+16bb).
 // OP_L1: EMD.  OP_SQ / OP_SQ_ENERGY: sum_k (a-b)^2 -> Euclidean / Energy computed WITHOUT the Gram form; used
 // as the fix-up of whole tiles that the DMMA epilogue (or derive_kernel) found full of cancelling entries.
-enum DirectOp { OP_L1 = 0, OP_SQ = 1, OP_SQ_ENERGY = 2 };
+enum DirectOp { OP_L1 = 0, OP_SQ = 1, OP_SQ_ENERGY = 2, OP_PERIODIC = 3 };
+
+// |a - b| mod p folded onto [0, p/2] (Distances.PeriodicEuclidean eval_op): the mod is exact (fmod) and only
+// taken when the difference reaches the period.
+__device__ __noinline__ double periodic_wrap_slow(double s, double per) { return fmod(s, per); }
+__device__ __forceinline__ double periodic_fold(double d, double per) {
+  double s = fabs(d);
+  if (s >= per) s = periodic_wrap_slow(s, per);
+  return fmin(s, per - s);
+}
 
 template <int OP>
 __global__ void __launch_bounds__(kTileThreads, 2)
@@ -320,6 +330,8 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
 #pragma unroll 2
       for (int c = 0; c < 8; ++c) {    // 16 B chunk = 2 consecutive k
         double2 fb[8];
+        double2 per = make_double2(1.0, 1.0);
+        if (OP == OP_PERIODIC) per = __ldg(reinterpret_cast<const double2*>(p.period + it * kTileK + 2 * c));
 #pragma unroll
         for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
 #pragma unroll
@@ -330,6 +342,10 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
             if (OP == OP_L1) {
               acc[a][b] += fabs(fa.x - fb[b].x);
               acc[a][b] += fabs(fa.y - fb[b].y);
+            } else if (OP == OP_PERIODIC) {
+              const double sx = periodic_fold(fa.x - fb[b].x, per.x), sy = periodic_fold(fa.y - fb[b].y, per.y);
+              acc[a][b] = fma(sx, sx, acc[a][b]);
+              acc[a][b] = fma(sy, sy, acc[a][b]);
             } else {
               const double dx = fa.x - fb[b].x, dy = fa.y - fb[b].y;
               acc[a][b] = fma(dx, dx, acc[a][b]);

@@ -41,6 +41,7 @@ struct seqj_handle {
   // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
   std::vector<seqj_handle*> peers;   // additional devices driven by this handle (seqj_create with ndev > 1)
   std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
+  std::vector<double> periods;   // periods of SEQJ_PERIODIC (seqj_set_periods), empty = none
   std::multimap<size_t, void*> cache;
   size_t cached_bytes = 0;
 };
@@ -354,7 +355,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
 
 struct PrepBufs {
   double *P = nullptr, *logP = nullptr, *Uc = nullptr, *U = nullptr, *sP = nullptr, *sU = nullptr, *H = nullptr;
-  double *UwE = nullptr, *UwG = nullptr, *sUG = nullptr, *grid = nullptr;
+  double *UwE = nullptr, *UwG = nullptr, *sUG = nullptr, *grid = nullptr, *period = nullptr;
   double *mass = nullptr, *sR = nullptr, *sT = nullptr;
   int64_t ldn = 0, rows_pad = 0;
   int* m_of_chunk = nullptr;
@@ -426,6 +427,16 @@ int run_dense_tiles(Ctx& c, int metric, DistParams dd, const CUtensorMap& tm1, c
   return SEQJ_OK;
 }
 
+// Device copy of the PeriodicEuclidean periods, padded to the chunk's padded length with 1.0 (the operands are 0 there)
+int upload_periods(Ctx& c, PrepBufs& pb, const std::vector<double>& periods, int cl_pad) {
+  seqj_handle* h = c.h;
+  std::vector<double> padded((size_t)cl_pad, 1.0);
+  std::copy(periods.begin(), periods.end(), padded.begin());
+  CU_TRY(c.pool.alloc(&pb.period, (size_t)cl_pad));
+  CU_TRY(cudaMemcpy(pb.period, padded.data(), sizeof(double) * cl_pad, cudaMemcpyHostToDevice));
+  return SEQJ_OK;
+}
+
 // distance matrices of chunks [chunk0, chunk0+nb) of one scale into D (stride strideD)
 int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const int2* tiles_dev, int ntiles,
                  int N, double* D, int64_t ldD, int64_t strideD, int chunk0, int nb, double eps_floor,
@@ -437,14 +448,27 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   dp.mirror = 1; dp.kl_swap = 0;
   dp.tile_flags = nullptr; dp.tile_flag_stride = ntiles; dp.dense_thresh = 0x7fffffff; dp.dense_list = nullptr; dp.dense_count = nullptr;
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  const bool periodic = metric == SEQJ_PERIODIC;
+  if (periodic) metric = SEQJ_L2;                      // timed with the Euclidean phase
   const bool on_grid = metric >= SEQJ_EMD_GRID;        // EMD / Energy on the explicit grid: pre-scaled operands
   if (on_grid) metric = (metric == SEQJ_EMD_GRID) ? SEQJ_EMD : SEQJ_ENERGY;
+  dp.period = nullptr;
   const int phase = SEQJ_T_DIST_L2 + metric;
   int t = c.timer.begin(phase);
   const char* stg = getenv("SEQJ_STAGGER");
   dp.sm_slots = (stg && atoi(stg) == 0) ? nullptr : fb.sm_slots;
   if (dp.sm_slots) CU_TRY(cudaMemsetAsync(fb.sm_slots, 0, 256 * sizeof(int), c.st));
   dim3 grid(ntiles, nb);
+  if (periodic) {                 // Distances.PeriodicEuclidean: element-wise fold, direct tiles on the PDFs
+    CUtensorMap tmP;
+    ST_TRY(make_tmap(h, &tmP, pb.P, L.ldX, pb.rows_pad));
+    dp.normA = nullptr; dp.tau = 0; dp.period = pb.period;
+    direct_dist_kernel<OP_PERIODIC><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+    c.timer.end(t);
+    return SEQJ_OK;
+  }
   if (metric == SEQJ_EMD) {
     CUtensorMap tmU;
     ST_TRY(make_tmap(h, &tmU, on_grid ? pb.UwE : pb.Uc, L.ldX, pb.rows_pad));
@@ -576,6 +600,7 @@ int set_kernel_attrs(seqj_handle* h) {
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_PERIODIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(kl_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes));
   CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_L2, kDeriveMaxFine)));
   CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_KL, kDeriveMaxFine)));
@@ -836,6 +861,16 @@ int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M) {
   return SEQJ_OK;
 }
 
+int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M) {
+  if (!h) return SEQJ_E_BADARG;
+  h->periods.clear();
+  if (!periods || M <= 0) return SEQJ_OK;
+  for (int64_t i = 0; i < M; ++i)
+    if (!(periods[i] > 0.0) || !std::isfinite(periods[i])) return fail(h, SEQJ_E_BADARG, "periods must be finite and positive");
+  h->periods.assign(periods, periods + M);
+  return SEQJ_OK;
+}
+
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
   if (!h) return SEQJ_E_BADARG;
   h->ws_limit = bytes;
@@ -862,7 +897,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     return fail(h, SEQJ_E_BADARG, "bad argument (need M >= 1, N >= 2, at least one metric and one scale)");
   const int M = (int)M64, N = (int)N64;
   for (int k = 0; k < nmetrics; ++k)
-    if (metric_ids[k] < 0 || metric_ids[k] > SEQJ_ENERGY_GRID) return fail(h, SEQJ_E_BADARG, "unknown metric id");
+    if (metric_ids[k] < 0 || metric_ids[k] > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "unknown metric id");
   for (int l = 0; l < nscales; ++l)
     if (scales[l] < 1 || scales[l] > M)
       return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scales[l]) +
@@ -870,9 +905,10 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   *out = nullptr;
   Ctx c(h);
   const int G = nmetrics * nscales;
-  bool needP = false, needLog = false, needUc = false, needWE = false, needWG = false;
+  bool needP = false, needLog = false, needUc = false, needWE = false, needWG = false, needPer = false;
   for (int k = 0; k < nmetrics; ++k) {
-    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD;
+    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_PERIODIC;
+    needPer |= metric_ids[k] == SEQJ_PERIODIC;
     needLog |= metric_ids[k] == SEQJ_KLD;
     needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;
     needWE |= metric_ids[k] == SEQJ_EMD_GRID;
@@ -888,6 +924,15 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     layouts.push_back(make_layout(M, scales[l]));
     max_ldX = std::max(max_ldX, layouts.back().ldX);
     max_chunks = std::max(max_chunks, layouts.back().nchunks);
+  }
+  if (needPer) {                  // PeriodicEuclidean(periods) only evaluates vectors of length(periods)
+    if ((int64_t)h->periods.size() != M64)
+      return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean needs one period per row. Got periods:" +
+                                        std::to_string(h->periods.size()) + " and A:" + std::to_string(M64));
+    for (int l = 0; l < nscales; ++l)
+      if (layouts[l].nchunks != 1)
+        return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean(periods) applies to whole columns only; scale " +
+                                          std::to_string(scales[l]) + " splits them into chunks of " + std::to_string(layouts[l].cl) + " rows");
   }
   const bool partial = (chunk_lo != nullptr);
   if (partial && (!chunk_hi || !S_out)) return fail(h, SEQJ_E_BADARG, "partial mode needs chunk_hi and S_out");
@@ -924,6 +969,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(c.pool.alloc(&pb.grid, (size_t)M));
     CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c.st));
   }
+  if (needPer) ST_TRY(upload_periods(c, pb, h->periods, layouts[0].cl_pad));
   FixBufs fb;
   std::vector<int2> tiles = make_tiles(N, true);
   ST_TRY(alloc_fix(c, fb, 1u << 24, (size_t)max_chunks * tiles.size()));     // 16M flagged entries (256 MB) in the list
@@ -1317,7 +1363,7 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   struct Unit { double cost; std::vector<int> groups; };
   std::vector<Unit> units;
   for (int k = 0; k < nmetrics; ++k) {
-    const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID;
+    const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID || metric_ids[k] == SEQJ_PERIODIC;
     const bool contraction = metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_ENERGY;
     if (nested && contraction) {
       Unit u;
@@ -1344,6 +1390,7 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   std::vector<std::thread> threads;
   for (int d = 0; d < ndev; ++d) {
     hs[d]->grid = h->grid;
+    hs[d]->periods = h->periods;
     threads.emplace_back([&, d]() {
       bool any = false;
       for (uint8_t b : masks[d]) any |= b != 0;
@@ -1609,16 +1656,20 @@ int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, in
 int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m64, int64_t N64, int normalize,
                   int kl_full, double eps_floor, double l2_thresh, double* D_out) {
   ST_TRY(check_ready(h));
-  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_ENERGY_GRID) return fail(h, SEQJ_E_BADARG, "bad argument");
-  if (metric >= SEQJ_EMD_GRID && (int64_t)h->grid.size() != m64)
+  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "bad argument");
+  const bool grid_metric = metric == SEQJ_EMD_GRID || metric == SEQJ_ENERGY_GRID;
+  if (grid_metric && (int64_t)h->grid.size() != m64)
     return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of the chunk");
+  if (metric == SEQJ_PERIODIC && (int64_t)h->periods.size() != m64)
+    return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean needs one period per row of the chunk");
   const int m = (int)m64, N = (int)N64;
   Ctx c(h);
   ScaleLayout L = make_layout(m, 1);
   PrepBufs pb;
-  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD, metric == SEQJ_KLD,
+  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD || metric == SEQJ_PERIODIC, metric == SEQJ_KLD,
                     metric == SEQJ_EMD || metric == SEQJ_ENERGY, false, metric == SEQJ_EMD_GRID, metric == SEQJ_ENERGY_GRID));
-  if (metric >= SEQJ_EMD_GRID) {
+  if (metric == SEQJ_PERIODIC) ST_TRY(upload_periods(c, pb, h->periods, L.cl_pad));
+  if (grid_metric) {
     CU_TRY(c.pool.alloc(&pb.grid, (size_t)m));
     CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * m, cudaMemcpyHostToDevice, c.st));
   }

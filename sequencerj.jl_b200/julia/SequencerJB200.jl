@@ -17,7 +17,7 @@ using SimpleWeightedGraphs
 using SparseArrays: sparse
 
 export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!, emd, energy
-export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS
+export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS, PERIODIC, set_periods!
 
 const libseqj = get(ENV, "SEQJ_B200_LIB", joinpath(@__DIR__, "..", "libseqj_b200.so"))
 
@@ -233,6 +233,15 @@ function _cdf_distance(mid::Integer, u, v, uw, vw)
                    Vector{Float64}(v), Vector{Float64}(vw), length(v), out))
     out[]
 end
+# ---- Distances.PeriodicEuclidean(periods) on the B200 path (metric id 6; reference test/runtests.jl:189-236) ----
+const PERIODIC = B200Metric(6, "PeriodicEuclidean")
+"Set the periods used by the `PERIODIC` metric: `set_periods!(P); sequence(A; metrics=(PERIODIC,), scales=(1,))`."
+function set_periods!(periods::AbstractVector{<:Real})
+    h = handle()
+    p = Vector{Float64}(periods)
+    check(h, ccall((:seqj_set_periods, libseqj), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, p, length(p)))
+end
+
 "`emd(u, v, uw, vw)`: EMD between the weighted ECDFs on the grids `u`, `v` (reference :108)."
 emd(u, v, uw, vw) = _cdf_distance(1, u, v, uw, vw)
 "`emd(u, v)`: weights on the default unit grids `axes(u,1)`, `axes(v,1)` (reference :101)."

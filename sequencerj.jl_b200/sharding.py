@@ -14,7 +14,7 @@ import numpy as np
 from . import api
 
 # relative FP64 issue cost per pair-element (EMD = 2 DADD, contractions = 1 DMMA lane-FMA)
-METRIC_COST = {0: 1.0, 1: 2.0, 2: 1.0, 3: 1.0}
+METRIC_COST = {0: 1.0, 1: 2.0, 2: 1.0, 3: 1.0, 4: 2.0, 5: 1.0, 6: 2.0}     # direct (FP64 ALU) tiles cost twice the DMMA ones
 PRIM_COST_ROWS = 600.0     # one Prim row pass costs about as much as this many k-elements of distance work
 
 

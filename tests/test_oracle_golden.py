@@ -205,3 +205,19 @@ def test_explicit_grid_same_grid_branch(oracle):
     unit = np.arange(1, 16, dtype=float)
     assert np.allclose(oracle.chunk_distance(oracle.EMD_GRID, P, lgrid=unit), oracle.chunk_distance(oracle.EMD, P), rtol=1e-13)
     assert np.allclose(oracle.chunk_distance(oracle.ENERGY_GRID, P, lgrid=unit), oracle.chunk_distance(oracle.ENERGY, P), rtol=1e-13)
+
+
+def test_periodic_euclidean_restatement(oracle):
+    """Distances.PeriodicEuclidean is an un-vendored dependency (Distances.jl, Project.toml compat 0.10) with no
+    known-answer vector in the reference's tests (test/runtests.jl:189-236 only bounds a loss); these are hand
+    evaluations of its published definition  sqrt(sum min(s, p - s)^2), s = |a - b| mod p."""
+    assert abs(oracle.periodic_euclidean([0.1], [0.9], [1.0]) - 0.2) < 1e-15            # fold: 0.8 -> 0.2
+    assert abs(oracle.periodic_euclidean([0.0], [2.3], [1.0]) - 0.3) < 1e-12            # wrap: 2.3 -> 0.3
+    d = oracle.periodic_euclidean([0.0, 0.0], [0.75, 0.0], [0.5, 1.0])                  # 0.75 mod 0.5 = 0.25
+    assert abs(d - 0.25) < 1e-15
+    big = oracle.periodic_euclidean([0.1, 0.2], [0.3, 0.1], [10.0, 10.0])               # large periods = Euclidean
+    assert abs(big - oracle.euclidean([0.1, 0.2], [0.3, 0.1])) < 1e-15
+    P = np.random.default_rng(0).random((7, 5))
+    per = np.full(7, 0.3)
+    rel = np.abs(oracle.pairwise_periodic(P, per) - oracle.pairwise_periodic(P, per, faithful=True)).max()
+    assert rel < 1e-15
