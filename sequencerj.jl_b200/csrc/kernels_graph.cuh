@@ -32,6 +32,7 @@ struct PrimParams {
   double* key_g;        // global scratch [graph][ldv] (used when the keys do not fit in smem)
   int* from_g;
   int use_smem;
+  int prefetch;         // cluster kernel: prefetch the losing candidates' rows into L2 (few graphs in flight)
 };
 
 __device__ __forceinline__ void argmin_combine(double& k, int& v, double ok, int ov) {
@@ -201,8 +202,8 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
 // its 16-byte candidate to all peers with st.async (distributed shared memory) that completes a
 // transaction on the receiver's mbarrier; each CTA waits on its own mbarrier and reduces the C
 // candidates locally.  Buffers and mbarriers are double-buffered by step parity.
-constexpr int kPrimClThreads = 256;
-constexpr int kPrimClUnroll = 4;
+constexpr int kPrimClThreads = 512;
+constexpr int kPrimClUnroll = 2;
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -222,13 +223,16 @@ __device__ __forceinline__ uint32_t ld_dsmem_u32(uint32_t addr) {
   asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void prefetch_l2_bulk(const void* src, uint32_t bytes) {     // bytes % 16 == 0, src 16 B aligned
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void st_async_u64x2(uint32_t dst, unsigned long long a, unsigned long long b, uint32_t mbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
                ::"r"(dst), "l"(a), "l"(b), "r"(mbar) : "memory");
 }
 
 template <int C>
-__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 4)
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 2)
 prim_cluster_kernel(PrimParams p, int W) {
   constexpr int kU = kPrimClUnroll;
   extern __shared__ unsigned long long primc_sm[];
@@ -338,7 +342,14 @@ prim_cluster_kernel(PrimParams p, int W) {
         return (int)ld_dsmem_u32(mapa_u32(from_u32 + (uint32_t)((v - owner * W) * 4), (uint32_t)owner));
       };
       auto fence = [&]() { cluster_sync_all(); };
+      const int cv = bv;                              // lane j < C: the candidate of CTA j
       warp_argmin_edge(bk, bv, getf_remote, fence, fence);
+      // The C - 1 losers stay candidates for the next steps (their keys only compete with newly relaxed
+      // vertices), so the next winner is usually one of them: pull this CTA's slice of their rows into L2 now and
+      // the next step's row fetch costs an L2 hit instead of a DRAM round trip.  Rows already resident cost no
+      // DRAM traffic, so the extra traffic is about one row per step.
+      if (p.prefetch && warp == 0 && lane < C && cv != bv && cv != 0x7fffffff && Wn > 1)
+        prefetch_l2_bulk(D + (int64_t)cv * p.ldD + v0, (uint32_t)((Wn * 8) & ~15));
     }
     u = bv;
     const int ul = u - v0;

@@ -325,12 +325,13 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   pp.D = D; pp.ldD = ldD; pp.strideD = strideD; pp.N = g.N; pp.eps_floor = eps_floor; pp.mat_slot = mat_slot;
   pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
+  pp.prefetch = getenv("SEQJ_PRIM_PREFETCH") ? atoi(getenv("SEQJ_PRIM_PREFETCH")) : 1;
   int t = c.timer.begin(SEQJ_T_PRIM);
   // Measured on B200 at N = 10k (profiles/r01_prim_variants.md): with >= ~50 graphs in flight the single-CTA
   // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
   // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.
   const bool force_cluster = getenv("SEQJ_PRIM") && !strcmp(getenv("SEQJ_PRIM"), "cluster");
-  if (g.cluster && (force_cluster || nb * 3 <= h->sm_count)) {
+  if (g.cluster && (force_cluster || nb * kPrimCluster <= 2 * h->sm_count)) {    // all clusters co-resident, 2 CTAs per SM
     int W = 0;
     size_t smem = 0;
     prim_cluster_geometry(g.N, kPrimCluster, &W, &smem);
