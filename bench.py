@@ -333,14 +333,14 @@ def main():
     if emd_ms > 0:
         ach = emd_instr / (emd_ms * 1e-3) / 1e12
         pk = peaks.get("dabsdiff_b2_t512_tinstr", 17.6)
-        roof_emd = {"kernel": "emd_dist_kernel", "bound": "fp64-issue", "achieved": ach, "peak": pk, "unit": "Tinstr/s",
+        roof_emd = {"kernel": "direct_dist_kernel<OP_L1> (EMD tiles)", "bound": "fp64-issue", "achieved": ach, "peak": pk, "unit": "Tinstr/s",
                     "frac": ach / pk}
     roof_prim = None
     if phases.get("prim", 0) > 0:
         ach = prim_bytes / (phases["prim"] * 1e-3) / 1e9
         roof_prim = {"kernel": "prim_kernel + prim_cluster_kernel (all launches of the step)", "bound": "hbm", "achieved": ach,
                      "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                     "note": "the 124-graph launch alone streams 99.2 GB in 23.2 ms = 4.28 TB/s = 65.5 % "
+                     "note": "the 124-graph launch alone streams 99.2 GB in 23.4 ms = 4.24 TB/s = 65 % "
                              "(profiles/r01_ncu_config3_metrics.json); the small launches are latency-bound"}
     if roof is None:
         roof = roof_emd
@@ -361,7 +361,7 @@ def main():
                       "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
            "sequence_wall_s": elapsed / args.steps, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
            "roofline_emd": roof_emd, "roofline_prim": roof_prim,
-           "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "emd_dist_kernel (FP64 ALU issue-bound, see roofline_emd)"),
+           "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "direct_dist_kernel<OP_L1> = EMD tiles (FP64 ALU issue-bound, see roofline_emd)"),
                                            (gemm_ms, "gemm_dist_kernel (FP64 tensor pipe, see roofline)"),
                                            (phases.get("prim", 0), "prim kernels (HBM / latency, see roofline_prim)")))[1], "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},

@@ -202,8 +202,8 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
 // its 16-byte candidate to all peers with st.async (distributed shared memory) that completes a
 // transaction on the receiver's mbarrier; each CTA waits on its own mbarrier and reduces the C
 // candidates locally.  Buffers and mbarriers are double-buffered by step parity.
-constexpr int kPrimClThreads = 512;
-constexpr int kPrimClUnroll = 2;
+// T threads per CTA: 512 (one pair per thread at N = 10k, shortest per-warp chain; 2 CTAs per SM) when all clusters
+// are co-resident that way, else 256 (4 CTAs per SM).
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -231,15 +231,15 @@ __device__ __forceinline__ void st_async_u64x2(uint32_t dst, unsigned long long 
                ::"r"(dst), "l"(a), "l"(b), "r"(mbar) : "memory");
 }
 
-template <int C>
-__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(kPrimClThreads, 2)
+template <int C, int T>
+__global__ void __cluster_dims__(C, 1, 1) __launch_bounds__(T, 1024 / T)
 prim_cluster_kernel(PrimParams p, int W) {
-  constexpr int kU = kPrimClUnroll;
+  constexpr int kU = 1024 / T;                        // 16-byte loads in flight per thread: slices of <= 2048 vertices in one pass
   extern __shared__ unsigned long long primc_sm[];
   __shared__ __align__(16) ulonglong2 cand[2][C];
   __shared__ __align__(8) uint64_t mbar[2];
-  __shared__ unsigned long long wk[kPrimClThreads / 32];
-  __shared__ int wv[kPrimClThreads / 32];
+  __shared__ unsigned long long wk[T / 32];
+  __shared__ int wv[T / 32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int graph = blockIdx.x / C;
@@ -258,7 +258,7 @@ prim_cluster_kernel(PrimParams p, int W) {
   const unsigned long long kInf = 0x7ff0000000000000ull;
   const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
 
-  for (int v = tid; v < Wp; v += kPrimClThreads) { key[v] = (v < Wn) ? kInf : 0ull; from[v] = 0; }
+  for (int v = tid; v < Wp; v += T) { key[v] = (v < Wn) ? kInf : 0ull; from[v] = 0; }
   if (tid == 0) {
     mbar_init(&mbar[0], 1);
     mbar_init(&mbar[1], 1);
@@ -277,16 +277,16 @@ prim_cluster_kernel(PrimParams p, int W) {
     const double* __restrict__ row = D + (int64_t)u * p.ldD + v0;
     unsigned long long bk = kPrimNone;
     int bv = 0x7fffffff, bl = 0x7fffffff;
-    for (int base = 2 * tid; base < Wn; base += 2 * kPrimClThreads * kU) {
+    for (int base = 2 * tid; base < Wn; base += 2 * T * kU) {
       ulonglong2 dv[kU];
 #pragma unroll
       for (int r = 0; r < kU; ++r) {
-        const int v = base + r * 2 * kPrimClThreads;
+        const int v = base + r * 2 * T;
         if (v < Wn) dv[r] = ldg_stream_u64x2(row + v);
       }
 #pragma unroll
       for (int r = 0; r < kU; ++r) {
-        const int v = base + r * 2 * kPrimClThreads;
+        const int v = base + r * 2 * T;
         if (v < Wn) {
           ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
           const int gv = v0 + v;                                         // global vertex id
@@ -307,7 +307,7 @@ prim_cluster_kernel(PrimParams p, int W) {
       }
     }
     if (bl != bv) {                                        // rare: two of this thread's candidates tie at its minimum
-      for (int v = 2 * tid; v < Wn; v += 2 * kPrimClThreads) {
+      for (int v = 2 * tid; v < Wn; v += 2 * T) {
         const ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
         const int gv = v0 + v;
         if (k2.x - 1ull == bk && gv != bv && edge_less(gv, from[v], bv, from[bv - v0])) bv = gv;
@@ -319,8 +319,8 @@ prim_cluster_kernel(PrimParams p, int W) {
     if (lane == 0) { wk[warp] = bk; wv[warp] = bv; }
     __syncthreads();
     if (warp == 0) {
-      bk = (lane < kPrimClThreads / 32) ? wk[lane] : kPrimNone;
-      bv = (lane < kPrimClThreads / 32) ? wv[lane] : 0x7fffffff;
+      bk = (lane < T / 32) ? wk[lane] : kPrimNone;
+      bv = (lane < T / 32) ? wv[lane] : 0x7fffffff;
       warp_argmin_edge(bk, bv, getf);
       if (lane == 0) mbar_expect_tx(&mbar[par], C * 16);
       if (lane < C) {                                  // lane j delivers this CTA's candidate to CTA j
@@ -353,7 +353,7 @@ prim_cluster_kernel(PrimParams p, int W) {
     }
     u = bv;
     const int ul = u - v0;
-    if (ul >= 0 && ul < Wn && ((ul >> 1) & (kPrimClThreads - 1)) == tid) {   // the owner of key[u] retires it
+    if (ul >= 0 && ul < Wn && ((ul >> 1) & (T - 1)) == tid) {   // the owner of key[u] retires it
       order[step] = u;
       parent[u] = from[ul];
       weight[u] = __longlong_as_double((long long)(bk + 1ull));

@@ -305,7 +305,8 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
     prim_cluster_geometry(N, kPrimCluster, nullptr, &smem2);
     if (smem2 + 4096 > h->max_smem) g.cluster = 0;
     else {
-      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<kPrimCluster, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<kPrimCluster, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     }
   }
   g.tree_smem = (size_t)N * 8;
@@ -331,14 +332,17 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
   // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.
   const bool force_cluster = getenv("SEQJ_PRIM") && !strcmp(getenv("SEQJ_PRIM"), "cluster");
-  if (g.cluster && (force_cluster || nb * kPrimCluster <= 2 * h->sm_count)) {    // all clusters co-resident, 2 CTAs per SM
-    int W = 0;
-    size_t smem = 0;
-    prim_cluster_geometry(g.N, kPrimCluster, &W, &smem);
-    prim_cluster_kernel<kPrimCluster><<<nb * kPrimCluster, kPrimClThreads, smem, c.st>>>(pp, W);
-  } else {
+  // cluster kernel while every cluster is resident at once: 512-thread CTAs (2 per SM) up to 2*SMs/8 graphs,
+  // 256-thread CTAs up to SMs/3 graphs (profiles/r01_prim_variants.md); beyond that one CTA per graph
+  int W = 0;
+  size_t smem = 0;
+  prim_cluster_geometry(g.N, kPrimCluster, &W, &smem);
+  if (g.cluster && nb * kPrimCluster <= 2 * h->sm_count)
+    prim_cluster_kernel<kPrimCluster, 512><<<nb * kPrimCluster, 512, smem, c.st>>>(pp, W);
+  else if (g.cluster && (force_cluster || nb * 3 <= h->sm_count))
+    prim_cluster_kernel<kPrimCluster, 256><<<nb * kPrimCluster, 256, smem, c.st>>>(pp, W);
+  else
     prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
-  }
   c.timer.end(t); c.launches++;
   CU_TRY(cudaGetLastError());
   TreeParams tp;
