@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   if (tid == 0) {
     int v = root, prev = root;
     while (true) {
-      const int nxt = parent[v];
+      const int nxt = par_s[v];                      // shared-memory copy when it fits: the path can be ~N long
       newparent[v] = prev;
       if (v == r0) break;
       prev = v;
@@ -875,7 +875,7 @@ struct RootTreeParams {
   int* deg;      // global scratch [N+1]      (used when the CSR does not fit in shared memory)
   int* adj;      // global scratch [2(N-1)]
   int* queue;    // global scratch [N]
-  int use_smem;  // dynamic smem holds deg (N+1) + adj (2N) + queue (N) + visited bitmap (N/32 + 1) ints
+  int use_smem;  // dynamic smem holds deg (N+1) + adj (2N) + queue (N) + queue parents (N) ints
   int* parent;   // out [N]
   double* weight;
   int* order;
@@ -887,17 +887,35 @@ __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
   int* deg = p.use_smem ? rt_sm : p.deg;
   int* adj = p.use_smem ? rt_sm + (N + 1) : p.adj;
   int* queue = p.use_smem ? rt_sm + (3 * N + 1) : p.queue;
-  unsigned* visited = reinterpret_cast<unsigned*>(p.use_smem ? rt_sm + (4 * N + 1) : p.queue + N);
+  int* qpar = p.use_smem ? rt_sm + (4 * N + 1) : p.queue + N;     // parent of every queue entry
   int* fill = p.parent;                         // parent[] doubles as the CSR fill cursor before the BFS
   for (int v = tid; v <= N; v += 1024) deg[v] = 0;
-  for (int v = tid; v < (N + 31) / 32; v += 1024) visited[v] = 0u;
   __syncthreads();
   for (int e = tid; e < ne; e += 1024) { atomicAdd(&deg[p.ei[e]], 1); atomicAdd(&deg[p.ej[e]], 1); }
   __syncthreads();
-  if (tid == 0) {
-    int run = 0;
-    for (int v = 0; v < N; ++v) { const int d = deg[v]; deg[v] = run; fill[v] = run; run += d; }
-    deg[N] = run;
+  {                                             // exclusive scan of the degrees: chunk per thread + scan of the chunk sums
+    __shared__ int s_part[1024];
+    const int per = (N + 1023) / 1024, lo = min(N, tid * per), hi = min(N, lo + per);
+    int sum = 0;
+    for (int v = lo; v < hi; ++v) sum += deg[v];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid < 32) {                             // warp 0 scans the 1024 partial sums, 32 per lane
+      int run = 0;
+      for (int q = 0; q < 32; ++q) { const int x = s_part[tid * 32 + q]; s_part[tid * 32 + q] = run; run += x; }
+      int incl = run;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += y;
+      }
+      const int base = incl - run;
+      for (int q = 0; q < 32; ++q) s_part[tid * 32 + q] += base;
+    }
+    __syncthreads();
+    int run = s_part[tid];
+    for (int v = lo; v < hi; ++v) { const int d = deg[v]; deg[v] = run; fill[v] = run; run += d; }
+    if (tid == 1023) deg[N] = 2 * ne;
   }
   __syncthreads();
   for (int e = tid; e < ne; e += 1024) {
@@ -907,20 +925,26 @@ __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
   }
   __syncthreads();
   if (tid == 0) {                               // BFS from vertex 0; the final tree is path-like (depth ~ N)
+    // In a tree the only already-visited neighbour of u is its parent, so no visited set is needed: the parent
+    // travels with the queue entry.  ~4 dependent shared-memory reads per vertex.
     int head = 0, tail = 0;
-    queue[tail++] = 0;
-    visited[0] |= 1u;
+    queue[tail] = 0; qpar[tail++] = 0;
     p.parent[0] = 0;
-    while (head < tail) {
-      const int u = queue[head++];
-      for (int k = deg[u]; k < deg[u + 1]; ++k) {
+    int u = 0, pu = 0, k0 = deg[0], k1 = deg[1];
+    while (true) {
+      // one thread, one dependent chain: what counts is the instruction count per vertex, so the (degree ~2)
+      // neighbour loop is NOT unrolled (the unrolled remainder cascade cost ~30 extra instructions per vertex)
+#pragma unroll 1
+      for (int k = k0; k < k1; ++k) {
         const int v = adj[k];
-        if (!((visited[v >> 5] >> (v & 31)) & 1u)) {
-          visited[v >> 5] |= 1u << (v & 31);
+        if (v != pu || head == 0) {               // the root has no parent edge (its qpar entry is itself)
           p.parent[v] = u;
-          queue[tail++] = v;
+          queue[tail] = v; qpar[tail++] = u;
         }
       }
+      if (++head >= tail) break;
+      u = queue[head]; pu = qpar[head];
+      k0 = deg[u]; k1 = deg[u + 1];
     }
   }
   __syncthreads();

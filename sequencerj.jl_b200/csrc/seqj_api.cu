@@ -685,8 +685,8 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
     rp.deg = gws.fuse_i0; rp.adj = gws.fuse_i1; rp.queue = gws.fuse_i1 + 2 * (size_t)N;
     rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
-    const size_t rt_smem = ((size_t)4 * N + 1 + (N + 31) / 32 + 1) * 4;
-    rp.use_smem = rt_smem + 2048 <= h->max_smem;
+    const size_t rt_smem = ((size_t)5 * N + 2) * 4;          // deg (N+1) + adj (2N) + queue (N) + queue parents (N)
+    rp.use_smem = rt_smem + 8192 <= h->max_smem;      // + 4 KB of static shared memory in the kernel
     CU_TRY(cudaFuncSetAttribute(root_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rp.use_smem ? rt_smem : 0)));
     root_tree_kernel<<<1, 1024, rp.use_smem ? rt_smem : 0, c.st>>>(rp);
     c.launches += 2;
