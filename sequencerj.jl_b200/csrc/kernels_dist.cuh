@@ -47,7 +47,6 @@ struct DistParams {
   // without one (EMD) every CTA computes the tile (blockIdx.x, blockIdx.y)
   const int2* dense_list;
   const unsigned int* dense_count;
-  int* sm_slots;        // optional [#SMs] counters (zeroed before the launch) for the first-wave stagger
   int kl_swap;          // KL full mode: operand A = log P, B = P, so that D[r][c] = KL(p_c || p_r), i.e. the
                         // row-major buffer is the column-major pairwise matrix of the C ABI
   // fix-up list
@@ -74,28 +73,6 @@ __device__ __forceinline__ double fast_sqrt(double v) {
   double sq = v * y;
   sq = fma(fma(-sq, sq, v), 0.5 * y, sq);
   return v > 0.0 ? sq : 0.0;
-}
-
-// The two CTAs that share an SM start together and, with identical work per tile, stay in lock-step: both run
-// their epilogue (no DMMA) at the same time and the FP64 pipe idles (ncu: 72.6 % busy at 16 k-stages per tile).
-// The CTA that arrives second on an SM in the FIRST wave waits about half a shared-tile time; every later CTA
-// starts when its predecessor in the same slot retires, so the offset persists for the whole launch.
-__device__ __forceinline__ void stagger_first_wave(int* sm_slots, int nk, int cycles_per_stage) {
-  if (sm_slots == nullptr) return;
-  const unsigned lin = blockIdx.x + blockIdx.y * gridDim.x;
-  __shared__ int s_second;
-  if (lin < 2u * 148u) {                 // first wave only (2 CTAs per SM)
-    if (threadIdx.x == 0) {
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      s_second = atomicAdd(&sm_slots[smid % 256], 1) & 1;
-    }
-    __syncthreads();
-    if (s_second) {
-      const long long t0 = clock64(), wait = (long long)nk * cycles_per_stage;
-      while (clock64() - t0 < wait) __nanosleep(200);
-    }
-  }
 }
 
 template <int MODE, bool INTERIOR>
@@ -205,7 +182,6 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tma_prefetch_desc(&tmB);
   }
   __syncthreads();
-  stagger_first_wave(p.sm_slots, p.nk, 2048);
 
   if (threadIdx.x == 0)
     for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmA, &tmB, s, it, kbase, i0, j0);
@@ -310,7 +286,6 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
       tma_prefetch_desc(&tmU);
     }
     __syncthreads();
-    if (!listed) stagger_first_wave(p.sm_slots, p.nk, 4096);
     if (threadIdx.x == 0)
       for (int it = 0; it < min(kStages, p.nk); ++it) tile_issue(&tmU, &tmU, s, it, kbase, i0, j0);
 

@@ -399,7 +399,6 @@ struct FixBufs {
   unsigned int* dense_count = nullptr;
   unsigned char* tile_flags = nullptr;   // [max chunks per launch][ntiles] dense-tile flags
   size_t tile_flags_bytes = 0;
-  int* sm_slots = nullptr;        // per-SM arrival counters for the first-wave stagger of the tile kernels
   int4* list = nullptr;
   unsigned int* count = nullptr;
   int* overflow = nullptr;
@@ -422,7 +421,7 @@ int run_dense_tiles(Ctx& c, int metric, DistParams dd, const CUtensorMap& tm1, c
   CU_TRY(cudaMemsetAsync(fb.dense_count, 0, sizeof(unsigned int), c.st));
   const int total = ntiles * nb;
   compact_flags_kernel<<<(total + 255) / 256, 256, 0, c.st>>>(fb.tile_flags, total, ntiles, fb.dense_list, fb.dense_count);
-  dd.dense_list = fb.dense_list; dd.dense_count = fb.dense_count; dd.sm_slots = nullptr;
+  dd.dense_list = fb.dense_list; dd.dense_count = fb.dense_count;
   const int grid = h->sm_count * 2 * 4;
   if (metric == SEQJ_L2) direct_dist_kernel<OP_SQ><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
   else if (metric == SEQJ_ENERGY) direct_dist_kernel<OP_SQ_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
@@ -460,9 +459,6 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   dp.period = nullptr;
   const int phase = SEQJ_T_DIST_L2 + metric;
   int t = c.timer.begin(phase);
-  const char* stg = getenv("SEQJ_STAGGER");
-  dp.sm_slots = (stg && atoi(stg) == 0) ? nullptr : fb.sm_slots;
-  if (dp.sm_slots) CU_TRY(cudaMemsetAsync(fb.sm_slots, 0, 256 * sizeof(int), c.st));
   dim3 grid(ntiles, nb);
   if (periodic) {                 // Distances.PeriodicEuclidean: element-wise fold, direct tiles on the PDFs
     CUtensorMap tmP;
@@ -580,7 +576,7 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
     dd.N = N; dd.ldD = ldD; dd.strideD = strideD; dd.D = D; dd.nk = L.cl_pad / kTileK; dd.cl_pad = L.cl_pad;
     dd.chunk0 = c0; dd.normA = nullptr; dd.ldn = pb.ldn; dd.tiles = tiles_dev; dd.eps_floor = eps_floor; dd.tau = 0;
     dd.mirror = 1; dd.kl_swap = 0; dd.tile_flags = fb.tile_flags; dd.tile_flag_stride = ntiles; dd.dense_thresh = 0;
-    dd.dense_list = nullptr; dd.dense_count = nullptr; dd.sm_slots = nullptr;
+    dd.dense_list = nullptr; dd.dense_count = nullptr;
     dd.fix_list = fb.list; dd.fix_count = fb.count; dd.fix_cap = fb.cap; dd.fix_overflow = fb.overflow;
     CUtensorMap tm1, tm2;
     if (metric == SEQJ_ENERGY) {
@@ -645,7 +641,6 @@ int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap, size_t tile_flags_bytes = 0
   CU_TRY(c.pool.alloc(&fb.list, (size_t)cap));
   CU_TRY(c.pool.alloc(&fb.count, 1));
   CU_TRY(c.pool.alloc(&fb.overflow, 1));
-  CU_TRY(c.pool.alloc(&fb.sm_slots, 256));
   return SEQJ_OK;
 }
 
