@@ -363,6 +363,35 @@ prim_cluster_kernel(PrimParams p, int W) {
   cluster_sync_all();                                  // no CTA exits while a peer may still write to it
 }
 
+// in-place exclusive scan of a[0..n) by one CTA of 1024 threads; returns the total
+__device__ int block_excl_scan_i32(int* a, int n, int* s_part) {
+  const int tid = threadIdx.x;
+  const int per = (n + 1023) / 1024, lo = min(n, tid * per), hi = min(n, lo + per);
+  int sum = 0;
+  for (int v = lo; v < hi; ++v) sum += a[v];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid < 32) {                               // warp 0 scans the 1024 partial sums, 32 per lane
+    int run = 0;
+    for (int q = 0; q < 32; ++q) { const int x = s_part[tid * 32 + q]; s_part[tid * 32 + q] = run; run += x; }
+    int incl = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (tid >= o) incl += y;
+    }
+    const int base = incl - run;
+    for (int q = 0; q < 32; ++q) s_part[tid * 32 + q] += base;
+    if (tid == 31) s_part[1024] = incl;
+  }
+  __syncthreads();
+  int run = s_part[tid];
+  for (int v = lo; v < hi; ++v) { const int d = a[v]; a[v] = run; run += d; }
+  const int total = s_part[1024];
+  __syncthreads();
+  return total;
+}
+
 // ---- tree measurement -------------------------------------------------------------------------
 struct TreeParams {
   int N;
@@ -381,7 +410,7 @@ struct TreeParams {
   int* dep0;
   int* dep1;
   int use_smem;           // parent + size fit in dynamic shared memory (8N bytes)
-  int dfs_smem;           // the DFS scratch (16N + 16 bytes) fits in dynamic shared memory
+  int have_size;          // size[] already holds the subtree sizes (root_tree_kernel): skip the sequential pass
   // outputs (per graph g: index out0 + g)
   double* eta;            // [ngraphs]
   int* root;              // [ngraphs]
@@ -424,7 +453,7 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   for (int v = tid; v < N; v += kTreeThreads) {
     const int q = parent[v];
     if (p.use_smem) par_s[v] = q;
-    size_s[v] = 1;
+    size_s[v] = p.have_size ? size[v] : 1;
     newparent[v] = q;
   }
   if (p.mst_i) {
@@ -438,7 +467,7 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   __syncthreads();
 
   // 1. subtree sizes, sequential in reverse insertion order
-  if (tid == 0) {
+  if (tid == 0 && !p.have_size) {
     int t = N - 1;
     for (; t >= 4; t -= 4) {                      // order[] is read 4 ahead of the dependent chain
       const int v0 = order[t], v1 = order[t - 1], v2 = order[t - 2], v3 = order[t - 3];
@@ -582,35 +611,78 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
     }
   }
 
-  // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24)
+  // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24), without a sequential DFS:
+  // children lists in CSR form (sorted by a rank sort inside each list), then the Euler tour of the rooted tree --
+  // entering a vertex continues with its first child, returning from a child with the next sibling, else back to
+  // the parent -- ranked by pointer jumping (O(log N) rounds); the preorder number of a vertex is the count of
+  // "down" arcs up to the one that enters it.  Integers only.
   if (p.dfs_order) {
     __syncthreads();
-    // children CSR + explicit stack; in shared memory when the launch provided 16N+16 bytes (dfs_smem)
-    int* cstart = p.dfs_smem ? tree_sm : size;
-    int* clist = p.dfs_smem ? tree_sm + (N + 1) : anc_a;
-    int* stack = p.dfs_smem ? tree_sm + (2 * N + 1) : anc_b;
-    int* fill = p.dfs_smem ? tree_sm + (3 * N + 1) : dep_a;
-    int* pre = dep_b;                                   // global: written once, read by the parallel reverse copy
+    __shared__ int s_scan[1025];
+    const int M = N - 1, A = 2 * M;
+    if (N == 1) {
+      if (tid == 0) p.dfs_order[oofs] = root;
+      return;
+    }
+    int* cstart = size;                                 // [N + 1] children CSR offsets   (all arrays below are free now)
+    int* tmp = anc_a;                                   // [M] children in arrival order
+    int* clist = anc_b;                                 // [M] children, ascending inside every list
+    int* qpos = dep_a;                                  // [N] position of a vertex in its parent's list
+    int* fillc = dep_b;                                 // [N] fill cursors
+    int* succ_i = reinterpret_cast<int*>(p.wd + gofs);  // [A] each: arc 2q = parent -> clist[q], arc 2q+1 = back
+    int* rank_i = reinterpret_cast<int*>(p.wd2 + gofs);
+    int* succ_o = reinterpret_cast<int*>(p.S + gofs);
+    int* rank_o = reinterpret_cast<int*>(p.S2 + gofs);
     for (int v = tid; v <= N; v += kTreeThreads) cstart[v] = 0;
     __syncthreads();
     for (int v = tid; v < N; v += kTreeThreads)
       if (v != root) atomicAdd(&cstart[newparent[v]], 1);
     __syncthreads();
-    if (tid == 0) {
-      int run = 0;
-      for (int v = 0; v < N; ++v) { const int c = cstart[v]; cstart[v] = run; fill[v] = run; run += c; }
-      cstart[N] = run;
-      for (int v = 0; v < N; ++v) if (v != root) clist[fill[newparent[v]]++] = v;   // ascending v per parent
-      int sp = 0, np = 0;
-      stack[sp++] = root;
-      while (sp > 0) {
-        const int x = stack[--sp];
-        pre[np++] = x;
-        for (int q = cstart[x + 1] - 1; q >= cstart[x]; --q) stack[sp++] = clist[q];
-      }
+    block_excl_scan_i32(cstart, N, s_scan);
+    if (tid == 0) cstart[N] = M;
+    for (int v = tid; v < N; v += kTreeThreads) fillc[v] = cstart[v];
+    __syncthreads();
+    for (int v = tid; v < N; v += kTreeThreads)
+      if (v != root) tmp[atomicAdd(&fillc[newparent[v]], 1)] = v;
+    __syncthreads();
+    for (int q = tid; q < M; q += kTreeThreads) {       // rank sort inside the list (lists are short: the tree is path-like)
+      const int c = tmp[q], x = newparent[c];
+      const int s0 = cstart[x], s1 = cstart[x + 1];
+      int r = s0;
+      for (int k = s0; k < s1; ++k) r += (tmp[k] < c);
+      clist[r] = c;
+      qpos[c] = r;
     }
     __syncthreads();
-    for (int k = tid; k < N; k += kTreeThreads) p.dfs_order[oofs + k] = pre[N - 1 - k];
+    for (int q = tid; q < M; q += kTreeThreads) {
+      const int c = clist[q], x = newparent[c];
+      // entering c: first child of c, else straight back up
+      succ_i[2 * q] = (cstart[c] < cstart[c + 1]) ? 2 * cstart[c] : 2 * q + 1;
+      // returning to x from c: next sibling, else up from x (the tour ends at the root)
+      succ_i[2 * q + 1] = (q + 1 < cstart[x + 1]) ? 2 * (q + 1) : (x == root ? -1 : 2 * qpos[x] + 1);
+      rank_i[2 * q] = 1;
+      rank_i[2 * q + 1] = (succ_i[2 * q + 1] < 0) ? 0 : 1;
+    }
+    __syncthreads();
+    for (int span = 1; span < A; span <<= 1) {          // rank = number of arcs after this one
+      for (int a = tid; a < A; a += kTreeThreads) {
+        const int sa = succ_i[a];
+        if (sa >= 0) { rank_o[a] = rank_i[a] + rank_i[sa]; succ_o[a] = succ_i[sa]; }
+        else { rank_o[a] = rank_i[a]; succ_o[a] = -1; }
+      }
+      __syncthreads();
+      int* t = succ_i; succ_i = succ_o; succ_o = t;
+      t = rank_i; rank_i = rank_o; rank_o = t;
+    }
+    int* flag = succ_o;                                 // [A]: 1 at the tour positions of the down arcs
+    for (int a = tid; a < A; a += kTreeThreads) flag[A - 1 - rank_i[a]] = (a & 1) ? 0 : 1;
+    __syncthreads();
+    block_excl_scan_i32(flag, A, s_scan);               // flag[pos] = down arcs before pos = preorder number - 1
+    for (int q = tid; q < M; q += kTreeThreads) {
+      const int pre = flag[A - 1 - rank_i[2 * q]] + 1;  // 1 .. N-1; the root is 0
+      p.dfs_order[oofs + (N - 1 - pre)] = clist[q];
+    }
+    if (tid == 0) p.dfs_order[oofs + N - 1] = root;
   }
 }
 
@@ -864,97 +936,98 @@ __global__ void __launch_bounds__(kBoruvkaThreads, 1) boruvka_sparse_kernel(Boru
   }
 }
 
-// Root the MST edge list at vertex 0: produce the (parent, weight, order) arrays that tree_kernel consumes
-// (the same contract as Prim's output: parents precede children in `order`).  CSR adjacency is built in
-// parallel, the BFS itself is one thread (the final tree is path-like, depth ~ N).
+// Root the MST edge list at vertex 0: produce the (parent, weight, order, size) arrays that tree_kernel consumes
+// (the same contract as Prim's output: parents precede children in `order`).  The final tree is path-like
+// (depth ~ N), so a BFS is N dependent steps of one thread (1.2 ms at N = 10k, 16 ms at N = 20k where its arrays
+// no longer fit in shared memory).  Instead: Euler tour + list ranking, O(log N) parallel rounds whatever the
+// shape of the tree.  Every edge becomes two arcs stored in CSR order; the successor of arc (u -> v) is the arc
+// after (v -> u) in v's list (cyclically), which links all 2(N-1) arcs into one tour; cutting it at the root's first
+// arc and ranking the list by pointer jumping gives every arc its position.  Arc (u -> v) is a tree edge
+// parent -> child iff it comes before its twin; the child's subtree size is half the distance between the two,
+// its preorder number the count of parent -> child arcs up to it.  Integers only, so the result is exact.
 struct RootTreeParams {
   int N;
   const int* ei;
   const int* ej;
   const double* ew;
-  int* deg;      // global scratch [N+1]      (used when the CSR does not fit in shared memory)
-  int* adj;      // global scratch [2(N-1)]
-  int* queue;    // global scratch [N]
-  int use_smem;  // dynamic smem holds deg (N+1) + adj (2N) + queue (N) + queue parents (N) ints
+  int* scratch;  // global scratch, 16 N + 64 ints
   int* parent;   // out [N]
   double* weight;
   int* order;
+  int* size;     // out [N]: subtree sizes (tree_kernel skips its sequential pass when they are given)
 };
 
 __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
-  extern __shared__ int rt_sm[];
-  const int tid = threadIdx.x, N = p.N, ne = N - 1;
-  int* deg = p.use_smem ? rt_sm : p.deg;
-  int* adj = p.use_smem ? rt_sm + (N + 1) : p.adj;
-  int* queue = p.use_smem ? rt_sm + (3 * N + 1) : p.queue;
-  int* qpar = p.use_smem ? rt_sm + (4 * N + 1) : p.queue + N;     // parent of every queue entry
-  int* fill = p.parent;                         // parent[] doubles as the CSR fill cursor before the BFS
-  for (int v = tid; v <= N; v += 1024) deg[v] = 0;
+  __shared__ int s_part[1025];
+  const int tid = threadIdx.x, N = p.N, M = N - 1, A = 2 * M;
+  if (N == 1) {
+    if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; p.size[0] = 1; }
+    return;
+  }
+  int* off = p.scratch;              // [N + 1] CSR offsets
+  int* fill = off + (N + 1);         // [N]     fill cursors
+  int* adjv = fill + N;              // [A]     head vertex of every arc
+  int* twin = adjv + A;              // [A]     index of the reverse arc
+  int* eidx = twin + A;              // [A]     edge of the arc
+  int* succ0 = eidx + A;             // [A] x 4 ping-pong buffers of the list ranking
+  int* rank0 = succ0 + A;
+  int* succ1 = rank0 + A;
+  int* rank1 = succ1 + A;
+  for (int v = tid; v <= N; v += 1024) off[v] = 0;
   __syncthreads();
-  for (int e = tid; e < ne; e += 1024) { atomicAdd(&deg[p.ei[e]], 1); atomicAdd(&deg[p.ej[e]], 1); }
+  for (int e = tid; e < M; e += 1024) { atomicAdd(&off[p.ei[e]], 1); atomicAdd(&off[p.ej[e]], 1); }
   __syncthreads();
-  {                                             // exclusive scan of the degrees: chunk per thread + scan of the chunk sums
-    __shared__ int s_part[1024];
-    const int per = (N + 1023) / 1024, lo = min(N, tid * per), hi = min(N, lo + per);
-    int sum = 0;
-    for (int v = lo; v < hi; ++v) sum += deg[v];
-    s_part[tid] = sum;
-    __syncthreads();
-    if (tid < 32) {                             // warp 0 scans the 1024 partial sums, 32 per lane
-      int run = 0;
-      for (int q = 0; q < 32; ++q) { const int x = s_part[tid * 32 + q]; s_part[tid * 32 + q] = run; run += x; }
-      int incl = run;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int y = __shfl_up_sync(0xffffffffu, incl, o);
-        if (tid >= o) incl += y;
-      }
-      const int base = incl - run;
-      for (int q = 0; q < 32; ++q) s_part[tid * 32 + q] += base;
+  block_excl_scan_i32(off, N, s_part);
+  if (tid == 0) off[N] = A;
+  for (int v = tid; v < N; v += 1024) fill[v] = off[v];
+  __syncthreads();
+  for (int e = tid; e < M; e += 1024) {
+    const int i = p.ei[e], j = p.ej[e];
+    const int pi = atomicAdd(&fill[i], 1), pj = atomicAdd(&fill[j], 1);
+    adjv[pi] = j; adjv[pj] = i;
+    twin[pi] = pj; twin[pj] = pi;
+    eidx[pi] = e; eidx[pj] = e;
+  }
+  __syncthreads();
+  // Euler tour: succ(u -> v) = the arc after (v -> u) in v's list; the tour starts at the root's first arc and ends
+  // with the arc whose successor would wrap around to it
+  const int last = twin[off[1] - 1];
+  for (int a = tid; a < A; a += 1024) {
+    const int v = adjv[a], t = twin[a];
+    succ0[a] = (a == last) ? -1 : ((t + 1 < off[v + 1]) ? t + 1 : off[v]);
+    rank0[a] = (a == last) ? 0 : 1;
+  }
+  __syncthreads();
+  int *si = succ0, *ri = rank0, *so = succ1, *ro = rank1;
+  for (int span = 1; span < A; span <<= 1) {     // rank = number of arcs after this one (Wyllie pointer jumping)
+    for (int a = tid; a < A; a += 1024) {
+      const int sa = si[a];
+      if (sa >= 0) { ro[a] = ri[a] + ri[sa]; so[a] = si[sa]; }
+      else { ro[a] = ri[a]; so[a] = -1; }
     }
     __syncthreads();
-    int run = s_part[tid];
-    for (int v = lo; v < hi; ++v) { const int d = deg[v]; deg[v] = run; fill[v] = run; run += d; }
-    if (tid == 1023) deg[N] = 2 * ne;
+    int* t = si; si = so; so = t;
+    t = ri; ri = ro; ro = t;
+  }
+  // position in the tour = A - 1 - rank; flag the parent -> child arcs by position and count them
+  int* flag = so;                    // [A], free again
+  for (int a = tid; a < A; a += 1024) {
+    const int pa = A - 1 - ri[a], pt = A - 1 - ri[twin[a]];
+    flag[pa] = (pa < pt) ? 1 : 0;
   }
   __syncthreads();
-  for (int e = tid; e < ne; e += 1024) {
-    const int i = p.ei[e], j = p.ej[e];
-    adj[atomicAdd(&fill[i], 1)] = j;
-    adj[atomicAdd(&fill[j], 1)] = i;
-  }
-  __syncthreads();
-  if (tid == 0) {                               // BFS from vertex 0; the final tree is path-like (depth ~ N)
-    // In a tree the only already-visited neighbour of u is its parent, so no visited set is needed: the parent
-    // travels with the queue entry.  ~4 dependent shared-memory reads per vertex.
-    int head = 0, tail = 0;
-    queue[tail] = 0; qpar[tail++] = 0;
-    p.parent[0] = 0;
-    int u = 0, pu = 0, k0 = deg[0], k1 = deg[1];
-    while (true) {
-      // one thread, one dependent chain: what counts is the instruction count per vertex, so the (degree ~2)
-      // neighbour loop is NOT unrolled (the unrolled remainder cascade cost ~30 extra instructions per vertex)
-#pragma unroll 1
-      for (int k = k0; k < k1; ++k) {
-        const int v = adj[k];
-        if (v != pu || head == 0) {               // the root has no parent edge (its qpar entry is itself)
-          p.parent[v] = u;
-          queue[tail] = v; qpar[tail++] = u;
-        }
-      }
-      if (++head >= tail) break;
-      u = queue[head]; pu = qpar[head];
-      k0 = deg[u]; k1 = deg[u + 1];
+  block_excl_scan_i32(flag, A, s_part);          // flag[pos] = number of parent -> child arcs before position pos
+  for (int a = tid; a < A; a += 1024) {
+    const int pa = A - 1 - ri[a], pt = A - 1 - ri[twin[a]];
+    if (pa < pt) {
+      const int v = adjv[a], u = adjv[twin[a]];
+      p.parent[v] = u;
+      p.weight[v] = p.ew[eidx[a]];
+      p.size[v] = (pt - pa + 1) >> 1;
+      p.order[flag[pa] + 1] = v;                 // preorder: parents before children
     }
   }
-  __syncthreads();
-  for (int k = tid; k < N; k += 1024) p.order[k] = queue[k];
-  if (tid == 0) p.weight[0] = 0.0;
-  for (int e = tid; e < ne; e += 1024) {        // every tree edge joins a vertex to its parent
-    const int i = p.ei[e], j = p.ej[e];
-    if (p.parent[j] == i) p.weight[j] = p.ew[e];
-    else p.weight[i] = p.ew[e];
-  }
+  if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; p.size[0] = N; }
 }
 
 // Unit-level: Symmetric(dm) view of a column-major upload (upper triangle wins), clamped to eps.

@@ -218,7 +218,7 @@ struct GraphWS {
       *dep1 = nullptr, *from_g = nullptr;
   double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
   int prim_R = 0;
-  int *fuse_i0 = nullptr, *fuse_i1 = nullptr;   // scratch of the sparse final MST (root_tree_kernel)
+  int* fuse_i0 = nullptr;         // scratch of the final tree's rooting (root_tree_kernel, 16 N + 64 ints)
   int cluster = 0;                // cluster Prim available (N large enough, slices fit in shared memory)
   int tree_use_smem = 1;
   size_t tree_smem = 0;
@@ -286,7 +286,7 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
   CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
   CU_TRY(c.pool.alloc(&g.S, n)); CU_TRY(c.pool.alloc(&g.wd2, n)); CU_TRY(c.pool.alloc(&g.S2, n));
-  CU_TRY(c.pool.alloc(&g.fuse_i0, (size_t)2 * N + 64)); CU_TRY(c.pool.alloc(&g.fuse_i1, (size_t)4 * N + 64));
+  CU_TRY(c.pool.alloc(&g.fuse_i0, (size_t)16 * N + 64));
   g.prim_smem = (size_t)((N + 1) & ~1) * 8 + (size_t)N * 4;
   g.use_smem = g.prim_smem + 1024 <= h->max_smem;
   if (!g.use_smem) {
@@ -347,8 +347,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   CU_TRY(cudaGetLastError());
   TreeParams tp;
   tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
-  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
-  tp.dfs_smem = 0;
+  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.have_size = 0; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
   tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
   tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
   t = c.timer.begin(SEQJ_T_TREE);
@@ -678,26 +677,18 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
     RootTreeParams rp;
     rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
-    rp.deg = gws.fuse_i0; rp.adj = gws.fuse_i1; rp.queue = gws.fuse_i1 + 2 * (size_t)N;
-    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
-    const size_t rt_smem = ((size_t)5 * N + 2) * 4;          // deg (N+1) + adj (2N) + queue (N) + queue parents (N)
-    rp.use_smem = rt_smem + 8192 <= h->max_smem;      // + 4 KB of static shared memory in the kernel
-    CU_TRY(cudaFuncSetAttribute(root_tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(rp.use_smem ? rt_smem : 0)));
-    root_tree_kernel<<<1, 1024, rp.use_smem ? rt_smem : 0, c.st>>>(rp);
+    rp.scratch = gws.fuse_i0;
+    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order; rp.size = gws.size;
+    root_tree_kernel<<<1, 1024, 0, c.st>>>(rp);
     c.launches += 2;
     CU_TRY(cudaGetLastError());
     TreeParams tp;
     tp.N = N; tp.ldv = gws.ldv; tp.parent = gws.parent; tp.weight = gws.weight; tp.order = gws.order;
-    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem;
+    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem; tp.have_size = 1;
     tp.anc0 = gws.anc0; tp.anc1 = gws.anc1; tp.dep0 = gws.dep0; tp.dep1 = gws.dep1;
     tp.eta = eta_f; tp.root = root_f; tp.newparent = parents_f; tp.ldp = ldp;
     tp.mst_i = fmst_i; tp.mst_j = fmst_j; tp.mst_w = fmst_w; tp.dfs_order = order_f;
-    const size_t dfs_smem = ((size_t)4 * N + 8) * 4;
-    tp.dfs_smem = gws.tree_use_smem && dfs_smem + 2048 <= h->max_smem;
-    const size_t tsm = tp.dfs_smem ? dfs_smem : gws.tree_smem;
-    CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tsm));
-    tree_kernel<<<1, kTreeThreads, tsm, c.st>>>(tp);
-    CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gws.tree_smem));
+    tree_kernel<<<1, kTreeThreads, gws.tree_smem, c.st>>>(tp);
     c.launches++;
     CU_TRY(cudaGetLastError());
   }
