@@ -392,6 +392,66 @@ __device__ int block_excl_scan_i32(int* a, int n, int* s_part) {
   return total;
 }
 
+// Euler tour of a rooted tree given by parent pointers, ranked by pointer jumping (O(log N) rounds, 1024 threads,
+// integers only).  Children lists are built in CSR form (clist / cstart / qpos; ascending inside every list when
+// `sorted`); child position q owns two arcs, 2q = parent -> child ("down") and 2q + 1 = back ("up").  Entering a
+// vertex continues with its first child, returning from a child with the next sibling, else back to the parent; the
+// tour ends when the root's last child returns.  Returns rank[]: the number of arcs after each arc, so that
+// position = 2(N-1) - 1 - rank.  cstart has N entries (the end of the last list is N - 1).
+__device__ int* euler_tour_rank(int N, int root, const int* par, bool sorted, int* cstart, int* clist, int* qpos,
+                                int* fillc, int* tmp, int* b0, int* b1, int* b2, int* b3, int* s_scan) {
+  const int tid = threadIdx.x, M = N - 1, A = 2 * M;
+  auto cend = [&](int x) { return (x + 1 < N) ? cstart[x + 1] : M; };
+  for (int v = tid; v < N; v += 1024) cstart[v] = 0;
+  __syncthreads();
+  for (int v = tid; v < N; v += 1024)
+    if (v != root) atomicAdd(&cstart[par[v]], 1);
+  __syncthreads();
+  block_excl_scan_i32(cstart, N, s_scan);
+  for (int v = tid; v < N; v += 1024) fillc[v] = cstart[v];
+  __syncthreads();
+  int* first = sorted ? tmp : clist;
+  for (int v = tid; v < N; v += 1024)
+    if (v != root) {
+      const int q = atomicAdd(&fillc[par[v]], 1);
+      first[q] = v;
+      if (!sorted) qpos[v] = q;
+    }
+  __syncthreads();
+  if (sorted) {                                         // rank sort inside the list (short lists: trees here are path-like)
+    for (int q = tid; q < M; q += 1024) {
+      const int c = tmp[q], x = par[c];
+      const int s0 = cstart[x], s1 = cend(x);
+      int r = s0;
+      for (int k = s0; k < s1; ++k) r += (tmp[k] < c);
+      clist[r] = c;
+      qpos[c] = r;
+    }
+    __syncthreads();
+  }
+  int *succ_i = b0, *rank_i = b1, *succ_o = b2, *rank_o = b3;
+  for (int q = tid; q < M; q += 1024) {
+    const int c = clist[q], x = par[c];
+    const int up = (q + 1 < cend(x)) ? 2 * (q + 1) : (x == root ? -1 : 2 * qpos[x] + 1);
+    succ_i[2 * q] = (cstart[c] < cend(c)) ? 2 * cstart[c] : 2 * q + 1;
+    succ_i[2 * q + 1] = up;
+    rank_i[2 * q] = 1;
+    rank_i[2 * q + 1] = (up < 0) ? 0 : 1;
+  }
+  __syncthreads();
+  for (int span = 1; span < A; span <<= 1) {
+    for (int a = tid; a < A; a += 1024) {
+      const int sa = succ_i[a];
+      if (sa >= 0) { rank_o[a] = rank_i[a] + rank_i[sa]; succ_o[a] = succ_i[sa]; }
+      else { rank_o[a] = rank_i[a]; succ_o[a] = -1; }
+    }
+    __syncthreads();
+    int* t = succ_i; succ_i = succ_o; succ_o = t;
+    t = rank_i; rank_i = rank_o; rank_o = t;
+  }
+  return rank_i;
+}
+
 // ---- tree measurement -------------------------------------------------------------------------
 struct TreeParams {
   int N;
@@ -410,7 +470,6 @@ struct TreeParams {
   int* dep0;
   int* dep1;
   int use_smem;           // parent + size fit in dynamic shared memory (8N bytes)
-  int have_size;          // size[] already holds the subtree sizes (root_tree_kernel): skip the sequential pass
   // outputs (per graph g: index out0 + g)
   double* eta;            // [ngraphs]
   int* root;              // [ngraphs]
@@ -427,9 +486,11 @@ constexpr int kTreeThreads = 1024;
 // One CTA per tree.  Replaces _leastcentralpt (N Dijkstra runs in the reference, src/sequencer.jl:331)
 // by the O(N) rerooting identity  S(v) = S(parent) + w(v,parent) * (N - 2*size(v))  for the sums of
 // weighted tree distances S(v) = sum_x d_w(v, x); closeness(v) = (N-1)/S(v).
-//   1. subtree sizes: one thread, reverse Prim order (children after parents), arrays in shared memory;
+//   1. subtree sizes and tour positions from the Euler tour of the tree rooted at the Prim start (euler_tour_rank);
 //   2. wd(v) (weighted depth from the Prim start) and T(v) = S(v) - S(start): pointer jumping, log2 N rounds;
-//   3. root = first argmin closeness; re-root; hop depths by pointer jumping; eta; optional DFS order.
+//   3. root = first argmin closeness; re-root (the path root -> start = the vertices whose tour interval contains
+//      the root's); hop depths by pointer jumping; eta; optional DFS order from a second tour.
+// No step is a sequential walk over the tree, so the cost does not depend on its depth.
 __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   extern __shared__ int tree_sm[];
   __shared__ double sred_d[32];
@@ -450,12 +511,9 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
 
   int* par_s = p.use_smem ? tree_sm : const_cast<int*>(parent);
   int* size_s = p.use_smem ? tree_sm + N : size;
-  for (int v = tid; v < N; v += kTreeThreads) {
-    const int q = parent[v];
-    if (p.use_smem) par_s[v] = q;
-    size_s[v] = p.have_size ? size[v] : 1;
-    newparent[v] = q;
-  }
+  __shared__ int s_scan[1025];
+  for (int v = tid; v < N; v += kTreeThreads)
+    if (p.use_smem) par_s[v] = parent[v];
   if (p.mst_i) {
     for (int t = 1 + tid; t < N; t += kTreeThreads) {
       const int v = order[t], q = parent[v];
@@ -466,21 +524,23 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   }
   __syncthreads();
 
-  // 1. subtree sizes, sequential in reverse insertion order
-  if (tid == 0 && !p.have_size) {
-    int t = N - 1;
-    for (; t >= 4; t -= 4) {                      // order[] is read 4 ahead of the dependent chain
-      const int v0 = order[t], v1 = order[t - 1], v2 = order[t - 2], v3 = order[t - 3];
-      size_s[par_s[v0]] += size_s[v0];
-      size_s[par_s[v1]] += size_s[v1];
-      size_s[par_s[v2]] += size_s[v2];
-      size_s[par_s[v3]] += size_s[v3];
-    }
-    for (; t >= 1; --t) {
-      const int v = order[t];
-      size_s[par_s[v]] += size_s[v];
+  // 1. subtree sizes + position of every vertex's down arc in the tour from r0 (kept in newparent[] until the
+  //    re-rooting, which is where newparent gets its real contents)
+  int* pos_down = newparent;
+  if (N > 1) {
+    int* clist = p.anc1 + gofs;
+    const int* rk = euler_tour_rank(N, r0, par_s, false, p.anc0 + gofs, clist, p.dep0 + gofs, p.dep1 + gofs, nullptr,
+                                    reinterpret_cast<int*>(p.wd + gofs), reinterpret_cast<int*>(p.wd2 + gofs),
+                                    reinterpret_cast<int*>(p.S + gofs), reinterpret_cast<int*>(p.S2 + gofs), s_scan);
+    const int A = 2 * (N - 1);
+    for (int q = tid; q < N - 1; q += kTreeThreads) {
+      const int c = clist[q];
+      const int pd = A - 1 - rk[2 * q], pu = A - 1 - rk[2 * q + 1];
+      size_s[c] = (pu - pd + 1) >> 1;
+      pos_down[c] = pd;
     }
   }
+  if (tid == 0) { size_s[r0] = N; pos_down[r0] = -1; }
   __syncthreads();
 
   // 2. wd and T by pointer jumping: after round j, (a, b)[v] hold the sums over the first 2^j path edges
@@ -552,16 +612,37 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
   }
   const int root = s_root;
 
-  // re-root: reverse the parent pointers on the path root -> r0
-  if (tid == 0) {
-    int v = root, prev = root;
-    while (true) {
-      const int nxt = par_s[v];                      // shared-memory copy when it fits: the path can be ~N long
-      newparent[v] = prev;
-      if (v == r0) break;
-      prev = v;
-      v = nxt;
+  // re-root: reverse the parent pointers on the path root -> r0.  x lies on it iff the root's down arc falls inside
+  // x's tour interval [pos_down(x), pos_down(x) + 2 size(x) - 1]  (r0 always does).
+  {
+    const int pr = (root == r0) ? -1 : pos_down[root];
+    bool onpath[(16384 + kTreeThreads - 1) / kTreeThreads];
+    __syncthreads();
+    if (N <= 16384) {
+      int k = 0;
+      for (int v = tid; v < N; v += kTreeThreads, ++k) {
+        const int pd = pos_down[v];
+        onpath[k] = (v != r0) && (root != r0) && pd <= pr && pr <= pd + 2 * size_s[v] - 1;
+      }
+      __syncthreads();                                  // every pos_down has been read: newparent gets its contents
+      for (int v = tid; v < N; v += kTreeThreads) newparent[v] = par_s[v];
+      __syncthreads();
+      k = 0;
+      for (int v = tid; v < N; v += kTreeThreads, ++k)
+        if (onpath[k]) newparent[par_s[v]] = v;
+    } else {                                            // larger trees: the flags go through anc0 (free here)
+      int* flag = p.anc0 + gofs;
+      for (int v = tid; v < N; v += kTreeThreads) {
+        const int pd = pos_down[v];
+        flag[v] = (v != r0) && (root != r0) && pd <= pr && pr <= pd + 2 * size_s[v] - 1;
+      }
+      __syncthreads();
+      for (int v = tid; v < N; v += kTreeThreads) newparent[v] = par_s[v];
+      __syncthreads();
+      for (int v = tid; v < N; v += kTreeThreads)
+        if (flag[v]) newparent[par_s[v]] = v;
     }
+    if (tid == 0) newparent[root] = root;
   }
   __syncthreads();
 
@@ -611,75 +692,26 @@ __global__ void __launch_bounds__(kTreeThreads, 1) tree_kernel(TreeParams p) {
     }
   }
 
-  // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24), without a sequential DFS:
-  // children lists in CSR form (sorted by a rank sort inside each list), then the Euler tour of the rooted tree --
-  // entering a vertex continues with its first child, returning from a child with the next sibling, else back to
-  // the parent -- ranked by pointer jumping (O(log N) rounds); the preorder number of a vertex is the count of
-  // "down" arcs up to the one that enters it.  Integers only.
+  // order = reverse(DFS preorder, children ascending)   (src/utils.jl:15-24): the preorder number of a vertex is the
+  // number of down arcs up to the one that enters it in the tour of the re-rooted tree with ascending children.
   if (p.dfs_order) {
     __syncthreads();
-    __shared__ int s_scan[1025];
-    const int M = N - 1, A = 2 * M;
     if (N == 1) {
       if (tid == 0) p.dfs_order[oofs] = root;
       return;
     }
-    int* cstart = size;                                 // [N + 1] children CSR offsets   (all arrays below are free now)
-    int* tmp = anc_a;                                   // [M] children in arrival order
-    int* clist = anc_b;                                 // [M] children, ascending inside every list
-    int* qpos = dep_a;                                  // [N] position of a vertex in its parent's list
-    int* fillc = dep_b;                                 // [N] fill cursors
-    int* succ_i = reinterpret_cast<int*>(p.wd + gofs);  // [A] each: arc 2q = parent -> clist[q], arc 2q+1 = back
-    int* rank_i = reinterpret_cast<int*>(p.wd2 + gofs);
-    int* succ_o = reinterpret_cast<int*>(p.S + gofs);
-    int* rank_o = reinterpret_cast<int*>(p.S2 + gofs);
-    for (int v = tid; v <= N; v += kTreeThreads) cstart[v] = 0;
-    __syncthreads();
-    for (int v = tid; v < N; v += kTreeThreads)
-      if (v != root) atomicAdd(&cstart[newparent[v]], 1);
-    __syncthreads();
-    block_excl_scan_i32(cstart, N, s_scan);
-    if (tid == 0) cstart[N] = M;
-    for (int v = tid; v < N; v += kTreeThreads) fillc[v] = cstart[v];
-    __syncthreads();
-    for (int v = tid; v < N; v += kTreeThreads)
-      if (v != root) tmp[atomicAdd(&fillc[newparent[v]], 1)] = v;
-    __syncthreads();
-    for (int q = tid; q < M; q += kTreeThreads) {       // rank sort inside the list (lists are short: the tree is path-like)
-      const int c = tmp[q], x = newparent[c];
-      const int s0 = cstart[x], s1 = cstart[x + 1];
-      int r = s0;
-      for (int k = s0; k < s1; ++k) r += (tmp[k] < c);
-      clist[r] = c;
-      qpos[c] = r;
-    }
-    __syncthreads();
-    for (int q = tid; q < M; q += kTreeThreads) {
-      const int c = clist[q], x = newparent[c];
-      // entering c: first child of c, else straight back up
-      succ_i[2 * q] = (cstart[c] < cstart[c + 1]) ? 2 * cstart[c] : 2 * q + 1;
-      // returning to x from c: next sibling, else up from x (the tour ends at the root)
-      succ_i[2 * q + 1] = (q + 1 < cstart[x + 1]) ? 2 * (q + 1) : (x == root ? -1 : 2 * qpos[x] + 1);
-      rank_i[2 * q] = 1;
-      rank_i[2 * q + 1] = (succ_i[2 * q + 1] < 0) ? 0 : 1;
-    }
-    __syncthreads();
-    for (int span = 1; span < A; span <<= 1) {          // rank = number of arcs after this one
-      for (int a = tid; a < A; a += kTreeThreads) {
-        const int sa = succ_i[a];
-        if (sa >= 0) { rank_o[a] = rank_i[a] + rank_i[sa]; succ_o[a] = succ_i[sa]; }
-        else { rank_o[a] = rank_i[a]; succ_o[a] = -1; }
-      }
-      __syncthreads();
-      int* t = succ_i; succ_i = succ_o; succ_o = t;
-      t = rank_i; rank_i = rank_o; rank_o = t;
-    }
-    int* flag = succ_o;                                 // [A]: 1 at the tour positions of the down arcs
-    for (int a = tid; a < A; a += kTreeThreads) flag[A - 1 - rank_i[a]] = (a & 1) ? 0 : 1;
+    const int M = N - 1, A = 2 * M;
+    int* clist = anc_b;
+    int* b2 = reinterpret_cast<int*>(p.S + gofs);
+    int* b3 = reinterpret_cast<int*>(p.S2 + gofs);
+    const int* rk = euler_tour_rank(N, root, newparent, true, size, clist, dep_a, dep_b, anc_a,
+                                    reinterpret_cast<int*>(p.wd + gofs), reinterpret_cast<int*>(p.wd2 + gofs), b2, b3, s_scan);
+    int* flag = (rk == b3) ? b2 : b3;                   // a buffer the ranking no longer needs: 1 at the down-arc positions
+    for (int a = tid; a < A; a += kTreeThreads) flag[A - 1 - rk[a]] = (a & 1) ? 0 : 1;
     __syncthreads();
     block_excl_scan_i32(flag, A, s_scan);               // flag[pos] = down arcs before pos = preorder number - 1
     for (int q = tid; q < M; q += kTreeThreads) {
-      const int pre = flag[A - 1 - rank_i[2 * q]] + 1;  // 1 .. N-1; the root is 0
+      const int pre = flag[A - 1 - rk[2 * q]] + 1;      // 1 .. N-1; the root is 0
       p.dfs_order[oofs + (N - 1 - pre)] = clist[q];
     }
     if (tid == 0) p.dfs_order[oofs + N - 1] = root;
@@ -936,15 +968,15 @@ __global__ void __launch_bounds__(kBoruvkaThreads, 1) boruvka_sparse_kernel(Boru
   }
 }
 
-// Root the MST edge list at vertex 0: produce the (parent, weight, order, size) arrays that tree_kernel consumes
+// Root the MST edge list at vertex 0: produce the (parent, weight, order) arrays that tree_kernel consumes
 // (the same contract as Prim's output: parents precede children in `order`).  The final tree is path-like
 // (depth ~ N), so a BFS is N dependent steps of one thread (1.2 ms at N = 10k, 16 ms at N = 20k where its arrays
 // no longer fit in shared memory).  Instead: Euler tour + list ranking, O(log N) parallel rounds whatever the
 // shape of the tree.  Every edge becomes two arcs stored in CSR order; the successor of arc (u -> v) is the arc
 // after (v -> u) in v's list (cyclically), which links all 2(N-1) arcs into one tour; cutting it at the root's first
 // arc and ranking the list by pointer jumping gives every arc its position.  Arc (u -> v) is a tree edge
-// parent -> child iff it comes before its twin; the child's subtree size is half the distance between the two,
-// its preorder number the count of parent -> child arcs up to it.  Integers only, so the result is exact.
+// parent -> child iff it comes before its twin; the child's preorder number is the count of parent -> child arcs
+// up to it.  Integers only, so the result is exact.
 struct RootTreeParams {
   int N;
   const int* ei;
@@ -954,14 +986,13 @@ struct RootTreeParams {
   int* parent;   // out [N]
   double* weight;
   int* order;
-  int* size;     // out [N]: subtree sizes (tree_kernel skips its sequential pass when they are given)
 };
 
 __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
   __shared__ int s_part[1025];
   const int tid = threadIdx.x, N = p.N, M = N - 1, A = 2 * M;
   if (N == 1) {
-    if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; p.size[0] = 1; }
+    if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; }
     return;
   }
   int* off = p.scratch;              // [N + 1] CSR offsets
@@ -1023,11 +1054,10 @@ __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
       const int v = adjv[a], u = adjv[twin[a]];
       p.parent[v] = u;
       p.weight[v] = p.ew[eidx[a]];
-      p.size[v] = (pt - pa + 1) >> 1;
       p.order[flag[pa] + 1] = v;                 // preorder: parents before children
     }
   }
-  if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; p.size[0] = N; }
+  if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; }
 }
 
 // Unit-level: Symmetric(dm) view of a column-major upload (upper triangle wins), clamped to eps.

@@ -347,7 +347,7 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   CU_TRY(cudaGetLastError());
   TreeParams tp;
   tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
-  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.have_size = 0; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
+  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
   tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
   tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
   t = c.timer.begin(SEQJ_T_TREE);
@@ -678,13 +678,13 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     RootTreeParams rp;
     rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
     rp.scratch = gws.fuse_i0;
-    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order; rp.size = gws.size;
+    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
     root_tree_kernel<<<1, 1024, 0, c.st>>>(rp);
     c.launches += 2;
     CU_TRY(cudaGetLastError());
     TreeParams tp;
     tp.N = N; tp.ldv = gws.ldv; tp.parent = gws.parent; tp.weight = gws.weight; tp.order = gws.order;
-    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem; tp.have_size = 1;
+    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem;
     tp.anc0 = gws.anc0; tp.anc1 = gws.anc1; tp.dep0 = gws.dep0; tp.dep1 = gws.dep1;
     tp.eta = eta_f; tp.root = root_f; tp.newparent = parents_f; tp.ldp = ldp;
     tp.mst_i = fmst_i; tp.mst_j = fmst_j; tp.mst_w = fmst_w; tp.dfs_order = order_f;
