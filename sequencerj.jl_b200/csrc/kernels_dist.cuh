@@ -302,27 +302,35 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
       mbar_wait(&s.full[st], ph);
       const uint32_t sa = stages_u32 + st * kStageBytes + (8 * ti) * 128;
       const uint32_t sb = stages_u32 + st * kStageBytes + kStageBytesA + jrow0 * 128;
-#pragma unroll 2
+      // The j-side fragments of chunk c + 1 are loaded while chunk c is being accumulated (two register sets,
+      // fully unrolled so that the set index is static): without this every chunk started with nine back-to-back
+      // LDS.128 and ~60 cycles in which neither of the SMSP's two warps had a DADD to issue (ncu, end of r01).
+      double2 fb[2][8];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) fb[0][b] = lds128(sb + b * (16 * 128) + ((0 ^ jsw) << 4));
+#pragma unroll
       for (int c = 0; c < 8; ++c) {    // 16 B chunk = 2 consecutive k
-        double2 fb[8];
+        const int cur = c & 1;
+        if (c + 1 < 8) {
+#pragma unroll
+          for (int b = 0; b < 8; ++b) fb[cur ^ 1][b] = lds128(sb + b * (16 * 128) + (((c + 1) ^ jsw) << 4));
+        }
         double2 per = make_double2(1.0, 1.0);
         if (OP == OP_PERIODIC) per = __ldg(reinterpret_cast<const double2*>(p.period + it * kTileK + 2 * c));
-#pragma unroll
-        for (int b = 0; b < 8; ++b) fb[b] = lds128(sb + b * (16 * 128) + ((c ^ jsw) << 4));
 #pragma unroll
         for (int a = 0; a < 8; ++a) {
           const double2 fa = lds128(sa + a * 128 + ((c ^ a) << 4));
 #pragma unroll
           for (int b = 0; b < 8; ++b) {
             if (OP == OP_L1) {
-              acc[a][b] += fabs(fa.x - fb[b].x);
-              acc[a][b] += fabs(fa.y - fb[b].y);
+              acc[a][b] += fabs(fa.x - fb[cur][b].x);
+              acc[a][b] += fabs(fa.y - fb[cur][b].y);
             } else if (OP == OP_PERIODIC) {
-              const double sx = periodic_fold(fa.x - fb[b].x, per.x), sy = periodic_fold(fa.y - fb[b].y, per.y);
+              const double sx = periodic_fold(fa.x - fb[cur][b].x, per.x), sy = periodic_fold(fa.y - fb[cur][b].y, per.y);
               acc[a][b] = fma(sx, sx, acc[a][b]);
               acc[a][b] = fma(sy, sy, acc[a][b]);
             } else {
-              const double dx = fa.x - fb[b].x, dy = fa.y - fb[b].y;
+              const double dx = fa.x - fb[cur][b].x, dy = fa.y - fb[cur][b].y;
               acc[a][b] = fma(dx, dx, acc[a][b]);
               acc[a][b] = fma(dy, dy, acc[a][b]);
             }
