@@ -54,7 +54,14 @@ __device__ __forceinline__ ulonglong2 ldg_stream_u64x2(const double* p) {
 // column-major order (LightGraphs.kruskal_mst over SimpleWeightedGraph), i.e. the strict total order
 // (weight, max(u,v), min(u,v)).  The MST under a strict total order is unique, so Prim with the same order
 // returns exactly Kruskal's tree even when weights tie (duplicate objects, integer data).
-constexpr unsigned long long kPrimNone = ~0ull - 1ull;    // "no candidate": above every real key - 1, below (0 - 1)
+// Candidates are ordered by (key - kPrimDec): subtracting one from the HIGH word keeps the order of the real keys
+// (weights >= eps have a high word >= 1) and sends the in-tree marker 0 to the top (high word 0xffffffff), above
+// kPrimNone = "no candidate"; the decrement touches one register.  The relaxation test of the hot loop looks at high
+// words only (`hi(d) <= hi(key)` is a superset of d <= key and false for almost every vertex); the clamp, the relax
+// and the tie rule sit behind it.  (A high-word filter in front of the running argmin was measured slower: a
+// thread's minimum over its 5-10 vertices changes too often for the branch to be rare at warp level.)
+constexpr unsigned long long kPrimDec = 1ull << 32;
+constexpr unsigned long long kPrimNone = 0xfffffffe00000000ull;
 
 __device__ __forceinline__ bool edge_less(int v1, int f1, int v2, int f2) {      // weights equal
   const int h1 = max(v1, f1), h2 = max(v2, f2);
@@ -95,7 +102,7 @@ __device__ __forceinline__ void warp_argmin_edge(unsigned long long& k, int& v, 
 // per graph).  Keys live in shared memory as the bit patterns of non-negative doubles, which order
 // like unsigned integers: the inner loop and both argmin levels are integer-only (no FP64-pipe
 // compares).  key == 0 marks a vertex already in the tree: no weight (>= eps > 0) is smaller, so it is
-// never relaxed, and (key - 1) wraps to the largest value, so it never wins the argmin.
+// never relaxed, and (key - kPrimDec) wraps to the largest values, so it never wins the argmin.
 // Thread t owns the vertex pairs {2t, 2t+1} + 2048 r: rows are fetched with 16-byte streaming loads,
 // all R of them in flight at once.  R = 0 selects the generic path (any N, batches of 8 loads).
 template <int R>
@@ -147,10 +154,10 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
         const int v = base + r * 2 * kPrimThreads;
         if (v < N) {
           ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
-          if (dv[r].x <= k2.x || dv[r].y <= k2.y) {
+          if ((unsigned)(dv[r].x >> 32) <= (unsigned)(k2.x >> 32) || (unsigned)(dv[r].y >> 32) <= (unsigned)(k2.y >> 32)) {
             // Relaxation candidates: rare after the first steps, so everything careful lives in this branch -- the
             // eps clamp (keys are clamped values, so a clamped weight can only relax a key if the raw one passes the
-            // test above) and the tie rule: at equal weight the edge that comes first in Kruskal's order wins.
+            // high-word test above) and the tie rule: at equal weight the edge that comes first in Kruskal's order wins.
             const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
             const bool u0 = k2.x != 0ull && (d0 < k2.x || (d0 == k2.x && edge_less(v, u, v, from[v])));
             const bool u1 = k2.y != 0ull && (d1 < k2.y || (d1 == k2.y && edge_less(v + 1, u, v + 1, from[v + 1])));
@@ -159,7 +166,7 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
             if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
           }
           // bv = first, bl = last of this thread's vertices at its minimum key: bv != bl flags a tie
-          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;   // in-tree: ~0 > kPrimNone, never a candidate
+          const unsigned long long c0 = k2.x - kPrimDec, c1 = k2.y - kPrimDec;
           if (c0 < bk) { bk = c0; bv = v; }
           if (c0 <= bk) bl = v;
           if (c1 < bk) { bk = c1; bv = v + 1; }
@@ -171,8 +178,8 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
     if (bl != bv) {                                        // rare: order the tied candidates like Kruskal
       for (int base = 2 * tid; base < N; base += 2 * kPrimThreads) {
         const ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + base);
-        if (k2.x - 1ull == bk && base != bv && edge_less(base, from[base], bv, from[bv])) bv = base;
-        if (k2.y - 1ull == bk && base + 1 != bv && edge_less(base + 1, from[base + 1], bv, from[bv])) bv = base + 1;
+        if (k2.x - kPrimDec == bk && base != bv && edge_less(base, from[base], bv, from[bv])) bv = base;
+        if (k2.y - kPrimDec == bk && base + 1 != bv && edge_less(base + 1, from[base + 1], bv, from[bv])) bv = base + 1;
       }
     }
     auto getf = [&](int v) { return from[v]; };
@@ -186,7 +193,7 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
     if (((u >> 1) & (kPrimThreads - 1)) == tid) {       // the owner of key[u] retires it
       order[step] = u;
       parent[u] = from[u];
-      weight[u] = __longlong_as_double((long long)(bk + 1ull));
+      weight[u] = __longlong_as_double((long long)(bk + kPrimDec));
       key[u] = 0ull;
     }
     par ^= 1;
@@ -290,7 +297,7 @@ prim_cluster_kernel(PrimParams p, int W) {
         if (v < Wn) {
           ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
           const int gv = v0 + v;                                         // global vertex id
-          if (dv[r].x <= k2.x || dv[r].y <= k2.y) {                      // rare: clamp + tie rule as in prim_kernel
+          if ((unsigned)(dv[r].x >> 32) <= (unsigned)(k2.x >> 32) || (unsigned)(dv[r].y >> 32) <= (unsigned)(k2.y >> 32)) {                      // rare: clamp + tie rule as in prim_kernel
             const unsigned long long d0 = max(dv[r].x, eps_bits), d1 = max(dv[r].y, eps_bits);
             const bool u0 = k2.x != 0ull && (d0 < k2.x || (d0 == k2.x && edge_less(gv, u, gv, from[v])));
             const bool u1 = k2.y != 0ull && (d1 < k2.y || (d1 == k2.y && edge_less(gv + 1, u, gv + 1, from[v + 1])));
@@ -298,7 +305,7 @@ prim_cluster_kernel(PrimParams p, int W) {
             if (u1) { k2.y = d1; from[v + 1] = u; }
             if (u0 || u1) *reinterpret_cast<ulonglong2*>(key + v) = k2;
           }
-          const unsigned long long c0 = k2.x - 1ull, c1 = k2.y - 1ull;   // in-tree: ~0 > kPrimNone, never a candidate
+          const unsigned long long c0 = k2.x - kPrimDec, c1 = k2.y - kPrimDec;
           if (c0 < bk) { bk = c0; bv = gv; }
           if (c0 <= bk) bl = gv;
           if (c1 < bk) { bk = c1; bv = gv + 1; }
@@ -310,8 +317,8 @@ prim_cluster_kernel(PrimParams p, int W) {
       for (int v = 2 * tid; v < Wn; v += 2 * T) {
         const ulonglong2 k2 = *reinterpret_cast<ulonglong2*>(key + v);
         const int gv = v0 + v;
-        if (k2.x - 1ull == bk && gv != bv && edge_less(gv, from[v], bv, from[bv - v0])) bv = gv;
-        if (k2.y - 1ull == bk && gv + 1 != bv && edge_less(gv + 1, from[v + 1], bv, from[bv - v0])) bv = gv + 1;
+        if (k2.x - kPrimDec == bk && gv != bv && edge_less(gv, from[v], bv, from[bv - v0])) bv = gv;
+        if (k2.y - kPrimDec == bk && gv + 1 != bv && edge_less(gv + 1, from[v + 1], bv, from[bv - v0])) bv = gv + 1;
       }
     }
     auto getf = [&](int v) { return from[v - v0]; };
@@ -356,7 +363,7 @@ prim_cluster_kernel(PrimParams p, int W) {
     if (ul >= 0 && ul < Wn && ((ul >> 1) & (T - 1)) == tid) {   // the owner of key[u] retires it
       order[step] = u;
       parent[u] = from[ul];
-      weight[u] = __longlong_as_double((long long)(bk + 1ull));
+      weight[u] = __longlong_as_double((long long)(bk + kPrimDec));
       key[ul] = 0ull;
     }
   }
