@@ -55,6 +55,10 @@ struct DeriveParams {
   unsigned char* tile_flags;   // [coarse chunks of the launch][tile_flag_stride]; may be nullptr
   int tile_flag_stride;
   const int* tile_col_offset;  // index of the first tile of every 128-column block in the tile list
+  // per-object factors of every fine chunk, precomputed by derive_factors_kernel: fac[(f * NF + comp) * ldn + object]
+  // and, for Energy, the ramp moments {m, P1 = sum rho, P2 = sum rho^2} of every fine chunk: pm[3 f + 0..2]
+  double* fac;
+  double* pm;
 };
 
 // 64 x 64 tiles of the upper triangle; block = 32 x 8 threads, each thread owns 2 adjacent columns (one 16-byte
@@ -83,6 +87,43 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n cp.async.wait_group 0;" ::: "memory");
+}
+
+// Per-object factors for one (metric, coarse scale): one thread per (fine chunk, object).  Kept out of derive_kernel
+// so that its prologue is nothing but asynchronous copies (the division / log / dependent global loads used to sit
+// at the head of every block's critical path).
+template <int MODE>
+__global__ void __launch_bounds__(256) derive_factors_kernel(DeriveParams p) {
+  constexpr int NF = derive_nf(MODE);
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t total = (int64_t)p.nfine * p.ldn;
+  if (idx >= total) return;
+  const int f = (int)(idx / p.ldn), o = (int)(idx % p.ldn);
+  const int cc = f / p.ratio, fbeg = cc * p.ratio;
+  double* out = p.fac + (int64_t)f * NF * p.ldn + o;
+  const bool ok = o < p.N;
+  const int64_t fo = (int64_t)f * p.ldn + o;
+  const double cm = ok ? p.cmass[(int64_t)cc * p.ldn + o] : 1.0;
+  const double fmv = ok ? p.fmass[fo] : 1.0;
+  const double w = fmv / cm;
+  out[0] = w;
+  if (MODE == MODE_L2) {
+    out[p.ldn] = ok ? w * p.fg[fo] : 0.0;
+  } else if (MODE == MODE_KL) {
+    out[p.ldn] = log(w);
+  } else {
+    double run = 0.0;                                 // b = (mass of the preceding fine chunks of the coarse chunk) / cm
+    for (int q = fbeg; q < f; ++q) run += ok ? p.fmass[(int64_t)q * p.ldn + o] : 0.0;
+    out[p.ldn] = run / cm;
+    out[2 * p.ldn] = ok ? w * (p.fg[fo] + 2.0 * p.fR[fo]) : 0.0;
+    out[3 * p.ldn] = ok ? w * p.fT[fo] : 0.0;
+    if (o == 0) {
+      const double m = (double)p.fm[f];
+      p.pm[3 * f] = m;
+      p.pm[3 * f + 1] = 0.5 * (m + 1.0);                          // sum_{t=1..m} t/m
+      p.pm[3 * f + 2] = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);  // sum (t/m)^2
+    }
+  }
 }
 
 template <int MODE>
@@ -127,49 +168,22 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DeriveParams p) {
   };
   issue(0);
 
-  // per-object factors, all 256 threads: item = (side, q, object)
-  for (int t = tid; t < 2 * TS * nf; t += 256) {
-    const int oo = t & (TS - 1), side = (t / TS) & 1, q = t / (2 * TS);
-    const int o = (side ? j0 : i0) + oo;
-    const int64_t fo = (int64_t)(p.f0 + q) * p.ldn + o;
-    const bool ok = o < N;
-    const double cm = ok ? p.cmass[o] : 1.0;
-    const double fmv = ok ? p.fmass[fo] : 1.0;
-    const double w = fmv / cm;
-    double* d = fac(side, q, oo);
-    d[0] = w;
-    if (MODE == MODE_L2) {
-      d[TS] = ok ? w * p.fg[fo] : 0.0;
-    } else if (MODE == MODE_KL) {
-      d[TS] = log(w);
-    } else {
-      d[TS] = fmv;                                   // turned into b = (mass of the preceding fine chunks) / cm below
-      d[2 * TS] = ok ? w * (p.fg[fo] + 2.0 * p.fR[fo]) : 0.0;
-      d[3 * TS] = ok ? w * p.fT[fo] : 0.0;
-    }
+  // per-object factors: asynchronous copies of the precomputed rows, one 16-byte chunk (2 objects) per item.
+  // Objects beyond ldn (last tile) read into the next row / the buffer's tail padding; their results are dropped.
+  for (int t = tid; t < 2 * nf * NF * (TS / 2); t += 256) {
+    const int ch = t & (TS / 2 - 1), row = t / (TS / 2);          // row = (side * nf + q) * NF + comp
+    const int comp = row % NF, sq = row / NF, q = sq % nf, side = sq / nf;
+    const double* src = p.fac + ((int64_t)(p.f0 + q) * NF + comp) * p.ldn + (side ? j0 : i0) + 2 * ch;
+    cp_async16(smem_u32(facs + (size_t)row * TS + 2 * ch), src);
   }
   if (tid == 0) s_cnt = 0;
-  __syncthreads();
-  if (MODE == MODE_ENERGY) {
-    if (tid < 2 * TS) {
-      const int oo = tid & (TS - 1), side = tid / TS, o = (side ? j0 : i0) + oo;
-      const double cm = (o < N) ? p.cmass[o] : 1.0;
-      double run = 0.0;
-      for (int q = 0; q < nf; ++q) {
-        double* d = fac(side, q, oo);
-        const double fmv = d[TS];
-        d[TS] = run / cm;
-        run += fmv;
-      }
-    }
-    __syncthreads();
-  }
 
   double acc[8][2];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k][0] = acc[k][1] = 0.0;
   for (int qb = 0; qb < nf; qb += kDeriveStage) {
     cp_async_wait_all();
+    if (qb == 0) __syncthreads();                         // the factor rows were copied by other threads
 #pragma unroll
     for (int s_ = 0; s_ < kDeriveStage; ++s_) {
       const int q = qb + s_;
@@ -181,9 +195,9 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DeriveParams p) {
       if (MODE == MODE_ENERGY) {
         c2 = *reinterpret_cast<const double2*>(fc + 2 * TS);
         c3 = *reinterpret_cast<const double2*>(fc + 3 * TS);
-        m = (double)p.fm[p.f0 + q];
-        P1 = 0.5 * (m + 1.0);                                  // sum_{t=1..m} t/m
-        P2 = (m + 1.0) * (2.0 * m + 1.0) / (6.0 * m);          // sum (t/m)^2
+        m = p.pm[3 * (p.f0 + q)];
+        P1 = p.pm[3 * (p.f0 + q) + 1];                         // sum_{t=1..m} t/m
+        P2 = p.pm[3 * (p.f0 + q) + 2];                         // sum (t/m)^2
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {

@@ -527,6 +527,7 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
 // Fine-scale per-chunk vectors kept aside while the prep buffers are reused for the coarser scales.
 struct FineVecs {
   double *mass = nullptr, *sP = nullptr, *sU = nullptr, *sR = nullptr, *sT = nullptr;
+  double *fac = nullptr, *pm = nullptr;     // scratch of derive_factors_kernel: [nchunks][4][ldn] + tail padding, [nchunks][3]
   int* m_of_chunk = nullptr;
   int nchunks = 0, cl = 0;
 };
@@ -557,9 +558,19 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
   dp.cself = (metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU);
   const size_t dsmem = derive_smem_bytes(metric, std::min(ratio, fv.nchunks));
   const dim3 dgrid(T, T, (unsigned)(c1 - c0)), dblock(32, 8);
-  if (metric == SEQJ_L2) derive_kernel<MODE_L2><<<dgrid, dblock, dsmem, c.st>>>(dp);
-  else if (metric == SEQJ_KLD) derive_kernel<MODE_KL><<<dgrid, dblock, dsmem, c.st>>>(dp);
-  else derive_kernel<MODE_ENERGY><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  dp.fac = fv.fac; dp.pm = fv.pm;
+  const unsigned fgrid = (unsigned)(((int64_t)fv.nchunks * pb.ldn + 255) / 256);
+  if (metric == SEQJ_L2) {
+    derive_factors_kernel<MODE_L2><<<fgrid, 256, 0, c.st>>>(dp);
+    derive_kernel<MODE_L2><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  } else if (metric == SEQJ_KLD) {
+    derive_factors_kernel<MODE_KL><<<fgrid, 256, 0, c.st>>>(dp);
+    derive_kernel<MODE_KL><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  } else {
+    derive_factors_kernel<MODE_ENERGY><<<fgrid, 256, 0, c.st>>>(dp);
+    derive_kernel<MODE_ENERGY><<<dgrid, dblock, dsmem, c.st>>>(dp);
+  }
+  c.launches++;
   c.launches++;
   CU_TRY(cudaGetLastError());
   FixParams fp;
@@ -1085,6 +1096,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(c.pool.alloc(&fv.mass, nn)); CU_TRY(c.pool.alloc(&fv.sP, nn)); CU_TRY(c.pool.alloc(&fv.sU, nn));
     CU_TRY(c.pool.alloc(&fv.sR, nn)); CU_TRY(c.pool.alloc(&fv.sT, nn));
     CU_TRY(c.pool.alloc(&fv.m_of_chunk, (size_t)layouts[lf].nchunks));
+    CU_TRY(c.pool.alloc(&fv.fac, nn * 4 + 128)); CU_TRY(c.pool.alloc(&fv.pm, (size_t)layouts[lf].nchunks * 3));
   }
   std::vector<int> last_slot0(nmetrics, -1), last_scale(nmetrics, -1);
   int fv_scale = -1;                                  // scale whose vectors are currently in fv
