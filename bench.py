@@ -67,9 +67,11 @@ class ClockSampler:
         self.index = index
 
     def start(self):
+        if os.environ.get("BENCH_NO_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "500")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -79,6 +81,10 @@ class ClockSampler:
     def _read(self):
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
+
+    def mark(self):
+        """Start of the timed region: only samples from here on are reported."""
+        self.lines = []
 
     def stop(self):
         if not self.proc:
@@ -156,7 +162,7 @@ METRIC_NAME = "sequence() distance throughput at N=10k,L=4k all metrics (wall-s 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
@@ -227,11 +233,16 @@ def main():
         return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, allgather, device_ptr=dev.data_ptr(),
                                          gather_groups=gather_groups)
 
+    # the nvidia-smi sampler starts BEFORE the warm-up so that its start-up (NVML initialisation takes driver locks)
+    # does not land in the timed region; it samples every 500 ms until the timed steps are done (at 100 ms the
+    # polling itself cost 3-20 ms per sequence() call of host-side launch stalls, measured with BENCH_SMI_MS /
+    # BENCH_NO_SAMPLER)
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(args.warmup):
         r = step_dev()
-    sampler = ClockSampler(local)
     barrier()
-    sampler.start()
+    sampler.mark()
     t0 = time.perf_counter()
     phases = {}
     launches = 0

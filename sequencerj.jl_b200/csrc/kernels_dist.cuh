@@ -163,7 +163,9 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kTileThreads, 2)
+// KL runs 3 CTAs per SM (168 registers, the few spills land outside the DMMA loop: measured 13.6 -> 12.4 ms at config 3);
+// the sqrt epilogue of L2 / Energy spills more at 168 and is faster at 2 CTAs (14.2 vs 14.9 ms).
+__global__ void __launch_bounds__(kTileThreads, (MODE == MODE_KL) ? 3 : 2)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DistParams p) {
   __shared__ int s_cnt;
   extern __shared__ uint8_t smem_raw[];

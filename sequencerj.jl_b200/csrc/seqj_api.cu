@@ -6,6 +6,7 @@
 // leave the device between kernels, and the host only synchronises to read the final results.
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,6 +45,10 @@ struct seqj_handle {
   std::vector<double> periods;   // periods of SEQJ_PERIODIC (seqj_set_periods), empty = none
   std::multimap<size_t, void*> cache;
   size_t cached_bytes = 0;
+  // pinned landing buffer + event of the input check: its result is read back asynchronously and only looked at
+  // after the distance work has been enqueued, so the GPU never waits for the host at the start of a call
+  void* stats_pinned = nullptr;
+  cudaEvent_t stats_ev = nullptr;
 };
 
 struct GroupRes {
@@ -164,7 +169,11 @@ struct PhaseTimer {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
         timers[s.phase] += ms;
-        if (trace) fprintf(stderr, "[seqj] phase %2d  %9.3f ms\n", s.phase, ms);
+        if (trace) {
+          float at = 0;
+          cudaEventElapsedTime(&at, spans[0].a, s.a);
+          fprintf(stderr, "[seqj] phase %2d  %9.3f ms  (starts at %9.3f ms)\n", s.phase, ms, at);
+        }
       }
     }
   }
@@ -814,6 +823,8 @@ static int create_one(seqj_handle** out, const int* devices, int ndev) {
   const bool use_prio = pr ? atoi(pr) != 0 : false;
   cudaStreamCreateWithPriority(&h->st, cudaStreamNonBlocking, use_prio ? prio_lo : 0);
   cudaStreamCreateWithPriority(&h->st2, cudaStreamNonBlocking, use_prio ? prio_hi : 0);
+  cudaHostAlloc(&h->stats_pinned, 64, cudaHostAllocDefault);
+  cudaEventCreateWithFlags(&h->stats_ev, cudaEventDisableTiming);
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult q;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) {
@@ -836,6 +847,8 @@ void seqj_destroy(seqj_handle* h) {
   release_cache(h);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);
+  if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
+  if (h->stats_ev) cudaEventDestroy(h->stats_ev);
   delete h;
 }
 
@@ -951,22 +964,42 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   }
 
   int tt = c.timer.begin(SEQJ_T_TOTAL);
+  const bool htrace = getenv("SEQJ_TRACE") != nullptr;
+  const auto h0 = std::chrono::steady_clock::now();
+  auto hmark = [&](const char* what) {
+    if (htrace) fprintf(stderr, "[seqj] host %-14s at %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count());
+  };
 
   // `@assert all(A .>= 0) && no NaN/Inf` (src/sequencer.jl:111), checked on the device copy
   InputStats* stats_dev;
   CU_TRY(c.pool.alloc(&stats_dev, 1));
-  InputStats st0;
-  st0.minv = INFINITY; st0.maxv = 0.0; st0.has_nan = 0; st0.pad = 0;
-  CU_TRY(cudaMemcpyAsync(stats_dev, &st0, sizeof(st0), cudaMemcpyHostToDevice, c.st));
+  if (!h->stats_pinned || !h->stats_ev) return fail(h, SEQJ_E_CUDA, "pinned stats buffer missing");
+  InputStats* st0p = static_cast<InputStats*>(h->stats_pinned);
+  CU_TRY(cudaMemsetAsync(stats_dev, 0, sizeof(InputStats), c.st));
+  CU_TRY(cudaMemsetAsync(&stats_dev->minv, 0xff, sizeof(double), c.st));     // atomicMin on the bit pattern starts at the top
   input_stats_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(A_dev, (int64_t)M * N, stats_dev);
   c.launches++;
-  CU_TRY(cudaMemcpyAsync(&st0, stats_dev, sizeof(st0), cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaStreamSynchronize(c.st));
-  if (st0.has_nan || st0.pad || !std::isfinite(st0.maxv))
-    return fail(h, SEQJ_E_DOMAIN, "Input data cannot contain negative, NaN or infinite values.");
+  CU_TRY(cudaMemcpyAsync(st0p, stats_dev, sizeof(InputStats), cudaMemcpyDeviceToHost, c.st));
+  CU_TRY(cudaEventRecord(h->stats_ev, c.st));
+  bool stats_checked = false;
+  // Looked at once the distance kernels of the first wave are in the queue (they are memory-safe on any input: values
+  // are clamped on load, NaN / Inf only produce NaN distances).  A bad input then costs the queued work, not a hang.
+  auto check_input = [&]() -> int {
+    if (stats_checked) return SEQJ_OK;
+    stats_checked = true;
+    CU_TRY(cudaEventSynchronize(h->stats_ev));
+    if (st0p->has_nan || st0p->pad || !std::isfinite(st0p->maxv)) {
+      cudaStreamSynchronize(c.st_compute);
+      cudaStreamSynchronize(c.st_graph);
+      return fail(h, SEQJ_E_DOMAIN, "Input data cannot contain negative, NaN or infinite values.");
+    }
+    return SEQJ_OK;
+  };
 
+  hmark("stats queued");
   PrepBufs pb;
   ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false, needWE, needWG));
+  hmark("alloc_prep");
   if (needWE || needWG) {
     CU_TRY(c.pool.alloc(&pb.grid, (size_t)M));
     CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * M, cudaMemcpyHostToDevice, c.st));
@@ -996,8 +1029,10 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   const int64_t ldp = N;
   const int64_t ldD = round_up(N, 16);
   const size_t mat_elems = (size_t)N * ldD;
+  hmark("fix+tiles");
   size_t free_b = 0, total_b = 0;
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+  hmark("memgetinfo");
   free_b += h->cached_bytes;                    // blocks cached from the previous call are reusable
   size_t budget = free_b > (size_t(4) << 30) ? free_b - (size_t(4) << 30) : free_b / 2;
   if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
@@ -1090,6 +1125,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       l_prev = l;
     }
   }
+  hmark("waves planned");
   FineVecs fv;
   if (n_derived) {
     const size_t nn = (size_t)layouts[lf].nchunks * pb.ldn;
@@ -1139,6 +1175,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   CU_TRY(cudaEventRecord(ev_setup, c.st_compute));              // index arrays / tiles uploaded on the compute stream
   CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_setup, 0));
   int cur_scale = -1;
+  hmark("setup done");
   for (size_t wi = 0; wi < waves.size(); ++wi) {
     Wave& w = waves[wi];
     double* Dw = Dbuf + (wi % nbuf) * (size_t)max_wave * mat_elems;
@@ -1158,7 +1195,9 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
           CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * Lp.nchunks, cudaMemcpyDeviceToDevice, c.st));
           fv.nchunks = Lp.nchunks; fv.cl = Lp.cl; fv_scale = cur_scale;
         }
+        hmark("before prep");
         ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
+        hmark("after prep");
         cur_scale = sg.l;
       }
       const int gidx = sg.k * nscales + sg.l;
@@ -1180,6 +1219,9 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(cudaEventRecord(ev_dist[wi], c.st_compute));
     c.on_graph();
     CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_dist[wi], 0));
+    hmark("dist queued");
+    ST_TRY(check_input());
+    hmark("input checked");
     ST_TRY(run_measure(c, gws, Dw, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
                        par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
     int t = c.timer.begin(SEQJ_T_COMBINE);
@@ -1280,7 +1322,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   if (do_final) stash_triplets(r, G, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
   r->launches = c.launches;
-  r->in_min = st0.minv; r->in_max = st0.maxv;
+  r->in_min = st0p->minv; r->in_max = st0p->maxv;       // check_input() ran before the first Prim launch
   r->derived_groups = n_derived_done;
   *out = r;
   return SEQJ_OK;
