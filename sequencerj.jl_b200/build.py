@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libseqj_b200.so")
 SOURCES = ["seqj_api.cu"]
-DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))) + [os.path.join("..", "..", "include", "seqj.h")]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".inl"))) + [os.path.join("..", "..", "include", "seqj.h")]
 
 
 def _nvcc() -> str:

@@ -25,744 +25,9 @@
 
 using namespace seqj;
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#include "host_core.cuh"
+#include "host_stages.cuh"
 
-struct seqj_handle {
-  int dev = 0;
-  cudaStream_t st = nullptr;     // compute stream: prep + distance tiles
-  cudaStream_t st2 = nullptr;    // graph stream (higher priority): Prim, tree, combine, fuse
-  std::string err;
-  uint64_t ws_limit = 0;
-  EncodeTiledFn encode = nullptr;
-  int sm_count = 0;
-  size_t max_smem = 0;
-  // Device blocks kept between calls (exact-size reuse): repeated sequence() calls of the same shape do not
-  // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
-  std::vector<seqj_handle*> peers;   // additional devices driven by this handle (seqj_create with ndev > 1)
-  std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
-  std::vector<double> periods;   // periods of SEQJ_PERIODIC (seqj_set_periods), empty = none
-  std::multimap<size_t, void*> cache;
-  size_t cached_bytes = 0;
-  // pinned landing buffer + event of the input check: its result is read back asynchronously and only looked at
-  // after the distance work has been enqueued, so the GPU never waits for the host at the start of a call
-  void* stats_pinned = nullptr;
-  cudaEvent_t stats_ev = nullptr;
-};
-
-struct GroupRes {
-  int metric = 0, scale = 0, nchunks = 0, computed = 0;
-  int chunk_lo = 0, chunk_hi = 0;     // chunks of this group held by this result (partial / sharded runs)
-  std::vector<double> eta_chunk;
-  std::vector<int32_t> root_chunk, parents_chunk;
-  double eta = 0;
-  int32_t root = 0;
-  std::vector<int32_t> parents, mst_i, mst_j;
-  std::vector<double> mst_w;
-};
-
-struct seqj_result {
-  int64_t N = 0;
-  std::vector<GroupRes> groups;
-  int has_final = 0;
-  double eta = 0;
-  int32_t root = 0;
-  std::vector<int32_t> order, parents, mst_i, mst_j, Di, Dj;
-  std::vector<double> mst_w, Dv;
-  double timers[SEQJ_NTIMERS] = {0};
-  int64_t launches = 0;
-  double in_min = 0, in_max = 0;
-  int derived_groups = 0;
-  // raw group edge lists + D values; the deduplicated triplets (Di, Dj, Dv) are built on first request
-  mutable std::vector<int32_t> raw_i, raw_j;
-  mutable std::vector<double> raw_v;
-  mutable int raw_G = 0;
-  mutable int64_t raw_ldp = 0;
-  mutable bool triplets_ready = false;
-};
-
-// --------------------------------------------------------------------------------------------
-namespace {
-
-int fail(seqj_handle* h, int code, const std::string& msg) {
-  if (h) h->err = msg;
-  return code;
-}
-
-#define CU_TRY(call)                                                                              \
-  do {                                                                                            \
-    cudaError_t e__ = (call);                                                                     \
-    if (e__ != cudaSuccess)                                                                       \
-      return fail(h, e__ == cudaErrorMemoryAllocation ? SEQJ_E_OOM : SEQJ_E_CUDA,                 \
-                  std::string(#call) + ": " + cudaGetErrorString(e__));                           \
-  } while (0)
-
-#define ST_TRY(call)          \
-  do {                        \
-    int s__ = (call);         \
-    if (s__ != SEQJ_OK) return s__; \
-  } while (0)
-
-inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
-
-void release_cache(seqj_handle* h) {
-  for (auto& kv : h->cache) cudaFree(kv.second);
-  h->cache.clear();
-  h->cached_bytes = 0;
-}
-
-// RAII device allocations; blocks go back to the handle's cache when the owning call returns.
-struct DevPool {
-  seqj_handle* h;
-  std::vector<std::pair<size_t, void*>> blocks;
-  explicit DevPool(seqj_handle* hh) : h(hh) {}
-  ~DevPool() {
-    for (auto& b : blocks) {
-      h->cache.emplace(b.first, b.second);
-      h->cached_bytes += b.first;
-    }
-  }
-  template <typename T>
-  cudaError_t alloc(T** out, size_t count) {
-    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~size_t(255);
-    void* p = nullptr;
-    auto it = h->cache.find(bytes);
-    if (it != h->cache.end()) {
-      p = it->second;
-      h->cache.erase(it);
-      h->cached_bytes -= bytes;
-    } else {
-      cudaError_t e = cudaMalloc(&p, bytes);
-      if (e == cudaErrorMemoryAllocation && !h->cache.empty()) {
-        cudaGetLastError();
-        release_cache(h);
-        e = cudaMalloc(&p, bytes);
-      }
-      if (e != cudaSuccess) { *out = nullptr; return e; }
-    }
-    blocks.emplace_back(bytes, p);
-    *out = static_cast<T*>(p);
-    return cudaSuccess;
-  }
-};
-
-struct PhaseTimer {
-  struct Span { int phase; cudaEvent_t a, b; };
-  std::vector<Span> spans;
-  cudaStream_t* cur;             // the context's current stream
-  explicit PhaseTimer(cudaStream_t* s) : cur(s) {}
-  ~PhaseTimer() {
-    for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
-  }
-  int begin(int phase) {
-    Span s; s.phase = phase;
-    cudaEventCreate(&s.a); cudaEventCreate(&s.b);
-    cudaEventRecord(s.a, *cur);
-    spans.push_back(s);
-    return (int)spans.size() - 1;
-  }
-  void end(int id) { cudaEventRecord(spans[id].b, *cur); }
-  void collect(double* timers) {
-    const bool trace = getenv("SEQJ_TRACE") != nullptr;      // per-span listing on stderr (debugging)
-    for (auto& s : spans) {
-      float ms = 0;
-      if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
-        timers[s.phase] += ms;
-        if (trace) {
-          float at = 0;
-          cudaEventElapsedTime(&at, spans[0].a, s.a);
-          fprintf(stderr, "[seqj] phase %2d  %9.3f ms  (starts at %9.3f ms)\n", s.phase, ms, at);
-        }
-      }
-    }
-  }
-};
-
-struct ScaleLayout {
-  int scale = 1, cl = 0, cl_pad = 0, nchunks = 0;
-  int64_t ldX = 0;
-  std::vector<int> m_of_chunk;
-};
-
-// _splitnorm chunking (reference src/sequencer.jl:389-397): chunklen = cld(M, scale); starts 1:chunklen:M
-ScaleLayout make_layout(int M, int scale) {
-  ScaleLayout L;
-  L.scale = scale;
-  L.cl = (M + scale - 1) / scale;
-  L.cl_pad = (int)round_up(L.cl, kTileK);
-  for (int r0 = 0; r0 < M; r0 += L.cl) L.m_of_chunk.push_back(std::min(L.cl, M - r0));
-  L.nchunks = (int)L.m_of_chunk.size();
-  L.ldX = (int64_t)L.nchunks * L.cl_pad;
-  return L;
-}
-
-std::vector<int2> make_tiles(int N, bool upper) {
-  std::vector<int2> t;
-  for (int j0 = 0; j0 < N; j0 += kTileN)
-    for (int i0 = 0; i0 < N; i0 += kTileM)
-      if (!upper || i0 < j0 + kTileN) t.push_back(make_int2(i0, j0));
-  return t;
-}
-
-int make_tmap(seqj_handle* h, CUtensorMap* tm, const double* base, int64_t ldX, int64_t rows) {
-  cuuint64_t dims[2] = {(cuuint64_t)ldX, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ldX * 8};
-  cuuint32_t box[2] = {(cuuint32_t)kTileK, (cuuint32_t)kTileM};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = h->encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(h, SEQJ_E_CUDA, "cuTensorMapEncodeTiled failed: " + std::to_string((int)r));
-  return SEQJ_OK;
-}
-
-// Everything the graph layer needs for up to `cap` graphs of N vertices.
-struct GraphWS {
-  int cap = 0, N = 0;
-  int64_t ldv = 0;
-  int use_smem = 1;
-  size_t prim_smem = 0;
-  int *parent = nullptr, *order = nullptr, *size = nullptr, *anc0 = nullptr, *anc1 = nullptr, *dep0 = nullptr,
-      *dep1 = nullptr, *from_g = nullptr;
-  double *weight = nullptr, *wd = nullptr, *wd2 = nullptr, *S = nullptr, *S2 = nullptr, *key_g = nullptr;
-  int prim_R = 0;
-  int* fuse_i0 = nullptr;         // scratch of the final tree's rooting (root_tree_kernel, 16 N + 64 ints)
-  int cluster = 0;                // cluster Prim available (N large enough, slices fit in shared memory)
-  int tree_use_smem = 1;
-  size_t tree_smem = 0;
-};
-
-constexpr int kPrimCluster = 8;     // CTAs per graph; 2 and 4 measured slower at every graph count (profiles/r01_prim_variants.md)
-
-// Slice width and dynamic shared memory of a C-CTA cluster Prim over N vertices.
-void prim_cluster_geometry(int N, int C, int* W_out, size_t* smem_out) {
-  const int W = (int)round_up((N + C - 1) / C, 2);
-  if (W_out) *W_out = W;
-  if (smem_out) *smem_out = (size_t)((W + 1) & ~1) * 8 + (size_t)W * 4 + 16;
-}
-
-typedef void (*PrimFn)(PrimParams);
-PrimFn prim_fn(int R) {
-  switch (R) {
-    case 1: return prim_kernel<1>;
-    case 2: return prim_kernel<2>;
-    case 3: return prim_kernel<3>;
-    case 4: return prim_kernel<4>;
-    case 5: return prim_kernel<5>;
-    case 6: return prim_kernel<6>;
-    case 7: return prim_kernel<7>;
-    case 8: return prim_kernel<8>;
-    default: return prim_kernel<0>;
-  }
-}
-
-struct Ctx {
-  seqj_handle* h;
-  cudaStream_t st;               // current stream: every run_* helper enqueues on it
-  cudaStream_t st_compute, st_graph;
-  DevPool pool;
-  PhaseTimer timer;
-  int64_t launches = 0;
-  bool overlap = false;
-  std::vector<cudaEvent_t> events;
-  explicit Ctx(seqj_handle* hh) : h(hh), st(hh->st), st_compute(hh->st), st_graph(hh->st2), pool(hh), timer(&st) {
-    // Default: one stream.  SEQJ_OVERLAP=1 runs the graph layer on a second stream so that it overlaps the
-    // distance tiles of the next wave; measured on B200 (profiles/r01_overlap_experiments.md) the
-    // interference costs more than it hides at config 3, so it is off until the graph kernels shrink.
-    const char* ov = getenv("SEQJ_OVERLAP");
-    overlap = ov && atoi(ov) != 0;
-    if (!overlap) st_graph = st_compute;
-  }
-  ~Ctx() {
-    for (auto e : events) cudaEventDestroy(e);
-  }
-  void on_compute() { st = st_compute; }
-  void on_graph() { st = st_graph; }
-  cudaEvent_t new_event() {
-    cudaEvent_t e;
-    cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    events.push_back(e);
-    return e;
-  }
-};
-
-int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
-  seqj_handle* h = c.h;
-  g.cap = cap; g.N = N; g.ldv = round_up(N, 32);
-  const size_t n = (size_t)cap * g.ldv + 64;
-  CU_TRY(c.pool.alloc(&g.parent, n)); CU_TRY(c.pool.alloc(&g.order, n)); CU_TRY(c.pool.alloc(&g.size, n));
-  CU_TRY(c.pool.alloc(&g.anc0, n)); CU_TRY(c.pool.alloc(&g.anc1, n)); CU_TRY(c.pool.alloc(&g.dep0, n));
-  CU_TRY(c.pool.alloc(&g.dep1, n)); CU_TRY(c.pool.alloc(&g.weight, n)); CU_TRY(c.pool.alloc(&g.wd, n));
-  CU_TRY(c.pool.alloc(&g.S, n)); CU_TRY(c.pool.alloc(&g.wd2, n)); CU_TRY(c.pool.alloc(&g.S2, n));
-  CU_TRY(c.pool.alloc(&g.fuse_i0, (size_t)16 * N + 64));
-  g.prim_smem = (size_t)((N + 1) & ~1) * 8 + (size_t)N * 4;
-  g.use_smem = g.prim_smem + 1024 <= h->max_smem;
-  if (!g.use_smem) {
-    g.prim_smem = 0;
-    CU_TRY(c.pool.alloc(&g.key_g, n)); CU_TRY(c.pool.alloc(&g.from_g, n));
-  }
-  const int R = (N + 2 * kPrimThreads - 1) / (2 * kPrimThreads);
-  g.prim_R = (g.use_smem && R <= 8) ? R : 0;
-  CU_TRY(cudaFuncSetAttribute(prim_fn(g.prim_R), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.prim_smem));
-  // cluster Prim for graphs large enough that one SM's load rate / argmin latency is the limit
-  const char* force = getenv("SEQJ_PRIM");
-  g.cluster = (N >= 1024) ? 1 : 0;
-  if (force && !strcmp(force, "single")) g.cluster = 0;
-  if (g.cluster) {
-    size_t smem2 = 0;
-    prim_cluster_geometry(N, kPrimCluster, nullptr, &smem2);
-    if (smem2 + 4096 > h->max_smem) g.cluster = 0;
-    else {
-      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<kPrimCluster, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-      CU_TRY(cudaFuncSetAttribute(prim_cluster_kernel<kPrimCluster, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-    }
-  }
-  g.tree_smem = (size_t)N * 8;
-  g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
-  if (!g.tree_use_smem) g.tree_smem = 0;
-  CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.tree_smem));
-  return SEQJ_OK;
-}
-
-// _measure_dm for `nb` dense matrices: Prim + tree kernels.  Outputs go to device arrays.
-int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t strideD, int nb, double eps_floor,
-                double* eta_out, int* root_out, int* parents_out, int64_t ldp, int* mst_i, int* mst_j, double* mst_w,
-                int* dfs_order, const int* mat_slot = nullptr) {
-  seqj_handle* h = c.h;
-  if (nb > g.cap) return fail(h, SEQJ_E_INTERNAL, "graph workspace too small");
-  PrimParams pp;
-  pp.D = D; pp.ldD = ldD; pp.strideD = strideD; pp.N = g.N; pp.eps_floor = eps_floor; pp.mat_slot = mat_slot;
-  pp.parent = g.parent; pp.weight = g.weight; pp.order = g.order; pp.ldv = g.ldv;
-  pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
-  pp.prefetch = getenv("SEQJ_PRIM_PREFETCH") ? atoi(getenv("SEQJ_PRIM_PREFETCH")) : 1;
-  int t = c.timer.begin(SEQJ_T_PRIM);
-  // Measured on B200 at N = 10k (profiles/r01_prim_variants.md): with >= ~50 graphs in flight the single-CTA
-  // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
-  // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.
-  const bool force_cluster = getenv("SEQJ_PRIM") && !strcmp(getenv("SEQJ_PRIM"), "cluster");
-  // cluster kernel while every cluster is resident at once: 512-thread CTAs (2 per SM) up to 2*SMs/8 graphs,
-  // 256-thread CTAs up to SMs/3 graphs (profiles/r01_prim_variants.md); beyond that one CTA per graph
-  int W = 0;
-  size_t smem = 0;
-  prim_cluster_geometry(g.N, kPrimCluster, &W, &smem);
-  if (g.cluster && nb * kPrimCluster <= 2 * h->sm_count)
-    prim_cluster_kernel<kPrimCluster, 512><<<nb * kPrimCluster, 512, smem, c.st>>>(pp, W);
-  else if (g.cluster && (force_cluster || nb * 3 <= h->sm_count))
-    prim_cluster_kernel<kPrimCluster, 256><<<nb * kPrimCluster, 256, smem, c.st>>>(pp, W);
-  else
-    prim_fn(g.prim_R)<<<nb, kPrimThreads, g.prim_smem, c.st>>>(pp);
-  c.timer.end(t); c.launches++;
-  CU_TRY(cudaGetLastError());
-  TreeParams tp;
-  tp.N = g.N; tp.ldv = g.ldv; tp.parent = g.parent; tp.weight = g.weight; tp.order = g.order;
-  tp.size = g.size; tp.wd = g.wd; tp.wd2 = g.wd2; tp.S = g.S; tp.S2 = g.S2; tp.use_smem = g.tree_use_smem; tp.anc0 = g.anc0; tp.anc1 = g.anc1; tp.dep0 = g.dep0; tp.dep1 = g.dep1;
-  tp.eta = eta_out; tp.root = root_out; tp.newparent = parents_out; tp.ldp = ldp;
-  tp.mst_i = mst_i; tp.mst_j = mst_j; tp.mst_w = mst_w; tp.dfs_order = dfs_order;
-  t = c.timer.begin(SEQJ_T_TREE);
-  tree_kernel<<<nb, kTreeThreads, g.tree_smem, c.st>>>(tp);
-  c.timer.end(t); c.launches++;
-  CU_TRY(cudaGetLastError());
-  return SEQJ_OK;
-}
-
-struct PrepBufs {
-  double *P = nullptr, *logP = nullptr, *Uc = nullptr, *U = nullptr, *sP = nullptr, *sU = nullptr, *H = nullptr;
-  double *UwE = nullptr, *UwG = nullptr, *sUG = nullptr, *grid = nullptr, *period = nullptr;
-  double *mass = nullptr, *sR = nullptr, *sT = nullptr;
-  int64_t ldn = 0, rows_pad = 0;
-  int* m_of_chunk = nullptr;
-};
-
-int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const ScaleLayout& L, PrepBufs& b,
-             int normalize) {
-  seqj_handle* h = c.h;
-  PrepParams pp;
-  pp.A = A_dev; pp.ldA = ldA; pp.M = M; pp.N = N; pp.cl = L.cl; pp.cl_pad = L.cl_pad; pp.nchunks = L.nchunks;
-  pp.ldX = L.ldX; pp.ldn = b.ldn; pp.P = b.P; pp.logP = b.logP; pp.Uc = b.Uc; pp.U = b.U;
-  pp.sP = b.sP; pp.sU = b.sU; pp.H = b.H; pp.normalize = normalize;
-  pp.grid = b.grid; pp.UwE = b.UwE; pp.UwG = b.UwG; pp.sUG = b.sUG;
-  pp.mass = b.mass; pp.sR = b.sR; pp.sT = b.sT;
-  int t = c.timer.begin(SEQJ_T_PREP);
-  // rows [N, rows_pad) are read by TMA boxes of the last tiles: keep them zero
-  const size_t tail = (size_t)(b.rows_pad - N) * L.ldX * 8;
-  if (tail) {
-    if (b.P) CU_TRY(cudaMemsetAsync(b.P + (size_t)N * L.ldX, 0, tail, c.st));
-    if (b.logP) CU_TRY(cudaMemsetAsync(b.logP + (size_t)N * L.ldX, 0, tail, c.st));
-    if (b.Uc) CU_TRY(cudaMemsetAsync(b.Uc + (size_t)N * L.ldX, 0, tail, c.st));
-    if (b.UwE) CU_TRY(cudaMemsetAsync(b.UwE + (size_t)N * L.ldX, 0, tail, c.st));
-    if (b.UwG) CU_TRY(cudaMemsetAsync(b.UwG + (size_t)N * L.ldX, 0, tail, c.st));
-  }
-  CU_TRY(cudaMemcpyAsync(b.m_of_chunk, L.m_of_chunk.data(), sizeof(int) * L.nchunks, cudaMemcpyHostToDevice, c.st));
-  const int64_t warps = (int64_t)N * L.nchunks;
-  const int wpb = 8;
-  prep_kernel<<<(unsigned)((warps + wpb - 1) / wpb), wpb * 32, 0, c.st>>>(pp);
-  c.timer.end(t); c.launches++;
-  CU_TRY(cudaGetLastError());
-  return SEQJ_OK;
-}
-
-struct FixBufs {
-  int2* dense_list = nullptr;            // compacted (chunk_local, tile) entries of the flagged tiles
-  unsigned int* dense_count = nullptr;
-  unsigned char* tile_flags = nullptr;   // [max chunks per launch][ntiles] dense-tile flags
-  size_t tile_flags_bytes = 0;
-  int4* list = nullptr;
-  unsigned int* count = nullptr;
-  int* overflow = nullptr;
-  unsigned int cap = 0;
-};
-
-// Relative fix-up thresholds (see kernels_dist.cuh).  Rounding in the DMMA accumulation over m terms behaves like
-// a random walk: |dv| ~ sqrt(m/4) * 2^-53 * (s_i + s_j) ~ 4e-15 * selfterms at m = 4096 (worst case m/4 times
-// that).  A distance is within 1e-9 relative when dv / v <= 2e-9, i.e. v >= 2e-6 * selfterms typically;
-// 1e-4 leaves a 50x margin and keeps the flagged set small on smooth data (neighbouring objects that differ
-// by < 1 %).  KL: |d(H - C)| ~ 3e-14 against results compared as d + 1e-6, flagged below 1e-4 * |H|.
-constexpr double kTauGram = 1e-4;
-constexpr double kTauKL = 1e-4;
-
-// Dense fix-up: compact the tile flags into a list, then a small persistent grid of the direct tile kernel
-// recomputes the listed tiles from the operands (no Gram form).  With nothing flagged this costs two tiny launches.
-int run_dense_tiles(Ctx& c, int metric, DistParams dd, const CUtensorMap& tm1, const CUtensorMap& tm2, FixBufs& fb,
-                    int ntiles, int nb) {
-  seqj_handle* h = c.h;
-  CU_TRY(cudaMemsetAsync(fb.dense_count, 0, sizeof(unsigned int), c.st));
-  const int total = ntiles * nb;
-  compact_flags_kernel<<<(total + 255) / 256, 256, 0, c.st>>>(fb.tile_flags, total, ntiles, fb.dense_list, fb.dense_count);
-  dd.dense_list = fb.dense_list; dd.dense_count = fb.dense_count;
-  const int grid = h->sm_count * 2 * 4;
-  if (metric == SEQJ_L2) direct_dist_kernel<OP_SQ><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
-  else if (metric == SEQJ_ENERGY) direct_dist_kernel<OP_SQ_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tm1, dd);
-  else kl_direct_kernel<<<grid, kTileThreads, kKlSmemBytes, c.st>>>(tm1, tm2, dd);
-  c.launches += 2;
-  CU_TRY(cudaGetLastError());
-  return SEQJ_OK;
-}
-
-// Device copy of the PeriodicEuclidean periods, padded to the chunk's padded length with 1.0 (the operands are 0 there)
-int upload_periods(Ctx& c, PrepBufs& pb, const std::vector<double>& periods, int cl_pad) {
-  seqj_handle* h = c.h;
-  std::vector<double> padded((size_t)cl_pad, 1.0);
-  std::copy(periods.begin(), periods.end(), padded.begin());
-  CU_TRY(c.pool.alloc(&pb.period, (size_t)cl_pad));
-  CU_TRY(cudaMemcpy(pb.period, padded.data(), sizeof(double) * cl_pad, cudaMemcpyHostToDevice));
-  return SEQJ_OK;
-}
-
-// distance matrices of chunks [chunk0, chunk0+nb) of one scale into D (stride strideD)
-int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const int2* tiles_dev, int ntiles,
-                 int N, double* D, int64_t ldD, int64_t strideD, int chunk0, int nb, double eps_floor,
-                 double l2_thresh, int kl_full, FixBufs& fb) {
-  seqj_handle* h = c.h;
-  DistParams dp;
-  dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.D = D; dp.nk = L.cl_pad / kTileK; dp.cl_pad = L.cl_pad;
-  dp.chunk0 = chunk0; dp.ldn = pb.ldn; dp.tiles = tiles_dev; dp.eps_floor = eps_floor;
-  dp.mirror = 1; dp.kl_swap = 0;
-  dp.tile_flags = nullptr; dp.tile_flag_stride = ntiles; dp.dense_thresh = 0x7fffffff; dp.dense_list = nullptr; dp.dense_count = nullptr;
-  dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
-  const bool periodic = metric == SEQJ_PERIODIC;
-  if (periodic) metric = SEQJ_L2;                      // timed with the Euclidean phase
-  const bool on_grid = metric >= SEQJ_EMD_GRID;        // EMD / Energy on the explicit grid: pre-scaled operands
-  if (on_grid) metric = (metric == SEQJ_EMD_GRID) ? SEQJ_EMD : SEQJ_ENERGY;
-  dp.period = nullptr;
-  const int phase = SEQJ_T_DIST_L2 + metric;
-  int t = c.timer.begin(phase);
-  dim3 grid(ntiles, nb);
-  if (periodic) {                 // Distances.PeriodicEuclidean: element-wise fold, direct tiles on the PDFs
-    CUtensorMap tmP;
-    ST_TRY(make_tmap(h, &tmP, pb.P, L.ldX, pb.rows_pad));
-    dp.normA = nullptr; dp.tau = 0; dp.period = pb.period;
-    direct_dist_kernel<OP_PERIODIC><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp);
-    c.launches++;
-    CU_TRY(cudaGetLastError());
-    c.timer.end(t);
-    return SEQJ_OK;
-  }
-  if (metric == SEQJ_EMD) {
-    CUtensorMap tmU;
-    ST_TRY(make_tmap(h, &tmU, on_grid ? pb.UwE : pb.Uc, L.ldX, pb.rows_pad));
-    dp.normA = nullptr; dp.tau = 0; dp.tile_flags = nullptr; dp.dense_list = nullptr; dp.dense_count = nullptr;
-    direct_dist_kernel<OP_L1><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmU, dp);
-    c.launches++;
-    CU_TRY(cudaGetLastError());
-    c.timer.end(t);
-    return SEQJ_OK;
-  }
-  CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
-  CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
-  CUtensorMap tmA, tmB;
-  // dense-tile path (L2 / Energy with mirrored output): tiles with > 1/32 of their entries flagged
-  const bool dense_ok = (metric == SEQJ_L2 || metric == SEQJ_ENERGY || (metric == SEQJ_KLD && !kl_full)) && fb.tile_flags &&
-                        (size_t)nb * ntiles <= fb.tile_flags_bytes && !(getenv("SEQJ_DENSE_TILES") && atoi(getenv("SEQJ_DENSE_TILES")) == 0);
-  if (dense_ok) {
-    CU_TRY(cudaMemsetAsync(fb.tile_flags, 0, (size_t)nb * ntiles, c.st));
-    dp.tile_flags = fb.tile_flags; dp.dense_thresh = kTileM * kTileN / 32;
-  }
-  FixParams fp;
-  fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
-  fp.chunk0 = chunk0; fp.m_of_chunk = pb.m_of_chunk; fp.eps_floor = eps_floor; fp.mirror = 1; fp.kl_swap = 0;
-  fp.fix_list = fb.list; fp.fix_count = fb.count; fp.fix_cap = fb.cap; fp.fix_overflow = fb.overflow;
-  if (metric == SEQJ_L2) {
-    ST_TRY(make_tmap(h, &tmA, pb.P, L.ldX, pb.rows_pad));
-    dp.normA = pb.sP; dp.tau = std::max(kTauGram, l2_thresh); fp.X = pb.P;
-    gemm_dist_kernel<MODE_L2><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
-  } else if (metric == SEQJ_ENERGY) {
-    ST_TRY(make_tmap(h, &tmA, on_grid ? pb.UwG : pb.Uc, L.ldX, pb.rows_pad));
-    dp.normA = on_grid ? pb.sUG : pb.sU; dp.tau = kTauGram; fp.X = on_grid ? pb.UwG : pb.Uc;
-    gemm_dist_kernel<MODE_ENERGY><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmA, dp);
-  } else {  // KL
-    ST_TRY(make_tmap(h, &tmA, pb.P, L.ldX, pb.rows_pad));
-    ST_TRY(make_tmap(h, &tmB, pb.logP, L.ldX, pb.rows_pad));
-    dp.normA = pb.H; dp.tau = kTauKL; fp.X = pb.P;
-    if (kl_full) {
-      dp.mirror = 0; dp.kl_swap = 1; fp.mirror = 0; fp.kl_swap = 1;
-      gemm_dist_kernel<MODE_KL><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmB, tmA, dp);
-    } else {
-      gemm_dist_kernel<MODE_KL><<<grid, kTileThreads, kTileSmemBytes, c.st>>>(tmA, tmB, dp);
-    }
-  }
-  c.launches++;
-  CU_TRY(cudaGetLastError());
-  fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
-  fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, nb);
-  c.launches += 2;
-  if (dense_ok)              // whole tiles full of cancelling entries: recompute them without the Gram form
-    ST_TRY(run_dense_tiles(c, metric, dp, tmA, metric == SEQJ_KLD ? tmB : tmA, fb, ntiles, nb));
-  CU_TRY(cudaGetLastError());
-  c.timer.end(t);
-  return SEQJ_OK;
-}
-
-// Fine-scale per-chunk vectors kept aside while the prep buffers are reused for the coarser scales.
-struct FineVecs {
-  double *mass = nullptr, *sP = nullptr, *sU = nullptr, *sR = nullptr, *sT = nullptr;
-  double *fac = nullptr, *pm = nullptr;     // scratch of derive_factors_kernel: [nchunks][4][ldn] + tail padding, [nchunks][3]
-  int* m_of_chunk = nullptr;
-  int nchunks = 0, cl = 0;
-};
-
-// chunk matrices [c0, c1) of a coarse (metric, scale) group derived from the finished fine matrices
-int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const FineVecs& fv, const double* Dfine,
-               int N, double* D, int64_t ldD, int64_t strideD, int c0, int c1, double eps_floor, double l2_thresh,
-               FixBufs& fb, const int2* tiles_dev, int ntiles, const int* tile_col_offset) {
-  seqj_handle* h = c.h;
-  int t = c.timer.begin(SEQJ_T_DERIVE);
-  CU_TRY(cudaMemsetAsync(fb.count, 0, sizeof(unsigned int), c.st));
-  CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
-  const int ratio = L.cl / fv.cl;
-  DeriveParams dp;
-  dp.mode = metric; dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.Dfine = Dfine; dp.ldn = pb.ldn;
-  dp.fmass = fv.mass; dp.fg = (metric == SEQJ_ENERGY) ? fv.sU : fv.sP; dp.fR = fv.sR; dp.fT = fv.sT; dp.fm = fv.m_of_chunk;
-  dp.eps_floor = eps_floor;
-  dp.tau = (metric == SEQJ_L2) ? std::max(kTauGram, l2_thresh) : (metric == SEQJ_KLD ? kTauKL : kTauGram);
-  dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
-  const bool dense_ok = fb.tile_flags && tile_col_offset && (size_t)(c1 - c0) * ntiles <= fb.tile_flags_bytes &&
-                        !(getenv("SEQJ_DENSE_TILES") && atoi(getenv("SEQJ_DENSE_TILES")) == 0);
-  dp.tile_flags = dense_ok ? fb.tile_flags : nullptr; dp.tile_flag_stride = ntiles; dp.tile_col_offset = tile_col_offset;
-  if (dense_ok) CU_TRY(cudaMemsetAsync(fb.tile_flags, 0, (size_t)(c1 - c0) * ntiles, c.st));
-  const unsigned T = (unsigned)((N + kDeriveTile - 1) / kDeriveTile);
-  dp.ratio = ratio; dp.nfine = fv.nchunks; dp.c_first = c0; dp.f0 = 0; dp.nf = 0; dp.chunk_local = 0;
-  dp.Dout = D;
-  dp.cmass = pb.mass;
-  dp.cself = (metric == SEQJ_L2) ? pb.sP : (metric == SEQJ_KLD ? pb.H : pb.sU);
-  const size_t dsmem = derive_smem_bytes(metric, std::min(ratio, fv.nchunks));
-  const dim3 dgrid(T, T, (unsigned)(c1 - c0)), dblock(32, 8);
-  dp.fac = fv.fac; dp.pm = fv.pm;
-  const unsigned fgrid = (unsigned)(((int64_t)fv.nchunks * pb.ldn + 255) / 256);
-  if (metric == SEQJ_L2) {
-    derive_factors_kernel<MODE_L2><<<fgrid, 256, 0, c.st>>>(dp);
-    derive_kernel<MODE_L2><<<dgrid, dblock, dsmem, c.st>>>(dp);
-  } else if (metric == SEQJ_KLD) {
-    derive_factors_kernel<MODE_KL><<<fgrid, 256, 0, c.st>>>(dp);
-    derive_kernel<MODE_KL><<<dgrid, dblock, dsmem, c.st>>>(dp);
-  } else {
-    derive_factors_kernel<MODE_ENERGY><<<fgrid, 256, 0, c.st>>>(dp);
-    derive_kernel<MODE_ENERGY><<<dgrid, dblock, dsmem, c.st>>>(dp);
-  }
-  c.launches++;
-  c.launches++;
-  CU_TRY(cudaGetLastError());
-  FixParams fp;
-  fp.mode = metric; fp.N = N; fp.ldD = ldD; fp.strideD = strideD; fp.D = D; fp.ldX = L.ldX; fp.cl_pad = L.cl_pad;
-  fp.chunk0 = c0; fp.m_of_chunk = pb.m_of_chunk; fp.eps_floor = eps_floor; fp.mirror = 1; fp.kl_swap = 0;
-  fp.fix_list = fb.list; fp.fix_count = fb.count; fp.fix_cap = fb.cap; fp.fix_overflow = fb.overflow;
-  fp.X = (metric == SEQJ_ENERGY) ? pb.Uc : pb.P;
-  fixup_list_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp);
-  fixup_dense_kernel<<<h->sm_count * 4, 256, 0, c.st>>>(fp, c1 - c0);
-  c.launches += 2;
-  if (dense_ok) {            // tiles full of near-duplicate pairs: recompute them directly from the coarse operands
-    DistParams dd;
-    dd.N = N; dd.ldD = ldD; dd.strideD = strideD; dd.D = D; dd.nk = L.cl_pad / kTileK; dd.cl_pad = L.cl_pad;
-    dd.chunk0 = c0; dd.normA = nullptr; dd.ldn = pb.ldn; dd.tiles = tiles_dev; dd.eps_floor = eps_floor; dd.tau = 0;
-    dd.mirror = 1; dd.kl_swap = 0; dd.tile_flags = fb.tile_flags; dd.tile_flag_stride = ntiles; dd.dense_thresh = 0;
-    dd.dense_list = nullptr; dd.dense_count = nullptr;
-    dd.fix_list = fb.list; dd.fix_count = fb.count; dd.fix_cap = fb.cap; dd.fix_overflow = fb.overflow;
-    CUtensorMap tm1, tm2;
-    if (metric == SEQJ_ENERGY) {
-      ST_TRY(make_tmap(h, &tm1, pb.Uc, L.ldX, pb.rows_pad));
-      tm2 = tm1;
-    } else {
-      ST_TRY(make_tmap(h, &tm1, pb.P, L.ldX, pb.rows_pad));
-      if (metric == SEQJ_KLD) ST_TRY(make_tmap(h, &tm2, pb.logP, L.ldX, pb.rows_pad));
-      else tm2 = tm1;
-    }
-    ST_TRY(run_dense_tiles(c, metric, dd, tm1, tm2, fb, ntiles, c1 - c0));
-  }
-  CU_TRY(cudaGetLastError());
-  c.timer.end(t);
-  return SEQJ_OK;
-}
-
-int set_kernel_attrs(seqj_handle* h) {
-  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(gemm_dist_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_L1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_PERIODIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(kl_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes));
-  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_L2, kDeriveMaxFine)));
-  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_KL, kDeriveMaxFine)));
-  CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_ENERGY, kDeriveMaxFine)));
-  return SEQJ_OK;
-}
-
-int alloc_prep(Ctx& c, PrepBufs& pb, int N, int64_t max_ldX, int max_chunks, bool needP, bool needLog, bool needUc,
-               bool needU, bool needWE = false, bool needWG = false) {
-  seqj_handle* h = c.h;
-  pb.rows_pad = round_up(N, kTileN);
-  pb.ldn = round_up(N, 8);
-  const size_t n = (size_t)pb.rows_pad * max_ldX;
-  if (needP) CU_TRY(c.pool.alloc(&pb.P, n));
-  if (needLog) CU_TRY(c.pool.alloc(&pb.logP, n));
-  if (needUc) CU_TRY(c.pool.alloc(&pb.Uc, n));
-  if (needU) CU_TRY(c.pool.alloc(&pb.U, n));
-  if (needWE) CU_TRY(c.pool.alloc(&pb.UwE, n));
-  if (needWG) CU_TRY(c.pool.alloc(&pb.UwG, n));
-  const size_t nn = (size_t)max_chunks * pb.ldn;
-  CU_TRY(c.pool.alloc(&pb.sP, nn)); CU_TRY(c.pool.alloc(&pb.sU, nn)); CU_TRY(c.pool.alloc(&pb.H, nn));
-  CU_TRY(c.pool.alloc(&pb.sUG, nn));
-  CU_TRY(c.pool.alloc(&pb.mass, nn)); CU_TRY(c.pool.alloc(&pb.sR, nn)); CU_TRY(c.pool.alloc(&pb.sT, nn));
-  CU_TRY(c.pool.alloc(&pb.m_of_chunk, (size_t)max_chunks));
-  return SEQJ_OK;
-}
-
-int alloc_fix(Ctx& c, FixBufs& fb, unsigned int cap, size_t tile_flags_bytes = 0) {
-  seqj_handle* h = c.h;
-  fb.cap = cap;
-  fb.tile_flags_bytes = tile_flags_bytes;
-  if (tile_flags_bytes) {
-    CU_TRY(c.pool.alloc(&fb.tile_flags, tile_flags_bytes));
-    CU_TRY(c.pool.alloc(&fb.dense_list, tile_flags_bytes));
-    CU_TRY(c.pool.alloc(&fb.dense_count, 1));
-  }
-  CU_TRY(c.pool.alloc(&fb.list, (size_t)cap));
-  CU_TRY(c.pool.alloc(&fb.count, 1));
-  CU_TRY(c.pool.alloc(&fb.overflow, 1));
-  return SEQJ_OK;
-}
-
-// final fuse on device: group MSTs (device arrays, [G][ldp]) -> D (in Sbuf) -> final measure
-// `perm[g]` = index (in the device arrays) of the g-th group in the reference's metric-major order;
-// the scatter and the eta sum follow that order so the rounding matches the reference's loop.
-int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, const double* eta_g, const int* mst_i,
-             const int* mst_j, const double* mst_w, int64_t ldp, double eps_floor, double* eta_f, int* root_f,
-             int* parents_f, int* fmst_i, int* fmst_j, double* fmst_w, int* order_f, double* edge_val,
-             const std::vector<int>& perm, const int* perm_dev) {
-  seqj_handle* h = c.h;
-  int t = c.timer.begin(SEQJ_T_FUSE);
-  CU_TRY(cudaMemsetAsync(Sbuf, 0, (size_t)N * ldD * 8, c.st));
-  const int ne = N - 1;
-  for (int gg = 0; gg < G; ++gg) {
-    const int g = perm[gg];
-    fuse_scatter_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
-                                                          mst_w + (int64_t)g * ldp, eta_g + g, ne);
-    c.launches++;
-  }
-  fuse_finalize_kernel<<<h->sm_count * 8, 256, 0, c.st>>>(Sbuf, ldD, N, eta_g, perm_dev, G, eps_floor);
-  c.launches++;
-  for (int g = 0; g < G; ++g) {
-    gather_edges_kernel<<<(ne + 255) / 256, 256, 0, c.st>>>(Sbuf, ldD, mst_i + (int64_t)g * ldp, mst_j + (int64_t)g * ldp,
-                                                          edge_val + (int64_t)g * ldp, ne);
-    c.launches++;
-  }
-  CU_TRY(cudaGetLastError());
-  // final MST on the sparse edge union (Boruvka), rooted at vertex 0, then the usual tree measurement
-  {
-    BoruvkaParams bp;
-    bp.N = N; bp.G = G; bp.ldp = ldp; bp.mi = mst_i; bp.mj = mst_j; bp.val = edge_val; bp.eps_floor = eps_floor;
-    bp.comp = gws.anc0; bp.best = reinterpret_cast<unsigned long long*>(gws.wd); bp.bestp = reinterpret_cast<unsigned long long*>(gws.wd2);
-    bp.out_i = gws.dep0; bp.out_j = gws.dep1; bp.out_w = gws.S; bp.out_count = gws.size;
-    boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
-    RootTreeParams rp;
-    rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
-    rp.scratch = gws.fuse_i0;
-    rp.parent = gws.parent; rp.weight = gws.weight; rp.order = gws.order;
-    root_tree_kernel<<<1, 1024, 0, c.st>>>(rp);
-    c.launches += 2;
-    CU_TRY(cudaGetLastError());
-    TreeParams tp;
-    tp.N = N; tp.ldv = gws.ldv; tp.parent = gws.parent; tp.weight = gws.weight; tp.order = gws.order;
-    tp.size = gws.size; tp.wd = gws.wd; tp.wd2 = gws.wd2; tp.S = gws.S; tp.S2 = gws.S2; tp.use_smem = gws.tree_use_smem;
-    tp.anc0 = gws.anc0; tp.anc1 = gws.anc1; tp.dep0 = gws.dep0; tp.dep1 = gws.dep1;
-    tp.eta = eta_f; tp.root = root_f; tp.newparent = parents_f; tp.ldp = ldp;
-    tp.mst_i = fmst_i; tp.mst_j = fmst_j; tp.mst_w = fmst_w; tp.dfs_order = order_f;
-    tree_kernel<<<1, kTreeThreads, gws.tree_smem, c.st>>>(tp);
-    c.launches++;
-    CU_TRY(cudaGetLastError());
-  }
-  c.timer.end(t);
-  return SEQJ_OK;
-}
-
-void stash_triplets(seqj_result* r, int G, int64_t ldp, std::vector<int>& mi, std::vector<int>& mj, std::vector<double>& val) {
-  r->raw_i.swap(mi); r->raw_j.swap(mj); r->raw_v.swap(val);
-  r->raw_G = G; r->raw_ldp = ldp; r->triplets_ready = false;
-}
-
-void dedup_triplets_impl(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
-                         const std::vector<double>& val);
-
-// D triplets are rarely read (the wrapper materialises D(r) on demand): deduplicate on first access
-void ensure_triplets(const seqj_result* cr) {
-  if (cr->triplets_ready) return;
-  seqj_result* r = const_cast<seqj_result*>(cr);
-  if (r->raw_G > 0) dedup_triplets_impl(r, r->raw_G, (int)r->N, r->raw_ldp, r->raw_i, r->raw_j, r->raw_v);
-  r->raw_i.clear(); r->raw_i.shrink_to_fit(); r->raw_j.clear(); r->raw_j.shrink_to_fit(); r->raw_v.clear(); r->raw_v.shrink_to_fit();
-  r->triplets_ready = true;
-}
-
-void dedup_triplets_impl(seqj_result* r, int G, int N, int64_t ldp, const std::vector<int>& mi, const std::vector<int>& mj,
-                         const std::vector<double>& val) {
-  // first occurrence of every (i, j) in group-major edge order, via an open-addressing table
-  const size_t total = (size_t)G * (N - 1);
-  size_t cap = 16;
-  while (cap < 2 * total) cap <<= 1;
-  std::vector<uint64_t> table(cap, ~uint64_t(0));
-  r->Di.reserve(total); r->Dj.reserve(total); r->Dv.reserve(total);
-  for (int g = 0; g < G; ++g)
-    for (int e = 0; e < N - 1; ++e) {
-      const int64_t k = (int64_t)g * ldp + e;
-      const uint64_t key = (uint64_t)mi[k] * (uint64_t)N + (uint64_t)mj[k];
-      size_t hpos = (key * 0x9E3779B97F4A7C15ull) & (cap - 1);
-      bool seen = false;
-      while (table[hpos] != ~uint64_t(0)) {
-        if (table[hpos] == key) { seen = true; break; }
-        hpos = (hpos + 1) & (cap - 1);
-      }
-      if (seen) continue;
-      table[hpos] = key;
-      r->Di.push_back(mi[k]); r->Dj.push_back(mj[k]); r->Dv.push_back(val[k]);
-    }
-}
-
-template <typename T>
-void copy_out(T* dst, const std::vector<T>& v) {
-  if (dst && !v.empty()) std::memcpy(dst, v.data(), v.size() * sizeof(T));
-}
-
-}  // namespace
 
 // --------------------------------------------------------------------------------------------
 extern "C" {
@@ -1667,167 +932,6 @@ int seqj_result_input_range(const seqj_result* r, double* minv, double* maxv) {
 }
 void seqj_result_free(seqj_result* r) { delete r; }
 
-// ---- unit-level entry points ------------------------------------------------------------------
-int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, int32_t scale, double* P_out,
-                   double* U_out, int32_t* nchunks_out) {
-  ST_TRY(check_ready(h));
-  if (!A || M64 < 1 || N64 < 1 || scale < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
-  if (scale > M64)
-    return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scale) + ") cannot be larger than the number of data elements (" +
-                                      std::to_string(M64) + ").");
-  const int M = (int)M64, N = (int)N64;
-  Ctx c(h);
-  ScaleLayout L = make_layout(M, scale);
-  PrepBufs pb;
-  ST_TRY(alloc_prep(c, pb, N, L.ldX, L.nchunks, true, false, false, true));
-  double *A_dev, *out_dev;
-  CU_TRY(c.pool.alloc(&A_dev, (size_t)M * N)); CU_TRY(c.pool.alloc(&out_dev, (size_t)M * N));
-  CU_TRY(cudaMemcpyAsync(A_dev, A, (size_t)M * N * 8, cudaMemcpyHostToDevice, c.st));
-  ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
-  const int64_t tot = (int64_t)M * N;
-  if (P_out) {
-    unpad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(pb.P, L.ldX, L.cl, L.cl_pad, M, N, out_dev);
-    CU_TRY(cudaMemcpyAsync(P_out, out_dev, tot * 8, cudaMemcpyDeviceToHost, c.st));
-  }
-  if (U_out) {
-    unpad_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(pb.U, L.ldX, L.cl, L.cl_pad, M, N, out_dev);
-    CU_TRY(cudaMemcpyAsync(U_out, out_dev, tot * 8, cudaMemcpyDeviceToHost, c.st));
-  }
-  CU_TRY(cudaStreamSynchronize(c.st));
-  if (nchunks_out) *nchunks_out = L.nchunks;
-  return SEQJ_OK;
-}
-
-int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m64, int64_t N64, int normalize,
-                  int kl_full, double eps_floor, double l2_thresh, double* D_out) {
-  ST_TRY(check_ready(h));
-  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "bad argument");
-  const bool grid_metric = metric == SEQJ_EMD_GRID || metric == SEQJ_ENERGY_GRID;
-  if (grid_metric && (int64_t)h->grid.size() != m64)
-    return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of the chunk");
-  if (metric == SEQJ_PERIODIC && (int64_t)h->periods.size() != m64)
-    return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean needs one period per row of the chunk");
-  const int m = (int)m64, N = (int)N64;
-  Ctx c(h);
-  ScaleLayout L = make_layout(m, 1);
-  PrepBufs pb;
-  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD || metric == SEQJ_PERIODIC, metric == SEQJ_KLD,
-                    metric == SEQJ_EMD || metric == SEQJ_ENERGY, false, metric == SEQJ_EMD_GRID, metric == SEQJ_ENERGY_GRID));
-  if (metric == SEQJ_PERIODIC) ST_TRY(upload_periods(c, pb, h->periods, L.cl_pad));
-  if (grid_metric) {
-    CU_TRY(c.pool.alloc(&pb.grid, (size_t)m));
-    CU_TRY(cudaMemcpyAsync(pb.grid, h->grid.data(), sizeof(double) * m, cudaMemcpyHostToDevice, c.st));
-  }
-  FixBufs fb;
-  ST_TRY(alloc_fix(c, fb, 1u << 20));
-  const bool full = (metric == SEQJ_KLD) && kl_full;
-  std::vector<int2> tiles = make_tiles(N, !full);
-  int2* tiles_dev;
-  CU_TRY(c.pool.alloc(&tiles_dev, tiles.size()));
-  CU_TRY(cudaMemcpyAsync(tiles_dev, tiles.data(), tiles.size() * sizeof(int2), cudaMemcpyHostToDevice, c.st));
-  const int64_t ldD = round_up(N, 16);
-  double *A_dev, *D_dev;
-  CU_TRY(c.pool.alloc(&A_dev, (size_t)m * N)); CU_TRY(c.pool.alloc(&D_dev, (size_t)N * ldD));
-  CU_TRY(cudaMemcpyAsync(A_dev, chunk, (size_t)m * N * 8, cudaMemcpyHostToDevice, c.st));
-  ST_TRY(run_prep(c, A_dev, m, m, N, L, pb, normalize));
-  ST_TRY(run_distance(c, metric, L, pb, tiles_dev, (int)tiles.size(), N, D_dev, ldD, 0, 0, 1, eps_floor, l2_thresh,
-                      full ? 1 : 0, fb));
-  CU_TRY(cudaMemcpy2DAsync(D_out, (size_t)N * 8, D_dev, (size_t)ldD * 8, (size_t)N * 8, N, cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaStreamSynchronize(c.st));
-  return SEQJ_OK;
-}
-
-int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N64, double eps_floor, double* eta, int32_t* root,
-                    int32_t* parents, int32_t* mst_i, int32_t* mst_j, double* mst_w, int32_t* order) {
-  ST_TRY(check_ready(h));
-  if (!D || N64 < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
-  const int N = (int)N64;
-  Ctx c(h);
-  const int64_t ldD = round_up(N, 16), ldp = N;
-  double *up, *Dsym, *eta_d, *w_d;
-  int *root_d, *par_d, *mi_d, *mj_d, *ord_d;
-  CU_TRY(c.pool.alloc(&up, (size_t)N * N)); CU_TRY(c.pool.alloc(&Dsym, (size_t)N * ldD));
-  CU_TRY(c.pool.alloc(&eta_d, 1)); CU_TRY(c.pool.alloc(&root_d, 1)); CU_TRY(c.pool.alloc(&par_d, (size_t)ldp));
-  CU_TRY(c.pool.alloc(&mi_d, (size_t)ldp)); CU_TRY(c.pool.alloc(&mj_d, (size_t)ldp)); CU_TRY(c.pool.alloc(&w_d, (size_t)ldp));
-  CU_TRY(c.pool.alloc(&ord_d, (size_t)ldp));
-  CU_TRY(cudaMemcpyAsync(up, D, (size_t)N * N * 8, cudaMemcpyHostToDevice, c.st));
-  const int64_t tot = (int64_t)N * N;
-  symmetrize_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.st>>>(up, N, Dsym, ldD, eps_floor);
-  GraphWS gws;
-  ST_TRY(graphws_alloc(c, gws, 1, N));
-  ST_TRY(run_measure(c, gws, Dsym, ldD, 0, 1, eps_floor, eta_d, root_d, par_d, ldp, mi_d, mj_d, w_d, order ? ord_d : nullptr));
-  if (eta) CU_TRY(cudaMemcpyAsync(eta, eta_d, 8, cudaMemcpyDeviceToHost, c.st));
-  if (root) CU_TRY(cudaMemcpyAsync(root, root_d, 4, cudaMemcpyDeviceToHost, c.st));
-  if (parents) CU_TRY(cudaMemcpyAsync(parents, par_d, 4 * (size_t)N, cudaMemcpyDeviceToHost, c.st));
-  if (mst_i) CU_TRY(cudaMemcpyAsync(mst_i, mi_d, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
-  if (mst_j) CU_TRY(cudaMemcpyAsync(mst_j, mj_d, 4 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
-  if (mst_w) CU_TRY(cudaMemcpyAsync(mst_w, w_d, 8 * (size_t)(N - 1), cudaMemcpyDeviceToHost, c.st));
-  if (order) CU_TRY(cudaMemcpyAsync(order, ord_d, 4 * (size_t)N, cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaStreamSynchronize(c.st));
-  return SEQJ_OK;
-}
-
-int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, int n, int64_t N64, double* Dkl_out) {
-  ST_TRY(check_ready(h));
-  if (!Dchunks || !etas || !Dkl_out || n < 1 || N64 < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
-  const int N = (int)N64;
-  Ctx c(h);
-  const size_t mat = (size_t)N * N, matp = (mat + 1) & ~size_t(1);     // 16 B aligned matrices for double2 access
-  double *D_dev, *S_dev, *eta_dev;
-  const int B = std::min(n, kCombineMax);
-  CU_TRY(c.pool.alloc(&D_dev, matp * B)); CU_TRY(c.pool.alloc(&S_dev, matp)); CU_TRY(c.pool.alloc(&eta_dev, (size_t)n));
-  CU_TRY(cudaMemsetAsync(D_dev, 0, matp * B * 8, c.st));
-  CU_TRY(cudaMemcpyAsync(eta_dev, etas, sizeof(double) * n, cudaMemcpyHostToDevice, c.st));
-  for (int c0 = 0; c0 < n; c0 += B) {
-    const int nb = std::min(B, n - c0);
-    for (int q = 0; q < nb; ++q)
-      CU_TRY(cudaMemcpyAsync(D_dev + (size_t)q * matp, Dchunks + (size_t)(c0 + q) * mat, mat * 8, cudaMemcpyHostToDevice, c.st));
-    combine_kernel<<<h->sm_count * 16, 256, 0, c.st>>>(S_dev, D_dev, (int64_t)matp, nb, eta_dev + c0, c0 == 0, c0 + nb >= n,
-                                                      eta_dev, n, (int64_t)(matp / 2));
-    CU_TRY(cudaGetLastError());
-  }
-  CU_TRY(cudaMemcpyAsync(Dkl_out, S_dev, mat * 8, cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaStreamSynchronize(c.st));
-  return SEQJ_OK;
-}
-
-int seqj_cdf_distance(seqj_handle* h, int32_t metric, const double* u, const double* uw, int64_t nu64, const double* v,
-                      const double* vw, int64_t nv64, double* out) {
-  ST_TRY(check_ready(h));
-  if (!u || !uw || !v || !vw || !out || nu64 < 1 || nv64 < 1 || nu64 + nv64 >= (1ll << 26))
-    return fail(h, SEQJ_E_BADARG, "bad argument");
-  if (metric != SEQJ_EMD && metric != SEQJ_ENERGY) return fail(h, SEQJ_E_BADARG, "metric must be SEQJ_EMD or SEQJ_ENERGY");
-  const int nu = (int)nu64, nv = (int)nv64;
-  auto pow2 = [](int n) { int q = 1; while (q < n) q <<= 1; return q; };
-  Ctx c(h);
-  CdfPairParams pp;
-  pp.nu = nu; pp.nv = nv; pp.p = (metric == SEQJ_EMD) ? 1 : 2;
-  pp.pu = pow2(nu); pp.pv = pow2(nv); pp.pa = pow2(nu + nv + 1);
-  double *u_d, *uw_d, *v_d, *vw_d, *out_d;
-  int* status_d;
-  CU_TRY(c.pool.alloc(&u_d, (size_t)nu)); CU_TRY(c.pool.alloc(&uw_d, (size_t)nu));
-  CU_TRY(c.pool.alloc(&v_d, (size_t)nv)); CU_TRY(c.pool.alloc(&vw_d, (size_t)nv));
-  CU_TRY(c.pool.alloc(&pp.su, (size_t)pp.pu)); CU_TRY(c.pool.alloc(&pp.sv, (size_t)pp.pv)); CU_TRY(c.pool.alloc(&pp.A, (size_t)pp.pa));
-  CU_TRY(c.pool.alloc(&pp.iu, (size_t)pp.pu)); CU_TRY(c.pool.alloc(&pp.iv, (size_t)pp.pv));
-  CU_TRY(c.pool.alloc(&pp.cu, (size_t)nu)); CU_TRY(c.pool.alloc(&pp.cv, (size_t)nv));
-  CU_TRY(c.pool.alloc(&pp.dx, (size_t)nu + nv)); CU_TRY(c.pool.alloc(&pp.pos, (size_t)nu + nv + 1));
-  CU_TRY(c.pool.alloc(&out_d, 1)); CU_TRY(c.pool.alloc(&status_d, 1));
-  CU_TRY(cudaMemcpyAsync(u_d, u, 8 * (size_t)nu, cudaMemcpyHostToDevice, c.st));
-  CU_TRY(cudaMemcpyAsync(uw_d, uw, 8 * (size_t)nu, cudaMemcpyHostToDevice, c.st));
-  CU_TRY(cudaMemcpyAsync(v_d, v, 8 * (size_t)nv, cudaMemcpyHostToDevice, c.st));
-  CU_TRY(cudaMemcpyAsync(vw_d, vw, 8 * (size_t)nv, cudaMemcpyHostToDevice, c.st));
-  pp.u = u_d; pp.uw = uw_d; pp.v = v_d; pp.vw = vw_d; pp.out = out_d; pp.status = status_d;
-  cdf_pair_kernel<<<1, kPairThreads, 0, c.st>>>(pp);
-  CU_TRY(cudaGetLastError());
-  double res = 0.0;
-  int status = 0;
-  CU_TRY(cudaMemcpyAsync(&res, out_d, 8, cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaMemcpyAsync(&status, status_d, 4, cudaMemcpyDeviceToHost, c.st));
-  CU_TRY(cudaStreamSynchronize(c.st));
-  if (status == 1) return fail(h, SEQJ_E_DOMAIN, "grid values and weights must be finite");
-  if (status == 2) return fail(h, SEQJ_E_DOMAIN, "identical grids: the non-zero grid steps do not match the grid length (the reference fails with a DimensionMismatch)");
-  *out = (metric == SEQJ_ENERGY) ? 1.4142135623730951 * res : res;
-  return SEQJ_OK;
-}
+#include "api_units.inl"
 
 }  // extern "C"
