@@ -246,8 +246,11 @@ def main():
     t0 = time.perf_counter()
     phases = {}
     launches = 0
+    step_walls = []
     for _ in range(args.steps):
+        tc = time.perf_counter()
         r = step_dev()
+        step_walls.append(round((time.perf_counter() - tc) * 1e3, 1))
         launches += r.launches
         for k, v in r.timings.items():
             if k not in ("input_min", "derived_groups"):
@@ -280,8 +283,13 @@ def main():
         barrier()
         t0 = time.perf_counter()
         d2h = 0
+        e2e_ph, walls = {}, []
         for _ in range(args.steps):
+            tc = time.perf_counter()
             rr = step_e2e()
+            walls.append((time.perf_counter() - tc) * 1e3)
+            for k in ("total", "h2d", "d2h"):
+                e2e_ph[k] = e2e_ph.get(k, 0.0) + rr.timings.get(k, 0.0) / args.steps
         barrier()
         el = time.perf_counter() - t0
         if dist is not None:
@@ -294,7 +302,8 @@ def main():
         assert np.array_equal(rr.order, order_ref)
         e2e = {"value": args.steps * pairs / el / 1e9, "unit": "Gpair/s", "h2d_bytes_per_step": 8 * N * L,
                "d2h_bytes_per_step": int(d2h), "sequence_wall_s": el / args.steps,
-               "api": "sequencerj_b200.sequence(A_host) -> seqj_sequence (C ABI), pinned host input"}
+               "api": "sequencerj_b200.sequence(A_host) -> seqj_sequence (C ABI), pinned host input",
+               "device_ms_per_step": {k: round(v, 3) for k, v in e2e_ph.items()}, "wall_ms_each_step": [round(w, 1) for w in walls]}
 
     if rank != 0:
         if dist is not None:
@@ -370,7 +379,7 @@ def main():
            "config": {"workload": cfg["name"], "pairs_per_step": pairs,
                       "cache": "inputs (8*N*L bytes) and every N x N chunk matrix are larger than the 126 MB L2; no flush needed",
                       "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
-           "sequence_wall_s": elapsed / args.steps, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+           "sequence_wall_s": elapsed / args.steps, "wall_ms_each_step": step_walls, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
            "roofline_emd": roof_emd, "roofline_prim": roof_prim,
            "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "direct_dist_kernel<OP_L1> = EMD tiles (FP64 ALU issue-bound, see roofline_emd)"),
                                            (gemm_ms, "gemm_dist_kernel (FP64 tensor pipe, see roofline)"),
