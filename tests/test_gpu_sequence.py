@@ -344,3 +344,61 @@ def test_derived_equals_direct_tiles(seqj, handle, monkeypatch):
     for key in a.EOAlgScale:
         rel_close(a.EOSeg[key][0], b.EOSeg[key][0], 1e-12)
         assert np.array_equal(a.EOAlgScale[key][1].parents, b.EOAlgScale[key][1].parents)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_chunk_major_partials_and_finish_on_one_gpu(seqj, handle, world):
+    """`seqj_sequence_partial` + `seqj_groups_finish` (the chunk-major multi-GPU path) driven on ONE GPU:
+    the `world` virtual ranks run one after the other, their eta-weighted N x N partials are added like the owner's
+    reduce does, and the finished groups must equal those of the plain call (chunk trees and etas exactly; group
+    etas to rounding, since the partial sums associate differently from the sequential chunk loop)."""
+    torch = pytest.importorskip("torch")
+    from sequencerj_b200 import api, sharding
+    rng = np.random.default_rng(21)
+    M, N = 240, 400
+    A = rng.random((M, N))
+    scales, metrics = (1, 2, 4, 8), seqj.ALL_METRICS
+    ref = seqj.sequence(A.copy(), scales=scales, metrics=metrics)
+    At = np.ascontiguousarray(A.T)
+    dev = torch.from_numpy(At).cuda()
+    G = len(metrics) * len(scales)
+    ldD = -(-N // 16) * 16
+    stride = N * ldD
+    lo, hi = sharding.chunk_partition(M, metrics, scales, world)
+    S_total = torch.zeros((G, stride), dtype=torch.float64, device="cuda")
+    for r in range(world):
+        active = [g for g in range(G) if lo[r, g] < hi[r, g]]
+        assert active
+        S = torch.empty((len(active), stride), dtype=torch.float64, device="cuda")
+        local = api._sequence_partial((N, M), scales, metrics, lo[r], hi[r], S.data_ptr(), stride, dev.data_ptr(), handle)
+        torch.cuda.synchronize()
+        for slot, g in enumerate(active):
+            S_total[g] += S[slot]
+            key = (metrics[g // len(scales)], scales[g % len(scales)])
+            a, b = local.chunk_ranges[key]
+            assert (a, b) == (int(lo[r, g]), int(hi[r, g]))
+            etas, trees = local.EOSeg[key]
+            ref_etas, ref_trees = ref.EOSeg[key]
+            assert etas == ref_etas[a:b]
+            for t, rt in zip(trees, ref_trees[a:b]):
+                assert t.root == rt.root and np.array_equal(t.parents, rt.parents)
+    # every chunk of every group is covered exactly once
+    for g in range(G):
+        cover = sorted((int(lo[r, g]), int(hi[r, g])) for r in range(world) if lo[r, g] < hi[r, g])
+        assert cover[0][0] == 0 and cover[-1][1] == sharding.nchunks(M, scales[g % len(scales)])
+        assert all(x[1] == y[0] for x, y in zip(cover, cover[1:]))
+    sums = []
+    for g in range(G):
+        tot = 0.0
+        for e in ref.EOSeg[(metrics[g // len(scales)], scales[g % len(scales)])][0]:
+            tot += e
+        sums.append(tot)
+    torch.cuda.synchronize()
+    fin = api.groups_finish(S_total.data_ptr(), stride, list(range(G)), N, sums, handle=handle)
+    for g, (eta, tree, mst) in enumerate(fin):
+        key = (metrics[g // len(scales)], scales[g % len(scales)])
+        ref_eta, ref_tree = ref.EOAlgScale[key]
+        rel_close([eta], [ref_eta], 1e-12)
+        assert tree.root == ref_tree.root and np.array_equal(tree.parents, ref_tree.parents)
+        rm = ref.group_msts[key]
+        assert set(zip(mst.src.tolist(), mst.dst.tolist())) == set(zip(rm.src.tolist(), rm.dst.tolist()))
