@@ -402,3 +402,12 @@ def test_chunk_major_partials_and_finish_on_one_gpu(seqj, handle, world):
         assert tree.root == ref_tree.root and np.array_equal(tree.parents, ref_tree.parents)
         rm = ref.group_msts[key]
         assert set(zip(mst.src.tolist(), mst.dst.tolist())) == set(zip(rm.src.tolist(), rm.dst.tolist()))
+
+
+@pytest.mark.parametrize("N", [2, 3, 37, 64, 65, 129, 257, 320])
+def test_edge_object_counts(seqj, oracle, handle, N):
+    """Object counts around the tile edges: fewer objects than one 64-wide tile, exact multiples of 64 (ldD == N),
+    odd counts (the 16-byte column pairs of the derive / combine kernels end in the row padding).  Nested scales, so
+    the tile, derive, symmetric-combine, Prim, Euler-tour and fuse kernels all see the edge."""
+    A = np.random.default_rng(1000 + N).random((48, N))
+    _compare(seqj, oracle, A, (1, 2, 4), (0, 1, 2, 3))
