@@ -71,7 +71,7 @@ class ClockSampler:
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "500")],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "250")],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,8 +83,9 @@ class ClockSampler:
             self.lines.append(ln.strip())
 
     def mark(self):
-        """Start of the timed region: only samples from here on are reported."""
-        self.lines = []
+        """Start of the timed region: samples from here on are reported (or, if the region is shorter than one
+        sampling period, the last sample taken under load during the warm-up)."""
+        self.start_idx = len(self.lines)
 
     def stop(self):
         if not self.proc:
@@ -96,7 +97,8 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        lines = self.lines[getattr(self, "start_idx", 0):] or self.lines[-1:]
+        for ln in lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -234,7 +236,7 @@ def main():
                                          gather_groups=gather_groups)
 
     # the nvidia-smi sampler starts BEFORE the warm-up so that its start-up (NVML initialisation takes driver locks)
-    # does not land in the timed region; it samples every 500 ms until the timed steps are done (at 100 ms the
+    # does not land in the timed region; it samples every 250 ms until the timed steps are done (at 100 ms the
     # polling itself cost 3-20 ms per sequence() call of host-side launch stalls, measured with BENCH_SMI_MS /
     # BENCH_NO_SAMPLER)
     sampler = ClockSampler(local)
