@@ -5,6 +5,46 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// One persistent host thread per peer device (single-process multi-GPU): a thread that has used CUDA is expensive to
+// create and to tear down, so the workers live as long as the handle and are handed one job per sequence() call.
+struct DeviceWorker {
+  std::thread th;
+  std::mutex m;
+  std::condition_variable cv;
+  std::function<void()> job;
+  bool has_job = false, done = false, stop = false;
+  DeviceWorker() {
+    th = std::thread([this]() {
+      std::unique_lock<std::mutex> lk(m);
+      while (true) {
+        cv.wait(lk, [this]() { return has_job || stop; });
+        if (stop) return;
+        std::function<void()> j = std::move(job);
+        has_job = false;
+        lk.unlock();
+        j();
+        lk.lock();
+        done = true;
+        cv.notify_all();
+      }
+    });
+  }
+  void post(std::function<void()> j) {
+    std::lock_guard<std::mutex> lk(m);
+    job = std::move(j); has_job = true; done = false;
+    cv.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(m);
+    cv.wait(lk, [this]() { return done; });
+  }
+  ~DeviceWorker() {
+    { std::lock_guard<std::mutex> lk(m); stop = true; }
+    cv.notify_all();
+    if (th.joinable()) th.join();
+  }
+};
+
 struct seqj_handle {
   int dev = 0;
   cudaStream_t st = nullptr;     // compute stream: prep + distance tiles
@@ -17,6 +57,7 @@ struct seqj_handle {
   // Device blocks kept between calls (exact-size reuse): repeated sequence() calls of the same shape do not
   // pay cudaMalloc/cudaFree of ~100 GB of workspace each time.  Released by seqj_release_workspace/destroy.
   std::vector<seqj_handle*> peers;   // additional devices driven by this handle (seqj_create with ndev > 1)
+  std::vector<DeviceWorker*> workers; // one per peer, created on first use
   std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
   std::vector<double> periods;   // periods of SEQJ_PERIODIC (seqj_set_periods), empty = none
   std::multimap<size_t, void*> cache;

@@ -10,7 +10,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
 #include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -104,6 +107,8 @@ static int create_one(seqj_handle** out, const int* devices, int ndev) {
 
 void seqj_destroy(seqj_handle* h) {
   if (!h) return;
+  for (DeviceWorker* w : h->workers) delete w;          // joins the worker threads before their devices go away
+  h->workers.clear();
   for (seqj_handle* p : h->peers) seqj_destroy(p);
   h->peers.clear();
   cudaSetDevice(h->dev);
@@ -697,19 +702,21 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   }
   std::vector<seqj_result*> parts(ndev, nullptr);
   std::vector<int> status(ndev, SEQJ_OK);
-  std::vector<std::thread> threads;
+  while ((int)h->workers.size() < ndev - 1) h->workers.push_back(new DeviceWorker());
+  auto run_device = [&](int d) {
+    bool any = false;
+    for (uint8_t b : masks[d]) any |= b != 0;
+    if (!any) return;
+    status[d] = sequence_host_one(hs[d], A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh,
+                                  masks[d].data(), &parts[d]);
+  };
   for (int d = 0; d < ndev; ++d) {
     hs[d]->grid = h->grid;
     hs[d]->periods = h->periods;
-    threads.emplace_back([&, d]() {
-      bool any = false;
-      for (uint8_t b : masks[d]) any |= b != 0;
-      if (!any) return;
-      status[d] = sequence_host_one(hs[d], A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh,
-                                    masks[d].data(), &parts[d]);
-    });
   }
-  for (auto& t : threads) t.join();
+  for (int d = 1; d < ndev; ++d) h->workers[d - 1]->post([&, d]() { run_device(d); });
+  run_device(0);                                          // the primary device runs on the calling thread
+  for (int d = 1; d < ndev; ++d) h->workers[d - 1]->wait();
   cudaSetDevice(h->dev);
   for (int d = 0; d < ndev; ++d)
     if (status[d] != SEQJ_OK) {
