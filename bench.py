@@ -333,7 +333,8 @@ def main():
     roof = None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "r01_ncu_config3_metrics.json")
-    if args.config == 3 and not (args.objects or args.length) and world == 1 and os.path.exists(tpath):
+    is_cfg3 = args.config == 3 and not (args.objects or args.length)
+    if is_cfg3 and world == 1 and os.path.exists(tpath):
         # dram__bytes_read.sum + dram__bytes_write.sum per launch of the DMMA launches that still run (finest scale:
         # gridDim.y = 16 chunks); the coarser scales are derived and run no tiles
         fin = max(sharding.nchunks(L, sc) for sc in scales)
@@ -345,9 +346,9 @@ def main():
         ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
         roof = {"kernel": "gemm_dist_kernel<L2|KL|Energy> (+ fix-up)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
                 "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                "traffic_note": "bytes per launch (finest-scale launches: 16 chunk matrices each), ncu capture in "
-                                "profiles/r01_ncu_config3_metrics.json; algorithmic bytes per launch = 16 x 0.8e9 output "
-                                "+ 0.33e9 operands",
+                "traffic_note": ("bytes per launch (finest-scale launches: 16 chunk matrices each), ncu capture in "
+                                 "profiles/r01_ncu_config3_metrics.json; algorithmic bytes per launch = 16 x 0.8e9 output "
+                                 "+ 0.33e9 operands") if traffic is not None else "no ncu capture for this workload",
                 "launches_per_step": int(max(gemm_groups, 0)), "derived_groups_per_step": int(derived),
                 "peak_source": "FP64 DMMA.8x8x4 rate measured on this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.json); "
                                "MEASURED_PEAKS.json has no FP64 figure"}
@@ -362,8 +363,9 @@ def main():
         ach = prim_bytes / (phases["prim"] * 1e-3) / 1e9
         roof_prim = {"kernel": "prim_kernel + prim_cluster_kernel (all launches of the step)", "bound": "hbm", "achieved": ach,
                      "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                     "note": "the 124-graph launch alone streams 99.2 GB in 23.4 ms = 4.24 TB/s = 65 % "
-                             "(profiles/r01_ncu_config3_metrics.json); the small launches are latency-bound"}
+                     "note": ("the 124-graph launch alone streams 99.2 GB in 23.4 ms = 4.24 TB/s = 65 % "
+                              "(profiles/r01_ncu_config3_metrics.json); the small launches are latency-bound")
+                     if is_cfg3 else "all Prim launches of the step (8 N^2 bytes per graph)"}
     if roof is None:
         roof = roof_emd
 

@@ -247,7 +247,15 @@ struct GraphWS {
   int cluster = 0;                // cluster Prim available (N large enough, slices fit in shared memory)
   int tree_use_smem = 1;
   size_t tree_smem = 0;
+  // kNN-Boruvka MST for launches of few graphs (kernels_mst.cuh): its own buffers for up to knn_cap graphs; the
+  // per-vertex scratch of the rounds lives in the tree kernel's buffers above (free until tree_kernel runs)
+  int knn_cap = 0, knn_use_smem = 1;
+  size_t knn_smem = 0;
+  unsigned long long* knn_lk = nullptr;
+  int *knn_lj = nullptr, *knn_ei = nullptr, *knn_ej = nullptr, *knn_root = nullptr, *knn_flags = nullptr;
 };
+
+constexpr int kKnnRounds = 6;       // Boruvka launches per measurement (each runs rounds until rows need a rescan)
 
 constexpr int kPrimCluster = 8;     // CTAs per graph; 2 and 4 measured slower at every graph count (profiles/r01_prim_variants.md)
 

@@ -39,6 +39,66 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
   if (!g.tree_use_smem) g.tree_smem = 0;
   CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.tree_smem));
+  // kNN-Boruvka: launches of up to SMs/3 graphs (where Prim is latency-bound: profiles/r01_prim_variants.md),
+  // within 512 MB of lists.  SEQJ_MST=prim turns it off, SEQJ_MST=knn uses it for every launch that fits 2 GB.
+  const char* menv = getenv("SEQJ_MST");
+  const bool knn_all = menv && !strcmp(menv, "knn");
+  const size_t per_graph = (size_t)g.ldv * (kKnnK * 12 + 8) + ((size_t)16 * N + 64) * 4;
+  const size_t knn_budget = knn_all ? (size_t(2) << 30) : (size_t(512) << 20);
+  g.knn_cap = (menv && !strcmp(menv, "prim")) ? 0
+            : (int)std::min<size_t>(std::min<size_t>((size_t)cap, knn_all ? (size_t)cap : (size_t)std::max(1, h->sm_count / 3)),
+                                    knn_budget / per_graph);
+  if (N < 2) g.knn_cap = 0;
+  if (g.knn_cap > 0) {
+    const size_t nk = (size_t)g.knn_cap * g.ldv;
+    CU_TRY(c.pool.alloc(&g.knn_lk, nk * kKnnK)); CU_TRY(c.pool.alloc(&g.knn_lj, nk * kKnnK));
+    CU_TRY(c.pool.alloc(&g.knn_ei, nk)); CU_TRY(c.pool.alloc(&g.knn_ej, nk));
+    CU_TRY(c.pool.alloc(&g.knn_root, (size_t)g.knn_cap * ((size_t)16 * N + 64)));
+    CU_TRY(c.pool.alloc(&g.knn_flags, (size_t)3 * g.knn_cap + 16));
+    g.knn_smem = (size_t)N * 4;
+    g.knn_use_smem = g.knn_smem + 1024 <= h->max_smem;
+    if (!g.knn_use_smem) g.knn_smem = 0;
+    CU_TRY(cudaFuncSetAttribute(boruvka_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.knn_smem));
+  }
+  return SEQJ_OK;
+}
+
+// MST of `nb` dense matrices by kNN-filtered Boruvka (kernels_mst.cuh): lists, rounds with rescans, rooting.  Leaves
+// (parent, weight, order) of every finished graph in the workspace and done[graph] = 1; the caller runs Prim with
+// skip_done for whatever is left.
+int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t strideD, int nb, double eps_floor,
+                const int* mat_slot) {
+  seqj_handle* h = c.h;
+  int* ncount = g.knn_flags;
+  int* ecount = g.knn_flags + g.knn_cap;
+  int* done = g.knn_flags + 2 * g.knn_cap;
+  KnnParams kp;
+  kp.D = D; kp.ldD = ldD; kp.strideD = strideD; kp.mat_slot = mat_slot; kp.N = g.N; kp.eps_floor = eps_floor; kp.ldv = g.ldv;
+  kp.lk = g.knn_lk; kp.lj = g.knn_lj; kp.cnt = g.size; kp.ptr = g.dep1;
+  kp.bound = reinterpret_cast<unsigned long long*>(g.S);
+  kp.comp = g.anc0; kp.needy = g.dep0; kp.ncount = ncount; kp.done = done;
+  BorKnnParams bp;
+  bp.N = g.N; bp.ldv = g.ldv; bp.lk = g.knn_lk; bp.lj = g.knn_lj; bp.cnt = g.size; bp.bound = kp.bound;
+  bp.ptr = g.dep1; bp.comp = g.anc0; bp.best = reinterpret_cast<unsigned long long*>(g.wd);
+  bp.bestp = reinterpret_cast<unsigned long long*>(g.wd2); bp.stuck = g.anc1; bp.needy = g.dep0;
+  bp.ncount = ncount; bp.ecount = ecount; bp.done = done;
+  bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
+  const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
+  const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
+  const dim3 grid_rescan((unsigned)gx, (unsigned)nb);
+  knn_rows_kernel<false><<<grid_all, kKnnWarps * 32, 0, c.st>>>(kp);
+  for (int r = 0; r < kKnnRounds; ++r) {
+    if (r > 0) knn_rows_kernel<true><<<grid_rescan, kKnnWarps * 32, 0, c.st>>>(kp);
+    bp.first = (r == 0);
+    boruvka_knn_kernel<<<nb, kBorKnnThreads, g.knn_smem, c.st>>>(bp);
+  }
+  RootTreeParams rp;
+  rp.N = g.N; rp.ei = g.knn_ei; rp.ej = g.knn_ej; rp.ew = g.S2; rp.scratch = g.knn_root;
+  rp.parent = g.parent; rp.weight = g.weight; rp.order = g.order;
+  rp.ld_e = g.ldv; rp.ld_s = (int64_t)16 * g.N + 64; rp.ld_o = g.ldv; rp.done = done;
+  root_tree_kernel<<<nb, 1024, 0, c.st>>>(rp);
+  c.launches += 2 * kKnnRounds + 1;
+  CU_TRY(cudaGetLastError());
   return SEQJ_OK;
 }
 
@@ -54,6 +114,10 @@ int run_measure(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   pp.key_g = g.key_g; pp.from_g = g.from_g; pp.use_smem = g.use_smem;
   pp.prefetch = getenv("SEQJ_PRIM_PREFETCH") ? atoi(getenv("SEQJ_PRIM_PREFETCH")) : 1;
   int t = c.timer.begin(SEQJ_T_PRIM);
+  if (g.knn_cap > 0 && nb <= g.knn_cap) {
+    ST_TRY(run_knn_mst(c, g, D, ldD, strideD, nb, eps_floor, mat_slot));
+    pp.skip_done = g.knn_flags + 2 * g.knn_cap;
+  }
   // Measured on B200 at N = 10k (profiles/r01_prim_variants.md): with >= ~50 graphs in flight the single-CTA
   // kernel streams 4.3 TB/s (66 % of HBM) and beats the cluster kernel, whose 8x more CTAs only add
   // contention; with few graphs every step is latency-bound and the cluster kernel's shorter step wins.

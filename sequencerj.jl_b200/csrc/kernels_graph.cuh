@@ -33,6 +33,7 @@ struct PrimParams {
   int* from_g;
   int use_smem;
   int prefetch;         // cluster kernel: prefetch the losing candidates' rows into L2 (few graphs in flight)
+  const int* skip_done = nullptr;   // optional [graph]: graphs already solved by the kNN-Boruvka path (kernels_mst.cuh)
 };
 
 __device__ __forceinline__ void argmin_combine(double& k, int& v, double ok, int ov) {
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int Npad = (N + 1) & ~1;
+  if (p.skip_done && p.skip_done[blockIdx.x]) return;
   const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
   const int slot = p.mat_slot ? p.mat_slot[blockIdx.x] : (int)blockIdx.x;
   const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
@@ -250,6 +252,7 @@ prim_cluster_kernel(PrimParams p, int W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int graph = blockIdx.x / C;
+  if (p.skip_done && p.skip_done[graph]) return;      // the whole cluster leaves together, before any barrier
   const uint32_t rank = cluster_ctarank();
   const int v0 = (int)rank * W;                       // first vertex of this CTA's slice (W is even)
   const int Wn = max(0, min(W, N - v0));              // vertices in the slice
@@ -993,11 +996,19 @@ struct RootTreeParams {
   int* parent;   // out [N]
   double* weight;
   int* order;
+  // batched use (one CTA per graph, kernels_mst.cuh): strides of the edge lists, the scratch and the outputs, and an
+  // optional per-graph flag (only graphs with done == 1 are rooted)
+  int64_t ld_e = 0, ld_s = 0, ld_o = 0;
+  const int* done = nullptr;
 };
 
 __global__ void __launch_bounds__(1024, 1) root_tree_kernel(RootTreeParams p) {
   __shared__ int s_part[1025];
   const int tid = threadIdx.x, N = p.N, M = N - 1, A = 2 * M;
+  if (p.done && p.done[blockIdx.x] != 1) return;
+  p.ei += blockIdx.x * p.ld_e; p.ej += blockIdx.x * p.ld_e; p.ew += blockIdx.x * p.ld_e;
+  p.scratch += blockIdx.x * p.ld_s;
+  p.parent += blockIdx.x * p.ld_o; p.weight += blockIdx.x * p.ld_o; p.order += blockIdx.x * p.ld_o;
   if (N == 1) {
     if (tid == 0) { p.parent[0] = 0; p.weight[0] = 0.0; p.order[0] = 0; }
     return;

@@ -1,0 +1,273 @@
+// K5b: dense MST for FEW graphs per launch -- kNN-filtered Boruvka.  Replaces `_mst` (reference
+// src/sequencer.jl:358-374, LightGraphs.kruskal_mst) when a launch holds too few graphs for the batched Prim
+// (kernels_graph.cuh) to be bandwidth-bound: Prim is N dependent steps of one DRAM round trip each (~1.6 us), so 6
+// group graphs at N = 20,000 cost 40 ms whatever the hardware could stream.  Here the matrix is read ONCE, by every SM:
+//
+//   1. knn_rows_kernel<false>: one warp per row keeps, per lane, the 4 smallest (weight, j) of its interleaved share;
+//      the row's list is the 16 smallest entries that are <= L, L = the smallest "last entry" among the lanes that
+//      overflowed, plus a bound B: every edge of the row that is NOT listed weighs >= B.  HBM-bound, 8 N^2 bytes.
+//   2. boruvka_knn_kernel (one CTA per graph): Boruvka rounds over the lists.  The first list entry outside a vertex's
+//      component IS its lightest outgoing edge (the list is sorted and everything unlisted is heavier).  A vertex whose
+//      list is used up ("exhausted") can be ignored while B > the component's current candidate; otherwise the
+//      component is stuck for this round (it does not hook; others may hook onto it) and the vertex goes on the needy
+//      list.
+//   3. knn_rows_kernel<true>: the needy vertices' rows are re-read by the whole GPU, now keeping only vertices outside
+//      the component; then back to 2.  On unstructured data nothing is ever rescanned; on clustered data (tight
+//      clusters larger than the list) one round rescans about one matrix worth of rows (tools/knn_boruvka_proto.py).
+//   4. root_tree_kernel turns the edge list into the (parent, weight, order) arrays tree_kernel consumes.
+//
+// Edges are ordered like the reference's Kruskal visits them, (weight, max(u,v), min(u,v)); within one row that order
+// is (weight, j).  Under a strict total order the MST is unique and every edge Boruvka adds belongs to it, so the
+// result is Prim's / Kruskal's tree bit for bit, also with tied weights.  A graph that is not finished after the
+// fixed number of rounds launched (or is disconnected) keeps done = 0 and is handed to the Prim kernel, which
+// skips the finished ones.
+#pragma once
+#include "common.cuh"
+#include "kernels_graph.cuh"
+
+namespace seqj {
+
+constexpr int kKnnK = 16;          // list entries per vertex
+constexpr int kKnnWarps = 8;       // rows per CTA of the list kernels
+constexpr unsigned long long kKnnNone = ~0ull;
+
+struct KnnParams {
+  const double* D;
+  int64_t ldD, strideD;
+  const int* mat_slot;
+  int N;
+  double eps_floor;
+  int64_t ldv;
+  unsigned long long* lk;      // [graph][ldv][K] weights (bit patterns), ascending by (weight, j)
+  int* lj;                     // [graph][ldv][K] neighbours
+  int* cnt;                    // [graph][ldv] entries in the list
+  int* ptr;                    // [graph][ldv] first entry not known to be inside the component
+  unsigned long long* bound;   // [graph][ldv] every unlisted edge weighs >= bound; ~0 = the list is complete
+  const int* comp;             // rescan: component labels, needy vertices and their count, done flags
+  const int* needy;
+  const int* ncount;
+  const int* done;
+};
+
+// One warp per row.  Lane l owns the 16-byte pairs l, l + 32, ... of the row (coalesced 512-byte requests, four in
+// flight per lane) and keeps its four smallest eligible entries sorted in registers; the test against the fourth
+// is the only work on the common path.  Eligible = not the diagonal (first pass) / not in the row's component
+// (rescan).  Scanning j in ascending order with a strict comparison keeps ties in ascending j.
+template <bool RESCAN>
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
+  const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int N = p.N;
+  const int64_t gofs = (int64_t)g * p.ldv;
+  if (RESCAN && p.done[g]) return;
+  const int nrows = RESCAN ? p.ncount[g] : N;
+  const int slot = p.mat_slot ? p.mat_slot[g] : g;
+  const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
+  const int* __restrict__ comp = RESCAN ? p.comp + gofs : nullptr;
+  const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
+  constexpr int U = 4;
+  for (int r = blockIdx.x * kKnnWarps + warp; r < nrows; r += gridDim.x * kKnnWarps) {
+    const int v = RESCAN ? p.needy[gofs + r] : r;
+    const int cv = RESCAN ? comp[v] : 0;
+    const double* __restrict__ row = D + (int64_t)v * p.ldD;
+    unsigned long long k0 = kKnnNone, k1 = kKnnNone, k2 = kKnnNone, k3 = kKnnNone;
+    int j0 = 0x7fffffff, j1 = 0x7fffffff, j2 = 0x7fffffff, j3 = 0x7fffffff;
+    auto consider = [&](unsigned long long x, int idx) {
+      if (x < k3) {                                        // rare once the list has settled
+        const bool ok = idx < N && (RESCAN ? (comp[idx] != cv) : (idx != v));
+        if (ok) {
+          x = max(x, eps_bits);
+          if (x < k3) {
+            if (x < k2) {
+              k3 = k2; j3 = j2;
+              if (x < k1) {
+                k2 = k1; j2 = j1;
+                if (x < k0) { k1 = k0; j1 = j0; k0 = x; j0 = idx; }
+                else { k1 = x; j1 = idx; }
+              } else { k2 = x; j2 = idx; }
+            } else { k3 = x; j3 = idx; }
+          }
+        }
+      }
+    };
+    for (int base = 2 * lane; base < N; base += 64 * U) {
+      ulonglong2 dv[U];
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int idx = base + 64 * q;
+        if (idx < N) dv[q] = ldg_stream_u64x2(row + idx);   // idx even, ldD % 16 == 0: aligned, idx + 1 < ldD
+      }
+#pragma unroll
+      for (int q = 0; q < U; ++q) {
+        const int idx = base + 64 * q;
+        if (idx < N) { consider(dv[q].x, idx); consider(dv[q].y, idx + 1); }
+      }
+    }
+    // L = the smallest (k3, j3) among the lanes whose list is full: whatever such a lane did not list is larger
+    const bool full = k3 != kKnnNone;
+    const unsigned fh = full ? (unsigned)(k3 >> 32) : 0xffffffffu;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, fh);
+    const unsigned fl = (full && fh == mh) ? (unsigned)k3 : 0xffffffffu;
+    const unsigned ml = __reduce_min_sync(0xffffffffu, fl);
+    const unsigned fj = (full && fh == mh && fl == ml) ? (unsigned)j3 : 0x7fffffffu;
+    const unsigned mj = __reduce_min_sync(0xffffffffu, fj);
+    const bool anyfull = __any_sync(0xffffffffu, full);
+    const unsigned long long Lk = anyfull ? (((unsigned long long)mh << 32) | ml) : kKnnNone;
+    const int Lj = anyfull ? (int)mj : 0x7fffffff;
+    // the K smallest entries <= L, by K warp-argmins over the lanes' heads
+    unsigned long long myk = kKnnNone, lastk = kKnnNone;
+    int myj = -1, count = 0;
+    for (int t = 0; t < kKnnK; ++t) {
+      const unsigned hh = (unsigned)(k0 >> 32);
+      const unsigned mhh = __reduce_min_sync(0xffffffffu, hh);
+      const unsigned hl = (hh == mhh) ? (unsigned)k0 : 0xffffffffu;
+      const unsigned mhl = __reduce_min_sync(0xffffffffu, hl);
+      const unsigned long long mk = ((unsigned long long)mhh << 32) | mhl;
+      if (mk == kKnnNone) break;                            // every head is empty (uniform)
+      const unsigned hj = (k0 == mk) ? (unsigned)j0 : 0x7fffffffu;
+      const int mjj = (int)__reduce_min_sync(0xffffffffu, hj);
+      if (mk > Lk || (mk == Lk && mjj > Lj)) break;         // beyond what the lanes can vouch for
+      if (lane == t) { myk = mk; myj = mjj; }
+      if (k0 == mk && j0 == mjj) { k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = k3; j2 = j3; k3 = kKnnNone; j3 = 0x7fffffff; }
+      lastk = mk;
+      ++count;
+    }
+    const int64_t vo = gofs + v;
+    if (lane < kKnnK) { p.lk[vo * kKnnK + lane] = myk; p.lj[vo * kKnnK + lane] = myj; }
+    if (lane == 0) {
+      p.cnt[vo] = count;
+      p.ptr[vo] = 0;
+      p.bound[vo] = (count == kKnnK) ? lastk : Lk;
+    }
+  }
+}
+
+struct BorKnnParams {
+  int N;
+  int64_t ldv;
+  const unsigned long long* lk;
+  const int* lj;
+  const int* cnt;
+  const unsigned long long* bound;
+  int* ptr;
+  int* comp;                   // [graph][ldv] labels between launches
+  unsigned long long* best;    // [graph][ldv] scratch per component: lightest outgoing weight / hook target
+  unsigned long long* bestp;   // [graph][ldv] scratch per component: (max << 32 | min) of that edge
+  int* stuck;                  // [graph][ldv] scratch per component
+  int* needy;                  // [graph][ldv] vertices to rescan
+  int* ncount;                 // [graph]
+  int* ecount;                 // [graph] MST edges found so far
+  int* done;                   // [graph] 1 = all N-1 edges found
+  int* out_i;                  // [graph][ldv] MST edges (i < j)
+  int* out_j;
+  double* out_w;
+  int use_smem;                // labels fit in dynamic shared memory (4 N bytes)
+  int first;                   // first launch: initialise the state
+};
+
+constexpr int kBorKnnThreads = 1024;
+
+__global__ void __launch_bounds__(kBorKnnThreads, 1) boruvka_knn_kernel(BorKnnParams p) {
+  extern __shared__ int borknn_sm[];
+  __shared__ int s_count, s_needy, s_hooks;
+  const int tid = threadIdx.x, N = p.N, g = blockIdx.x;
+  const int64_t gofs = (int64_t)g * p.ldv;
+  if (!p.first && p.done[g]) return;
+  int* compg = p.comp + gofs;
+  int* comp = p.use_smem ? borknn_sm : compg;
+  int* ptr = p.ptr + gofs;
+  const int* __restrict__ cnt = p.cnt + gofs;
+  const unsigned long long* __restrict__ bound = p.bound + gofs;
+  const unsigned long long* __restrict__ lk = p.lk + gofs * kKnnK;
+  const int* __restrict__ lj = p.lj + gofs * kKnnK;
+  unsigned long long* best = p.best + gofs;
+  unsigned long long* bestp = p.bestp + gofs;
+  int* stuck = p.stuck + gofs;
+  int* needy = p.needy + gofs;
+  int* out_i = p.out_i + gofs;
+  int* out_j = p.out_j + gofs;
+  double* out_w = p.out_w + gofs;
+  if (p.first) {
+    for (int v = tid; v < N; v += kBorKnnThreads) comp[v] = v;
+  } else if (p.use_smem) {
+    for (int v = tid; v < N; v += kBorKnnThreads) comp[v] = compg[v];
+  }
+  if (tid == 0) s_count = p.first ? 0 : p.ecount[g];
+  __syncthreads();
+  int status = (N <= 1) ? 1 : 0;       // 1 = complete, 2 = rows to rescan, 3 = no progress (disconnected input)
+  for (int it = 0; it < 64 && status == 0; ++it) {
+    for (int v = tid; v < N; v += kBorKnnThreads) { best[v] = ~0ull; bestp[v] = ~0ull; stuck[v] = 0; }
+    if (tid == 0) { s_needy = 0; s_hooks = 0; }
+    __syncthreads();
+    // 1. every vertex: skip the list entries that have joined its component; lightest outgoing weight per component
+    for (int v = tid; v < N; v += kBorKnnThreads) {
+      const int c = comp[v], n = cnt[v];
+      int q = ptr[v];
+      while (q < n && comp[lj[(int64_t)v * kKnnK + q]] == c) ++q;
+      ptr[v] = q;
+      if (q < n) atomicMin(&best[c], lk[(int64_t)v * kKnnK + q]);
+    }
+    __syncthreads();
+    // 2. among the lightest, the first vertex pair in Kruskal's order; exhausted vertices that could hide a lighter
+    //    edge make their component stuck and ask for a rescan
+    for (int v = tid; v < N; v += kBorKnnThreads) {
+      const int c = comp[v], n = cnt[v], q = ptr[v];
+      if (q < n) {
+        if (lk[(int64_t)v * kKnnK + q] == best[c]) {
+          const int j = lj[(int64_t)v * kKnnK + q];
+          atomicMin(&bestp[c], ((unsigned long long)(unsigned)max(v, j) << 32) | (unsigned)min(v, j));
+        }
+      } else {
+        const unsigned long long b = bound[v];
+        if (b != kKnnNone && b <= best[c]) {
+          stuck[c] = 1;
+          needy[atomicAdd(&s_needy, 1)] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // 3. hook every component that knows its lightest outgoing edge; a mutual pair keeps the smaller id as root
+    for (int c = tid; c < N; c += kBorKnnThreads) {
+      if (comp[c] != c || stuck[c]) continue;
+      const unsigned long long pr = bestp[c];
+      if (pr == ~0ull) continue;
+      const int i = (int)(unsigned)(pr & 0xffffffffull), j = (int)(unsigned)(pr >> 32);
+      const int ci = comp[i], cj = comp[j];
+      const int other = (ci == c) ? cj : ci;
+      const bool mutual = !stuck[other] && bestp[other] == pr;
+      if (mutual && c < other) continue;                  // `other` hooks onto c and records the edge
+      const int k = atomicAdd(&s_count, 1);
+      out_i[k] = i;
+      out_j[k] = j;
+      out_w[k] = __longlong_as_double((long long)best[c]);
+      best[c] = (1ull << 63) | (unsigned long long)(unsigned)other;   // only this thread reads best[c] from here on
+      atomicAdd(&s_hooks, 1);
+    }
+    __syncthreads();
+    for (int c = tid; c < N; c += kBorKnnThreads)
+      if (comp[c] == c && !stuck[c] && bestp[c] != ~0ull && (best[c] >> 63)) comp[c] = (int)(best[c] & 0xffffffffull);
+    __syncthreads();
+    for (int jt = 0; jt < 32; ++jt) {                      // pointer jumping until every vertex points at its root
+      int changed = 0;
+      for (int v = tid; v < N; v += kBorKnnThreads) {
+        const int c = comp[v], cc = comp[c];
+        if (c != cc) { comp[v] = cc; changed = 1; }
+      }
+      if (!__syncthreads_or(changed)) break;
+    }
+    __syncthreads();
+    const int ec = s_count, nd = s_needy, hk = s_hooks;
+    __syncthreads();
+    if (ec == N - 1) status = 1;
+    else if (nd > 0) status = 2;
+    else if (hk == 0) status = 3;
+  }
+  if (p.use_smem)
+    for (int v = tid; v < N; v += kBorKnnThreads) compg[v] = comp[v];
+  if (tid == 0) {
+    p.ecount[g] = s_count;
+    p.ncount[g] = (status == 2) ? s_needy : 0;
+    p.done[g] = (status == 1) ? 1 : 0;
+  }
+}
+
+}  // namespace seqj

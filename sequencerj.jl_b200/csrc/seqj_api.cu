@@ -23,6 +23,7 @@
 #include "kernels_dist.cuh"
 #include "kernels_derive.cuh"
 #include "kernels_graph.cuh"
+#include "kernels_mst.cuh"
 #include "kernels_pair.cuh"
 #include "kernels_prep.cuh"
 
