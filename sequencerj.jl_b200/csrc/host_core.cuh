@@ -255,7 +255,7 @@ struct GraphWS {
   int *knn_lj = nullptr, *knn_ei = nullptr, *knn_ej = nullptr, *knn_root = nullptr, *knn_flags = nullptr;
 };
 
-constexpr int kKnnRounds = 6;       // Boruvka launches per measurement (each runs rounds until rows need a rescan)
+constexpr int kKnnRounds = 12;      // Boruvka launches per measurement (each runs rounds until rows need a rescan)
 
 constexpr int kPrimCluster = 8;     // CTAs per graph; 2 and 4 measured slower at every graph count (profiles/r01_prim_variants.md)
 

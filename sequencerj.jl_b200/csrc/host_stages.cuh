@@ -87,7 +87,8 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
   const dim3 grid_rescan((unsigned)gx, (unsigned)nb);
   knn_rows_kernel<false><<<grid_all, kKnnWarps * 32, 0, c.st>>>(kp);
-  for (int r = 0; r < kKnnRounds; ++r) {
+  const int rounds = getenv("SEQJ_KNN_ROUNDS") ? std::max(1, atoi(getenv("SEQJ_KNN_ROUNDS"))) : kKnnRounds;
+  for (int r = 0; r < rounds; ++r) {
     if (r > 0) knn_rows_kernel<true><<<grid_rescan, kKnnWarps * 32, 0, c.st>>>(kp);
     bp.first = (r == 0);
     boruvka_knn_kernel<<<nb, kBorKnnThreads, g.knn_smem, c.st>>>(bp);
@@ -97,7 +98,7 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   rp.parent = g.parent; rp.weight = g.weight; rp.order = g.order;
   rp.ld_e = g.ldv; rp.ld_s = (int64_t)16 * g.N + 64; rp.ld_o = g.ldv; rp.done = done;
   root_tree_kernel<<<nb, 1024, 0, c.st>>>(rp);
-  c.launches += 2 * kKnnRounds + 1;
+  c.launches += 2 * rounds + 1;
   CU_TRY(cudaGetLastError());
   return SEQJ_OK;
 }
