@@ -361,10 +361,11 @@ def main():
     roof_prim = None
     if phases.get("prim", 0) > 0:
         ach = prim_bytes / (phases["prim"] * 1e-3) / 1e9
-        roof_prim = {"kernel": "prim_kernel + prim_cluster_kernel (all launches of the step)", "bound": "hbm", "achieved": ach,
+        roof_prim = {"kernel": "MST launches of the step: prim_kernel (large batches) + knn_rows_kernel / boruvka_knn_kernel (few graphs)", "bound": "hbm", "achieved": ach,
                      "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
                      "note": ("the 124-graph launch alone streams 99.2 GB in 23.4 ms = 4.24 TB/s = 65 % "
-                              "(profiles/r01_ncu_config3_metrics.json); the small launches are latency-bound")
+                              "(profiles/r01_ncu_config3_metrics.json); the 20 group graphs go through the kNN-filtered "
+                              "Boruvka (one bandwidth-bound pass over their matrices)")
                      if is_cfg3 else "all Prim launches of the step (8 N^2 bytes per graph)"}
     if roof is None:
         roof = roof_emd
@@ -387,7 +388,7 @@ def main():
            "roofline_emd": roof_emd, "roofline_prim": roof_prim,
            "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "direct_dist_kernel<OP_L1> = EMD tiles (FP64 ALU issue-bound, see roofline_emd)"),
                                            (gemm_ms, "gemm_dist_kernel (FP64 tensor pipe, see roofline)"),
-                                           (phases.get("prim", 0), "prim kernels (HBM / latency, see roofline_prim)")))[1], "cpu_baseline": cpu, "clocks": clocks,
+                                           (phases.get("prim", 0), "MST kernels (HBM, see roofline_prim)")))[1], "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
            "final_eta": float(r.eta)}
     print(json.dumps(out), flush=True)

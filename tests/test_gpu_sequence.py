@@ -346,6 +346,40 @@ def test_derived_equals_direct_tiles(seqj, handle, monkeypatch):
         assert np.array_equal(a.EOAlgScale[key][1].parents, b.EOAlgScale[key][1].parents)
 
 
+@pytest.mark.parametrize("kind", ["random", "smooth+duplicates"])
+def test_mst_back_ends_agree(seqj, handle, monkeypatch, kind):
+    """A/B of the two `_mst` back ends over a whole sequence() call: SEQJ_MST=prim (batched / cluster Prim for every
+    launch), the default (kNN-filtered Boruvka for launches of few graphs, Prim for large batches) and SEQJ_MST=knn
+    (Boruvka everywhere).  The MST under the reference's Kruskal order is unique, so everything downstream -- every
+    chunk and group eta, every BFS tree, the final order -- must be bit-identical, also with exact duplicates."""
+    rng = np.random.default_rng(12)
+    if kind == "random":
+        A = rng.random((96, 333))
+    else:
+        x = np.arange(96)[:, None]
+        mu = np.linspace(12, 84, 120)[None, :]
+        B = np.exp(-0.5 * ((x - mu) / 7.0) ** 2) + 1e-3
+        A = np.concatenate([B, B, B[:, :60]], axis=1)[:, rng.permutation(300)]     # smooth family with duplicates
+    scales = (1, 2, 4, 8)                                    # 4 metrics x 15 chunks = 60 chunk graphs, then 16 groups
+    runs = []
+    for mode in ("prim", None, "knn"):
+        if mode is None:
+            monkeypatch.delenv("SEQJ_MST", raising=False)
+        else:
+            monkeypatch.setenv("SEQJ_MST", mode)
+        runs.append(seqj.sequence(A.copy(), scales=scales, metrics=seqj.ALL_METRICS))
+    monkeypatch.delenv("SEQJ_MST", raising=False)
+    a = runs[0]
+    for b in runs[1:]:
+        assert np.array_equal(a.order, b.order) and a.eta == b.eta
+        for key in a.EOAlgScale:
+            assert np.array_equal(a.EOSeg[key][0], b.EOSeg[key][0])
+            assert a.EOAlgScale[key][0] == b.EOAlgScale[key][0]
+            assert np.array_equal(a.EOAlgScale[key][1].parents, b.EOAlgScale[key][1].parents)
+            for ta, tb in zip(a.EOSeg[key][1], b.EOSeg[key][1]):
+                assert np.array_equal(ta.parents, tb.parents)
+
+
 @pytest.mark.parametrize("world", [2, 3])
 def test_chunk_major_partials_and_finish_on_one_gpu(seqj, handle, world):
     """`seqj_sequence_partial` + `seqj_groups_finish` (the chunk-major multi-GPU path) driven on ONE GPU:

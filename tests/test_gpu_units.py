@@ -225,21 +225,65 @@ def _edge_set(t):
     return set(zip(np.minimum(t.src, t.dst).tolist(), np.maximum(t.src, t.dst).tolist()))
 
 
+MST_MODES = ("auto", "prim")      # auto = kNN-filtered Boruvka for a single graph (kernels_mst.cuh); prim = the Prim kernels
+
+
+def _measure_modes(seqj, monkeypatch, Dm, **kw):
+    """`_measure_dm` through both MST back ends of the library (SEQJ_MST is read at every call)."""
+    out = []
+    for mode in MST_MODES:
+        if mode == "auto":
+            monkeypatch.delenv("SEQJ_MST", raising=False)
+        else:
+            monkeypatch.setenv("SEQJ_MST", mode)
+        out.append(seqj.measure_dm(Dm, **kw))
+    monkeypatch.delenv("SEQJ_MST", raising=False)
+    return out
+
+
 @pytest.mark.parametrize("N", [2, 3, 17, 100, 1000, 1024, 1031, 2500, 4099])
-def test_measure_dm_matches_oracle(seqj, oracle, handle, N):
+def test_measure_dm_matches_oracle(seqj, oracle, handle, monkeypatch, N):
     Dm = _random_dist(N, N)
     ref = oracle.measure_dm(Dm)
-    got = seqj.measure_dm(Dm, want_order=True)
-    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
-    rel_close(np.sort(got.mst.weight), np.sort(ref.mst_w), 1e-15)
-    assert got.root == ref.root
-    assert got.eta == ref.eta                      # pure function of integers -> bit-identical
-    assert np.array_equal(got.bfs.parents, ref.parents)
-    assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
+    for got in _measure_modes(seqj, monkeypatch, Dm, want_order=True):
+        assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+        rel_close(np.sort(got.mst.weight), np.sort(ref.mst_w), 1e-15)
+        assert got.root == ref.root
+        assert got.eta == ref.eta                      # pure function of integers -> bit-identical
+        assert np.array_equal(got.bfs.parents, ref.parents)
+        assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
+
+
+@pytest.mark.parametrize("kind", ["clusters", "duplicates", "smooth"])
+def test_measure_dm_structured_inputs_take_the_rescan_path(seqj, oracle, handle, monkeypatch, kind):
+    """Inputs whose neighbour lists fill up with vertices of the same component (tight clusters larger than the
+    list, exact duplicates, a smooth one-parameter family): the kNN-filtered Boruvka has to rescan rows, and both
+    back ends must still return the reference's Kruskal tree."""
+    rng = np.random.default_rng(5)
+    if kind == "clusters":
+        pts = np.concatenate([rng.normal(3.0 * c, 0.01, (6, 150)) for c in range(5)], axis=1)
+        Dm = np.sqrt(((pts[:, :, None] - pts[:, None, :]) ** 2).sum(0)) + 1e-6
+    elif kind == "duplicates":
+        base = rng.random((250, 250)) + 0.01
+        base = np.triu(base, 1); base = base + base.T
+        Dm = np.kron(np.ones((3, 3)), base) + 1e-6
+    else:
+        x = np.arange(96)[:, None]
+        mu = np.linspace(10, 86, 500)[None, :]
+        F = np.exp(-0.5 * ((x - mu) / 6.0) ** 2) + 1e-3
+        U = np.cumsum(F / F.sum(0), axis=0)[:, rng.permutation(500)]
+        Dm = np.abs(U[:, :, None] - U[:, None, :]).sum(0) + 1e-6
+    np.fill_diagonal(Dm, 1e-6)
+    ref = oracle.measure_dm(Dm, faithful_root=False)
+    for got in _measure_modes(seqj, monkeypatch, Dm, want_order=True):
+        assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+        assert got.eta == ref.eta
+    a, b = _measure_modes(seqj, monkeypatch, Dm, want_order=True)
+    assert a.root == b.root and np.array_equal(a.bfs.parents, b.bfs.parents) and np.array_equal(a.order, b.order)
 
 
 @pytest.mark.parametrize("N,levels", [(7, 2), (64, 3), (300, 4), (1031, 3), (2500, 5), (4099, 2)])
-def test_measure_dm_tied_weights_follow_kruskal_order(seqj, oracle, handle, N, levels):
+def test_measure_dm_tied_weights_follow_kruskal_order(seqj, oracle, handle, monkeypatch, N, levels):
     """Heavily tied weights (a handful of distinct integer values): the reference's Kruskal visits equal-weight
     edges in column-major order of the upper triangle; the device MST uses the same strict total order, so
     the tree -- not only its weight -- is the reference's."""
@@ -247,42 +291,42 @@ def test_measure_dm_tied_weights_follow_kruskal_order(seqj, oracle, handle, N, l
     Dm = rng.integers(1, levels + 1, size=(N, N)).astype(np.float64)
     Dm = np.triu(Dm, 1); Dm = Dm + Dm.T
     ref = oracle.measure_dm(Dm)
-    got = seqj.measure_dm(Dm, want_order=True)
-    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
-    assert got.root == ref.root
-    assert got.eta == ref.eta
-    assert np.array_equal(got.bfs.parents, ref.parents)
-    assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
+    for got in _measure_modes(seqj, monkeypatch, Dm, want_order=True):
+        assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+        assert got.root == ref.root
+        assert got.eta == ref.eta
+        assert np.array_equal(got.bfs.parents, ref.parents)
+        assert np.array_equal(got.order, oracle.unroll(ref.parents, ref.root))
 
 
-def test_measure_dm_all_equal_weights(seqj, oracle, handle):
+def test_measure_dm_all_equal_weights(seqj, oracle, handle, monkeypatch):
     """Every edge ties (duplicate objects: all distances collapse to the 1e-6 offset)."""
     N = 200
     Dm = np.full((N, N), 1e-6); np.fill_diagonal(Dm, 0.0)
     ref = oracle.measure_dm(Dm)
-    got = seqj.measure_dm(Dm)
-    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
-    assert got.root == ref.root and got.eta == ref.eta
-    assert np.array_equal(got.bfs.parents, ref.parents)
+    for got in _measure_modes(seqj, monkeypatch, Dm):
+        assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+        assert got.root == ref.root and got.eta == ref.eta
+        assert np.array_equal(got.bfs.parents, ref.parents)
 
 
-def test_measure_dm_upper_triangle_wins_and_inf_nonedges(seqj, oracle, handle):
+def test_measure_dm_upper_triangle_wins_and_inf_nonedges(seqj, oracle, handle, monkeypatch):
     rng = np.random.default_rng(3)
     N = 60
     Dm = rng.random((N, N)) + 0.01                 # asymmetric: Symmetric(dm) keeps the upper triangle
-    got = seqj.measure_dm(Dm)
     sym = np.triu(Dm) + np.triu(Dm, 1).T
     ref = oracle.measure_dm(sym)
-    assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
-    assert got.root == ref.root and got.eta == ref.eta
+    for got in _measure_modes(seqj, monkeypatch, Dm):
+        assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
+        assert got.root == ref.root and got.eta == ref.eta
     # a path graph with Inf non-edges: the MST must be the path itself, eta = N
     P = np.full((N, N), np.inf); np.fill_diagonal(P, 0.0)
     for i in range(N - 1):
         P[i, i + 1] = P[i + 1, i] = 1.0 + 0.001 * i
-    got = seqj.measure_dm(P, want_order=True)
-    assert _edge_set(got.mst) == {(i, i + 1) for i in range(N - 1)}
-    assert got.eta == float(N)
-    assert got.order.tolist() in (list(range(N)), list(range(N))[::-1])
+    for got in _measure_modes(seqj, monkeypatch, P, want_order=True):
+        assert _edge_set(got.mst) == {(i, i + 1) for i in range(N - 1)}
+        assert got.eta == float(N)
+        assert got.order.tolist() in (list(range(N)), list(range(N))[::-1])
 
 
 def test_accumulate_matches_reference_formula(seqj, handle):
