@@ -1,0 +1,59 @@
+"""CPU: the NumPy model of the kNN-filtered Boruvka (tools/knn_boruvka_proto.py, the algorithm of
+sequencerj.jl_b200/csrc/kernels_mst.cuh) against the oracle's Kruskal (reference `_mst`, src/sequencer.jl:358-374):
+every edge it adds belongs to the reference's MST, it always finishes once exhausted rows are rescanned, and the tree
+is the reference's also when weights tie."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+import knn_boruvka_proto as model  # noqa: E402
+
+
+def _sym(W):
+    W = np.triu(W, 1)
+    return W + W.T
+
+
+def _cases():
+    rng = np.random.default_rng(5)
+    yield "random", _sym(rng.random((150, 150)) + 0.01)
+    yield "integer ties", _sym(rng.integers(1, 4, (120, 120)).astype(float))
+    yield "all equal", _sym(np.full((60, 60), 1e-6))
+    pts = np.concatenate([rng.normal(3.0 * c, 0.01, (4, 40)) for c in range(4)], axis=1)
+    yield "clusters larger than the list", np.sqrt(((pts[:, :, None] - pts[:, None, :]) ** 2).sum(0)) + 1e-6
+    base = _sym(rng.random((50, 50)) + 0.01)
+    yield "triplicated objects", np.kron(np.ones((3, 3)), base) + 1e-6
+    for n in (2, 3, 5, 33):
+        yield f"tiny {n}", _sym(rng.random((n, n)) + 0.01)
+
+
+@pytest.mark.parametrize("name,D", list(_cases()), ids=[c[0] for c in _cases()])
+def test_model_returns_the_reference_tree(oracle, name, D):
+    D = D.copy()
+    np.fill_diagonal(D, 1e-6)
+    lists, bound = model.knn_lists(D)
+    for v, lv in enumerate(lists):                       # lists are sorted by (weight, j) and exclude the diagonal
+        assert lv == sorted(lv) and all(j != v for _, j in lv) and len(lv) <= model.K
+    edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True)
+    ei, ej, ew = oracle.kruskal_mst(D)
+    assert ncomp == 1
+    assert {(a, b) for a, b, _ in edges} == set(zip(ei.tolist(), ej.tolist()))
+    wref = dict(zip(zip(ei.tolist(), ej.tolist()), model.bits(ew).tolist()))
+    assert all(wref[(a, b)] == w for a, b, w in edges)
+
+
+def test_model_without_rescans_only_adds_mst_edges(oracle):
+    """Stuck components simply stop hooking: what has been added so far is still part of the reference's tree (this
+    is what makes the Prim fallback of unfinished graphs safe)."""
+    rng = np.random.default_rng(7)
+    pts = np.concatenate([rng.normal(3.0 * c, 0.01, (4, 60)) for c in range(3)], axis=1)
+    D = np.sqrt(((pts[:, :, None] - pts[:, None, :]) ** 2).sum(0)) + 1e-6
+    np.fill_diagonal(D, 1e-6)
+    lists, bound = model.knn_lists(D)
+    edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=False)
+    ei, ej, _ = oracle.kruskal_mst(D)
+    assert ncomp > 1                                       # the clusters exhaust their 16-entry lists
+    assert {(a, b) for a, b, _ in edges} <= set(zip(ei.tolist(), ej.tolist()))
