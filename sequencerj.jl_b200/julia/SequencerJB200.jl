@@ -17,7 +17,7 @@ using SimpleWeightedGraphs
 using SparseArrays: sparse
 
 export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!, emd, energy
-export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS, PERIODIC, set_periods!
+export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS, PERIODIC, set_periods!, EMD, Energy
 
 const libseqj = get(ENV, "SEQJ_B200_LIB", joinpath(@__DIR__, "..", "libseqj_b200.so"))
 
@@ -37,6 +37,24 @@ const WASS1D = B200Metric(1, "EMD(nothing)")       # :247
 const KLD = B200Metric(2, "KLDivergence()")        # :239
 const ENERGY = B200Metric(3, "Energy(nothing)")    # :254
 const ALL_METRICS = (L2, WASS1D, KLD, ENERGY)      # :257
+
+# The TYPES `EMD` / `Energy` (reference src/distancemetrics.jl:16-21, 121-132).  Passed as TYPES in `metrics`
+# (`metrics = (EMD, Energy)`, with or without `grid`) they select the grid-aware branch of the reference
+# (src/sequencer.jl:217-219): metric ids 4 / 5 + seqj_set_grid.  Their INSTANCES `EMD()` / `Energy()` are what
+# WASS1D / ENERGY are: the reference never hands them the grid (quirk Q1), each chunk gets its own unit grid.
+struct EMD
+    grid::Union{Nothing,Tuple}
+end
+EMD() = EMD(nothing)
+struct Energy
+    grid::Union{Nothing,Tuple}
+end
+Energy() = Energy(nothing)
+metric_id(m::B200Metric) = m.id
+metric_id(::Type{EMD}) = Int32(4)
+metric_id(::Type{Energy}) = Int32(5)
+metric_id(::EMD) = Int32(1)
+metric_id(::Energy) = Int32(3)
 
 "Scales used in the autoscale option (reference src/sequencer.jl:148)."
 const FIB = [1,2,3,5,8,13,21,34,55,89,144,233,377,610,987,1597,2584,5168]
@@ -118,7 +136,7 @@ runs on the GPU behind one `ccall`.
 function sequence(A::VecOrMat{T}; scales = nothing, metrics = ALL_METRICS, grid = nothing) where {T <: Real}
     A = A isa Vector ? hcat(A...) : A
     @info "Sequencing data with\n    shape: $(size(A))\n    metric(s): $(metrics)\n    scale(s): $(scales)"
-    tuplify(x::B200Metric) = tuple(x)
+    tuplify(x::Union{B200Metric,EMD,Energy,Type}) = tuple(x)
     tuplify(x) = tuple(x...)
     G = ensuregrid!(A, grid)
     metrics = (metrics !== nothing) ? tuplify(metrics) : ALL_METRICS
@@ -130,18 +148,22 @@ function sequence(A::VecOrMat{T}; scales = nothing, metrics = ALL_METRICS, grid 
         @info "After autoscaling, best scale = $(scales)"
     end
     scales = tuplify(scales)
-    r, inmin = _sequence(A64, scales, metrics)
+    r, inmin = _sequence(A64, scales, metrics, G)
     # the reference clamps the caller's array in place (src/sequencer.jl:130); the device already
     # computed on clamped values, so touch host memory only when something was below eps()
     inmin < eps() && A isa Matrix{Float64} && clamp!(A, eps(), typemax(Float64))
     return r
 end
 
-function _sequence(A::Matrix{Float64}, scales, metrics)
+function _sequence(A::Matrix{Float64}, scales, metrics, grid)
     h = handle()
     M, N = size(A)
-    mids = Int32[m.id for m in metrics]
+    mids = Int32[metric_id(m) for m in metrics]
     scs = Int32[s for s in scales]
+    if any(id -> id == 4 || id == 5, mids)                 # the TYPES EMD / Energy: distances on `grid`
+        g64 = Vector{Float64}(grid)
+        check(h, ccall((:seqj_set_grid, libseqj), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, g64, length(g64)))
+    end
     res = Ref{Ptr{Cvoid}}(C_NULL)
     st = ccall((:seqj_sequence, libseqj), Cint,
                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Float64, Float64,
@@ -209,9 +231,10 @@ function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid 
     maxscale = M ÷ 10
     @assert maxscale > 0 "Matrix A contains too few rows ($(M)) for autoscale. The minimum is 10 rows. It is recommended to set scale=(1,)."
     bestscale, max_η = 1, 0.0
-    mets = metrics isa B200Metric ? (metrics,) : tuple(metrics...)
+    mets = metrics isa Union{B200Metric,EMD,Energy,Type} ? (metrics,) : tuple(metrics...)
+    G = ensuregrid!(A, grid)
     for s in filter(i -> i < maxscale, FIB)
-        r, _ = _sequence(Asamp, (s,), mets)
+        r, _ = _sequence(Asamp, (s,), mets, G)
         if elong(r) > max_η
             max_η = elong(r); bestscale = s
         end
@@ -249,5 +272,11 @@ emd(u::AbstractVector, v = u) = _cdf_distance(1, collect(1.0:length(u)), collect
 "`energy(u, v, uw, vw)` (reference :167) and `energy(u, v)` (:172)."
 energy(u, v, uw, vw) = _cdf_distance(3, u, v, uw, vw)
 energy(u::AbstractVector, v = u) = _cdf_distance(3, collect(1.0:length(u)), collect(1.0:length(v)), u, v)
+
+# functor and four-argument forms of the types (reference src/distancemetrics.jl:46-50, 82-93, 143-162)
+(m::EMD)(u::AbstractVector, v::AbstractVector = u) = m.grid === nothing ? emd(u, v) : emd(m.grid[1], m.grid[2], u, v)
+(m::Energy)(u::AbstractVector, v::AbstractVector = u) = m.grid === nothing ? energy(u, v) : energy(m.grid[1], m.grid[2], u, v)
+EMD(u::AbstractVector, v::AbstractVector, uw::AbstractVector, vw::AbstractVector) = emd(u, v, uw, vw)
+Energy(u::AbstractVector, v::AbstractVector, uw::AbstractVector, vw::AbstractVector) = energy(u, v, uw, vw)
 
 end # module
