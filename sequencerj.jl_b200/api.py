@@ -462,7 +462,9 @@ def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None,
     assert maxscale > 0, (f"Matrix A contains too few rows ({M}) for autoscale. The minimum is 10 rows. "
                           "It is recommended to set scale=(1,).")
     gen = rng if isinstance(rng, np.random.Generator) else np.random.default_rng(rng)
-    idx = np.sort(gen.choice(N, size=nsamp, replace=False))                   # sample(..., ordered=true)
+    # StatsBase.sample(a, dims; ordered=true) draws WITH replacement by default, so the reference's sample can hold
+    # a column more than once (duplicates sit at distance 0 + eps of each other)
+    idx = np.sort(gen.choice(N, size=nsamp, replace=True))
     Asamp = np.ascontiguousarray(At[idx])
     metrics = _normalize_metrics(metrics)
     best, max_eta = 1, 0.0

@@ -226,7 +226,7 @@ function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid 
     M, N = size(A)
     Ŋ = round(Int, N * p, RoundDown)
     @assert Ŋ > 1 "Matrix A contains too few columns ($(N)) to sample with p = $(p). Use a larger p."
-    sampidx = sort(randperm(N)[1:Ŋ])
+    sampidx = sort(rand(1:N, Ŋ))          # StatsBase.sample(..., ordered=true): with replacement, as the reference
     Asamp = convert(Matrix{Float64}, A[:, sampidx])
     maxscale = M ÷ 10
     @assert maxscale > 0 "Matrix A contains too few rows ($(M)) for autoscale. The minimum is 10 rows. It is recommended to set scale=(1,)."
@@ -241,7 +241,6 @@ function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid 
     end
     return bestscale
 end
-using Random: randperm
 
 # ---- pair distances on explicit grids (reference src/distancemetrics.jl:82-87, 143-148) -----------
 function _cdf_distance(mid::Integer, u, v, uw, vw)
