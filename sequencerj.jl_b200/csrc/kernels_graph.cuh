@@ -1,13 +1,14 @@
 // K5-K8: graph layer.  Replaces `_measure_dm` (reference src/sequencer.jl:284-290):
-//   _mst            (:358-374, LightGraphs.kruskal_mst)      -> batched dense Prim, one CTA per graph
+//   _mst            (:358-374, LightGraphs.kruskal_mst)      -> batched dense Prim, one CTA (or cluster) per graph;
+//                                                                launches of few graphs: kernels_mst.cuh
 //   _leastcentralpt (:331, closeness_centrality)             -> O(N) rerooted tree-distance sums
 //   elongation      (:334-354)                               -> hop depths by pointer jumping
 //   bfs_tree        (:288, src/bfs.jl:6-9)                   -> re-rooted parent vector
 //   unroll          (src/utils.jl:15-24)                     -> reverse DFS preorder, children ascending
 // plus the eta-weighted combine (:231-247) and the proximity fuse (:310-328, :269).
 //
-// The MST is unique whenever edge weights are distinct, so Prim and the reference's Kruskal agree;
-// ties are broken by (weight, vertex index) to keep the result deterministic.
+// Edges are compared in the order the reference's Kruskal visits them, (weight, max(u,v), min(u,v)): a strict
+// total order, under which the MST is unique, so Prim, Boruvka and Kruskal return the same tree also when weights tie.
 #pragma once
 #include <math_constants.h>
 #include "common.cuh"
