@@ -3,6 +3,8 @@
 * hummingbird_gray_u8.npy -- the reference's test image resources/Hummingbird!.jpeg converted to 8-bit gray
   (PIL 'L'), the input of the reference's only exact end-to-end test (test/runtests.jl:167-175).  Needs
   /root/reference (present in the build container only).
+* colony_gray_u8.npy, aged_whisky_gray_u8.npy -- the reference's SMALL and MED test images (resources/colony.png,
+  resources/Aged Whisky.jpg) as 8-bit gray, inputs of its loss-bound tests (test/runtests.jl:72-140).
 * config1_oracle.npz -- BASELINE config 1 (rand(50,100), ALL_METRICS, scales (1,2,4)) run through the CPU
   oracle.  The reference itself (Julia) cannot be executed in this image, so these vectors are oracle output,
   not Julia output; they pin the oracle against regressions and give the GPU tests a committed target.
@@ -23,6 +25,9 @@ def main():
         from PIL import Image
         a = np.asarray(Image.open(ref_img).convert("L"), dtype=np.uint8)
         np.save(os.path.join(HERE, "hummingbird_gray_u8.npy"), a)
+        for src, out in (("colony.png", "colony_gray_u8.npy"), ("Aged Whisky.jpg", "aged_whisky_gray_u8.npy")):
+            a = np.asarray(Image.open(os.path.join(os.path.dirname(ref_img), src)).convert("L"), dtype=np.uint8)
+            np.save(os.path.join(HERE, out), a)
     A = np.random.default_rng(2732).random((50, 100))
     r = O.sequence_oracle(A, (1, 2, 4), keep_matrices=False)
     np.savez_compressed(

@@ -221,3 +221,28 @@ def test_periodic_euclidean_restatement(oracle):
     per = np.full(7, 0.3)
     rel = np.abs(oracle.pairwise_periodic(P, per) - oracle.pairwise_periodic(P, per, faithful=True)).max()
     assert rel < 1e-15
+
+
+@pytest.mark.parametrize("image,transpose,scales,metrics,bound", [
+    ("colony_gray_u8.npy", False, (1,), (0, 1, 2, 3), 500.0),        # test/runtests.jl:72-83  (SMALL, all metrics)
+    ("aged_whisky_gray_u8.npy", False, (1, 2), (2, 0), 700.0),       # :98-108 (MED portrait, (KLD, L2))
+    ("aged_whisky_gray_u8.npy", True, (1, 2), (2, 0), 1100.0),       # :120-131 (MED landscape)
+])
+def test_reference_image_loss_bounds(oracle, image, transpose, scales, metrics, bound):
+    """The reference's loss-bound tests on its small and medium images: shuffle the columns, sequence, un-shuffle,
+    Euclidean loss against the original below the reference's threshold.  (The thresholds are loose -- gray values
+    live in [0,1] -- so this is the smoke test the reference makes of it; the oracle also has to return a
+    permutation and beat a random order.)"""
+    img = np.load(os.path.join(GOLDEN, image)).astype(np.float64) / 255.0
+    if transpose:
+        img = np.ascontiguousarray(img.T)
+    rng = np.random.default_rng(2732)
+    idx = rng.permutation(img.shape[1])
+    shuffled = img[:, idx]
+    r = oracle.sequence_oracle(shuffled, scales, metrics)
+    assert sorted(r.order.tolist()) == list(range(img.shape[1]))
+    res = shuffled[:, r.order]
+    loss = float(np.sqrt(((img - res) ** 2).sum()))
+    assert loss < bound
+    rand_loss = float(np.sqrt(((img - shuffled) ** 2).sum()))
+    assert min(loss, float(np.sqrt(((img - res[:, ::-1]) ** 2).sum()))) < rand_loss
