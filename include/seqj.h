@@ -58,7 +58,7 @@ extern "C" {
 #define SEQJ_T_DIST_EMD 4
 #define SEQJ_T_DIST_KLD 5
 #define SEQJ_T_DIST_ENERGY 6
-#define SEQJ_T_PRIM 7     /* batched dense Prim */
+#define SEQJ_T_PRIM 7     /* MST stage: batched dense Prim / kNN-filtered Boruvka */
 #define SEQJ_T_TREE 8     /* root / elongation / BFS-tree kernels */
 #define SEQJ_T_COMBINE 9  /* eta-weighted accumulation */
 #define SEQJ_T_FUSE 10    /* proximity fuse + final MST / order */
