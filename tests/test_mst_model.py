@@ -57,3 +57,25 @@ def test_model_without_rescans_only_adds_mst_edges(oracle):
     ei, ej, _ = oracle.kruskal_mst(D)
     assert ncomp > 1                                       # the clusters exhaust their 16-entry lists
     assert {(a, b) for a, b, _ in edges} <= set(zip(ei.tolist(), ej.tolist()))
+
+
+def test_streaming_threshold_variant_keeps_the_list_contract(oracle):
+    """Round-2 candidate for the list kernel (a warp-wide threshold, tools/knn_boruvka_proto.py:row_list_streaming):
+    its lists must satisfy the same contract -- sorted by (weight, j), every unlisted edge weighs >= the bound and
+    comes after every listed one in (weight, j) order -- and drive Boruvka to the reference's tree, ties included."""
+    rng = np.random.default_rng(3)
+    for D in (_sym(rng.random((200, 200)) + 0.01), _sym(rng.integers(1, 4, (150, 150)).astype(float))):
+        np.fill_diagonal(D, 1e-6)
+        N = D.shape[0]
+        W = model.bits(np.maximum(D, model.EPS))
+        lists, bound = [], np.empty(N, dtype=np.uint64)
+        for v in range(N):
+            ex = np.zeros(N, dtype=bool); ex[v] = True
+            lv, B, _ = model.row_list_streaming(W, v, ex)
+            allv = sorted((int(W[v, j]), j) for j in range(N) if j != v)
+            assert lv == allv[:len(lv)]                          # exactly the smallest entries, in order
+            assert all(w >= B for w, _ in allv[len(lv):]) or B == int(model.NONE)
+            lists.append(lv); bound[v] = B
+        edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True)
+        ei, ej, _ = oracle.kruskal_mst(D)
+        assert ncomp == 1 and {(a, b) for a, b, _ in edges} == set(zip(ei.tolist(), ej.tolist()))

@@ -47,6 +47,56 @@ def row_list(W, v, exclude):
     return cand, B
 
 
+def row_list_streaming(W, v, exclude, refresh=8):
+    """Candidate for round 2 (lead 2): the same list, built the way the kernel streams the row
+    (lane l sees pair t*32 + l at step t), with a warp-wide threshold tau = the K-th smallest weight currently held
+    by any lane, refreshed every `refresh` steps.  An element is skipped when its weight is STRICTLY above tau
+    (ties pass, so no skipped edge can tie with a listed one), otherwise it goes through the lane-local insertion.
+    Whatever a lane did not keep is then > min(its last entry if its list is full, (tau, +inf)), so
+    L = min(smallest last entry of the full lanes, (tau, +inf)).  Returns (list, bound, steps_with_an_insertion)."""
+    N = W.shape[0]
+    npairs = (N + 1) // 2
+    steps = (npairs + LANES - 1) // LANES
+    lane = [[] for _ in range(LANES)]
+    tau = int(NONE)
+    slow = 0
+    for t in range(steps):
+        hit = False
+        for l in range(LANES):
+            for e in (2 * (t * LANES + l), 2 * (t * LANES + l) + 1):
+                if e >= N or exclude[e]:
+                    continue
+                x = (int(W[v, e]), e)
+                if x[0] > tau:
+                    continue
+                if len(lane[l]) < M_LOCAL or x < lane[l][-1]:
+                    hit = True
+                    lane[l].append(x)
+                    lane[l].sort()
+                    del lane[l][M_LOCAL:]
+        slow += hit
+        if t % refresh == refresh - 1:
+            held = sorted(w for ls in lane for w, _ in ls)
+            if len(held) >= K:
+                tau = min(tau, held[K - 1])
+    L = None
+    for ls in lane:
+        if len(ls) == M_LOCAL and (L is None or ls[-1] < L):
+            L = ls[-1]
+    if tau != int(NONE):
+        tb = (tau, 1 << 62)
+        L = tb if L is None or tb < L else L
+    cand = sorted(x for ls in lane for x in ls)
+    if L is not None:
+        cand = [x for x in cand if x <= L]
+    if len(cand) > K:
+        cand = cand[:K]
+        B = cand[-1][0]
+    else:
+        B = L[0] if L is not None else int(NONE)
+    return cand, B, slow
+
+
 def knn_lists(D):
     """Per row v: entries sorted by (w, j), at most K of them, plus a bound weight B such that every edge of v that
     is not listed has weight >= B (exactly: (w, j) > (B, jB)); B = NONE when the list holds every edge."""
