@@ -133,6 +133,29 @@ def cpu_sample(cfg, procs, sample_objects):
     return pairs / dt / 1e9, dt, pairs
 
 
+def cpu_faithful(cfg, procs, sizes=(16, 32, 48)):
+    """The path the reference really executes for EMD / Energy: one ECDF construction with sorts PER PAIR
+    (src/distancemetrics.jl:82-93,143-162,191-223), restated by the oracle's `faithful` mode.  Timed on the first n
+    objects for a few n, fitted to t = a + b n^2 (the sizes are smaller than the 100/300/1000
+    planned there because the timing has to stay bounded: ~1e3 pairs/s on 8 cores at L = 4096), extrapolated to N."""
+    from oracle import seq_oracle as O
+    A = synth(cfg["N"], cfg["L"])[:max(sizes)].T.copy()
+    pts = []
+    for n in sizes:
+        t0 = time.perf_counter()
+        O.sequence_oracle_parallel(A[:, :n], cfg["scales"], cfg["metrics"], procs=procs, faithful_root=True, faithful=True)
+        pts.append((n, time.perf_counter() - t0))
+    n2 = np.array([[1.0, n * n] for n, _ in pts])
+    a, b = np.linalg.lstsq(n2, np.array([t for _, t in pts]), rcond=None)[0]
+    G = len(cfg["metrics"]) * len(cfg["scales"])
+    rate = G * 0.5 / max(b, 1e-30) / 1e9                       # pairs per second from the n^2 coefficient, in Gpair/s
+    return {"value": rate, "unit": "Gpair/s", "cores": min(procs, G), "kind": "port",
+            "sample": f"faithful per-pair ECDF path on the first n = {list(sizes)} objects x L={cfg['L']}, same metrics/scales: "
+                      f"{[round(t, 2) for _, t in pts]} s; fit t = {a:.3g} + {b:.3g} n^2",
+            "extrapolated_sequence_wall_s": float(a + b * cfg["N"] ** 2),
+            "note": "extrapolation by the N^2 law, not a measurement at full size"}
+
+
 def run_reference(args, cfg):
     """--impl reference: the reference's CPU algorithm (oracle port; Julia absent) on the host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -162,6 +185,67 @@ def run_reference(args, cfg):
     print(json.dumps(out), flush=True)
 
 
+NCU_TRAFFIC = "profiles/r02_ncu_config3_traffic.json"
+
+
+def load_ncu_traffic():
+    """Per-launch DRAM bytes of the dominant kernels from the committed ncu --set full capture of this command."""
+    path = os.path.join(ROOT, NCU_TRAFFIC)
+    if not os.path.exists(path):
+        return {}
+    try:
+        return json.load(open(path)).get("kernels", {})
+    except Exception:
+        return {}
+
+
+def rank_work(r, N, L, scales, derived):
+    """Algorithmic work of the groups / chunks THIS rank computed in one step (from the result's own bookkeeping):
+    EMD 2 FP64 instr per pair-element, DMMA tiles 2 flop per pair-element (derived groups run no tiles), MST 8 N^2
+    bytes per graph, derive / combine bytes as in DESIGN.md section 4."""
+    from sequencerj_b200 import sharding
+    npair = N * (N - 1) // 2
+    emd_rows = gemm_rows = 0
+    graphs = 0
+    gemm_groups = 0
+    comb = 0.0
+    ranges = getattr(r, "chunk_ranges", None) or {}
+    for (m, sc), (etas, _) in r.EOSeg.items():
+        lens = sharding.chunk_lengths(L, sc)
+        a, b = ranges.get((m, sc), (0, len(lens)))
+        rows = sum(lens[a:b])
+        graphs += (b - a)
+        comb += 8.0 * ((b - a) * npair + N * N)
+        if m.id in (1, 4, 6):
+            emd_rows += rows
+        else:
+            gemm_rows += rows
+            gemm_groups += 1
+    graphs += len(r.EOAlgScale)
+    if getattr(r, "order", None) is not None:
+        graphs += 0            # the final tree is built from the sparse edge union: no N x N read
+    gemm_rows -= int(derived) * L                    # a derived group covers all L rows and runs no tiles
+    gemm_groups -= int(derived)
+    # derive: each derived group reads the upper halves of the next finer scale's chunk matrices and writes its own
+    der_bytes = 0.0
+    if derived:
+        order = sorted(set(scales), key=lambda sc: -sharding.nchunks(L, sc))
+        cnt = {}
+        for (m, sc) in r.EOSeg:
+            if m.id in (0, 2, 3):
+                cnt.setdefault(m.id, []).append(sc)
+        left = int(derived)
+        for mid, scs in cnt.items():
+            scs = sorted(scs, key=lambda sc: -sharding.nchunks(L, sc))
+            for fine, coarse in zip(scs, scs[1:]):
+                if left <= 0:
+                    break
+                der_bytes += 8.0 * (sharding.nchunks(L, fine) * npair + sharding.nchunks(L, coarse) * N * N)
+                left -= 1
+    return {"emd_instr": 2.0 * emd_rows * npair, "gemm_flops": 2.0 * max(gemm_rows, 0) * npair, "gemm_groups": max(gemm_groups, 0),
+            "mst_bytes": 8.0 * N * N * graphs, "graphs": graphs, "derive_bytes": der_bytes, "combine_bytes": comb}
+
+
 METRIC_NAME = "sequence() distance throughput at N=10k,L=4k all metrics (wall-s per call in sequence_wall_s)"
 
 
@@ -177,6 +261,7 @@ def main():
     ap.add_argument("--sample-objects", type=int, default=320, help="objects in the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-faithful", action="store_true", help="skip the per-pair (faithful) CPU timing")
     ap.add_argument("--sharding", default="group", choices=["group", "chunk"],
                     help="multi-GPU split: whole (metric, scale) groups, or equal-cost chunk ranges + NCCL reduce")
     args = ap.parse_args()
@@ -259,7 +344,7 @@ def main():
             step_walls.append(round((time.perf_counter() - tc) * 1e3, 1))
             launches += r.launches
             for k, v in r.timings.items():
-                if k not in ("input_min", "derived_groups"):
+                if k not in ("input_min", "derived_groups", "waves"):
                     phases[k] = phases.get(k, 0.0) + v
             derived = r.timings.get("derived_groups", 0)
         barrier()
@@ -325,76 +410,90 @@ def main():
                "api": "sequencerj_b200.sequence(A_host) -> seqj_sequence (C ABI), pinned host input",
                "device_ms_per_step": {k: round(v, 3) for k, v in e2e_ph.items()}, "wall_ms_each_step": [round(w, 1) for w in walls]}
 
+    # the same call from a PAGEABLE host array (what a Julia `Matrix` or a plain NumPy array is)
+    if e2e is not None and world == 1:
+        A_page = np.array(At.T, order="F", copy=True)
+        s.sequence(A_page, scales=scales, metrics=metrics, handle=handle)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            rp = s.sequence(A_page, scales=scales, metrics=metrics, handle=handle)
+        torch.cuda.synchronize()
+        elp = time.perf_counter() - t0
+        assert np.array_equal(rp.order, order_ref)
+        e2e["pageable"] = {"value": args.steps * pairs / elp / 1e9, "unit": "Gpair/s", "sequence_wall_s": elp / args.steps,
+                           "h2d_ms": rp.timings.get("h2d", 0.0),
+                           "note": "same public call on a pageable (plain NumPy / Julia Matrix) input"}
+        del A_page
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (FP64 DMMA distance tiles) ----
+    # ---- rooflines, computed from the work THIS rank ran (rank 0 prints) ----
     peaks = json.load(open(FP64_PEAKS)) if os.path.exists(FP64_PEAKS) else {}
-    fp64_peak = peaks.get("dmma884_sustained_tflops", 37.06)
-    ngemm = sum(1 for m in cfg["metrics"] if m != 1)
-    nemd = sum(1 for m in cfg["metrics"] if m == 1)
-    npair1 = N * (N - 1) // 2
-    # DMMA flops actually executed: groups whose chunk matrices were derived from the finest scale ran no tiles
-    gemm_groups = len(scales) * ngemm / world - derived                             # this rank's share (approx. for N>1)
-    gemm_flops = 2.0 * L * npair1 * max(gemm_groups, 0) * args.steps
-    gemm_ms = phases.get("dist_l2", 0) + phases.get("dist_kld", 0) + phases.get("dist_energy", 0)
-    emd_instr = 2.0 * L * npair1 * len(scales) * nemd * args.steps / world
-    emd_ms = phases.get("dist_emd", 0)
-    nprim = (sum(sharding.nchunks(L, sc) + 1 for sc in scales) * len(metrics) + 1) * args.steps / world
-    prim_bytes = 8.0 * N * N * nprim
     hbm = 6533.5
     mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_src = "fallback 6533.5 GB/s (MEASURED_PEAKS.json absent)"
     if os.path.exists(mp):
         hbm = json.load(open(mp)).get("hbm_gbs", hbm)
-    roof = None
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_ncu_config3_metrics.json")
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (driver-written)"
+    work = rank_work(r, N, L, scales, derived)
     is_cfg3 = args.config == 3 and not (args.objects or args.length)
-    if is_cfg3 and world == 1 and os.path.exists(tpath):
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch of the DMMA launches that still run (finest scale:
-        # gridDim.y = 16 chunks); the coarser scales are derived and run no tiles
-        fin = max(sharding.nchunks(L, sc) for sc in scales)
-        ls = [x for x in json.load(open(tpath))["launches"]
-              if x["kernel"].startswith("gemm_dist") and x["grid"].replace(" ", "").split(",")[1] == str(fin)]
-        if ls:
-            traffic = sum(x["dram_read_GB"] + x["dram_write_GB"] for x in ls) * 1e9 / len(ls)
-    if gemm_ms > 0:
-        ach = gemm_flops / (gemm_ms * 1e-3) / 1e12
-        roof = {"kernel": "gemm_dist_kernel<L2|KL|Energy> (+ fix-up)", "bound": "tensor", "achieved": ach, "peak": fp64_peak,
-                "unit": "TFLOP/s", "frac": ach / fp64_peak, "traffic": traffic,
-                "traffic_note": ("bytes per launch (finest-scale launches: 16 chunk matrices each), ncu capture in "
-                                 "profiles/r01_ncu_config3_metrics.json; algorithmic bytes per launch = 16 x 0.8e9 output "
-                                 "+ 0.33e9 operands") if traffic is not None else "no ncu capture for this workload",
-                "launches_per_step": int(max(gemm_groups, 0)), "derived_groups_per_step": int(derived),
-                "peak_source": "FP64 DMMA.8x8x4 rate measured on this pool (tools/fp64_peaks.cu, profiles/r01_fp64_peaks.json); "
-                               "MEASURED_PEAKS.json has no FP64 figure"}
-    roof_emd = None
-    if emd_ms > 0:
-        ach = emd_instr / (emd_ms * 1e-3) / 1e12
-        pk = peaks.get("dabsdiff_b2_t512_tinstr", 17.6)
-        roof_emd = {"kernel": "direct_dist_kernel<OP_L1> (EMD tiles)", "bound": "fp64-issue", "achieved": ach, "peak": pk, "unit": "Tinstr/s",
-                    "frac": ach / pk}
-    roof_prim = None
-    if phases.get("prim", 0) > 0:
-        ach = prim_bytes / (phases["prim"] * 1e-3) / 1e9
-        roof_prim = {"kernel": "MST launches of the step: prim_kernel (large batches) + knn_rows_kernel / boruvka_knn_kernel (few graphs)", "bound": "hbm", "achieved": ach,
-                     "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
-                     "note": ("the 124-graph launch alone streams 99.2 GB in 23.4 ms = 4.24 TB/s = 65 % "
-                              "(profiles/r01_ncu_config3_metrics.json); the 20 group graphs go through the kNN-filtered "
-                              "Boruvka (one bandwidth-bound pass over their matrices)")
-                     if is_cfg3 else "all Prim launches of the step (8 N^2 bytes per graph)"}
-    if roof is None:
-        roof = roof_emd
+    ncu = load_ncu_traffic() if (is_cfg3 and world == 1) else {}
+    fp64_note = ("builder-measured on this pool by tools/fp64_peaks.cu (profiles/r01_fp64_peaks.json); "
+                 "MEASURED_PEAKS.json holds no FP64 figure")
+    steps = args.steps
+
+    def roof(kernel, bound, work_per_step, ms_total, peak, unit, scale, peak_source, ncu_key, note=None):
+        if ms_total <= 0 or work_per_step <= 0:
+            return None
+        ach = work_per_step * steps / (ms_total * 1e-3) / scale
+        d = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+             "ms_per_step": ms_total / steps, "work_per_step": work_per_step, "peak_source": peak_source,
+             "traffic": None, "traffic_note": "no ncu capture for this workload"}
+        if ncu_key in ncu:
+            d["traffic"] = ncu[ncu_key]["bytes_per_launch"]
+            d["traffic_note"] = ("dram__bytes_read.sum + dram__bytes_write.sum per launch, STATIC ncu --set full capture of "
+                                 f"this command ({NCU_TRAFFIC}); algorithmic bytes per launch {ncu[ncu_key]['algorithmic_bytes']:.4g}")
+        if note:
+            d["note"] = note
+        return d
+
+    gemm_ms = phases.get("dist_l2", 0) + phases.get("dist_kld", 0) + phases.get("dist_energy", 0)
+    roofs = {
+        "emd": roof("direct_dist_kernel<OP_L1> (EMD tiles: 2 DADD per element)", "fp64-issue", work["emd_instr"],
+                    phases.get("dist_emd", 0), peaks.get("dabsdiff_b2_t512_tinstr", 17.6), "Tinstr/s", 1e12, fp64_note, "emd"),
+        "gemm": roof("gemm_dist_kernel<L2|KL|Energy> (DMMA tiles + fix-up)", "tensor", work["gemm_flops"], gemm_ms,
+                     peaks.get("dmma884_sustained_tflops", 37.06), "TFLOP/s", 1e12, fp64_note, "gemm",
+                     note=f"{work['gemm_groups']} tile launches per step, {int(derived)} groups derived instead"),
+        "mst": roof("MST stage: knn_rows_kernel + boruvka_knn_kernel (+ prim_kernel for graphs over the rescan budget)", "hbm",
+                    work["mst_bytes"], phases.get("prim", 0), hbm, "GB/s", 1e9, hbm_src, "knn_rows",
+                    note="8 N^2 bytes per graph (every matrix read once)"),
+        "derive": roof("derive_kernel<L2|KL|Energy> (coarse scales from the next finer one)", "hbm", work["derive_bytes"],
+                       phases.get("derive", 0), hbm, "GB/s", 1e9, hbm_src, "derive",
+                       note="8 bytes x (upper halves of the fine matrices read + whole coarse matrices written)"),
+        "combine": roof("combine_sym_kernel (eta-weighted accumulation)", "hbm", work["combine_bytes"], phases.get("combine", 0),
+                        hbm, "GB/s", 1e9, hbm_src, "combine",
+                        note="8 bytes x (upper halves of the chunk matrices read + the group matrix written)"),
+    }
+    live = {k: v for k, v in roofs.items() if v}
+    dominant = max(live, key=lambda k: live[k]["ms_per_step"]) if live else None
+    roof_main = dict(live[dominant], dominant_by_time=True) if dominant else None
+    if roof_main and roof_main["bound"] == "fp64-issue":
+        roof_main["bound_note"] = ("FP64 CUDA-core issue rate (neither HBM nor tensor pipe): L1 between CDFs is not a "
+                                   "contraction, the floor is 2 DADD per element")
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         procs = os.cpu_count() or 1
         v, dt, cp = cpu_sample(cfg, procs, args.sample_objects)
         cpu = {"value": v, "unit": "Gpair/s", "cores": procs, "kind": "port",
-               "sample": f"oracle (NumPy port of the reference; Julia absent) on the first {args.sample_objects} of {N} objects x "
-                         f"L={L}, same metrics/scales, {dt:.1f} s"}
+               "sample": f"vectorised oracle (NumPy port of the reference; Julia absent) on the first {args.sample_objects} of {N} "
+                         f"objects x L={L}, same metrics/scales, {dt:.1f} s"}
+        if not args.no_faithful:
+            cpu["faithful"] = cpu_faithful(cfg, procs)
 
     out = {"metric": METRIC_NAME, "value": value, "unit": "Gpair/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": elapsed / args.steps * 1e3, "higher_is_better": True,
@@ -403,11 +502,10 @@ def main():
                       "cache": "inputs (8*N*L bytes) and every N x N chunk matrix are larger than the 126 MB L2; no flush needed",
                       "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
            "sequence_wall_s": elapsed / args.steps, "wall_ms_each_step": step_walls, "retimed_after_unsettled_first_attempt": first_attempt,
-           "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-           "roofline_emd": roof_emd, "roofline_prim": roof_prim,
-           "dominant_kernel_by_time": max(((phases.get("dist_emd", 0), "direct_dist_kernel<OP_L1> = EMD tiles (FP64 ALU issue-bound, see roofline_emd)"),
-                                           (gemm_ms, "gemm_dist_kernel (FP64 tensor pipe, see roofline)"),
-                                           (phases.get("prim", 0), "MST kernels (HBM, see roofline_prim)")))[1], "cpu_baseline": cpu, "clocks": clocks,
+           "e2e": e2e, "gpu_launches": int(launches), "roofline": roof_main,
+           "roofline_emd": roofs["emd"], "roofline_gemm": roofs["gemm"], "roofline_mst": roofs["mst"],
+           "roofline_derive": roofs["derive"], "roofline_combine": roofs["combine"],
+           "roofline_rank": 0, "dominant_kernel_by_time": dominant, "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
            "final_eta": float(r.eta)}
     print(json.dumps(out), flush=True)

@@ -99,6 +99,15 @@ int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M);
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
 
+/* Diagnostic probes (parity tests at sizes where a whole N x N matrix is too large to copy out): during the following
+ * seqj_sequence / seqj_sequence_dev calls on this single-device handle, entry (i[q], j[q]) of chunk matrix chunk[q]
+ * of group group[q] (metric-major index k*nscales + l) is sampled right after the distance stage produced it --
+ * `abs.(pairwise(alg, m; dims=2)) .+ eps`, src/sequencer.jl:226, whichever kernel path (tiles or derivation from the
+ * finer scale) computed it; chunk[q] = -1 samples the combined group matrix `Dkl` (src/sequencer.jl:247).  Read the
+ * values with seqj_result_probes (NaN = entry not produced by that call).  n = 0 or group == NULL clears the probes. */
+int seqj_set_probes(seqj_handle* h, const int32_t* group, const int32_t* chunk, const int32_t* i, const int32_t* j,
+                    int64_t n);
+
 /* ---- the hot call --------------------------------------------------------------------
  * Replaces `_sequence(A, scales, metrics, grid)`  (src/sequencer.jl:184-276) for the metric
  * instances of ALL_METRICS on the shared unit grid:  _splitnorm (:383-407), the metric x scale x
@@ -185,9 +194,15 @@ int seqj_result_D_triplets(const seqj_result* r, int32_t* i, int32_t* j, double*
 int seqj_result_timings(const seqj_result* r, double* ms /* SEQJ_NTIMERS */);
 /* min / max of the input as seen by the device-side check (min < 2.22e-16 => values were clamped) */
 int seqj_result_input_range(const seqj_result* r, double* minv, double* maxv);
+/* values of the handle's probes (seqj_set_probes) as sampled by the call that produced this result; n must equal
+ * the number of probes that were set */
+int seqj_result_probes(const seqj_result* r, double* vals, int64_t n);
 /* number of (metric, scale) groups whose chunk matrices were derived from the finest scale instead of being
  * computed by the tile kernels (they are excluded from the DMMA flop count of the roofline) */
 int seqj_result_derived_groups(const seqj_result* r, int* n);
+/* number of waves (HBM-fulls of chunk matrices) the call was streamed in: 1 when every chunk matrix was resident at
+ * once, more under seqj_set_workspace_limit or when N is large (BASELINE config 4) */
+int seqj_result_waves(const seqj_result* r, int* n);
 /* number of kernels the library launched for this result */
 int seqj_result_launches(const seqj_result* r, int64_t* launches);
 void seqj_result_free(seqj_result* r);

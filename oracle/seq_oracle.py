@@ -588,11 +588,11 @@ _PAR_A = None
 
 
 def _par_group(args):
-    k, l, faithful_root = args
-    return compute_group(_PAR_A, k, l, False, faithful_root)[0]
+    k, l, faithful_root, faithful = args
+    return compute_group(_PAR_A, k, l, faithful, faithful_root)[0]
 
 
-def sequence_oracle_parallel(A, scales, metrics=ALL_METRICS, procs=None, faithful_root=True) -> OracleResult:
+def sequence_oracle_parallel(A, scales, metrics=ALL_METRICS, procs=None, faithful_root=True, faithful=False) -> OracleResult:
     """Same result as sequence_oracle, with the independent (metric, scale) groups spread over host
     processes (fork). Used only as the CPU baseline of bench.py: the reference itself is single-threaded."""
     import multiprocessing as mp
@@ -601,7 +601,7 @@ def sequence_oracle_parallel(A, scales, metrics=ALL_METRICS, procs=None, faithfu
     A = clamp_input(A)
     M, N = A.shape
     scales, metrics = _norm_args(scales, metrics)
-    tasks = [(k, l, faithful_root) for k in metrics for l in scales]
+    tasks = [(k, l, faithful_root, faithful) for k in metrics for l in scales]
     procs = procs or os.cpu_count() or 1
     _PAR_A = A
     try:

@@ -28,6 +28,8 @@ SIGNATURES = {
     "seqj_release_workspace": (C.c_int, [vp]),
     "seqj_set_grid": (C.c_int, [vp, c_dp, C.c_int64]),
     "seqj_set_periods": (C.c_int, [vp, c_dp, C.c_int64]),
+    "seqj_set_probes": (C.c_int, [vp, c_ip, c_ip, c_ip, c_ip, C.c_int64]),
+    "seqj_result_probes": (C.c_int, [vp, c_dp, C.c_int64]),
     "seqj_sequence": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
                                 C.c_double, c_u8p, C.POINTER(vp)]),
     "seqj_sequence_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
@@ -48,6 +50,7 @@ SIGNATURES = {
     "seqj_result_D_triplets": (C.c_int, [vp, c_ip, c_ip, c_dp]),
     "seqj_result_timings": (C.c_int, [vp, c_dp]),
     "seqj_result_derived_groups": (C.c_int, [vp, C.POINTER(C.c_int)]),
+    "seqj_result_waves": (C.c_int, [vp, C.POINTER(C.c_int)]),
     "seqj_result_launches": (C.c_int, [vp, C.POINTER(C.c_int64)]),
     "seqj_result_input_range": (C.c_int, [vp, c_dp, c_dp]),
     "seqj_result_free": (None, [vp]),

@@ -329,10 +329,19 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     nder = C.c_int()
     handle.check(lib.seqj_result_derived_groups(res, C.byref(nder)))
     timings["derived_groups"] = nder.value
+    nw = C.c_int()
+    handle.check(lib.seqj_result_waves(res, C.byref(nw)))
+    timings["waves"] = nw.value
+    probe_vals = None
+    nprobes = getattr(handle, "_nprobes", 0)
+    if nprobes:
+        probe_vals = np.empty(nprobes)
+        handle.check(lib.seqj_result_probes(res, _lib.dptr(probe_vals), nprobes))
     if not want_final:
         r = SequencerResult(N, EOSeg, EOAlgScale, None, None, None, None, None, None, timings, launches.value,
                             group_msts)
         r.chunk_ranges = chunk_ranges
+        r.probes = probe_vals
         return r
     eta = C.c_double(); root = C.c_int32()
     order_ = np.empty(N, dtype=np.int32); par = np.empty(N, dtype=np.int32)
@@ -342,6 +351,7 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     r = SequencerResult(N, EOSeg, EOAlgScale, None, WeightedTree(N, mi, mj, mw), eta.value, order_,
                         root.value, par, timings, launches.value, group_msts)
     r._lazy = (handle, res)        # the result object now owns the C result until the triplets are fetched
+    r.probes = probe_vals
     return r
 
 
@@ -356,10 +366,21 @@ def _collect_and_release(handle, res, N, metrics, scales, want_final=True, parti
             handle.lib.seqj_result_free(res)
 
 
-def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None):
+def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None, probes=None):
     """`_sequence` (src/sequencer.jl:184-276) through the C ABI. At: (N, M) float64 C-contiguous host
-    array, or (with device_ptr) the shape only."""
+    array, or (with device_ptr) the shape only.  `probes` = (group, chunk, i, j) int arrays (seqj_set_probes):
+    the sampled matrix entries come back as `result.probes`."""
     handle = handle or default_handle()
+    if probes is not None:
+        pg, pc, pi, pj = (np.ascontiguousarray(x, dtype=np.int32) for x in probes)
+        assert pg.shape == pc.shape == pi.shape == pj.shape and pg.ndim == 1
+        handle.check(handle.lib.seqj_set_probes(handle.h, _lib.iptr(pg), _lib.iptr(pc), _lib.iptr(pi), _lib.iptr(pj), len(pg)))
+        handle._nprobes = len(pg)
+        try:
+            return _sequence(At, scales, metrics, handle, group_mask, device_ptr)
+        finally:
+            handle._nprobes = 0
+            handle.lib.seqj_set_probes(handle.h, None, None, None, None, 0)
     N, M = At.shape
     mids = np.array([m.id for m in metrics], dtype=np.int32)
     scs = np.array(scales, dtype=np.int32)
@@ -450,7 +471,7 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
     return r
 
 
-def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None, rng=None, _At=None):
+def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None, rng=None, _At=None, trace=None):
     """src/sequencer.jl:158-179: run the Sequencer on a random p-sample of the columns for each
     Fibonacci scale < M ÷ 10 and keep the scale with the largest elongation.  The reference samples
     with an unseeded StatsBase.sample; pass `rng` (numpy Generator or seed) for reproducibility."""
@@ -470,6 +491,8 @@ def autoscale(A, scales=FIB, metrics=ALL_METRICS, grid=None, p=0.1, handle=None,
     best, max_eta = 1, 0.0
     for s in [f for f in FIB if f < maxscale]:
         r = _sequence(Asamp, (s,), metrics, handle)
+        if trace is not None:
+            trace.append((s, r.eta))          # (scale, elongation) of every scale tried, for the parity test
         if r.eta > max_eta:
             max_eta, best = r.eta, s
     return best

@@ -60,12 +60,16 @@ struct seqj_handle {
   std::vector<DeviceWorker*> workers; // one per peer, created on first use
   std::vector<double> grid;      // explicit grid for the EMD / Energy TYPES (seqj_set_grid), empty = none
   std::vector<double> periods;   // periods of SEQJ_PERIODIC (seqj_set_periods), empty = none
+  // entries of the chunk / group matrices to sample during the next sequence calls (seqj_set_probes): group index
+  // (metric-major), chunk (-1 = the combined group matrix Dkl), row, column
+  std::vector<int32_t> probe_g, probe_c, probe_i, probe_j;
   std::multimap<size_t, void*> cache;
   size_t cached_bytes = 0;
   // pinned landing buffer + event of the input check: its result is read back asynchronously and only looked at
   // after the distance work has been enqueued, so the GPU never waits for the host at the start of a call
   void* stats_pinned = nullptr;
   cudaEvent_t stats_ev = nullptr;
+  UploadStage upload;            // pinned staging of pageable inputs (host_upload.cuh), allocated on first use
 };
 
 struct GroupRes {
@@ -91,6 +95,8 @@ struct seqj_result {
   int64_t launches = 0;
   double in_min = 0, in_max = 0;
   int derived_groups = 0;
+  int waves = 0;                      // HBM-fulls the chunk matrices were streamed in
+  std::vector<double> probe_vals;     // one value per probe of the handle (NaN: the entry was not produced by this call)
   // raw group edge lists + D values; the deduplicated triplets (Di, Dj, Dv) are built on first request
   mutable std::vector<int32_t> raw_i, raw_j;
   mutable std::vector<double> raw_v;
@@ -134,6 +140,12 @@ struct DevPool {
   std::vector<std::pair<size_t, void*>> blocks;
   explicit DevPool(seqj_handle* hh) : h(hh) {}
   ~DevPool() {
+    // kernels of a call that failed half-way may still be queued on the handle's streams: the blocks must not be
+    // handed to the next call under them (a completed call has synchronised already, so this costs nothing then)
+    if (!blocks.empty()) {
+      if (h->st) cudaStreamSynchronize(h->st);
+      if (h->st2) cudaStreamSynchronize(h->st2);
+    }
     for (auto& b : blocks) {
       h->cache.emplace(b.first, b.second);
       h->cached_bytes += b.first;

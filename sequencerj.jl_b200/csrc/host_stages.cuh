@@ -39,14 +39,15 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
   g.tree_use_smem = g.tree_smem + 2048 <= h->max_smem;
   if (!g.tree_use_smem) g.tree_smem = 0;
   CU_TRY(cudaFuncSetAttribute(tree_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.tree_smem));
-  // kNN-Boruvka: launches of up to SMs/3 graphs (where Prim is latency-bound: profiles/r01_prim_variants.md),
-  // within 512 MB of lists.  SEQJ_MST=prim turns it off, SEQJ_MST=knn uses it for every launch that fits 2 GB.
+  // kNN-Boruvka for every launch whose lists fit 2 GB (config 3: 124 graphs = 0.33 GB); large batches run under a
+  // rescan budget and hand graphs that exceed it to the batched Prim (run_knn_mst).  SEQJ_MST=prim turns the path
+  // off, SEQJ_MST=small restores the round-1 rule (only launches of up to SMs/3 graphs).
   const char* menv = getenv("SEQJ_MST");
-  const bool knn_all = menv && !strcmp(menv, "knn");
+  const bool knn_small = menv && !strcmp(menv, "small");
   const size_t per_graph = (size_t)g.ldv * (kKnnK * 12 + 8) + ((size_t)16 * N + 64) * 4;
-  const size_t knn_budget = knn_all ? (size_t(2) << 30) : (size_t(512) << 20);
+  const size_t knn_budget = size_t(2) << 30;
   g.knn_cap = (menv && !strcmp(menv, "prim")) ? 0
-            : (int)std::min<size_t>(std::min<size_t>((size_t)cap, knn_all ? (size_t)cap : (size_t)std::max(1, h->sm_count / 3)),
+            : (int)std::min<size_t>(std::min<size_t>((size_t)cap, knn_small ? (size_t)std::max(1, h->sm_count / 3) : (size_t)cap),
                                     knn_budget / per_graph);
   if (N < 2) g.knn_cap = 0;
   if (g.knn_cap > 0) {
@@ -54,7 +55,7 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
     CU_TRY(c.pool.alloc(&g.knn_lk, nk * kKnnK)); CU_TRY(c.pool.alloc(&g.knn_lj, nk * kKnnK));
     CU_TRY(c.pool.alloc(&g.knn_ei, nk)); CU_TRY(c.pool.alloc(&g.knn_ej, nk));
     CU_TRY(c.pool.alloc(&g.knn_root, (size_t)g.knn_cap * ((size_t)16 * N + 64)));
-    CU_TRY(c.pool.alloc(&g.knn_flags, (size_t)3 * g.knn_cap + 16));
+    CU_TRY(c.pool.alloc(&g.knn_flags, (size_t)4 * g.knn_cap + 16));
     g.knn_smem = (size_t)N * 4;
     g.knn_use_smem = g.knn_smem + 1024 <= h->max_smem;
     if (!g.knn_use_smem) g.knn_smem = 0;
@@ -81,7 +82,11 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   bp.N = g.N; bp.ldv = g.ldv; bp.lk = g.knn_lk; bp.lj = g.knn_lj; bp.cnt = g.size; bp.bound = kp.bound;
   bp.ptr = g.dep1; bp.comp = g.anc0; bp.best = reinterpret_cast<unsigned long long*>(g.wd);
   bp.bestp = reinterpret_cast<unsigned long long*>(g.wd2); bp.stuck = g.anc1; bp.needy = g.dep0;
-  bp.ncount = ncount; bp.ecount = ecount; bp.done = done;
+  bp.ncount = ncount; bp.ecount = ecount; bp.done = done; bp.nresc = g.knn_flags + 3 * g.knn_cap;
+  // launches of few graphs may rescan freely (a row costs the same 8N bytes however many graphs share the launch,
+  // and Prim would be latency-bound there); large batches get N/4 rows per graph (profiles/r02_mst.md)
+  const char* benv = getenv("SEQJ_KNN_BUDGET");
+  bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : std::max(16, g.N / 4));
   bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int Npad = (N + 1) & ~1;
-  if (p.skip_done && p.skip_done[blockIdx.x]) return;
+  if (p.skip_done && p.skip_done[blockIdx.x] == 1) return;   // 1 = solved by the Boruvka path (2 = handed back to Prim)
   const int64_t gofs = (int64_t)blockIdx.x * p.ldv;
   const int slot = p.mat_slot ? p.mat_slot[blockIdx.x] : (int)blockIdx.x;
   const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
@@ -253,7 +253,7 @@ prim_cluster_kernel(PrimParams p, int W) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int graph = blockIdx.x / C;
-  if (p.skip_done && p.skip_done[graph]) return;      // the whole cluster leaves together, before any barrier
+  if (p.skip_done && p.skip_done[graph] == 1) return; // the whole cluster leaves together, before any barrier
   const uint32_t rank = cluster_ctarank();
   const int v0 = (int)rank * W;                       // first vertex of this CTA's slice (W is even)
   const int Wn = max(0, min(W, N - v0));              // vertices in the slice
@@ -838,6 +838,13 @@ __global__ void __launch_bounds__(256) scale_div_kernel(double* __restrict__ S, 
   for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x)
     S[idx] = S[idx] / tot;
+}
+
+// Diagnostic sampling of matrix entries (seqj_set_probes): out[idx[q]] = base[off[q]]
+__global__ void probe_gather_kernel(const double* __restrict__ base, const long long* __restrict__ off,
+                                    const int* __restrict__ idx, int n, double* __restrict__ out) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n) out[idx[q]] = base[off[q]];
 }
 
 // ---- proximity fuse ---------------------------------------------------------------------------

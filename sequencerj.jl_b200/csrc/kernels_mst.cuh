@@ -156,7 +156,9 @@ struct BorKnnParams {
   int* needy;                  // [graph][ldv] vertices to rescan
   int* ncount;                 // [graph]
   int* ecount;                 // [graph] MST edges found so far
-  int* done;                   // [graph] 1 = all N-1 edges found
+  int* done;                   // [graph] 1 = all N-1 edges found, 2 = handed back to Prim (rescan budget used up)
+  int* nresc;                  // [graph] rows rescanned so far
+  int rescan_budget;           // rows a graph may have rescanned in total before it is handed to the batched Prim
   int* out_i;                  // [graph][ldv] MST edges (i < j)
   int* out_j;
   double* out_w;
@@ -264,9 +266,17 @@ __global__ void __launch_bounds__(kBorKnnThreads, 1) boruvka_knn_kernel(BorKnnPa
   if (p.use_smem)
     for (int v = tid; v < N; v += kBorKnnThreads) compg[v] = comp[v];
   if (tid == 0) {
+    // Rescan budget: every needy row is one more 8N-byte read by the whole GPU.  That is cheap for a launch of few
+    // graphs and unbounded for a large batch of tightly clustered graphs (a cluster larger than the list is rescanned
+    // in every round in which it runs dry), so a graph whose rescans would exceed the budget is handed to the
+    // batched Prim instead (done = 2: the list kernels and later rounds skip it, Prim does not).
+    int nd = (status == 2) ? s_needy : 0, dn = (status == 1) ? 1 : 0;
+    const int used = p.first ? 0 : p.nresc[g];
+    if (nd > 0 && used + nd > p.rescan_budget) { nd = 0; dn = 2; }
+    p.nresc[g] = used + nd;
     p.ecount[g] = s_count;
-    p.ncount[g] = (status == 2) ? s_needy : 0;
-    p.done[g] = (status == 1) ? 1 : 0;
+    p.ncount[g] = nd;
+    p.done[g] = dn;
   }
 }
 

@@ -29,6 +29,7 @@
 
 using namespace seqj;
 
+#include "host_upload.cuh"
 #include "host_core.cuh"
 #include "host_stages.cuh"
 
@@ -118,6 +119,7 @@ void seqj_destroy(seqj_handle* h) {
   release_cache(h);
   if (h->st) cudaStreamDestroy(h->st);
   if (h->st2) cudaStreamDestroy(h->st2);
+  upload_stage_free(h->upload);
   if (h->stats_pinned) cudaFreeHost(h->stats_pinned);
   if (h->stats_ev) cudaEventDestroy(h->stats_ev);
   delete h;
@@ -154,6 +156,16 @@ int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M) {
   for (int64_t i = 0; i < M; ++i)
     if (!(periods[i] > 0.0) || !std::isfinite(periods[i])) return fail(h, SEQJ_E_BADARG, "periods must be finite and positive");
   h->periods.assign(periods, periods + M);
+  return SEQJ_OK;
+}
+
+int seqj_set_probes(seqj_handle* h, const int32_t* group, const int32_t* chunk, const int32_t* i, const int32_t* j, int64_t n) {
+  if (!h) return SEQJ_E_BADARG;
+  h->probe_g.clear(); h->probe_c.clear(); h->probe_i.clear(); h->probe_j.clear();
+  if (n <= 0 || !group) return SEQJ_OK;
+  if (!chunk || !i || !j || n > (1 << 24)) return fail(h, SEQJ_E_BADARG, "bad probe arguments");
+  h->probe_g.assign(group, group + n); h->probe_c.assign(chunk, chunk + n);
+  h->probe_i.assign(i, i + n); h->probe_j.assign(j, j + n);
   return SEQJ_OK;
 }
 
@@ -324,6 +336,27 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   // overlap mode: two D buffers (double buffering between the compute and the graph stream), each nD matrices
   const int nbuf = c.overlap ? 2 : 1;
   int nD = (int)std::min<int64_t>((mats - nS) / nbuf, total_chunks);
+  if (total_chunks == 0) {
+    // nothing selected (an all-zero group mask, or a rank of a chunk-major run that was assigned no chunk): a valid
+    // call with an empty result, so that the rank can still join every collective of the sharded driver
+    ST_TRY(check_input());
+    seqj_result* r = new seqj_result();
+    r->N = N;
+    r->groups.resize(G);
+    for (int k = 0; k < nmetrics; ++k)
+      for (int l = 0; l < nscales; ++l) {
+        GroupRes& gr = r->groups[k * nscales + l];
+        gr.metric = metric_ids[k]; gr.scale = scales[l]; gr.nchunks = layouts[l].nchunks; gr.computed = 0;
+      }
+    c.timer.end(tt);
+    CU_TRY(cudaStreamSynchronize(c.st));
+    c.timer.collect(r->timers);
+    r->launches = c.launches;
+    r->in_min = st0p->minv; r->in_max = st0p->maxv;
+    r->probe_vals.assign(h->probe_g.size(), NAN);
+    *out = r;
+    return SEQJ_OK;
+  }
   if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for two N x N chunk matrices plus the accumulator");
   const char* wenv = getenv("SEQJ_WAVES");
   const int nwaves_target = std::max(1, wenv ? atoi(wenv) : (c.overlap ? 2 : 1));
@@ -439,6 +472,36 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, std::max(max_wave, max_done), N));
 
+  // diagnostic probes (seqj_set_probes): values land in probe_out, NaN where this call did not produce the entry
+  const int nprobe = (int)h->probe_g.size();
+  double* probe_out = nullptr;
+  std::vector<std::vector<long long>> probe_offs;      // kept alive until the final synchronisation
+  std::vector<std::vector<int>> probe_idxs;
+  if (nprobe) {
+    CU_TRY(c.pool.alloc(&probe_out, (size_t)nprobe));
+    CU_TRY(cudaMemsetAsync(probe_out, 0xff, sizeof(double) * nprobe, c.st));
+    probe_offs.reserve(2 * waves.size() + 2); probe_idxs.reserve(2 * waves.size() + 2);
+  }
+  // gathers the probes selected by `pick(q, &offset)` from `base` on the current stream
+  auto run_probes = [&](const double* base, const std::function<bool(int, long long*)>& pick) -> int {
+    std::vector<long long> offs; std::vector<int> idxs;
+    for (int q = 0; q < nprobe; ++q) {
+      long long o;
+      if (pick(q, &o)) { offs.push_back(o); idxs.push_back(q); }
+    }
+    if (offs.empty()) return SEQJ_OK;
+    probe_offs.push_back(std::move(offs)); probe_idxs.push_back(std::move(idxs));
+    const std::vector<long long>& ov = probe_offs.back(); const std::vector<int>& iv = probe_idxs.back();
+    long long* off_d; int* idx_d;
+    CU_TRY(c.pool.alloc(&off_d, ov.size())); CU_TRY(c.pool.alloc(&idx_d, iv.size()));
+    CU_TRY(cudaMemcpyAsync(off_d, ov.data(), ov.size() * sizeof(long long), cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(idx_d, iv.data(), iv.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
+    probe_gather_kernel<<<(unsigned)((ov.size() + 255) / 256), 256, 0, c.st>>>(base, off_d, idx_d, (int)ov.size(), probe_out);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+    return SEQJ_OK;
+  };
+
   // Two streams: distance tiles of wave w+1 (FP64-bound) run while the graph stream measures wave w
   // (latency/HBM-bound, small CTAs that fit next to the tiles).  D buffers alternate between waves.
   std::vector<cudaEvent_t> ev_dist(waves.size()), ev_graph(waves.size());
@@ -493,6 +556,17 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     hmark("dist queued");
     ST_TRY(check_input());
     hmark("input checked");
+    if (nprobe)
+      ST_TRY(run_probes(Dw, [&](int q, long long* o) {
+        const int pc = h->probe_c[q], pi = h->probe_i[q], pj = h->probe_j[q];
+        if (pc < 0 || pi < 0 || pj < 0 || pi >= N || pj >= N) return false;
+        for (auto& sg : w.segs)
+          if (g_of_gp[sg.gp] == h->probe_g[q] && pc >= sg.c0 && pc < sg.c1) {
+            *o = (long long)(sg.slot0 + pc - sg.c0) * (long long)mat_elems + (long long)pi * ldD + pj;
+            return true;
+          }
+        return false;
+      }));
     ST_TRY(run_measure(c, gws, Dw, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
                        par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
     int t = c.timer.begin(SEQJ_T_COMBINE);
@@ -514,6 +588,14 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(cudaGetLastError());
     ev_graph[wi] = c.new_event();
     CU_TRY(cudaEventRecord(ev_graph[wi], c.st_graph));          // D buffer of this wave is no longer read
+    if (nprobe && !partial && w.gp_done1 > w.gp_done0)
+      ST_TRY(run_probes(Spool, [&](int q, long long* o) {
+        const int pg = h->probe_g[q], pi = h->probe_i[q], pj = h->probe_j[q];
+        if (h->probe_c[q] >= 0 || pg < 0 || pg >= G || gp_of[pg] < w.gp_done0 || gp_of[pg] >= w.gp_done1 || pi < 0 ||
+            pj < 0 || pi >= N || pj >= N) return false;
+        *o = (long long)(gp_of[pg] % nS) * (long long)mat_elems + (long long)pi * ldD + pj;
+        return true;
+      }));
     if (w.gp_done1 > w.gp_done0) {
       const int a = w.gp_done0, nd = w.gp_done1 - w.gp_done0;
       ST_TRY(run_measure(c, gws, Spool, ldD, (int64_t)mat_elems, nd, eps_floor, eta_g + a, root_g + a, par_g + (int64_t)a * ldp,
@@ -560,6 +642,10 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     d2h(r->mst_w.data(), fmst_w, sizeof(double) * (N - 1));
     d2h(h_val.data(), edge_val, sizeof(double) * (size_t)G * ldp);
   }
+  if (nprobe) {
+    r->probe_vals.resize(nprobe);
+    d2h(r->probe_vals.data(), probe_out, sizeof(double) * nprobe);
+  }
   c.timer.end(td);
   c.timer.end(tt);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c.st_graph);
@@ -595,6 +681,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   r->launches = c.launches;
   r->in_min = st0p->minv; r->in_max = st0p->maxv;       // check_input() ran before the first Prim launch
   r->derived_groups = n_derived_done;
+  r->waves = (int)waves.size();
   *out = r;
   return SEQJ_OK;
 }
@@ -786,7 +873,12 @@ static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->st);
-  cudaError_t e = cudaMemcpyAsync(A_dev, A, (size_t)M * N * 8, cudaMemcpyHostToDevice, h->st);
+  // pinned / registered callers: one DMA; pageable callers (a Julia Matrix, a NumPy array): staged upload
+  const size_t abytes = (size_t)M * N * 8;
+  const char* up = getenv("SEQJ_UPLOAD");
+  const bool staged = !(up && !strcmp(up, "direct")) && abytes >= (size_t(4) << 20) && !host_pointer_is_pinned(A);
+  cudaError_t e = staged ? upload_pageable(h->upload, h->dev, A_dev, A, abytes, h->st)
+                         : cudaMemcpyAsync(A_dev, A, abytes, cudaMemcpyHostToDevice, h->st);
   cudaEventRecord(e1, h->st);
   if (e != cudaSuccess) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -922,9 +1014,19 @@ int seqj_result_timings(const seqj_result* r, double* ms) {
   std::memcpy(ms, r->timers, sizeof(r->timers));
   return SEQJ_OK;
 }
+int seqj_result_probes(const seqj_result* r, double* vals, int64_t n) {
+  if (!r || !vals || n != (int64_t)r->probe_vals.size()) return SEQJ_E_BADARG;
+  copy_out(vals, r->probe_vals);
+  return SEQJ_OK;
+}
 int seqj_result_derived_groups(const seqj_result* r, int* n) {
   if (!r || !n) return SEQJ_E_BADARG;
   *n = r->derived_groups;
+  return SEQJ_OK;
+}
+int seqj_result_waves(const seqj_result* r, int* n) {
+  if (!r || !n) return SEQJ_E_BADARG;
+  *n = r->waves;
   return SEQJ_OK;
 }
 int seqj_result_launches(const seqj_result* r, int64_t* launches) {
