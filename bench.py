@@ -300,29 +300,20 @@ def main():
     dev = host.cuda(non_blocking=False)
     At = host.numpy()
 
-    def allgather(obj):
-        outl = [None] * world
-        dist.all_gather_object(outl, obj)
-        return outl
-
     def barrier():
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    gather_groups = None
-    if world > 1:
-        def gather_groups(mine, owner):
-            return sharding.torch_allgather_groups(mine, owner, metrics, scales, N, rank, world, dist,
-                                                   torch.device("cuda", local))
+    device = torch.device("cuda", local)
 
     def step_dev():
         if world > 1 and args.sharding == "chunk":
-            return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist,
-                                                    torch.device("cuda", local), dev.data_ptr())
-        return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, allgather, device_ptr=dev.data_ptr(),
-                                         gather_groups=gather_groups)
+            return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist, device, dev.data_ptr())
+        # group-major: groups packed on the device, ONE NCCL all-gather, fuse from the gathered device buffer
+        return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, device_ptr=dev.data_ptr(), dist=dist,
+                                         device=device)
 
     # the nvidia-smi sampler starts BEFORE the warm-up so that its start-up (NVML initialisation takes driver locks)
     # does not land in the timed region; it samples every 250 ms until the timed steps are done (at 100 ms the
@@ -380,10 +371,11 @@ def main():
             if world == 1:
                 return s.sequence(A_pub, scales=scales, metrics=metrics, handle=handle)
             if args.sharding == "chunk":
-                d = host.to(torch.device("cuda", local), non_blocking=True)      # H2D of A inside the timed region
-                return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist,
-                                                        torch.device("cuda", local), d.data_ptr())
-            return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, allgather, gather_groups=gather_groups)
+                d = sharding.upload_sharded(At, rank, world, dist, device)       # H2D of A inside the timed region
+                torch.cuda.current_stream().synchronize()
+                return sharding.sequence_sharded_chunks((N, L), scales, metrics, rank, world, handle, dist, device, d.data_ptr())
+            # every rank uploads 1/world of A over its own PCIe link, NVLink all-gather, then as step_dev
+            return sharding.sequence_sharded(At, scales, metrics, rank, world, handle, dist=dist, device=device)
         rr = step_e2e()
         barrier()
         t0 = time.perf_counter()
@@ -407,8 +399,34 @@ def main():
         assert np.array_equal(rr.order, order_ref)
         e2e = {"value": args.steps * pairs / el / 1e9, "unit": "Gpair/s", "h2d_bytes_per_step": 8 * N * L,
                "d2h_bytes_per_step": int(d2h), "sequence_wall_s": el / args.steps,
-               "api": "sequencerj_b200.sequence(A_host) -> seqj_sequence (C ABI), pinned host input",
+               "api": ("sequencerj_b200.sequence(A_host) -> seqj_sequence (C ABI), pinned host input" if world == 1 else
+                       "sharding.sequence_sharded(A_host): 1/world of A uploaded per rank + NVLink all-gather, seqj_sequence_shard, "
+                       "all-gather of the packed group results, seqj_fuse_dev"),
                "device_ms_per_step": {k: round(v, 3) for k, v in e2e_ph.items()}, "wall_ms_each_step": [round(w, 1) for w in walls]}
+
+    # ---- multi-GPU: the sharded result against the unsharded call, and the slowest rank's phases (outside the timed region)
+    parity = None
+    phases_max = None
+    if world > 1:
+        keys = list(s._lib.TIMER_NAMES) + ["host_upload_ms", "host_local_ms", "host_gather_ms", "host_fuse_ms", "host_reduce_ms",
+                                           "host_finish_ms"]
+        t = torch.tensor([phases.get(k, 0.0) / args.steps for k in keys], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        phases_max = {k: round(float(v), 3) for k, v in zip(keys, t.tolist()) if v > 0}
+        etas_all = [None] * world
+        dist.all_gather_object(etas_all, {(m.id, sc): e for (m, sc), (e, _) in r.EOAlgScale.items()})
+        if rank == 0:
+            single = api._sequence(At, scales, metrics, handle, device_ptr=dev.data_ptr())
+            merged = {}
+            for d_ in etas_all:
+                merged.update(d_)
+            ref_eta = {(m.id, sc): e for (m, sc), (e, _) in single.EOAlgScale.items()}
+            worst = max(abs(merged[k] - ref_eta[k]) / abs(ref_eta[k]) for k in ref_eta) if merged.keys() == ref_eta.keys() else float("inf")
+            parity = {"order_identical": bool(np.array_equal(single.order, r.order)), "final_eta_identical": bool(single.eta == r.eta),
+                      "groups_compared": len(ref_eta), "worst_group_eta_rel_diff": worst,
+                      "ok": bool(np.array_equal(single.order, r.order) and abs(single.eta - r.eta) <= 1e-9 * abs(single.eta)
+                                 and worst <= 1e-9)}
+        dist.barrier()
 
     # the same call from a PAGEABLE host array (what a Julia `Matrix` or a plain NumPy array is)
     if e2e is not None and world == 1:
@@ -505,7 +523,7 @@ def main():
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof_main,
            "roofline_emd": roofs["emd"], "roofline_gemm": roofs["gemm"], "roofline_mst": roofs["mst"],
            "roofline_derive": roofs["derive"], "roofline_combine": roofs["combine"],
-           "roofline_rank": 0, "dominant_kernel_by_time": dominant, "cpu_baseline": cpu, "clocks": clocks,
+           "roofline_rank": 0, "parity_vs_single_gpu": parity, "phases_ms_per_step_rank_max": phases_max, "dominant_kernel_by_time": dominant, "cpu_baseline": cpu, "clocks": clocks,
            "phases_ms_per_step": {k: v / args.steps for k, v in phases.items()},
            "final_eta": float(r.eta)}
     print(json.dumps(out), flush=True)

@@ -96,6 +96,13 @@ int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M);
  * rejected with SEQJ_E_BADARG where Julia throws a DimensionMismatch.  periods == NULL clears them. */
 int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M);
 
+/* Diagnostic (pure host code, needs no GPU): the static schedule seqj_sequence uses for an M-row input with these
+ * metrics / scales / group mask when `mats` N x N matrices fit the device -- which chunks of the loop
+ * src/sequencer.jl:194-258 are resident together (waves), which are computed by the tile kernels and which derived from
+ * the next finer scale, and where the accumulators live -- as text lines ("plan ...", "wave ...", "seg ...") in buf. */
+int seqj_plan_describe(int64_t M, const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
+                       const uint8_t* group_mask, int64_t mats, int hier, char* buf, int64_t buflen);
+
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
 
@@ -167,6 +174,20 @@ int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngro
 int seqj_fuse(seqj_handle* h, int64_t N, int ngroups, const double* eta_group,
               const int32_t* mst_i, const int32_t* mst_j, const double* mst_w,
               double eps_floor, seqj_result** out);
+
+/* Group-major sharding without host bounces ("gather of per-group (eta_kl, N-1 MST edges)").
+ * seqj_sequence_shard = seqj_sequence_dev with a group mask that ALSO leaves every computed group's (eta_kl, MST
+ * edges) -- the inputs of `_weighted_p_matrix`, src/sequencer.jl:310-328 -- in the caller's device buffer: the q-th
+ * computed group (metric-major order) at pack_dev + q * seqj_pack_stride(N) doubles, laid out as
+ * { eta, w[N-1], (i, j) int32 pairs [N-1], pad }.  The ranks all-gather these buffers (NCCL over NVLink) and every rank
+ * calls seqj_fuse_dev on the gathered buffer: group g (metric-major over ALL groups) sits in slot slot_of_group[g]
+ * (host array).  Same results as seqj_fuse on the same data. */
+int64_t seqj_pack_stride(int64_t N);
+int seqj_sequence_shard(seqj_handle* h, const double* A_dev, int64_t M, int64_t N, const int32_t* metric_ids,
+                        int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                        const uint8_t* group_mask, double* pack_dev, seqj_result** out);
+int seqj_fuse_dev(seqj_handle* h, int64_t N, int ngroups, const double* pack_dev, const int32_t* slot_of_group,
+                  double eps_floor, seqj_result** out);
 
 /* ---- result copy-out ------------------------------------------------------------------
  * Mirrors SequencerResult (src/sequencer.jl:13-20): EOSeg -> group chunks, EOAlgScale -> group,

@@ -24,6 +24,7 @@ SIGNATURES = {
     "seqj_create": (C.c_int, [C.POINTER(vp), c_ip, C.c_int]),
     "seqj_destroy": (None, [vp]),
     "seqj_last_error": (C.c_char_p, [vp]),
+    "seqj_plan_describe": (C.c_int, [C.c_int64, c_ip, C.c_int, c_ip, C.c_int, c_u8p, C.c_int64, C.c_int, C.c_char_p, C.c_int64]),
     "seqj_set_workspace_limit": (C.c_int, [vp, C.c_uint64]),
     "seqj_release_workspace": (C.c_int, [vp]),
     "seqj_set_grid": (C.c_int, [vp, c_dp, C.c_int64]),
@@ -38,6 +39,10 @@ SIGNATURES = {
                                         C.c_double, c_ip, c_ip, vp, C.c_int64, C.POINTER(vp)]),
     "seqj_groups_finish": (C.c_int, [vp, vp, C.c_int64, C.c_int, c_ip, C.c_int64, c_dp, C.c_double, c_dp, c_ip, c_ip,
                                      c_ip, c_ip, c_dp]),
+    "seqj_pack_stride": (C.c_int64, [C.c_int64]),
+    "seqj_sequence_shard": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
+                                      C.c_double, c_u8p, vp, C.POINTER(vp)]),
+    "seqj_fuse_dev": (C.c_int, [vp, C.c_int64, C.c_int, vp, c_ip, C.c_double, C.POINTER(vp)]),
     "seqj_fuse": (C.c_int, [vp, C.c_int64, C.c_int, c_dp, c_ip, c_ip, c_dp, C.c_double, C.POINTER(vp)]),
     "seqj_result_dims": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "seqj_result_group_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),

@@ -366,10 +366,12 @@ def _collect_and_release(handle, res, N, metrics, scales, want_final=True, parti
             handle.lib.seqj_result_free(res)
 
 
-def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None, probes=None):
+def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None, probes=None, pack=None):
     """`_sequence` (src/sequencer.jl:184-276) through the C ABI. At: (N, M) float64 C-contiguous host
     array, or (with device_ptr) the shape only.  `probes` = (group, chunk, i, j) int arrays (seqj_set_probes):
-    the sampled matrix entries come back as `result.probes`."""
+    the sampled matrix entries come back as `result.probes`.  `pack` = device tensor (anything with .data_ptr())
+    of at least [computed groups, seqj_pack_stride(N)] doubles: with a group mask and a device input the computed
+    groups' (eta, MST) are also left there for the device-side exchange (seqj_sequence_shard)."""
     handle = handle or default_handle()
     if probes is not None:
         pg, pc, pi, pj = (np.ascontiguousarray(x, dtype=np.int32) for x in probes)
@@ -377,7 +379,7 @@ def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None
         handle.check(handle.lib.seqj_set_probes(handle.h, _lib.iptr(pg), _lib.iptr(pc), _lib.iptr(pi), _lib.iptr(pj), len(pg)))
         handle._nprobes = len(pg)
         try:
-            return _sequence(At, scales, metrics, handle, group_mask, device_ptr)
+            return _sequence(At, scales, metrics, handle, group_mask, device_ptr, pack=pack)
         finally:
             handle._nprobes = 0
             handle.lib.seqj_set_probes(handle.h, None, None, None, None, 0)
@@ -390,7 +392,12 @@ def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None
         mask = np.ascontiguousarray(group_mask, dtype=np.uint8).reshape(-1)
         assert mask.size == len(mids) * len(scs)
     maskp = mask.ctypes.data_as(_lib.c_u8p) if mask is not None else None
-    if device_ptr is not None:
+    if pack is not None:
+        assert device_ptr is not None and mask is not None, "the device-side exchange needs a device input and a group mask"
+        st = handle.lib.seqj_sequence_shard(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
+                                            _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp,
+                                            C.c_void_p(pack.data_ptr()), C.byref(res))
+    elif device_ptr is not None:
         st = handle.lib.seqj_sequence_dev(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
                                           _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
     else:
@@ -583,6 +590,18 @@ def fuse(N, etas, msts, eps_floor=EPS_FLOOR, handle=None) -> SequencerResult:
     res = C.c_void_p()
     handle.check(handle.lib.seqj_fuse(handle.h, N, G, _lib.dptr(etas), _lib.iptr(mi), _lib.iptr(mj), _lib.dptr(mw),
                                       eps_floor, C.byref(res)))
+    return _collect_and_release(handle, res, N, None, None, want_final=True)
+
+
+def fuse_dev(N, ngroups, pack, slot_of_group, eps_floor=EPS_FLOOR, handle=None) -> SequencerResult:
+    """Final fuse (src/sequencer.jl:266-273) from group results in the device exchange format (seqj_fuse_dev):
+    `pack` = device tensor of slots, group g (metric-major) in slot slot_of_group[g]."""
+    handle = handle or default_handle()
+    slots = np.ascontiguousarray(slot_of_group, dtype=np.int32)
+    assert slots.size == ngroups
+    res = C.c_void_p()
+    handle.check(handle.lib.seqj_fuse_dev(handle.h, N, ngroups, C.c_void_p(pack.data_ptr()), _lib.iptr(slots), eps_floor,
+                                          C.byref(res)))
     return _collect_and_release(handle, res, N, None, None, want_final=True)
 
 

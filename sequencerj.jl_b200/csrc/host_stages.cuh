@@ -84,9 +84,11 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   bp.bestp = reinterpret_cast<unsigned long long*>(g.wd2); bp.stuck = g.anc1; bp.needy = g.dep0;
   bp.ncount = ncount; bp.ecount = ecount; bp.done = done; bp.nresc = g.knn_flags + 3 * g.knn_cap;
   // launches of few graphs may rescan freely (a row costs the same 8N bytes however many graphs share the launch,
-  // and Prim would be latency-bound there); large batches get N/4 rows per graph (profiles/r02_mst.md)
+  // and Prim would be latency-bound there); in a large batch a graph may re-read two matrices worth of rows before it
+  // is handed to the batched Prim, whose N dependent steps cost ~25-65 ms whatever the number of graphs
+  // (profiles/r02_mst.md): only pathological inputs get there
   const char* benv = getenv("SEQJ_KNN_BUDGET");
-  bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : std::max(16, g.N / 4));
+  bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : 2 * g.N);
   bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
@@ -330,7 +332,7 @@ struct FineVecs {
 
 // chunk matrices [c0, c1) of a coarse (metric, scale) group derived from the finished fine matrices
 int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, const FineVecs& fv, const double* Dfine,
-               int N, double* D, int64_t ldD, int64_t strideD, int c0, int c1, double eps_floor, double l2_thresh,
+               int fbase, int N, double* D, int64_t ldD, int64_t strideD, int c0, int c1, double eps_floor, double l2_thresh,
                FixBufs& fb, const int2* tiles_dev, int ntiles, const int* tile_col_offset) {
   seqj_handle* h = c.h;
   int t = c.timer.begin(SEQJ_T_DERIVE);
@@ -338,7 +340,7 @@ int run_derive(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, con
   CU_TRY(cudaMemsetAsync(fb.overflow, 0, sizeof(int), c.st));
   const int ratio = L.cl / fv.cl;
   DeriveParams dp;
-  dp.mode = metric; dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.Dfine = Dfine; dp.ldn = pb.ldn;
+  dp.mode = metric; dp.N = N; dp.ldD = ldD; dp.strideD = strideD; dp.Dfine = Dfine; dp.f_base = fbase; dp.ldn = pb.ldn;
   dp.fmass = fv.mass; dp.fg = (metric == SEQJ_ENERGY) ? fv.sU : fv.sP; dp.fR = fv.sR; dp.fT = fv.sT; dp.fm = fv.m_of_chunk;
   dp.eps_floor = eps_floor;
   dp.tau = (metric == SEQJ_L2) ? std::max(kTauGram, l2_thresh) : (metric == SEQJ_KLD ? kTauKL : kTauGram);

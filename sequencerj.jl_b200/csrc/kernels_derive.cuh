@@ -31,7 +31,8 @@ struct DeriveParams {
   int mode;               // MODE_L2 / MODE_KL / MODE_ENERGY
   int N;
   int64_t ldD, strideD;
-  const double* Dfine;    // fine chunk matrices: chunk f at Dfine + (f - 0) * strideD  (f = fine chunk index in the group)
+  const double* Dfine;    // fine chunk matrices: chunk f of the fine scale at Dfine + (f - f_base) * strideD
+  int f_base;             // first fine chunk resident at Dfine (a wave may hold only a block of the fine scale)
   double* Dout;           // coarse chunk matrix
   int ratio, nfine;       // coarse chunk z = blockIdx.z covers fine chunks [z*ratio + f_base, ...) (at most `ratio`, nfine in total)
   int c_first;            // first coarse chunk of this launch
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(256, 3) derive_kernel(DeriveParams p) {
 
   const int j = j0 + 2 * tx;                          // this thread's columns: j, j + 1 (j even, j + 1 < ldD)
   const int jc = min(j, (N - 1) & ~1);                // clamped load column (results of columns >= N are dropped)
-  const double* gbase = p.Dfine + (int64_t)p.f0 * p.strideD + jc;
+  const double* gbase = p.Dfine + (int64_t)(p.f0 - p.f_base) * p.strideD + jc;
   auto issue = [&](int qb) {                          // stage fine chunks qb, qb + 1 (this thread's 16 chunks)
 #pragma unroll
     for (int s_ = 0; s_ < kDeriveStage; ++s_)

@@ -840,11 +840,46 @@ __global__ void __launch_bounds__(256) scale_div_kernel(double* __restrict__ S, 
     S[idx] = S[idx] / tot;
 }
 
+// chunk etas from task (wave) order into (group, chunk) order, where the combine reads them: dst[pos[t]] = src[t]
+__global__ void scatter_eta_kernel(const double* __restrict__ src, const int* __restrict__ pos, int n, double* __restrict__ dst) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) dst[pos[t]] = src[t];
+}
+
 // Diagnostic sampling of matrix entries (seqj_set_probes): out[idx[q]] = base[off[q]]
 __global__ void probe_gather_kernel(const double* __restrict__ base, const long long* __restrict__ off,
                                     const int* __restrict__ idx, int n, double* __restrict__ out) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n) out[idx[q]] = base[off[q]];
+}
+
+// Device-side exchange format of a group's result (seqj_sequence_shard / seqj_fuse_dev): one slot of 2 N doubles per
+// group = { eta, w[N-1], (i, j) int32 pairs [N-1], pad }.  pack: slot q <- group arrays row perm[q]; unpack: group
+// arrays row g <- slot slot_of[g].  Grid (ceil(N / 256), groups).
+__global__ void pack_groups_kernel(double* __restrict__ pack, int64_t stride, const int* __restrict__ perm,
+                                   const double* __restrict__ eta, const int* __restrict__ mi, const int* __restrict__ mj,
+                                   const double* __restrict__ mw, int64_t ldp, int N) {
+  const int q = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = perm[q];
+  double* slot = pack + (int64_t)q * stride;
+  if (e == 0) { slot[0] = eta[g]; slot[2 * N - 1] = 0.0; }
+  if (e < N - 1) {
+    slot[1 + e] = mw[(int64_t)g * ldp + e];
+    reinterpret_cast<int2*>(slot + N)[e] = make_int2(mi[(int64_t)g * ldp + e], mj[(int64_t)g * ldp + e]);
+  }
+}
+__global__ void unpack_groups_kernel(const double* __restrict__ pack, int64_t stride, const int* __restrict__ slot_of,
+                                     double* __restrict__ eta, int* __restrict__ mi, int* __restrict__ mj,
+                                     double* __restrict__ mw, int64_t ldp, int N) {
+  const int g = blockIdx.y, e = blockIdx.x * blockDim.x + threadIdx.x;
+  const double* slot = pack + (int64_t)slot_of[g] * stride;
+  if (e == 0) eta[g] = slot[0];
+  if (e < N - 1) {
+    mw[(int64_t)g * ldp + e] = slot[1 + e];
+    const int2 ij = reinterpret_cast<const int2*>(slot + N)[e];
+    mi[(int64_t)g * ldp + e] = ij.x;
+    mj[(int64_t)g * ldp + e] = ij.y;
+  }
 }
 
 // ---- proximity fuse ---------------------------------------------------------------------------

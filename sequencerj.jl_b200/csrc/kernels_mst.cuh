@@ -53,6 +53,13 @@ struct KnnParams {
 // flight per lane) and keeps its four smallest eligible entries sorted in registers; the test against the fourth
 // is the only work on the common path.  Eligible = not the diagonal (first pass) / not in the row's component
 // (rescan).  Scanning j in ascending order with a strict comparison keeps ties in ascending j.
+//
+// Rescan lists hold at most ONE entry per component (the lightest edge into it): an edge into a component that is
+// heavier than another edge of the same row into the same component can never be the row's lightest outgoing edge --
+// components only merge, so the two far ends stay together for ever.  Without this a tight cluster larger than the
+// list used up the list again after every merge with a neighbouring cluster and had to be rescanned in every round
+// (one matrix worth of rows per round, profiles/r01_knn_boruvka.md); with it a rescanned row knows its lightest edge
+// into each of the 16 nearest components.
 template <bool RESCAN>
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
   const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -71,20 +78,47 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
     const double* __restrict__ row = D + (int64_t)v * p.ldD;
     unsigned long long k0 = kKnnNone, k1 = kKnnNone, k2 = kKnnNone, k3 = kKnnNone;
     int j0 = 0x7fffffff, j1 = 0x7fffffff, j2 = 0x7fffffff, j3 = 0x7fffffff;
+    int c0 = -1, c1 = -1, c2 = -1, c3 = -1;               // rescan only: component of each kept entry
     auto consider = [&](unsigned long long x, int idx) {
       if (x < k3) {                                        // rare once the list has settled
-        const bool ok = idx < N && (RESCAN ? (comp[idx] != cv) : (idx != v));
-        if (ok) {
-          x = max(x, eps_bits);
-          if (x < k3) {
-            if (x < k2) {
-              k3 = k2; j3 = j2;
-              if (x < k1) {
-                k2 = k1; j2 = j1;
-                if (x < k0) { k1 = k0; j1 = j0; k0 = x; j0 = idx; }
-                else { k1 = x; j1 = idx; }
-              } else { k2 = x; j2 = idx; }
-            } else { k3 = x; j3 = idx; }
+        if (!RESCAN) {
+          if (idx < N && idx != v) {
+            x = max(x, eps_bits);
+            if (x < k3) {
+              if (x < k2) {
+                k3 = k2; j3 = j2;
+                if (x < k1) {
+                  k2 = k1; j2 = j1;
+                  if (x < k0) { k1 = k0; j1 = j0; k0 = x; j0 = idx; }
+                  else { k1 = x; j1 = idx; }
+                } else { k2 = x; j2 = idx; }
+              } else { k3 = x; j3 = idx; }
+            }
+          }
+        } else if (idx < N) {
+          const int cc = comp[idx];
+          if (cc != cv) {
+            x = max(x, eps_bits);
+            if (x < k3) {
+              // position of an entry of the same component, if the lane keeps one (4 = none)
+              const int q = (cc == c0) ? 0 : (cc == c1) ? 1 : (cc == c2) ? 2 : (cc == c3) ? 3 : 4;
+              const unsigned long long kq = (q == 0) ? k0 : (q == 1) ? k1 : (q == 2) ? k2 : k3;
+              if (q == 4 || x < kq) {
+                // remove entry q (or the last one) by shifting the tail up, then insert (x, idx, cc) in order
+                if (q <= 0) { k0 = k1; j0 = j1; c0 = c1; }
+                if (q <= 1) { k1 = k2; j1 = j2; c1 = c2; }
+                if (q <= 2) { k2 = k3; j2 = j3; c2 = c3; }
+                // now three sorted entries in 0..2 (slot 3 is free); x < old k3 or x < old kq
+                if (x < k2) {
+                  k3 = k2; j3 = j2; c3 = c2;
+                  if (x < k1) {
+                    k2 = k1; j2 = j1; c2 = c1;
+                    if (x < k0) { k1 = k0; j1 = j0; c1 = c0; k0 = x; j0 = idx; c0 = cc; }
+                    else { k1 = x; j1 = idx; c1 = cc; }
+                  } else { k2 = x; j2 = idx; c2 = cc; }
+                } else { k3 = x; j3 = idx; c3 = cc; }
+              }
+            }
           }
         }
       }
@@ -103,6 +137,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
       }
     }
     // L = the smallest (k3, j3) among the lanes whose list is full: whatever such a lane did not list is larger
+    // (or, in a rescan, heavier than a listed edge into the same component)
     const bool full = k3 != kKnnNone;
     const unsigned fh = full ? (unsigned)(k3 >> 32) : 0xffffffffu;
     const unsigned mh = __reduce_min_sync(0xffffffffu, fh);
@@ -113,10 +148,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
     const bool anyfull = __any_sync(0xffffffffu, full);
     const unsigned long long Lk = anyfull ? (((unsigned long long)mh << 32) | ml) : kKnnNone;
     const int Lj = anyfull ? (int)mj : 0x7fffffff;
-    // the K smallest entries <= L, by K warp-argmins over the lanes' heads
+    // the K smallest entries <= L (rescan: of distinct components), by warp-argmins over the lanes' heads
     unsigned long long myk = kKnnNone, lastk = kKnnNone;
-    int myj = -1, count = 0;
-    for (int t = 0; t < kKnnK; ++t) {
+    int myj = -1, myc = -2, count = 0;
+    for (int t = 0; t < (RESCAN ? 4 * 32 : kKnnK) && count < kKnnK; ++t) {
       const unsigned hh = (unsigned)(k0 >> 32);
       const unsigned mhh = __reduce_min_sync(0xffffffffu, hh);
       const unsigned hl = (hh == mhh) ? (unsigned)k0 : 0xffffffffu;
@@ -126,10 +161,20 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
       const unsigned hj = (k0 == mk) ? (unsigned)j0 : 0x7fffffffu;
       const int mjj = (int)__reduce_min_sync(0xffffffffu, hj);
       if (mk > Lk || (mk == Lk && mjj > Lj)) break;         // beyond what the lanes can vouch for
-      if (lane == t) { myk = mk; myj = mjj; }
-      if (k0 == mk && j0 == mjj) { k0 = k1; j0 = j1; k1 = k2; j1 = j2; k2 = k3; j2 = j3; k3 = kKnnNone; j3 = 0x7fffffff; }
-      lastk = mk;
-      ++count;
+      const bool mine = (k0 == mk && j0 == mjj);
+      bool dup = false;
+      int cstar = 0;
+      if (RESCAN) {                                         // one entry per component: skip what a lighter edge covers
+        const unsigned owner = __ballot_sync(0xffffffffu, mine);
+        cstar = __shfl_sync(0xffffffffu, c0, __ffs(owner) - 1);
+        dup = __any_sync(0xffffffffu, lane < count && myc == cstar);
+      }
+      if (!dup) {
+        if (lane == count) { myk = mk; myj = mjj; myc = cstar; }
+        lastk = mk;
+        ++count;
+      }
+      if (mine) { k0 = k1; j0 = j1; c0 = c1; k1 = k2; j1 = j2; c1 = c2; k2 = k3; j2 = j3; c2 = c3; k3 = kKnnNone; j3 = 0x7fffffff; c3 = -1; }
     }
     const int64_t vo = gofs + v;
     if (lane < kKnnK) { p.lk[vo * kKnnK + lane] = myk; p.lj[vo * kKnnK + lane] = myj; }

@@ -31,6 +31,7 @@ using namespace seqj;
 
 #include "host_upload.cuh"
 #include "host_core.cuh"
+#include "host_plan.cuh"
 #include "host_stages.cuh"
 
 
@@ -169,6 +170,40 @@ int seqj_set_probes(seqj_handle* h, const int32_t* group, const int32_t* chunk, 
   return SEQJ_OK;
 }
 
+int seqj_plan_describe(int64_t M, const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
+                       const uint8_t* group_mask, int64_t mats, int hier, char* buf, int64_t buflen) {
+  if (!metric_ids || !scales || nmetrics < 1 || nscales < 1 || M < 1 || !buf || buflen < 64) return SEQJ_E_BADARG;
+  std::vector<ScaleLayout> layouts;
+  for (int l = 0; l < nscales; ++l) {
+    if (scales[l] < 1 || scales[l] > M) return SEQJ_E_BADARG;
+    layouts.push_back(make_layout((int)M, scales[l]));
+  }
+  PlanInput pin;
+  pin.M = (int)M; pin.nmetrics = nmetrics; pin.nscales = nscales; pin.metric_ids = metric_ids; pin.layouts = &layouts;
+  pin.mask = [&](int k, int l) { return !group_mask || group_mask[k * nscales + l] != 0; };
+  pin.c_lo = [](int, int) { return 0; };
+  pin.c_hi = [&](int, int l) { return layouts[l].nchunks; };
+  pin.partial = false; pin.hier = hier != 0; pin.mats = mats; pin.max_fine = kDeriveMaxFine;
+  Plan plan = make_plan(pin);
+  std::string o;
+  if (!plan.error.empty()) o = "error " + plan.error + "\n";
+  o += "plan pool_slots " + std::to_string(plan.pool_slots) + " waves " + std::to_string(plan.waves.size()) + " total_chunks " +
+       std::to_string(plan.total_chunks) + " derived_groups " + std::to_string(plan.n_derived_groups) + "\n";
+  for (size_t wi = 0; wi < plan.waves.size(); ++wi) {
+    const PlanWave& w = plan.waves[wi];
+    o += "wave " + std::to_string(wi) + " tasks " + std::to_string(w.ntasks) + " out0 " + std::to_string(w.out0) + " done " +
+         std::to_string(w.gp_done0) + " " + std::to_string(w.gp_done1) + "\n";
+    for (const PlanSeg& sg : w.segs)
+      o += "seg g " + std::to_string(sg.g) + " l " + std::to_string(sg.l) + " c0 " + std::to_string(sg.c0) + " c1 " +
+           std::to_string(sg.c1) + " slot0 " + std::to_string(sg.slot0) + " sslot " + std::to_string(sg.sslot) + " src_slot0 " +
+           std::to_string(sg.src_slot0) + " src_l " + std::to_string(sg.src_l) + " fbase " + std::to_string(sg.fbase) + " first " +
+           std::to_string(sg.first) + " last " + std::to_string(sg.last) + " gp " + std::to_string(sg.gp) + "\n";
+  }
+  if ((int64_t)o.size() + 1 > buflen) return SEQJ_E_BADARG;
+  std::memcpy(buf, o.c_str(), o.size() + 1);
+  return SEQJ_OK;
+}
+
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
   if (!h) return SEQJ_E_BADARG;
   h->ws_limit = bytes;
@@ -188,7 +223,7 @@ static int check_ready(seqj_handle* h) {
 static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64_t N64, const int32_t* metric_ids,
                          int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                          const uint8_t* group_mask, const int32_t* chunk_lo, const int32_t* chunk_hi, double* S_out,
-                         int64_t S_stride, seqj_result** out) {
+                         int64_t S_stride, seqj_result** out, double* pack_out = nullptr) {
   ST_TRY(check_ready(h));
   if (!A_dev || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M64 < 1 || N64 < 2 ||
       M64 > (1 << 30) || N64 > (1 << 30))
@@ -302,13 +337,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   CU_TRY(c.pool.alloc(&col_off_dev, col_off.size()));
   CU_TRY(cudaMemcpyAsync(col_off_dev, col_off.data(), col_off.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
 
-  // ---- static schedule --------------------------------------------------------------------
-  // Processing order is scale-major (one prep per scale), metric inside, chunk innermost.  Chunk
-  // tasks are packed into waves: as many N x N chunk matrices as fit in HBM are produced first and
-  // measured by ONE batched Prim launch (one CTA per graph), which is what makes Prim HBM-bound
-  // instead of latency-bound.  Groups that finish in a wave are combined and measured together.
-  struct Seg { int gp, l, k, c0, c1, slot0, sslot, first, last, out0; };
-  struct Wave { std::vector<Seg> segs; int ntasks = 0, out0 = 0, gp_done0 = -1, gp_done1 = -1; };
+  // ---- static schedule (host_plan.cuh) -------------------------------------------------------
   const int64_t ldp = N;
   const int64_t ldD = round_up(N, 16);
   const size_t mat_elems = (size_t)N * ldD;
@@ -319,23 +348,26 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   free_b += h->cached_bytes;                    // blocks cached from the previous call are reusable
   size_t budget = free_b > (size_t(4) << 30) ? free_b - (size_t(4) << 30) : free_b / 2;
   if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
-  // scales with many chunks first: the graph work of the last (smallest) wave is the only part that cannot
-  // hide behind distance tiles of a following wave
-  std::vector<int> scale_order(nscales);
-  for (int l = 0; l < nscales; ++l) scale_order[l] = l;
-  std::stable_sort(scale_order.begin(), scale_order.end(),
-                   [&](int a, int b) { return layouts[a].nchunks > layouts[b].nchunks; });
-  std::vector<int> gp_of(G, -1), g_of_gp;       // g = k*nscales + l (reference order)  <->  gp (processing order)
-  int total_chunks = 0, ngp = 0;
-  for (int l : scale_order)
+  const char* henv = getenv("SEQJ_HIER");
+  PlanInput pin;
+  pin.M = M; pin.nmetrics = nmetrics; pin.nscales = nscales; pin.metric_ids = metric_ids; pin.layouts = &layouts;
+  pin.mask = mask; pin.c_lo = c_lo; pin.c_hi = c_hi; pin.partial = partial;
+  pin.hier = !(henv && atoi(henv) == 0);
+  pin.mats = (int64_t)(budget / (mat_elems * 8));
+  pin.max_fine = kDeriveMaxFine;
+  {
+    int total = 0;
     for (int k = 0; k < nmetrics; ++k)
-      if (mask(k, l)) { gp_of[k * nscales + l] = ngp++; g_of_gp.push_back(k * nscales + l); total_chunks += c_hi(k, l) - c_lo(k, l); }
-  const int64_t mats = (int64_t)(budget / (mat_elems * 8));
-  int nS = (int)std::min<int64_t>(std::max(1, ngp), std::max<int64_t>(1, mats / 6));
-  if (partial) nS = std::max(1, ngp);            // accumulators live in the caller's S_out, one slot per active group
-  // overlap mode: two D buffers (double buffering between the compute and the graph stream), each nD matrices
-  const int nbuf = c.overlap ? 2 : 1;
-  int nD = (int)std::min<int64_t>((mats - nS) / nbuf, total_chunks);
+      for (int l = 0; l < nscales; ++l) if (mask(k, l)) total += c_hi(k, l) - c_lo(k, l);
+    const char* wenv = getenv("SEQJ_WAVES");
+    if (wenv && atoi(wenv) > 1) pin.wave_target = (total + atoi(wenv) - 1) / atoi(wenv);
+    if (const char* wf = getenv("SEQJ_WAVE_FRAC")) pin.wave_target = std::max(1, (int)(atof(wf) * total));
+  }
+  Plan plan = make_plan(pin);
+  if (!plan.error.empty()) return fail(h, SEQJ_E_OOM, plan.error);
+  const int total_chunks = plan.total_chunks, ngp = plan.ngp;
+  const std::vector<int>& gp_of = plan.gp_of;
+  const std::vector<int>& chunk_off = plan.chunk_off;
   if (total_chunks == 0) {
     // nothing selected (an all-zero group mask, or a rank of a chunk-major run that was assigned no chunk): a valid
     // call with an empty result, so that the rank can still join every collective of the sharded driver
@@ -357,94 +389,24 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     *out = r;
     return SEQJ_OK;
   }
-  if (nD < 1) return fail(h, SEQJ_E_OOM, "not enough device memory for two N x N chunk matrices plus the accumulator");
-  const char* wenv = getenv("SEQJ_WAVES");
-  const int nwaves_target = std::max(1, wenv ? atoi(wenv) : (c.overlap ? 2 : 1));
-  int wave_target = (total_chunks + nwaves_target - 1) / nwaves_target;
-  if (const char* wf = getenv("SEQJ_WAVE_FRAC")) wave_target = std::max(1, (int)(atof(wf) * total_chunks));
-  std::vector<Wave> waves;
-  std::vector<int> chunk_off(G, 0);             // first output slot of each group's chunks
-  {
-    Wave w;
-    int out = 0, open_groups = 0;
-    auto close = [&]() { if (w.ntasks) { waves.push_back(w); } w = Wave(); w.out0 = out; open_groups = 0; };
-    w.out0 = 0;
-    for (int l : scale_order) {
-      // Waves end at scale boundaries once they hold about a third of all chunk graphs: every Prim launch is
-      // latency-bound (N dependent steps of ~1.2 us whatever the batch size), so few large launches win; three
-      // waves leave only the smallest one's graph work exposed after the last distance tile.
-      if (w.ntasks >= wave_target) close();
-      for (int k = 0; k < nmetrics; ++k) {
-        if (!mask(k, l)) continue;
-        const int g = k * nscales + l, gp = gp_of[g], nch = c_hi(k, l);
-        chunk_off[g] = out;
-        int c0 = c_lo(k, l);
-        while (c0 < nch) {
-          if (w.ntasks >= nD || open_groups >= nS) close();
-          const int take = std::min(nch - c0, nD - w.ntasks);
-          Seg sg;
-          sg.gp = gp; sg.l = l; sg.k = k; sg.c0 = c0; sg.c1 = c0 + take; sg.slot0 = w.ntasks; sg.sslot = gp % nS;
-          sg.first = (c0 == c_lo(k, l)); sg.last = (c0 + take == nch); sg.out0 = out;
-          w.segs.push_back(sg);
-          w.ntasks += take; out += take; c0 += take; open_groups++;
-          if (sg.last && !partial) { if (w.gp_done0 < 0) w.gp_done0 = gp; w.gp_done1 = gp + 1; }
-        }
-      }
-    }
-    close();
-  }
-  // A group's accumulator slot (gp % nS) stays live from its first wave to the wave it finishes in; a wave
-  // never touches more than nS groups, and groups finish in order, so slots never collide.
-  int max_wave = 1, max_done = 1;
-  for (auto& w : waves) { max_wave = std::max(max_wave, w.ntasks); max_done = std::max(max_done, w.gp_done1 - w.gp_done0); }
-
-  // Coarse scales of the contraction metrics are derived from the finest scale when chunk boundaries nest
-  // (kernels_derive.cuh); needs the whole call in one wave so the fine matrices are still resident.
-  const char* henv = getenv("SEQJ_HIER");
-  const bool hier_on = !partial && waves.size() == 1 && !(henv && atoi(henv) == 0) && nscales > 1;
-  const int lf = scale_order[0];                      // finest scale of the call
-  // Chain: every scale is derived from the scale processed just before it (the next finer one) when that one
-  // nests and the metric's group there is part of this call; e.g. 16 -> 8 -> 4 -> 2 -> 1, each step reading
-  // only the matrices of the previous scale (total traffic ~2x the output instead of n_f x per scale).
-  std::vector<uint8_t> derivable(G, 0);
-  std::vector<int> src_of(G, -1);
-  int n_derived = 0;
-  if (hier_on) {
-    int l_prev = -1;
-    for (int l : scale_order) {
-      bool any = false;
-      for (int k = 0; k < nmetrics; ++k) any |= mask(k, l);
-      if (!any) continue;
-      if (l_prev >= 0)
-        for (int k = 0; k < nmetrics; ++k) {
-          const int mid = metric_ids[k];
-          if (!(mid == SEQJ_L2 || mid == SEQJ_KLD || mid == SEQJ_ENERGY) || !mask(k, l) || !mask(k, l_prev)) continue;
-          const int ratio = layouts[l].cl / layouts[l_prev].cl;
-          if (layouts[l].cl % layouts[l_prev].cl == 0 && ratio <= kDeriveMaxFine && layouts[l].nchunks < layouts[l_prev].nchunks) {
-            derivable[k * nscales + l] = 1;
-            src_of[k * nscales + l] = l_prev;
-            n_derived++;
-          }
-        }
-      l_prev = l;
-    }
-  }
+  if (plan.pool_slots < 1 || plan.pool_slots > pin.mats)
+    return fail(h, SEQJ_E_OOM, "not enough device memory for two N x N chunk matrices plus the accumulator");
   hmark("waves planned");
+  const int lf = std::max_element(layouts.begin(), layouts.end(), [](const ScaleLayout& a, const ScaleLayout& b) { return a.nchunks < b.nchunks; }) - layouts.begin();
   FineVecs fv;
-  if (n_derived) {
+  if (plan.n_derived_groups) {
     const size_t nn = (size_t)layouts[lf].nchunks * pb.ldn;
     CU_TRY(c.pool.alloc(&fv.mass, nn)); CU_TRY(c.pool.alloc(&fv.sP, nn)); CU_TRY(c.pool.alloc(&fv.sU, nn));
     CU_TRY(c.pool.alloc(&fv.sR, nn)); CU_TRY(c.pool.alloc(&fv.sT, nn));
     CU_TRY(c.pool.alloc(&fv.m_of_chunk, (size_t)layouts[lf].nchunks));
     CU_TRY(c.pool.alloc(&fv.fac, nn * 4 + 128)); CU_TRY(c.pool.alloc(&fv.pm, (size_t)layouts[lf].nchunks * 3));
   }
-  std::vector<int> last_slot0(nmetrics, -1), last_scale(nmetrics, -1);
-  int fv_scale = -1;                                  // scale whose vectors are currently in fv
-  int n_derived_done = 0;
 
-  double *eta_c, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
-  int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f, *sslot_dev, *perm_dev;
+  double *eta_c, *eta_bg, *eta_g, *mstw_g, *eta_f, *fmst_w, *edge_val;
+  int *root_c, *par_c, *root_g, *par_g, *msti_g, *mstj_g, *root_f, *par_f, *fmst_i, *fmst_j, *order_f, *sslot_dev, *perm_dev,
+      *task_slot_dev, *task_pos_dev;
   CU_TRY(c.pool.alloc(&eta_c, (size_t)total_chunks)); CU_TRY(c.pool.alloc(&root_c, (size_t)total_chunks));
+  CU_TRY(c.pool.alloc(&eta_bg, (size_t)total_chunks));          // chunk etas in (group, chunk) order for the combine
   CU_TRY(c.pool.alloc(&par_c, (size_t)total_chunks * ldp));
   CU_TRY(c.pool.alloc(&eta_g, (size_t)G)); CU_TRY(c.pool.alloc(&root_g, (size_t)G));
   CU_TRY(c.pool.alloc(&par_g, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&msti_g, (size_t)G * ldp));
@@ -454,11 +416,14 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
   CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp));
   CU_TRY(c.pool.alloc(&sslot_dev, (size_t)G)); CU_TRY(c.pool.alloc(&perm_dev, (size_t)G));
+  CU_TRY(c.pool.alloc(&task_slot_dev, (size_t)total_chunks)); CU_TRY(c.pool.alloc(&task_pos_dev, (size_t)total_chunks));
   std::vector<int> sslot_host(G, 0), perm_host;
-  for (int gp = 0; gp < ngp; ++gp) sslot_host[gp] = gp % nS;
+  for (int gp = 0; gp < ngp; ++gp) sslot_host[gp] = std::max(0, plan.sslot_of_gp[gp]);
   for (int g = 0; g < G; ++g) if (gp_of[g] >= 0) perm_host.push_back(gp_of[g]);
   CU_TRY(cudaMemcpyAsync(sslot_dev, sslot_host.data(), sizeof(int) * G, cudaMemcpyHostToDevice, c.st));
   CU_TRY(cudaMemcpyAsync(perm_dev, perm_host.data(), sizeof(int) * perm_host.size(), cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(task_slot_dev, plan.task_slot.data(), sizeof(int) * total_chunks, cudaMemcpyHostToDevice, c.st));
+  CU_TRY(cudaMemcpyAsync(task_pos_dev, plan.task_pos.data(), sizeof(int) * total_chunks, cudaMemcpyHostToDevice, c.st));
 
   // active groups in metric-major order -> slot in S_out (partial mode)
   std::vector<int> out_slot(G, -1);
@@ -466,11 +431,11 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     int sidx = 0;
     for (int g = 0; g < G; ++g) if (gp_of[g] >= 0) out_slot[g] = sidx++;
   }
-  double *Spool = nullptr, *Dbuf;
-  if (!partial) CU_TRY(c.pool.alloc(&Spool, mat_elems * nS));
-  CU_TRY(c.pool.alloc(&Dbuf, mat_elems * (size_t)max_wave * nbuf));
+  // ONE pool of N x N matrices: every phase of the plan keeps its accumulators, wave slots and carry slots in it
+  double* Mpool;
+  CU_TRY(c.pool.alloc(&Mpool, mat_elems * (size_t)plan.pool_slots));
   GraphWS gws;
-  ST_TRY(graphws_alloc(c, gws, std::max(max_wave, max_done), N));
+  ST_TRY(graphws_alloc(c, gws, std::max(plan.max_tasks, std::max(1, plan.max_done)), N));
 
   // diagnostic probes (seqj_set_probes): values land in probe_out, NaN where this call did not produce the entry
   const int nprobe = (int)h->probe_g.size();
@@ -480,10 +445,10 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   if (nprobe) {
     CU_TRY(c.pool.alloc(&probe_out, (size_t)nprobe));
     CU_TRY(cudaMemsetAsync(probe_out, 0xff, sizeof(double) * nprobe, c.st));
-    probe_offs.reserve(2 * waves.size() + 2); probe_idxs.reserve(2 * waves.size() + 2);
+    probe_offs.reserve(2 * plan.waves.size() + 2); probe_idxs.reserve(2 * plan.waves.size() + 2);
   }
-  // gathers the probes selected by `pick(q, &offset)` from `base` on the current stream
-  auto run_probes = [&](const double* base, const std::function<bool(int, long long*)>& pick) -> int {
+  // gathers the probes selected by `pick(q, &offset)` from the matrix pool on the current stream
+  auto run_probes = [&](const std::function<bool(int, long long*)>& pick) -> int {
     std::vector<long long> offs; std::vector<int> idxs;
     for (int q = 0; q < nprobe; ++q) {
       long long o;
@@ -496,117 +461,120 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     CU_TRY(c.pool.alloc(&off_d, ov.size())); CU_TRY(c.pool.alloc(&idx_d, iv.size()));
     CU_TRY(cudaMemcpyAsync(off_d, ov.data(), ov.size() * sizeof(long long), cudaMemcpyHostToDevice, c.st));
     CU_TRY(cudaMemcpyAsync(idx_d, iv.data(), iv.size() * sizeof(int), cudaMemcpyHostToDevice, c.st));
-    probe_gather_kernel<<<(unsigned)((ov.size() + 255) / 256), 256, 0, c.st>>>(base, off_d, idx_d, (int)ov.size(), probe_out);
+    probe_gather_kernel<<<(unsigned)((ov.size() + 255) / 256), 256, 0, c.st>>>(Mpool, off_d, idx_d, (int)ov.size(), probe_out);
     c.launches++;
     CU_TRY(cudaGetLastError());
     return SEQJ_OK;
   };
 
-  // Two streams: distance tiles of wave w+1 (FP64-bound) run while the graph stream measures wave w
-  // (latency/HBM-bound, small CTAs that fit next to the tiles).  D buffers alternate between waves.
-  std::vector<cudaEvent_t> ev_dist(waves.size()), ev_graph(waves.size());
-  cudaEvent_t ev_setup = c.new_event();
-  CU_TRY(cudaEventRecord(ev_setup, c.st_compute));              // index arrays / tiles uploaded on the compute stream
-  CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_setup, 0));
-  int cur_scale = -1;
+  // prep state: `cur_scale` = scale whose operands / vectors are in pb, `fv_scale` = scale whose vectors are in fv
+  int cur_scale = -1, fv_scale = -1;
+  auto prep_scale = [&](int l) -> int {
+    if (cur_scale == l) return SEQJ_OK;
+    hmark("before prep");
+    ST_TRY(run_prep(c, A_dev, M, M, N, layouts[l], pb, 1));
+    hmark("after prep");
+    cur_scale = l;
+    return SEQJ_OK;
+  };
+  auto stash_fine = [&]() -> int {                 // the vectors of the scale in pb become the derivation source
+    const ScaleLayout& Lp = layouts[cur_scale];
+    const size_t nb8 = (size_t)Lp.nchunks * pb.ldn * 8;
+    CU_TRY(cudaMemcpyAsync(fv.mass, pb.mass, nb8, cudaMemcpyDeviceToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(fv.sP, pb.sP, nb8, cudaMemcpyDeviceToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(fv.sU, pb.sU, nb8, cudaMemcpyDeviceToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(fv.sR, pb.sR, nb8, cudaMemcpyDeviceToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(fv.sT, pb.sT, nb8, cudaMemcpyDeviceToDevice, c.st));
+    CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * Lp.nchunks, cudaMemcpyDeviceToDevice, c.st));
+    fv.nchunks = Lp.nchunks; fv.cl = Lp.cl; fv_scale = cur_scale;
+    return SEQJ_OK;
+  };
+  std::vector<uint8_t> group_derived(G, 0);
   hmark("setup done");
-  for (size_t wi = 0; wi < waves.size(); ++wi) {
-    Wave& w = waves[wi];
-    double* Dw = Dbuf + (wi % nbuf) * (size_t)max_wave * mat_elems;
-    c.on_compute();
-    if (c.overlap && wi >= 2) CU_TRY(cudaStreamWaitEvent(c.st_compute, ev_graph[wi - 2], 0));   // buffer free again
+  for (size_t wi = 0; wi < plan.waves.size(); ++wi) {
+    PlanWave& w = plan.waves[wi];
     for (auto& sg : w.segs) {
       const ScaleLayout& L = layouts[sg.l];
-      if (sg.l != cur_scale) {
-        if (n_derived && cur_scale >= 0) {           // the vectors of the scale just finished become the source
-          const ScaleLayout& Lp = layouts[cur_scale];
-          const size_t nb8 = (size_t)Lp.nchunks * pb.ldn * 8;
-          CU_TRY(cudaMemcpyAsync(fv.mass, pb.mass, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.sP, pb.sP, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.sU, pb.sU, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.sR, pb.sR, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.sT, pb.sT, nb8, cudaMemcpyDeviceToDevice, c.st));
-          CU_TRY(cudaMemcpyAsync(fv.m_of_chunk, pb.m_of_chunk, sizeof(int) * Lp.nchunks, cudaMemcpyDeviceToDevice, c.st));
-          fv.nchunks = Lp.nchunks; fv.cl = Lp.cl; fv_scale = cur_scale;
+      double* Dseg = Mpool + (size_t)sg.slot0 * mat_elems;
+      if (sg.src_slot0 >= 0) {
+        // derived from the chunks of the next finer scale (resident in this wave or in the carry slots)
+        if (fv_scale != sg.src_l) {
+          if (cur_scale != sg.src_l) ST_TRY(prep_scale(sg.src_l));
+          ST_TRY(stash_fine());
         }
-        hmark("before prep");
-        ST_TRY(run_prep(c, A_dev, M, M, N, L, pb, 1));
-        hmark("after prep");
-        cur_scale = sg.l;
-      }
-      const int gidx = sg.k * nscales + sg.l;
-      const bool whole = (sg.c0 == 0 && sg.c1 == L.nchunks);
-      if (derivable[gidx] && whole && last_scale[sg.k] == src_of[gidx] && fv_scale == src_of[gidx] && last_slot0[sg.k] >= 0) {
-        ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Dw + (size_t)last_slot0[sg.k] * mat_elems, N,
-                          Dw + (size_t)sg.slot0 * mat_elems, ldD, (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb,
-                          tiles_dev, (int)tiles.size(), col_off_dev));
-        last_slot0[sg.k] = sg.slot0; last_scale[sg.k] = sg.l;
-        n_derived_done++;
+        ST_TRY(prep_scale(sg.l));
+        ST_TRY(run_derive(c, metric_ids[sg.k], L, pb, fv, Mpool + (size_t)sg.src_slot0 * mat_elems, sg.fbase, N, Dseg, ldD,
+                          (int64_t)mat_elems, sg.c0, sg.c1, eps_floor, l2_thresh, fb, tiles_dev, (int)tiles.size(), col_off_dev));
+        group_derived[sg.g] = 1;
         continue;
       }
-      if (whole) { last_slot0[sg.k] = sg.slot0; last_scale[sg.k] = sg.l; }
-      else { last_slot0[sg.k] = -1; last_scale[sg.k] = -1; }
-      ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dw + (size_t)sg.slot0 * mat_elems, ldD,
-                          (int64_t)mat_elems, sg.c0, sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
+      ST_TRY(prep_scale(sg.l));
+      ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dseg, ldD, (int64_t)mat_elems, sg.c0,
+                          sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
     }
-    ev_dist[wi] = c.new_event();
-    CU_TRY(cudaEventRecord(ev_dist[wi], c.st_compute));
-    c.on_graph();
-    CU_TRY(cudaStreamWaitEvent(c.st_graph, ev_dist[wi], 0));
     hmark("dist queued");
     ST_TRY(check_input());
     hmark("input checked");
     if (nprobe)
-      ST_TRY(run_probes(Dw, [&](int q, long long* o) {
+      ST_TRY(run_probes([&](int q, long long* o) {
         const int pc = h->probe_c[q], pi = h->probe_i[q], pj = h->probe_j[q];
         if (pc < 0 || pi < 0 || pj < 0 || pi >= N || pj >= N) return false;
         for (auto& sg : w.segs)
-          if (g_of_gp[sg.gp] == h->probe_g[q] && pc >= sg.c0 && pc < sg.c1) {
+          if (sg.g == h->probe_g[q] && pc >= sg.c0 && pc < sg.c1) {
             *o = (long long)(sg.slot0 + pc - sg.c0) * (long long)mat_elems + (long long)pi * ldD + pj;
             return true;
           }
         return false;
       }));
-    ST_TRY(run_measure(c, gws, Dw, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
-                       par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr));
+    ST_TRY(run_measure(c, gws, Mpool, ldD, (int64_t)mat_elems, w.ntasks, eps_floor, eta_c + w.out0, root_c + w.out0,
+                       par_c + (int64_t)w.out0 * ldp, ldp, nullptr, nullptr, nullptr, nullptr, task_slot_dev + w.out0));
     int t = c.timer.begin(SEQJ_T_COMBINE);
+    scatter_eta_kernel<<<(w.ntasks + 255) / 256, 256, 0, c.st>>>(eta_c + w.out0, task_pos_dev + w.out0, w.ntasks, eta_bg);
+    c.launches++;
     for (auto& sg : w.segs) {
-      const int g = g_of_gp[sg.gp];
+      const int g = sg.g;
       const int nch = layouts[sg.l].nchunks;
       const int lo = c_lo(sg.k, sg.l);
-      double* Sg = partial ? S_out + (size_t)out_slot[g] * (size_t)S_stride : Spool + (size_t)sg.sslot * mat_elems;
+      double* Sg = partial ? S_out + (size_t)out_slot[g] * (size_t)S_stride : Mpool + (size_t)sg.sslot * mat_elems;
       for (int b0 = sg.c0; b0 < sg.c1; b0 += kCombineMax) {
         const int nb = std::min(kCombineMax, sg.c1 - b0);
         const unsigned T = (unsigned)((N + kCombineTile - 1) / kCombineTile);
         combine_sym_kernel<<<dim3(T, T), 256, 0, c.st>>>(
-            Sg, ldD, N, Dw + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
-            eta_c + sg.out0 + (b0 - sg.c0), b0 == lo, !partial && b0 + nb >= nch, eta_c + chunk_off[g], nch);
+            Sg, ldD, N, Mpool + (size_t)(sg.slot0 + b0 - sg.c0) * mat_elems, (int64_t)mat_elems, nb,
+            eta_bg + chunk_off[g] + (b0 - lo), b0 == lo, !partial && b0 + nb >= nch, eta_bg + chunk_off[g], nch);
         c.launches++;
       }
     }
     c.timer.end(t);
     CU_TRY(cudaGetLastError());
-    ev_graph[wi] = c.new_event();
-    CU_TRY(cudaEventRecord(ev_graph[wi], c.st_graph));          // D buffer of this wave is no longer read
     if (nprobe && !partial && w.gp_done1 > w.gp_done0)
-      ST_TRY(run_probes(Spool, [&](int q, long long* o) {
+      ST_TRY(run_probes([&](int q, long long* o) {
         const int pg = h->probe_g[q], pi = h->probe_i[q], pj = h->probe_j[q];
         if (h->probe_c[q] >= 0 || pg < 0 || pg >= G || gp_of[pg] < w.gp_done0 || gp_of[pg] >= w.gp_done1 || pi < 0 ||
             pj < 0 || pi >= N || pj >= N) return false;
-        *o = (long long)(gp_of[pg] % nS) * (long long)mat_elems + (long long)pi * ldD + pj;
+        *o = (long long)plan.sslot_of_gp[gp_of[pg]] * (long long)mat_elems + (long long)pi * ldD + pj;
         return true;
       }));
     if (w.gp_done1 > w.gp_done0) {
       const int a = w.gp_done0, nd = w.gp_done1 - w.gp_done0;
-      ST_TRY(run_measure(c, gws, Spool, ldD, (int64_t)mat_elems, nd, eps_floor, eta_g + a, root_g + a, par_g + (int64_t)a * ldp,
+      ST_TRY(run_measure(c, gws, Mpool, ldD, (int64_t)mat_elems, nd, eps_floor, eta_g + a, root_g + a, par_g + (int64_t)a * ldp,
                          ldp, msti_g + (int64_t)a * ldp, mstj_g + (int64_t)a * ldp, mstw_g + (int64_t)a * ldp, nullptr,
                          sslot_dev + a));
     }
   }
-  c.on_graph();
+  int n_derived_done = 0;
+  for (int g = 0; g < G; ++g) n_derived_done += group_derived[g];
   if (do_final)
-    ST_TRY(run_fuse(c, gws, Spool, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
+    ST_TRY(run_fuse(c, gws, Mpool, ldD, N, G, eta_g, msti_g, mstj_g, mstw_g, ldp, eps_floor, eta_f, root_f, par_f, fmst_i,
                     fmst_j, fmst_w, order_f, edge_val, perm_host, perm_dev));
+
+  // device-side exchange of the group results (group-major sharding): slot q = q-th computed group, metric-major
+  if (pack_out && !partial && !perm_host.empty()) {
+    pack_groups_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)perm_host.size()), 256, 0, c.st>>>(
+        pack_out, 2 * (int64_t)N, perm_dev, eta_g, msti_g, mstj_g, mstw_g, ldp, N);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+  }
 
   // ---- copy-out ----
   seqj_result* r = new seqj_result();
@@ -648,11 +616,9 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   }
   c.timer.end(td);
   c.timer.end(tt);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st_graph);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st_compute);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c.st);
   if (e != cudaSuccess) {
-    cudaStreamSynchronize(c.st_graph);
-    cudaStreamSynchronize(c.st_compute);
+    cudaStreamSynchronize(c.st);
     delete r;
     return fail(h, SEQJ_E_CUDA, std::string("sequence failed: ") + cudaGetErrorString(e));
   }
@@ -664,11 +630,8 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       if (!gr.computed) continue;
       gr.chunk_lo = c_lo(k, l); gr.chunk_hi = c_hi(k, l);
       const int nloc = gr.chunk_hi - gr.chunk_lo;
-      const int coff = chunk_off[g];
-      const size_t gp = (size_t)gp_of[g];        // row of this group in the device arrays (processing order)
-      gr.eta_chunk.assign(h_eta_c.begin() + coff, h_eta_c.begin() + coff + nloc);
-      gr.root_chunk.assign(h_root_c.begin() + coff, h_root_c.begin() + coff + nloc);
-      gr.parents_chunk.assign(h_par_c.begin() + (size_t)coff * ldp, h_par_c.begin() + (size_t)(coff + nloc) * ldp);
+      const size_t gp = (size_t)gp_of[g];        // row of this group in the device arrays (finishing order)
+      gr.eta_chunk.resize(nloc); gr.root_chunk.resize(nloc); gr.parents_chunk.resize((size_t)nloc * ldp);
       if (partial) continue;                     // group-level results come from seqj_groups_finish on the owner rank
       gr.eta = h_eta_g[gp]; gr.root = h_root_g[gp];
       gr.parents.assign(h_par_g.begin() + gp * ldp, h_par_g.begin() + gp * ldp + N);
@@ -676,12 +639,23 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       gr.mst_j.assign(h_mstj.begin() + gp * ldp, h_mstj.begin() + gp * ldp + N - 1);
       gr.mst_w.assign(h_mstw.begin() + gp * ldp, h_mstw.begin() + gp * ldp + N - 1);
     }
+  // chunk-level results arrive in task (wave) order: file them under (group, chunk)
+  for (auto& w : plan.waves)
+    for (auto& sg : w.segs) {
+      GroupRes& gr = r->groups[sg.g];
+      for (int cc = sg.c0; cc < sg.c1; ++cc) {
+        const size_t tsk = (size_t)sg.out0 + (cc - sg.c0), dst = (size_t)(cc - gr.chunk_lo);
+        gr.eta_chunk[dst] = h_eta_c[tsk];
+        gr.root_chunk[dst] = h_root_c[tsk];
+        std::memcpy(gr.parents_chunk.data() + dst * ldp, h_par_c.data() + tsk * ldp, sizeof(int) * (size_t)ldp);
+      }
+    }
   if (do_final) stash_triplets(r, G, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
   r->launches = c.launches;
   r->in_min = st0p->minv; r->in_max = st0p->maxv;       // check_input() ran before the first Prim launch
   r->derived_groups = n_derived_done;
-  r->waves = (int)waves.size();
+  r->waves = (int)plan.waves.size();
   *out = r;
   return SEQJ_OK;
 }
@@ -895,10 +869,11 @@ static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t
   return s;
 }
 
-int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
-              const int32_t* mst_j, const double* mst_w, double eps_floor, seqj_result** out) {
+// Shared body of seqj_fuse (per-group results in host arrays) and seqj_fuse_dev (in the device exchange format).
+static int fuse_impl(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
+                     const int32_t* mst_j, const double* mst_w, const double* pack_dev, const int32_t* slot_of_group,
+                     double eps_floor, seqj_result** out) {
   ST_TRY(check_ready(h));
-  if (!eta_group || !mst_i || !mst_j || !mst_w || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   const int N = (int)N64, G = ngroups;
   Ctx c(h);
   const int64_t ldp = N, ldD = round_up(N, 16);
@@ -911,11 +886,19 @@ int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group,
   CU_TRY(c.pool.alloc(&fmst_i, (size_t)ldp)); CU_TRY(c.pool.alloc(&fmst_j, (size_t)ldp));
   CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
   CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&Sbuf, (size_t)N * ldD));
-  CU_TRY(cudaMemcpyAsync(eta_g, eta_group, sizeof(double) * G, cudaMemcpyHostToDevice, c.st));
-  for (int g = 0; g < G; ++g) {
-    CU_TRY(cudaMemcpyAsync(msti_g + (size_t)g * ldp, mst_i + (size_t)g * (N - 1), sizeof(int) * (N - 1), cudaMemcpyHostToDevice, c.st));
-    CU_TRY(cudaMemcpyAsync(mstj_g + (size_t)g * ldp, mst_j + (size_t)g * (N - 1), sizeof(int) * (N - 1), cudaMemcpyHostToDevice, c.st));
-    CU_TRY(cudaMemcpyAsync(mstw_g + (size_t)g * ldp, mst_w + (size_t)g * (N - 1), sizeof(double) * (N - 1), cudaMemcpyHostToDevice, c.st));
+  if (pack_dev) {
+    int* slot_d;
+    CU_TRY(c.pool.alloc(&slot_d, (size_t)G));
+    CU_TRY(cudaMemcpyAsync(slot_d, slot_of_group, sizeof(int) * G, cudaMemcpyHostToDevice, c.st));
+    unpack_groups_kernel<<<dim3((unsigned)((N + 255) / 256), (unsigned)G), 256, 0, c.st>>>(pack_dev, 2 * (int64_t)N, slot_d, eta_g,
+                                                                                         msti_g, mstj_g, mstw_g, ldp, N);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+  } else {
+    CU_TRY(cudaMemcpyAsync(eta_g, eta_group, sizeof(double) * G, cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpy2DAsync(msti_g, sizeof(int) * ldp, mst_i, sizeof(int) * (N - 1), sizeof(int) * (N - 1), G, cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpy2DAsync(mstj_g, sizeof(int) * ldp, mst_j, sizeof(int) * (N - 1), sizeof(int) * (N - 1), G, cudaMemcpyHostToDevice, c.st));
+    CU_TRY(cudaMemcpy2DAsync(mstw_g, sizeof(double) * ldp, mst_w, sizeof(double) * (N - 1), sizeof(double) * (N - 1), G, cudaMemcpyHostToDevice, c.st));
   }
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, 1, N));
@@ -949,6 +932,31 @@ int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group,
   r->launches = c.launches;
   *out = r;
   return SEQJ_OK;
+}
+
+int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
+              const int32_t* mst_j, const double* mst_w, double eps_floor, seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  if (!eta_group || !mst_i || !mst_j || !mst_w || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
+  return fuse_impl(h, N64, ngroups, eta_group, mst_i, mst_j, mst_w, nullptr, nullptr, eps_floor, out);
+}
+
+int64_t seqj_pack_stride(int64_t N) { return 2 * N; }
+
+int seqj_sequence_shard(seqj_handle* h, const double* A_dev, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
+                        const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
+                        double* pack_dev, seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  if (!group_mask || !pack_dev) return fail(h, SEQJ_E_BADARG, "seqj_sequence_shard needs a group mask and a pack buffer");
+  return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, nullptr,
+                       nullptr, nullptr, 0, out, pack_dev);
+}
+
+int seqj_fuse_dev(seqj_handle* h, int64_t N64, int ngroups, const double* pack_dev, const int32_t* slot_of_group,
+                  double eps_floor, seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  if (!pack_dev || !slot_of_group || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
+  return fuse_impl(h, N64, ngroups, nullptr, nullptr, nullptr, nullptr, pack_dev, slot_of_group, eps_floor, out);
 }
 
 // ---- result accessors -------------------------------------------------------------------------

@@ -121,19 +121,53 @@ def torch_allgather_groups(mine, owner, metrics, scales, N, rank, world, dist, d
     return merged
 
 
+def slots_of_groups(owner: np.ndarray, cap: int) -> np.ndarray:
+    """Slot of every group (metric-major) in the all-gathered exchange buffer [world][cap]: rank r's q-th group
+    (metric-major among its own) sits in slot r * cap + q (the order seqj_sequence_shard packs them in)."""
+    flat = owner.reshape(-1)
+    seen = {}
+    slots = np.zeros(flat.size, dtype=np.int32)
+    for g, r in enumerate(flat.tolist()):
+        slots[g] = r * cap + seen.get(r, 0)
+        seen[r] = seen.get(r, 0) + 1
+    return slots
+
+
+def upload_sharded(At, rank: int, world: int, dist, device):
+    """Every rank uploads 1/world of the objects over its own PCIe link and the ranks all-gather the slabs over
+    NVLink, instead of `world` full copies of A crossing PCIe at once.  Returns the [>= N, M] device tensor."""
+    import torch
+    N, M = At.shape
+    rows = -(-N // world)
+    lo, hi = min(N, rank * rows), min(N, (rank + 1) * rows)
+    shard = torch.zeros((rows, M), dtype=torch.float64, device=device)
+    if hi > lo:
+        shard[:hi - lo].copy_(torch.from_numpy(At[lo:hi]), non_blocking=True)
+    full = torch.empty((world * rows, M), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(full, shard)
+    return full
+
+
 def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, allgather=None, device_ptr=None,
-                     gather_groups=None):
-    """`_sequence` over `world` ranks.  The only communication is the gather of per-group results:
-    `gather_groups(mine, owner) -> merged dict` (tensor all-gather, see torch_allgather_groups) or, as a
-    generic fallback, `allgather(obj) -> list of obj` (all_gather_object).  Every rank returns the same final
-    SequencerResult; per-group details are kept for the groups it owns.  `timings` gains host-side
-    wall-clock entries (host_local_ms, host_gather_ms, host_fuse_ms)."""
+                     gather_groups=None, dist=None, device=None):
+    """`_sequence` over `world` ranks, group-major.  The only communication is the gather of per-group results.
+
+    Device path (`dist` + `device` given; NCCL on GPUs, gloo in the CPU test): every rank packs its groups'
+    (eta, MST edges) on the device (seqj_sequence_shard), ONE all_gather_into_tensor moves the slots over NVLink and
+    every rank fuses straight from the gathered device buffer (seqj_fuse_dev): no host bounce between the last group
+    kernel and the fuse.  Without `device_ptr` the input is uploaded 1/world per rank and all-gathered.
+
+    Generic path (`gather_groups(mine, owner)` or `allgather(obj)`): the same exchange through host objects.
+    Every rank returns the same final SequencerResult; per-group details are kept for the groups it owns.
+    `timings` gains host-side wall-clock entries (host_local_ms, host_gather_ms, host_fuse_ms)."""
     N, M = At.shape
     scales = tuple(int(s) for s in scales)
     if world == 1:
         return api._sequence(At, scales, metrics, handle, device_ptr=device_ptr)
     owner = plan_groups(M, metrics, scales, world)
     mask = (owner == rank).astype(np.uint8)
+    if dist is not None and device is not None:
+        return _sequence_sharded_device(At, scales, metrics, rank, world, handle, device_ptr, dist, device, owner, mask)
     mine = {}
     local = None
     t0 = time.perf_counter()
@@ -151,15 +185,54 @@ def sequence_sharded(At, scales, metrics, rank: int, world: int, handle=None, al
     t2 = time.perf_counter()
     final = api.fuse(N, etas, msts, handle=handle)
     t3 = time.perf_counter()
+    return _finish_sharded(final, local, t0, t1, t2, t3)
+
+
+def _finish_sharded(final, local, t0, t1, t2, t3, t_up=0.0):
     if local is not None:
         final.EOSeg, final.EOAlgScale, final.group_msts = local.EOSeg, local.EOAlgScale, local.group_msts
         for k, v in local.timings.items():
             final.timings[k] = final.timings.get(k, 0.0) + v
         final.launches += local.launches
+    final.timings["host_upload_ms"] = t_up * 1e3
     final.timings["host_local_ms"] = (t1 - t0) * 1e3
     final.timings["host_gather_ms"] = (t2 - t1) * 1e3
     final.timings["host_fuse_ms"] = (t3 - t2) * 1e3
     return final
+
+
+def _sequence_sharded_device(At, scales, metrics, rank, world, handle, device_ptr, dist, device, owner, mask):
+    import torch
+    N, M = At.shape
+    G = owner.size
+    cuda = getattr(device, "type", str(device)) == "cuda"
+
+    def sync():
+        if cuda:
+            torch.cuda.current_stream(device).synchronize()      # the library runs on its own streams
+
+    tu = time.perf_counter()
+    keep = None
+    if device_ptr is None:
+        keep = upload_sharded(At, rank, world, dist, device)
+        device_ptr = keep.data_ptr()
+    cap = int(max(int((owner == r).sum()) for r in range(world)))
+    stride = 2 * N                                                  # seqj_pack_stride(N)
+    pack = torch.zeros((cap, stride), dtype=torch.float64, device=device)
+    sync()
+    t0 = time.perf_counter()
+    local = None
+    if mask.any():
+        local = api._sequence(At, scales, metrics, handle, group_mask=mask, device_ptr=device_ptr, pack=pack)
+    t1 = time.perf_counter()
+    allp = torch.empty((world * cap, stride), dtype=torch.float64, device=device)
+    dist.all_gather_into_tensor(allp, pack)
+    sync()
+    t2 = time.perf_counter()
+    final = api.fuse_dev(N, G, allp, slots_of_groups(owner, cap), handle=handle)
+    t3 = time.perf_counter()
+    del keep
+    return _finish_sharded(final, local, t0, t1, t2, t3, t_up=t0 - tu)
 
 
 # ---- chunk-major sharding: all-gather of chunk etas + reduce of N x N partials ----

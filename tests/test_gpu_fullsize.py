@@ -209,7 +209,7 @@ def test_config4_shape_streaming_waves(seqj, oracle, handle):
     At = oracle_clamp(np.random.default_rng(2736).random((N, L)))
     probes = _probe_plan(np.random.default_rng(13), N, L, mids, scales, per_chunk=60, per_group=60)
     full = seqj.api._sequence(At, scales, mets, handle, probes=probes)
-    assert full.timings["waves"] == 1
+    assert full.timings["waves"] == 1 and full.timings["derived_groups"] == 5
     _check_probes(seqj, oracle, At.T, mids, scales, full, probes)
     mat = N * N * 8
     handle.check(handle.lib.seqj_set_workspace_limit(handle.h, 40 * mat))
@@ -217,9 +217,17 @@ def test_config4_shape_streaming_waves(seqj, oracle, handle):
         st = seqj.api._sequence(At, scales, mets, handle, probes=probes)
     finally:
         handle.check(handle.lib.seqj_set_workspace_limit(handle.h, 0))
-    assert st.timings["waves"] >= 3
+    # streamed: Energy runs block waves + a top wave with every coarse scale still derived (host_plan.cuh)
+    assert st.timings["waves"] >= 3 and st.timings["derived_groups"] == 5
     _check_probes(seqj, oracle, At.T, mids, scales, st, probes)
     _same_trees(seqj, full, st)
+    handle.check(handle.lib.seqj_set_workspace_limit(handle.h, 14 * mat))       # tighter: blocks at a finer level
+    try:
+        st2 = seqj.api._sequence(At, scales, mets, handle)
+    finally:
+        handle.check(handle.lib.seqj_set_workspace_limit(handle.h, 0))
+    assert st2.timings["waves"] > st.timings["waves"]
+    _same_trees(seqj, full, st2)
 
 
 def test_autoscale_matches_oracle(seqj, oracle, handle):

@@ -56,3 +56,25 @@ def test_world_size_2_gloo(tmp_path):
     outs = [p.communicate(timeout=300)[0].decode() for p in procs]
     assert all(p.returncode == 0 for p in procs), "\n".join(outs)
     assert out.read_text() == "OK"
+
+
+def test_chunk_partition_covers_every_chunk_once_even_with_idle_ranks(seqj):
+    """Chunk-major split: every (group, chunk) task belongs to exactly one rank, ranges are contiguous per rank, and a
+    rank may legitimately end up with nothing (fewer tasks than ranks): the library then returns an empty result
+    (seqj_sequence_partial with empty ranges) so that the rank still joins every collective."""
+    from sequencerj_b200 import sharding
+    for M, scales, world in ((4096, (1, 2, 4, 8, 16), 8), (50, (1,), 8), (53, (3, 6, 7), 5), (2048, (1, 2, 4, 8, 16, 32), 8)):
+        metrics = seqj.ALL_METRICS
+        lo, hi = sharding.chunk_partition(M, metrics, scales, world)
+        G = len(metrics) * len(scales)
+        assert lo.shape == hi.shape == (world, G)
+        for g in range(G):
+            nch = sharding.nchunks(M, scales[g % len(scales)])
+            cover = np.zeros(nch, dtype=int)
+            for r in range(world):
+                assert 0 <= lo[r, g] <= hi[r, g] <= nch or lo[r, g] >= hi[r, g]
+                if lo[r, g] < hi[r, g]:
+                    cover[lo[r, g]:hi[r, g]] += 1
+            assert np.all(cover == 1), (M, scales, world, g, cover)
+    lo, hi = sharding.chunk_partition(50, seqj.ALL_METRICS, (1,), 8)
+    assert any(not (lo[r] < hi[r]).any() for r in range(8))          # the case ADVICE r01 flagged: idle ranks exist

@@ -13,8 +13,8 @@ BENCH_NO_SAMPLER=1 timeout 600 ncu --metrics gpu__time_duration.sum --clock-cont
 echo "ncu list rc=$?"
 PCMD="python tools/profile_case.py --N 10000 --L 4096 --scales 1 2 4 8 16"
 $PCMD > gpurun_out/r02_plain2.log 2>&1 &&
-timeout 1500 ncu --set full --clock-control none --import-source on \
+timeout 1200 ncu --set full --clock-control none --import-source on \
   -k regex:"direct_dist_kernel|gemm_dist_kernel|derive_kernel|combine_sym_kernel|knn_rows_kernel|boruvka_knn_kernel|prep_kernel|tree_kernel" \
-  -c 90 -o gpurun_out/r02_full $PCMD > gpurun_out/r02_ncu_full.log 2>&1
+  -c 75 -o gpurun_out/r02_full $PCMD > gpurun_out/r02_ncu_full.log 2>&1
 echo "ncu full rc=$?"; tail -3 gpurun_out/r02_ncu_full.log
 ls -la gpurun_out | tail -15
