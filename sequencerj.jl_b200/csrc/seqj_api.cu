@@ -13,6 +13,7 @@
 #include <condition_variable>
 #include <functional>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -57,6 +58,17 @@ int seqj_create(seqj_handle** out, const int* devices, int ndev) {
     }
     (*out)->peers.push_back(p);
   }
+  // peer access between every pair of the handle's devices (NVLink loads / stores and direct peer copies); a pair
+  // that cannot be mapped still works, cudaMemcpyPeerAsync then stages through the host
+  for (int a = 0; a < ndev; ++a)
+    for (int b = 0; b < ndev; ++b) {
+      if (a == b) continue;
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, devices[a], devices[b]) == cudaSuccess && can) {
+        cudaSetDevice(devices[a]);
+        if (cudaDeviceEnablePeerAccess(devices[b], 0) != cudaSuccess) cudaGetLastError();   // already enabled: fine
+      }
+    }
   cudaSetDevice((*out)->dev);
   return SEQJ_OK;
 }
@@ -717,6 +729,9 @@ int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngro
 static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids,
                              int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                              const uint8_t* group_mask, seqj_result** out);
+static int fuse_impl(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
+                     const int32_t* mst_j, const double* mst_w, const double* pack_dev, const int32_t* slot_of_group,
+                     double eps_floor, seqj_result** out);
 
 // Single-process multi-GPU: whole (metric, scale) groups are assigned to the devices of the handle by an LPT
 // greedy on estimated cost, one host thread per device runs the masked sequence, the per-group (eta, MST) are
@@ -765,20 +780,79 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   std::vector<seqj_result*> parts(ndev, nullptr);
   std::vector<int> status(ndev, SEQJ_OK);
   while ((int)h->workers.size() < ndev - 1) h->workers.push_back(new DeviceWorker());
-  auto run_device = [&](int d) {
-    bool any = false;
-    for (uint8_t b : masks[d]) any |= b != 0;
-    if (!any) return;
-    status[d] = sequence_host_one(hs[d], A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh,
-                                  masks[d].data(), &parts[d]);
-  };
   for (int d = 0; d < ndev; ++d) {
     hs[d]->grid = h->grid;
     hs[d]->periods = h->periods;
   }
-  for (int d = 1; d < ndev; ++d) h->workers[d - 1]->post([&, d]() { run_device(d); });
-  run_device(0);                                          // the primary device runs on the calling thread
+  // Every device uploads 1/ndev of the objects over its own PCIe link, then pulls the other slabs from its peers over
+  // NVLink; the group results are exchanged in the device format (pack slots) and the primary device fuses from them.
+  const int64_t rows = (N + ndev - 1) / ndev;                        // objects per slab
+  auto slab_lo = [&](int d) { return std::min<int64_t>(N, (int64_t)d * rows); };
+  auto slab_hi = [&](int d) { return std::min<int64_t>(N, (int64_t)(d + 1) * rows); };
+  int cap = 1;
+  for (int d = 0; d < ndev; ++d) {
+    int n = 0;
+    for (uint8_t b : masks[d]) n += b != 0;
+    cap = std::max(cap, n);
+  }
+  const int64_t pstride = 2 * N;
+  std::vector<std::unique_ptr<DevPool>> pools(ndev);
+  std::vector<double*> A_dev(ndev, nullptr), pack(ndev, nullptr);
+  std::vector<float> h2d_ms(ndev, 0.f);
+  auto fail_dev = [&](int d, cudaError_t e, const char* what) {
+    hs[d]->err = std::string(what) + ": " + cudaGetErrorString(e);
+    status[d] = (e == cudaErrorMemoryAllocation) ? SEQJ_E_OOM : SEQJ_E_CUDA;
+  };
+  auto phase_upload = [&](int d) {
+    seqj_handle* hd = hs[d];
+    if (check_ready(hd) != SEQJ_OK) { status[d] = SEQJ_E_CUDA; return; }
+    pools[d].reset(new DevPool(hd));
+    cudaError_t e = pools[d]->alloc(&A_dev[d], (size_t)M * N);
+    if (e == cudaSuccess) e = pools[d]->alloc(&pack[d], (size_t)cap * pstride);
+    if (e != cudaSuccess) { fail_dev(d, e, "device allocation"); return; }
+    const int64_t lo = slab_lo(d), hi = slab_hi(d);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    cudaEventRecord(e0, hd->st);
+    if (hi > lo) {
+      const double* src = A + lo * M;
+      double* dst = A_dev[d] + lo * M;
+      const size_t bytes = (size_t)(hi - lo) * M * 8;
+      const bool staged = bytes >= (size_t(4) << 20) && !host_pointer_is_pinned(src);
+      e = staged ? upload_pageable(hd->upload, hd->dev, dst, src, bytes, hd->st)
+                 : cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, hd->st);
+    }
+    cudaEventRecord(e1, hd->st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(hd->st);
+    if (e == cudaSuccess) cudaEventElapsedTime(&h2d_ms[d], e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) fail_dev(d, e, "H2D copy");
+  };
+  auto phase_compute = [&](int d) {
+    seqj_handle* hd = hs[d];
+    bool any = false;
+    for (uint8_t b : masks[d]) any |= b != 0;
+    if (!any || status[d] != SEQJ_OK) return;
+    cudaSetDevice(hd->dev);
+    for (int e = 0; e < ndev; ++e) {                                // all-gather of the slabs over NVLink (peer copies)
+      if (e == d || slab_hi(e) <= slab_lo(e)) continue;
+      cudaError_t ce = cudaMemcpyPeerAsync(A_dev[d] + slab_lo(e) * M, hd->dev, A_dev[e] + slab_lo(e) * M, hs[e]->dev,
+                                           (size_t)(slab_hi(e) - slab_lo(e)) * M * 8, hd->st);
+      if (ce != cudaSuccess) { fail_dev(d, ce, "peer copy of A"); return; }
+    }
+    status[d] = sequence_impl(hd, A_dev[d], M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, masks[d].data(),
+                              nullptr, nullptr, nullptr, 0, &parts[d], pack[d]);
+  };
+  for (int d = 1; d < ndev; ++d) h->workers[d - 1]->post([&, d]() { phase_upload(d); });
+  phase_upload(0);                                                  // the primary device runs on the calling thread
   for (int d = 1; d < ndev; ++d) h->workers[d - 1]->wait();
+  bool upload_ok = true;
+  for (int d = 0; d < ndev; ++d) upload_ok = upload_ok && status[d] == SEQJ_OK;
+  if (upload_ok) {
+    for (int d = 1; d < ndev; ++d) h->workers[d - 1]->post([&, d]() { phase_compute(d); });
+    phase_compute(0);
+    for (int d = 1; d < ndev; ++d) h->workers[d - 1]->wait();
+  }
   cudaSetDevice(h->dev);
   for (int d = 0; d < ndev; ++d)
     if (status[d] != SEQJ_OK) {
@@ -787,18 +861,24 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
       for (auto* r : parts) delete r;
       return st;
     }
-  // merge the groups, then fuse on the primary device
-  std::vector<double> etas(G), mw((size_t)G * (N - 1));
-  std::vector<int32_t> mi((size_t)G * (N - 1)), mj((size_t)G * (N - 1));
-  for (int g = 0; g < G; ++g) {
-    const GroupRes& gr = parts[owner[g]]->groups[g];
-    etas[g] = gr.eta;
-    std::copy(gr.mst_i.begin(), gr.mst_i.end(), mi.begin() + (size_t)g * (N - 1));
-    std::copy(gr.mst_j.begin(), gr.mst_j.end(), mj.begin() + (size_t)g * (N - 1));
-    std::copy(gr.mst_w.begin(), gr.mst_w.end(), mw.begin() + (size_t)g * (N - 1));
+  // gather the pack slots on the primary device (peer copies over NVLink), fuse from the device buffer
+  double* gathered = nullptr;
+  {
+    cudaError_t e = pools[0]->alloc(&gathered, (size_t)ndev * cap * pstride);
+    for (int d = 0; d < ndev && e == cudaSuccess; ++d)
+      e = cudaMemcpyPeerAsync(gathered + (size_t)d * cap * pstride, h->dev, pack[d], hs[d]->dev, (size_t)cap * pstride * 8, h->st);
+    if (e != cudaSuccess) {
+      for (auto* r : parts) delete r;
+      return fail(h, SEQJ_E_CUDA, std::string("gather of the group results: ") + cudaGetErrorString(e));
+    }
+  }
+  std::vector<int32_t> slot_of(G, 0);
+  {
+    std::vector<int> seen(ndev, 0);
+    for (int g = 0; g < G; ++g) slot_of[g] = owner[g] * cap + seen[owner[g]]++;
   }
   seqj_result* fin = nullptr;
-  int st = seqj_fuse(h, N, G, etas.data(), mi.data(), mj.data(), mw.data(), eps_floor, &fin);
+  int st = fuse_impl(h, N, G, nullptr, nullptr, nullptr, nullptr, gathered, slot_of.data(), eps_floor, &fin);
   if (st != SEQJ_OK) {
     for (auto* r : parts) delete r;
     return st;
@@ -820,7 +900,10 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
     fin->in_max = std::max(fin->in_max, parts[d]->in_max);
     delete parts[d];
   }
-  fin->timers[SEQJ_T_TOTAL] = slowest + fuse_total;
+  float h2d = 0.f;
+  for (float x : h2d_ms) h2d = std::max(h2d, x);
+  fin->timers[SEQJ_T_H2D] = h2d;
+  fin->timers[SEQJ_T_TOTAL] = h2d + slowest + fuse_total;
   *out = fin;
   return SEQJ_OK;
 }
