@@ -103,6 +103,14 @@ int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M);
 int seqj_plan_describe(int64_t M, const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,
                        const uint8_t* group_mask, int64_t mats, int hier, char* buf, int64_t buflen);
 
+/* Group-major sharding plan (pure host code): owner_out[k * nscales + l] = rank in [0, world) that computes the
+ * (metric, scale) group of the loop src/sequencer.jl:194-196.  EMD-type groups are units of their own; a contraction
+ * metric over nested scales stays on one rank (its coarse scales are derived from the finest there) unless cutting
+ * the chain balances the ranks better.  load_out (may be NULL): modelled cost per rank, in picoseconds per N^2 matrix
+ * entry.  The one-process-per-GPU driver (sharding.py) and the single-process multi-device handle use the same plan. */
+int seqj_plan_shards(int64_t M, const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales, int world,
+                     int32_t* owner_out, double* load_out);
+
 /* Limit the device memory the handle may use for chunk matrices (bytes; 0 = auto from free memory). */
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes);
 
@@ -195,6 +203,10 @@ int seqj_fuse_dev(seqj_handle* h, int64_t N, int ngroups, const double* pack_dev
 int seqj_result_dims(const seqj_result* r, int64_t* N, int* ngroups);
 int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale, int* nchunks,
                            int* computed);
+/* device time attributed to group g in milliseconds -- its own distance / derivation kernels plus its share of the
+ * batched MST + combine launches it took part in: the `tt = @elapsed` the reference prints per group
+ * (src/sequencer.jl:210,260) */
+int seqj_result_group_elapsed(const seqj_result* r, int g, double* ms);
 /* chunks of group g held by this result: [0, nchunks) except after seqj_sequence_partial */
 int seqj_result_group_range(const seqj_result* r, int g, int* chunk_lo, int* chunk_hi);
 /* eta_chunk[nchunks], root_chunk[nchunks], parents_chunk[nchunks*N] (BFS-tree parent of each

@@ -25,6 +25,7 @@ SIGNATURES = {
     "seqj_destroy": (None, [vp]),
     "seqj_last_error": (C.c_char_p, [vp]),
     "seqj_plan_describe": (C.c_int, [C.c_int64, c_ip, C.c_int, c_ip, C.c_int, c_u8p, C.c_int64, C.c_int, C.c_char_p, C.c_int64]),
+    "seqj_plan_shards": (C.c_int, [C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_int, c_ip, c_dp]),
     "seqj_set_workspace_limit": (C.c_int, [vp, C.c_uint64]),
     "seqj_release_workspace": (C.c_int, [vp]),
     "seqj_set_grid": (C.c_int, [vp, c_dp, C.c_int64]),
@@ -47,6 +48,7 @@ SIGNATURES = {
     "seqj_result_dims": (C.c_int, [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int)]),
     "seqj_result_group_info": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                          C.POINTER(C.c_int)]),
+    "seqj_result_group_elapsed": (C.c_int, [vp, C.c_int, c_dp]),
     "seqj_result_group_range": (C.c_int, [vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "seqj_result_group_chunks": (C.c_int, [vp, C.c_int, c_dp, c_ip, c_ip]),
     "seqj_result_group": (C.c_int, [vp, C.c_int, c_dp, c_ip, c_ip, c_ip, c_ip, c_dp]),

@@ -291,7 +291,7 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
     ngroups = C.c_int()
     n64 = C.c_int64()
     handle.check(lib.seqj_result_dims(res, C.byref(n64), C.byref(ngroups)))
-    EOSeg, EOAlgScale, group_msts = {}, {}, {}
+    EOSeg, EOAlgScale, group_msts, group_ms = {}, {}, {}, {}
     by_id = dict(_BY_ID)
     by_id.update({m.id: m for m in (metrics or ()) if isinstance(m, PeriodicEuclidean)})
     for g in range(ngroups.value):
@@ -309,6 +309,9 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
         handle.check(lib.seqj_result_group_chunks(res, g, _lib.dptr(etas), _lib.iptr(roots), _lib.iptr(pars)))
         EOSeg[key] = (etas.tolist(), [BFSTree(int(roots[c]), pars[c]) for c in range(nloc)])
         chunk_ranges[key] = (lo.value, hi.value)
+        gms = C.c_double()
+        handle.check(lib.seqj_result_group_elapsed(res, g, C.byref(gms)))
+        group_ms[key] = gms.value
         if partial:
             continue
         eta = C.c_double(); root = C.c_int32()
@@ -342,6 +345,7 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
                             group_msts)
         r.chunk_ranges = chunk_ranges
         r.probes = probe_vals
+        r.group_ms = group_ms
         return r
     eta = C.c_double(); root = C.c_int32()
     order_ = np.empty(N, dtype=np.int32); par = np.empty(N, dtype=np.int32)
@@ -352,6 +356,7 @@ def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
                         root.value, par, timings, launches.value, group_msts)
     r._lazy = (handle, res)        # the result object now owns the C result until the triplets are fetched
     r.probes = probe_vals
+    r.group_ms = group_ms
     return r
 
 
@@ -472,8 +477,8 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
     r = _sequence(At, scales, metrics, handle)
     if orig is not None and r.timings.get("input_min", 1.0) < JULIA_EPS:
         np.maximum(orig, JULIA_EPS, out=orig)            # clamp!(A, eps(), typemax): caller-visible (sequencer.jl:130)
-    for (m, l), (eta, _) in r.EOAlgScale.items():
-        logger.info("%s at scale %d: η = %.4g", m, l, eta)
+    for (m, l), (eta, _) in r.EOAlgScale.items():       # "$(k) at scale $(l): η = ... (...s)"  (src/sequencer.jl:260)
+        logger.info("%s at scale %d: η = %.4g (%.2gs)", m, l, eta, r.group_ms.get((m, l), 0.0) * 1e-3)
     logger.info("Final: η = %.4g sequence = %s", r.eta, prettyp(r.order, 5))
     return r
 

@@ -81,6 +81,7 @@ struct GroupRes {
   int32_t root = 0;
   std::vector<int32_t> parents, mst_i, mst_j;
   std::vector<double> mst_w;
+  double elapsed_ms = 0;              // device time attributed to this group (the reference's `tt = @elapsed`, src/sequencer.jl:210)
 };
 
 struct seqj_result {
@@ -176,15 +177,17 @@ struct DevPool {
 };
 
 struct PhaseTimer {
-  struct Span { int phase; cudaEvent_t a, b; };
+  struct Span { int phase, group, wave; cudaEvent_t a, b; };
   std::vector<Span> spans;
   cudaStream_t* cur;             // the context's current stream
+  int group = -1, wave = -1;     // tags of the spans opened from now on: (metric, scale) group / wave they belong to
+  std::vector<double> group_ms, wave_ms;   // filled by collect(): time of the spans tagged with a group / only a wave
   explicit PhaseTimer(cudaStream_t* s) : cur(s) {}
   ~PhaseTimer() {
     for (auto& s : spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   }
   int begin(int phase) {
-    Span s; s.phase = phase;
+    Span s; s.phase = phase; s.group = group; s.wave = wave;
     cudaEventCreate(&s.a); cudaEventCreate(&s.b);
     cudaEventRecord(s.a, *cur);
     spans.push_back(s);
@@ -197,6 +200,10 @@ struct PhaseTimer {
       float ms = 0;
       if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) {
         timers[s.phase] += ms;
+        if (s.phase != SEQJ_T_TOTAL && s.phase != SEQJ_T_D2H) {
+          if (s.group >= 0) { if ((int)group_ms.size() <= s.group) group_ms.resize(s.group + 1, 0.0); group_ms[s.group] += ms; }
+          else if (s.wave >= 0) { if ((int)wave_ms.size() <= s.wave) wave_ms.resize(s.wave + 1, 0.0); wave_ms[s.wave] += ms; }
+        }
         if (trace) {
           float at = 0;
           cudaEventElapsedTime(&at, spans[0].a, s.a);

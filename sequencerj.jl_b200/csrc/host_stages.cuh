@@ -84,14 +84,12 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   bp.bestp = reinterpret_cast<unsigned long long*>(g.wd2); bp.stuck = g.anc1; bp.needy = g.dep0;
   bp.ncount = ncount; bp.ecount = ecount; bp.done = done; bp.nresc = g.knn_flags + 3 * g.knn_cap;
   // launches of few graphs may rescan freely (a row costs the same 8N bytes however many graphs share the launch,
-  // and Prim would be latency-bound there).  In a large batch a graph that asks for more than N/2 rows in total is
-  // handed to the batched Prim: that is the signature of tight clusters of near-equidistant objects (every vertex of
-  // a cluster runs out of list while the cluster is still merging internally, round after round), where Prim's single
-  // pass over the matrix wins (profiles/r02_mst.md: 50 clusters of 200: Prim 42 ms, unlimited rescans 99-104 ms,
-  // this budget ~60 ms = one wasted list pass); smooth families and images stay below it.
+  // and Prim would be latency-bound there).  In a large batch a graph may re-read two matrices worth of rows before it
+  // is handed to the batched Prim, whose N dependent steps cost 25-65 ms whatever the number of graphs: with rescans
+  // only when a graph is completely blocked and one list entry per component (kernels_mst.cuh), structured inputs
+  // stay well below that (profiles/r02_mst.md)
   const char* benv = getenv("SEQJ_KNN_BUDGET");
-  bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : std::max(16, g.N / 2));
-  bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
+  bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : 2 * g.N);
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
   const dim3 grid_rescan((unsigned)gx, (unsigned)nb);

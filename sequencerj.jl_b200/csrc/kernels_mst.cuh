@@ -304,9 +304,11 @@ __global__ void __launch_bounds__(kBorKnnThreads, 1) boruvka_knn_kernel(BorKnnPa
     __syncthreads();
     const int ec = s_count, nd = s_needy, hk = s_hooks;
     __syncthreads();
+    // Keep going while any component hooks: the stuck ones wait (others may hook onto them) and the launch only asks
+    // for a rescan once nothing moves any more.  (Round 1 returned at the first needy vertex; on clustered data that
+    // spent the fixed schedule of launches on a handful of rows each and rescanned clusters that were still merging.)
     if (ec == N - 1) status = 1;
-    else if (nd > 0) status = 2;
-    else if (hk == 0) status = 3;
+    else if (hk == 0) status = (nd > 0) ? 2 : 3;
   }
   if (p.use_smem)
     for (int v = tid; v < N; v += kBorKnnThreads) compg[v] = comp[v];

@@ -33,6 +33,7 @@ using namespace seqj;
 #include "host_upload.cuh"
 #include "host_core.cuh"
 #include "host_plan.cuh"
+#include "host_shard.cuh"
 #include "host_stages.cuh"
 
 
@@ -213,6 +214,18 @@ int seqj_plan_describe(int64_t M, const int32_t* metric_ids, int nmetrics, const
   }
   if ((int64_t)o.size() + 1 > buflen) return SEQJ_E_BADARG;
   std::memcpy(buf, o.c_str(), o.size() + 1);
+  return SEQJ_OK;
+}
+
+int seqj_plan_shards(int64_t M, const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales, int world,
+                     int32_t* owner_out, double* load_out) {
+  if (!metric_ids || !scales || !owner_out || nmetrics < 1 || nscales < 1 || M < 1 || world < 1) return SEQJ_E_BADARG;
+  for (int l = 0; l < nscales; ++l) if (scales[l] < 1 || scales[l] > M) return SEQJ_E_BADARG;
+  std::vector<int> owner;
+  std::vector<double> load;
+  plan_shards(M, metric_ids, nmetrics, scales, nscales, world, owner, &load);
+  for (int g = 0; g < nmetrics * nscales; ++g) owner_out[g] = owner[g];
+  if (load_out) for (int r = 0; r < world; ++r) load_out[r] = load[r];
   return SEQJ_OK;
 }
 
@@ -505,9 +518,11 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   hmark("setup done");
   for (size_t wi = 0; wi < plan.waves.size(); ++wi) {
     PlanWave& w = plan.waves[wi];
+    c.timer.wave = (int)wi;
     for (auto& sg : w.segs) {
       const ScaleLayout& L = layouts[sg.l];
       double* Dseg = Mpool + (size_t)sg.slot0 * mat_elems;
+      c.timer.group = sg.g;                          // distance / derive spans are charged to the segment's group
       if (sg.src_slot0 >= 0) {
         // derived from the chunks of the next finer scale (resident in this wave or in the carry slots)
         if (fv_scale != sg.src_l) {
@@ -524,6 +539,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
       ST_TRY(run_distance(c, metric_ids[sg.k], L, pb, tiles_dev, (int)tiles.size(), N, Dseg, ldD, (int64_t)mat_elems, sg.c0,
                           sg.c1 - sg.c0, eps_floor, l2_thresh, 0, fb));
     }
+    c.timer.group = -1;                              // measure / combine spans: charged to the wave, split by task count
     hmark("dist queued");
     ST_TRY(check_input());
     hmark("input checked");
@@ -574,6 +590,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
                          sslot_dev + a));
     }
   }
+  c.timer.wave = -1;
   int n_derived_done = 0;
   for (int g = 0; g < G; ++g) n_derived_done += group_derived[g];
   if (do_final)
@@ -664,6 +681,15 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     }
   if (do_final) stash_triplets(r, G, ldp, h_msti, h_mstj, h_val);
   c.timer.collect(r->timers);
+  // per-group elapsed time (the reference prints `tt = @elapsed` of the group's chunk loop, src/sequencer.jl:210,260):
+  // the group's own distance / derive kernels plus its share (by chunk count) of its waves' batched measure + combine
+  for (int g = 0; g < G; ++g)
+    if ((int)c.timer.group_ms.size() > g) r->groups[g].elapsed_ms = c.timer.group_ms[g];
+  for (size_t wi = 0; wi < plan.waves.size(); ++wi) {
+    const PlanWave& w = plan.waves[wi];
+    if (c.timer.wave_ms.size() <= wi || w.ntasks == 0) continue;
+    for (auto& sg : w.segs) r->groups[sg.g].elapsed_ms += c.timer.wave_ms[wi] * (double)(sg.c1 - sg.c0) / (double)w.ntasks;
+  }
   r->launches = c.launches;
   r->in_min = st0p->minv; r->in_max = st0p->maxv;       // check_input() ran before the first Prim launch
   r->derived_groups = n_derived_done;
@@ -742,41 +768,11 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
   std::vector<seqj_handle*> hs;
   hs.push_back(h);
   for (auto* p : h->peers) hs.push_back(p);
-  // Units of work: every EMD group; every other group -- or, when the scales nest (each chunk length a multiple
-  // of the next finer one), all scales of a contraction metric together, because only the finest scale runs
-  // DMMA tiles and the others are derived from it on the same GPU.  LPT greedy on estimated cost.
-  auto nchunks_of = [&](int l) { const int64_t sc = std::max(1, scales[l]); const int64_t cl = (M + sc - 1) / sc; return (M + cl - 1) / cl; };
-  std::vector<int64_t> cls;
-  for (int l = 0; l < nscales; ++l) { const int64_t sc = std::max(1, scales[l]); cls.push_back((M + sc - 1) / sc); }
-  std::sort(cls.begin(), cls.end());
-  cls.erase(std::unique(cls.begin(), cls.end()), cls.end());
-  bool nested = cls.size() > 1;
-  for (size_t q = 1; q < cls.size(); ++q) nested = nested && (cls[q] % cls[q - 1] == 0);
-  struct Unit { double cost; std::vector<int> groups; };
-  std::vector<Unit> units;
-  for (int k = 0; k < nmetrics; ++k) {
-    const bool emd = metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_EMD_GRID || metric_ids[k] == SEQJ_PERIODIC;
-    const bool contraction = metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_ENERGY;
-    if (nested && contraction) {
-      Unit u;
-      double graphs = 0;
-      for (int l = 0; l < nscales; ++l) { u.groups.push_back(k * nscales + l); graphs += (double)nchunks_of(l) + 1; }
-      u.cost = 1.45 * (double)M + 0.15 * (double)M * (nscales - 1) + 150.0 * graphs;
-      units.push_back(u);
-    } else {
-      for (int l = 0; l < nscales; ++l)
-        units.push_back({(emd ? 2.0 : 1.0) * (double)M + 600.0 * (double)(nchunks_of(l) + 1), {k * nscales + l}});
-    }
-  }
-  std::stable_sort(units.begin(), units.end(), [](const Unit& a, const Unit& b) { return a.cost > b.cost; });
+  // which device owns which group: cost-model LPT over EMD groups and (sub-)chains of the contraction metrics (host_shard.cuh)
+  std::vector<int> owner;
+  plan_shards(M, metric_ids, nmetrics, scales, nscales, ndev, owner, nullptr);
   std::vector<std::vector<uint8_t>> masks(ndev, std::vector<uint8_t>(G, 0));
-  std::vector<double> load(ndev, 0.0);
-  std::vector<int> owner(G, 0);
-  for (auto& u : units) {
-    const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
-    for (int g : u.groups) { masks[d][g] = 1; owner[g] = d; }
-    load[d] += u.cost;
-  }
+  for (int g = 0; g < G; ++g) masks[owner[g]][g] = 1;
   std::vector<seqj_result*> parts(ndev, nullptr);
   std::vector<int> status(ndev, SEQJ_OK);
   while ((int)h->workers.size() < ndev - 1) h->workers.push_back(new DeviceWorker());
@@ -1056,6 +1052,11 @@ int seqj_result_group_info(const seqj_result* r, int g, int* metric, int* scale,
   if (scale) *scale = gr.scale;
   if (nchunks) *nchunks = gr.nchunks;
   if (computed) *computed = gr.computed;
+  return SEQJ_OK;
+}
+int seqj_result_group_elapsed(const seqj_result* r, int g, double* ms) {
+  if (!r || !ms || g < 0 || g >= (int)r->groups.size()) return SEQJ_E_BADARG;
+  *ms = r->groups[g].elapsed_ms;
   return SEQJ_OK;
 }
 int seqj_result_group_range(const seqj_result* r, int g, int* chunk_lo, int* chunk_hi) {

@@ -54,22 +54,23 @@ def assign_groups(costs: np.ndarray, world: int, bundles=None) -> np.ndarray:
     return owner
 
 
-def plan_groups(M: int, metrics, scales, world: int) -> np.ndarray:
-    """Group-major plan.  When the scales nest, all scales of a contraction metric (L2, KL, Energy) form one
-    unit: only its finest scale runs DMMA tiles, the others are derived on the same GPU; EMD groups stay
-    individual units (every EMD scale runs the tile kernel)."""
-    costs = group_costs(M, metrics, scales)
-    if not scales_chain_nested(M, scales):
-        return assign_groups(costs, world)
-    bundles = []
-    for k, m in enumerate(metrics):
-        if m.id in (0, 2, 3):
-            # finest scale: tiles at ~70 % efficiency for short chunks; each derived scale: one HBM-bound pass
-            cst = 1.45 * M + 0.15 * M * (len(scales) - 1) + PRIM_COST_ROWS * sum(nchunks(M, s) + 1 for s in scales) / 4
-            bundles.append((cst, [(k, l) for l in range(len(scales))]))
-        else:
-            bundles += [(costs[k, l], [(k, l)]) for l in range(len(scales))]
-    return assign_groups(costs, world, bundles)
+def plan_groups(M: int, metrics, scales, world: int, with_load: bool = False):
+    """Group-major plan, owner[k, l]: the library's cost-model LPT (seqj_plan_shards, csrc/host_shard.cuh -- pure
+    host code, also used by the single-process multi-device handle).  EMD groups are individual units; a contraction
+    metric over nested scales stays on one rank (only its finest scale runs DMMA tiles, the others are derived
+    there) unless cutting the chain balances the ranks better."""
+    from . import _lib
+    lib = _lib.load()
+    mids = np.array([m.id for m in metrics], dtype=np.int32)
+    scs = np.array([int(s) for s in scales], dtype=np.int32)
+    owner = np.zeros(len(mids) * len(scs), dtype=np.int32)
+    load = np.zeros(world)
+    st = lib.seqj_plan_shards(int(M), _lib.iptr(mids), len(mids), _lib.iptr(scs), len(scs), int(world), _lib.iptr(owner),
+                              _lib.dptr(load))
+    if st != 0:
+        raise ValueError("seqj_plan_shards: bad arguments")
+    owner = owner.reshape(len(mids), len(scs)).astype(np.int64)
+    return (owner, load) if with_load else owner
 
 
 def merge_group_results(parts, metrics, scales):

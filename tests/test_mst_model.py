@@ -45,6 +45,43 @@ def test_model_returns_the_reference_tree(oracle, name, D):
     assert all(wref[(a, b)] == w for a, b, w in edges)
 
 
+@pytest.mark.parametrize("name,D", list(_cases()), ids=[c[0] for c in _cases()])
+def test_round2_rescan_rules_return_the_reference_tree(oracle, name, D):
+    """The round-2 kernels rescan a row only when its graph is completely blocked and keep ONE list entry per
+    component in a rescanned list (kernels_mst.cuh): still the reference's tree, ties included, with fewer rescans."""
+    D = D.copy()
+    np.fill_diagonal(D, 1e-6)
+    ei, ej, ew = oracle.kruskal_mst(D)
+    ref = set(zip(ei.tolist(), ej.tolist()))
+    counts = {}
+    for dedupe, lazy in ((False, False), (True, False), (False, True), (True, True)):
+        lists, bound = model.knn_lists(D)
+        edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True, dedupe=dedupe, lazy=lazy)
+        assert ncomp == 1 and {(a, b) for a, b, _ in edges} == ref, (dedupe, lazy)
+        counts[(dedupe, lazy)] = model.boruvka.last_rescans
+    assert counts[(True, True)] <= counts[(False, False)]
+
+
+def test_dedupe_cuts_rescans_of_tight_clusters(oracle):
+    """20 tight clusters of 30 near-equidistant objects (more than the 16 list entries): with one entry per component
+    a rescanned row sees the lightest edge into each of the other clusters at once instead of running dry again after
+    a merge -- one pass over the rows instead of ~1.5."""
+    rng = np.random.default_rng(11)
+    centers = rng.random((64, 20))
+    A = np.abs(np.repeat(centers, 30, axis=1) * (1 + 0.01 * rng.standard_normal((64, 600))))
+    D = np.sqrt(((A[:, :, None] - A[:, None, :]) ** 2).sum(0)) + 1e-6
+    np.fill_diagonal(D, 1e-6)
+    ei, ej, _ = oracle.kruskal_mst(D)
+    res = {}
+    for key, (dedupe, lazy) in {"r01": (False, False), "r02": (True, True)}.items():
+        lists, bound = model.knn_lists(D)
+        edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True, dedupe=dedupe, lazy=lazy)
+        assert ncomp == 1 and {(a, b) for a, b, _ in edges} == set(zip(ei.tolist(), ej.tolist()))
+        res[key] = model.boruvka.last_rescans
+    assert res["r02"] < res["r01"], res
+    assert res["r02"] <= D.shape[0], res
+
+
 def test_model_without_rescans_only_adds_mst_edges(oracle):
     """Stuck components simply stop hooking: what has been added so far is still part of the reference's tree (this
     is what makes the Prim fallback of unfinished graphs safe)."""

@@ -78,3 +78,27 @@ def test_chunk_partition_covers_every_chunk_once_even_with_idle_ranks(seqj):
             assert np.all(cover == 1), (M, scales, world, g, cover)
     lo, hi = sharding.chunk_partition(50, seqj.ALL_METRICS, (1,), 8)
     assert any(not (lo[r] < hi[r]).any() for r in range(8))          # the case ADVICE r01 flagged: idle ranks exist
+
+
+def test_shard_plan_cuts_a_chain_only_when_it_balances(seqj):
+    """seqj_plan_shards (csrc/host_shard.cuh): config 3 keeps every contraction metric whole at 2 / 4 / 8 ranks (eight
+    units of ~equal cost); config 4 (EMD + Energy, scales 1..32) on 8 ranks cuts the Energy chain into consecutive
+    sub-chains so that no rank carries all 63 Energy matrices; config 5 (two chains) uses 4 ranks by cutting both."""
+    from sequencerj_b200 import sharding
+    for world in (2, 4, 8):
+        owner, load = sharding.plan_groups(4096, seqj.ALL_METRICS, (1, 2, 4, 8, 16), world, with_load=True)
+        assert load.min() > 0 and load.sum() / (world * load.max()) > 0.9
+    scales = (1, 2, 4, 8, 16, 32)
+    owner, load = sharding.plan_groups(2048, (seqj.WASS1D, seqj.ENERGY), scales, 8, with_load=True)
+    assert owner.shape == (2, 6) and owner.min() == 0 and owner.max() == 7
+    assert len(set(owner[0].tolist())) == 6                       # every EMD group on its own rank
+    en = owner[1].tolist()                                        # scales 1..32; the chain runs 32 -> 1
+    assert len(set(en)) >= 2
+    runs = [en[i] for i in range(len(en)) if i == 0 or en[i] != en[i - 1]]
+    assert len(runs) == len(set(runs)), "a rank's Energy scales must be consecutive (a sub-chain)"
+    single = sharding.plan_groups(2048, (seqj.WASS1D, seqj.ENERGY), scales, 1, with_load=True)[1].max()
+    assert single / load.max() > 5.0                              # modelled speed-up on 8 GPUs
+    owner, load = sharding.plan_groups(512, (seqj.L2, seqj.KLD), (1, 2, 4), 4, with_load=True)
+    assert len(set(owner.reshape(-1).tolist())) == 4
+    owner1 = sharding.plan_groups(512, (seqj.L2, seqj.KLD), (1, 2, 4), 1)
+    assert np.all(owner1 == 0)

@@ -18,10 +18,13 @@ def bits(x):
     return np.ascontiguousarray(x, dtype=np.float64).view(np.uint64)
 
 
-def row_list(W, v, exclude):
+def row_list(W, v, exclude, comp=None):
     """List + bound of row v over the vertices j with exclude[j] == False, as the device builds it: 32 lanes own
     interleaved 16-byte pairs and keep their M_LOCAL smallest (w, j); L = the smallest last entry among the lanes
-    that left something unlisted; the list = the K smallest entries <= L."""
+    that left something unlisted; the list = the K smallest entries <= L.
+    With `comp` (rescans, round 2): a lane keeps at most one entry per component -- its lightest edge into it -- and
+    the merged list holds one entry per component: an edge into a component that is heavier than another edge of the
+    row into the same component can never be the row's lightest outgoing edge (components only merge)."""
     N = W.shape[0]
     lane_of = (np.arange(N) // 2) % LANES
     cand, L = [], None
@@ -29,7 +32,15 @@ def row_list(W, v, exclude):
         js = np.nonzero((lane_of == l) & ~exclude)[0]
         if len(js) == 0:
             continue
-        o = np.lexsort((js, W[v, js]))[:M_LOCAL]
+        o = np.lexsort((js, W[v, js]))
+        if comp is not None:                       # first (lightest) entry of every component, in (w, j) order
+            seen, keep = set(), []
+            for t in o:
+                c = int(comp[js[t]])
+                if c not in seen:
+                    seen.add(c); keep.append(t)
+            o = np.array(keep, dtype=np.int64)
+        o = o[:M_LOCAL]
         ent = [(int(W[v, js[t]]), int(js[t])) for t in o]
         cand += ent
         if len(ent) == M_LOCAL:       # full lane list: whatever the lane did not list is > its last entry (the
@@ -39,8 +50,17 @@ def row_list(W, v, exclude):
     cand.sort()
     if L is not None:
         cand = [e for e in cand if e <= L]
+    if comp is not None:                           # the warp merge skips what a lighter listed edge already covers
+        seen, keep = set(), []
+        for e in cand:
+            c = int(comp[e[1]])
+            if c not in seen:
+                seen.add(c); keep.append(e)
+        cand = keep
     if len(cand) > K:
         cand = cand[:K]
+        B = cand[-1][0]
+    elif len(cand) == K:
         B = cand[-1][0]
     else:
         B = L[0] if L is not None else int(NONE)
@@ -111,7 +131,9 @@ def knn_lists(D):
     return lists, bound
 
 
-def boruvka(D, lists, bound, verbose=False, rescan=True):
+def boruvka(D, lists, bound, verbose=False, rescan=True, dedupe=False, lazy=False):
+    """dedupe: rescanned lists hold one entry per component; lazy: rescan only when no component can hook any more
+    (the round-2 kernels do both; the round-1 behaviour is dedupe=False, lazy=False)."""
     N = D.shape[0]
     W = bits(np.maximum(D, EPS))
     nrescan = 0
@@ -171,15 +193,16 @@ def boruvka(D, lists, bound, verbose=False, rescan=True):
         comp = np.array([find(c) for c in comp.tolist()])
         if len(set(comp.tolist())) == 1:
             break
-        if rescan:
+        if rescan and not (lazy and nh > 0):
             for v in needy:                       # the rescan kernel runs after the round's relabelling
-                lists[v], bound[v] = row_list(W, v, comp == comp[v])
+                lists[v], bound[v] = row_list(W, v, comp == comp[v], comp if dedupe else None)
                 ptr[v] = 0
             nrescan += len(needy)
         if rounds > 80:
             break
     if verbose:
         print(f"  rescans: {nrescan} rows = {nrescan / N:.2f} passes")
+    boruvka.last_rescans = nrescan
     return edges, len(set(comp.tolist())), rounds
 
 
