@@ -73,12 +73,12 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   int* ncount = g.knn_flags;
   int* ecount = g.knn_flags + g.knn_cap;
   int* done = g.knn_flags + 2 * g.knn_cap;
-  KnnParams kp;
+  KnnParams kp{};                                  // every field starts at 0 / nullptr
   kp.D = D; kp.ldD = ldD; kp.strideD = strideD; kp.mat_slot = mat_slot; kp.N = g.N; kp.eps_floor = eps_floor; kp.ldv = g.ldv;
   kp.lk = g.knn_lk; kp.lj = g.knn_lj; kp.cnt = g.size; kp.ptr = g.dep1;
   kp.bound = reinterpret_cast<unsigned long long*>(g.S);
   kp.comp = g.anc0; kp.needy = g.dep0; kp.ncount = ncount; kp.done = done;
-  BorKnnParams bp;
+  BorKnnParams bp{};
   bp.N = g.N; bp.ldv = g.ldv; bp.lk = g.knn_lk; bp.lj = g.knn_lj; bp.cnt = g.size; bp.bound = kp.bound;
   bp.ptr = g.dep1; bp.comp = g.anc0; bp.best = reinterpret_cast<unsigned long long*>(g.wd);
   bp.bestp = reinterpret_cast<unsigned long long*>(g.wd2); bp.stuck = g.anc1; bp.needy = g.dep0;
@@ -90,6 +90,7 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   // stay well below that (profiles/r02_mst.md)
   const char* benv = getenv("SEQJ_KNN_BUDGET");
   bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : 2 * g.N);
+  bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
   const dim3 grid_rescan((unsigned)gx, (unsigned)nb);
