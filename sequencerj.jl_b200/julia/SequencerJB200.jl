@@ -2,7 +2,8 @@
 #
 # Drop-in for the data-parallel core of SequencerJ.jl: same exported names and keyword arguments
 # (`sequence(A; scales, metrics, grid)`, `SequencerResult`, `D`, `mst`, `elong`, `order`, `L2`,
-# `WASS1D`, `KLD`, `ENERGY`, `ALL_METRICS`), with `_sequence` (reference src/sequencer.jl:184-276)
+# `WASS1D`, `KLD`, `ENERGY`, `ALL_METRICS`, `elongation`, `prettyp`, `emd`, `energy`, `ensuregrid!`; the metric
+# constants are the same Distances.jl / EMD / Energy objects), with `_sequence` (reference src/sequencer.jl:184-276)
 # replaced by ONE `ccall` into libseqj_b200.so (C ABI in include/seqj.h).  Julia is not installed in the
 # build image, so this file is syntax-reviewed only; the identical call sequence is exercised through
 # the Python ctypes mirror (sequencerj.jl_b200/api.py) by tests/test_gpu_*.py.
@@ -15,9 +16,13 @@ using Logging
 using LightGraphs
 using SimpleWeightedGraphs
 using SparseArrays: sparse
+using Distances                # the reference's metric constants ARE Distances.jl instances (src/distancemetrics.jl:234,239)
 
-export sequence, autoscale, D, mst, elong, order, prettyp, ensuregrid!, emd, energy
-export SequencerResult, L2, WASS1D, KLD, ENERGY, ALL_METRICS, PERIODIC, set_periods!, EMD, Energy
+# the reference's export list (src/SequencerJ.jl:24-31; `loss` is exported there but defined nowhere in src/)
+export sequence, autoscale, D, mst, elong, elongation, order, prettyp, ensuregrid!
+export emd, energy
+export SequencerResult, EMD, Energy
+export L2, WASS1D, KLD, ENERGY, ALL_METRICS
 
 const libseqj = get(ENV, "SEQJ_B200_LIB", joinpath(@__DIR__, "..", "libseqj_b200.so"))
 
@@ -26,35 +31,42 @@ const ϵ = 1e-6
 "Euclidean recompute threshold (reference src/distancemetrics.jl:6)."
 const L2THR = 1e-7
 
-# Metric instances: ids follow include/seqj.h (SEQJ_L2 .. SEQJ_ENERGY), names print like the reference's.
-struct B200Metric
-    id::Int32
-    name::String
-end
-Base.show(io::IO, m::B200Metric) = write(io, m.name)
-const L2 = B200Metric(0, "Euclidean(1.0e-7)")      # reference src/distancemetrics.jl:234
-const WASS1D = B200Metric(1, "EMD(nothing)")       # :247
-const KLD = B200Metric(2, "KLDivergence()")        # :239
-const ENERGY = B200Metric(3, "Energy(nothing)")    # :254
-const ALL_METRICS = (L2, WASS1D, KLD, ENERGY)      # :257
+# Metric instances are the reference's own (src/distancemetrics.jl:234-257): Distances.jl objects for Euclidean / KL,
+# the package's EMD / Energy types for the CDF distances.  `metric_id` maps them onto include/seqj.h (SEQJ_L2 ..).
+"""
+    EMD, Energy
 
-# The TYPES `EMD` / `Energy` (reference src/distancemetrics.jl:16-21, 121-132).  Passed as TYPES in `metrics`
-# (`metrics = (EMD, Energy)`, with or without `grid`) they select the grid-aware branch of the reference
-# (src/sequencer.jl:217-219): metric ids 4 / 5 + seqj_set_grid.  Their INSTANCES `EMD()` / `Energy()` are what
-# WASS1D / ENERGY are: the reference never hands them the grid (quirk Q1), each chunk gets its own unit grid.
-struct EMD
-    grid::Union{Nothing,Tuple}
+The reference's metric types (src/distancemetrics.jl:16-21, 121-132).  Passed as TYPES in `metrics`
+(`metrics = (EMD, Energy)`, with or without `grid`) they select the grid-aware branch of the reference
+(src/sequencer.jl:217-219): metric ids 4 / 5 + seqj_set_grid.  Their INSTANCES `EMD()` / `Energy()` are what WASS1D /
+ENERGY are: the reference never hands them the grid (quirk Q1), each chunk gets its own unit grid.
+"""
+struct EMD <: SemiMetric
+    grids::Union{Nothing,Tuple}
 end
 EMD() = EMD(nothing)
-struct Energy
-    grid::Union{Nothing,Tuple}
+struct Energy <: SemiMetric
+    grids::Union{Nothing,Tuple}
 end
 Energy() = Energy(nothing)
-metric_id(m::B200Metric) = m.id
+
+const L2 = Distances.Euclidean(L2THR)              # reference src/distancemetrics.jl:234
+const KLD = Distances.KLDivergence()               # :239
+const WASS1D = EMD()                               # :247
+const ENERGY = Energy()                            # :254
+const ALL_METRICS = (L2, WASS1D, KLD, ENERGY)      # :257
+"Less verbose output for PeriodicEuclidean (reference src/distancemetrics.jl:260)."
+Base.show(io::IO, s::PeriodicEuclidean) = write(io, "PeriodicEuclidean($(length(s.periods))) [$(minimum(s.periods)),$(maximum(s.periods))]")
+
+metric_id(::Distances.Euclidean) = Int32(0)        # any threshold: `Euclidean(thr)` passes thr as l2_thresh
+metric_id(::Distances.KLDivergence) = Int32(2)
+metric_id(::Distances.PeriodicEuclidean) = Int32(6)   # periods are handed to the library by `_sequence`
 metric_id(::Type{EMD}) = Int32(4)
 metric_id(::Type{Energy}) = Int32(5)
-metric_id(::EMD) = Int32(1)
-metric_id(::Energy) = Int32(3)
+metric_id(m::EMD) = m.grids === nothing ? Int32(1) : error("EMD with explicit grids is a pair functor; pass the TYPE `EMD` and `grid=` to sequence")
+metric_id(m::Energy) = m.grids === nothing ? Int32(3) : error("Energy with explicit grids is a pair functor; pass the TYPE `Energy` and `grid=` to sequence")
+metric_id(m) = error("unsupported metric $(m): the B200 path implements Euclidean, KLDivergence, PeriodicEuclidean, EMD and Energy (no CPU fallback)")
+l2_threshold(metrics) = (t = L2THR; for m in metrics; m isa Distances.Euclidean && (t = m.thresh); end; t)
 
 "Scales used in the autoscale option (reference src/sequencer.jl:148)."
 const FIB = [1,2,3,5,8,13,21,34,55,89,144,233,377,610,987,1597,2584,5168]
@@ -79,6 +91,40 @@ function prettyp(v::AbstractVector, len::Int = 3)    # reference src/utils.jl:48
     head = join(string.(v[1:len]), ",")
     tail = join(string.(v[(end-(len-1)):end]), ",")
     return join([head, tail], "...")
+end
+
+"Walk the graph from `idx`, returning the visited vertices (reference src/utils.jl:15-24)."
+function unroll(G::AbstractGraph, idx::Int; visited = Int[])
+    idx in visited && return visited
+    push!(visited, idx)
+    N = outneighbors(G, idx)
+    length(N) < 1 && length(visited) == nv(G) ? (return visited) : nothing
+    for n in N
+        unroll(G, n, visited = visited)
+    end
+    return reverse(visited)
+end
+
+"Print the sequence of outbound nodes of a graph starting from the given index (reference src/utils.jl:5-9)."
+function prettyp(G::AbstractGraph, strtidx::Int; pystyle = false)
+    arrow = G isa LightGraphs.SimpleDiGraph ? "->" : "--"
+    v = unroll(G, strtidx)
+    println(join(string.(pystyle ? reverse(v .- 1) : v), arrow))
+end
+
+"""
+    elongation(g, startidx)
+
+Half-length over half-width of the tree `g` seen from `startidx` (reference src/sequencer.jl:348-354): hop distances
+with unit weights, `hlen = mean(h)`, `hwid = mean(count per level) / 2`, both clamped to `[eps(), floatmax(Float32)]`.
+A host-side helper on an N-vertex graph (the hot path computes the same integers on the device, K6).
+"""
+function elongation(G, startidx)
+    h = gdistances(G, startidx)                      # = dijkstra_shortest_paths(G, startidx, DefaultDistance()).dists
+    hlen = clamp(sum(h) / length(h), eps(), floatmax(Float32))
+    levels = unique(h)
+    hwid = clamp(sum(count(==(k), h) for k in levels) / length(levels) / 2, eps(), floatmax(Float32))
+    return hlen / hwid + 1
 end
 
 function ensuregrid!(A, grid = nothing)::AbstractVector     # reference src/sequencer.jl:296-304
@@ -136,7 +182,8 @@ runs on the GPU behind one `ccall`.
 function sequence(A::VecOrMat{T}; scales = nothing, metrics = ALL_METRICS, grid = nothing) where {T <: Real}
     A = A isa Vector ? hcat(A...) : A
     @info "Sequencing data with\n    shape: $(size(A))\n    metric(s): $(metrics)\n    scale(s): $(scales)"
-    tuplify(x::Union{B200Metric,EMD,Energy,Type}) = tuple(x)
+    tuplify(x::PreMetric) = tuple(x)                  # reference src/sequencer.jl:126-127
+    tuplify(x::Type) = tuple(x)
     tuplify(x) = tuple(x...)
     G = ensuregrid!(A, grid)
     metrics = (metrics !== nothing) ? tuplify(metrics) : ALL_METRICS
@@ -151,7 +198,8 @@ function sequence(A::VecOrMat{T}; scales = nothing, metrics = ALL_METRICS, grid 
     r, inmin = _sequence(A64, scales, metrics, G)
     # the reference clamps the caller's array in place (src/sequencer.jl:130); the device already
     # computed on clamped values, so touch host memory only when something was below eps()
-    inmin < eps() && A isa Matrix{Float64} && clamp!(A, eps(), typemax(Float64))
+    # (any float eltype, as `clamp!(A, eps(), typemax(eltype(A)))` does; integer matrices make the reference throw)
+    inmin < eps() && eltype(A) <: AbstractFloat && clamp!(A, eltype(A)(eps()), typemax(eltype(A)))
     return r
 end
 
@@ -164,11 +212,17 @@ function _sequence(A::Matrix{Float64}, scales, metrics, grid)
         g64 = Vector{Float64}(grid)
         check(h, ccall((:seqj_set_grid, libseqj), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, g64, length(g64)))
     end
+    for m in metrics                                       # Distances.PeriodicEuclidean(periods): one period per row
+        if m isa Distances.PeriodicEuclidean
+            p64 = Vector{Float64}(m.periods)
+            check(h, ccall((:seqj_set_periods, libseqj), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, p64, length(p64)))
+        end
+    end
     res = Ref{Ptr{Cvoid}}(C_NULL)
     st = ccall((:seqj_sequence, libseqj), Cint,
                (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, Ptr{Int32}, Cint, Ptr{Int32}, Cint, Float64, Float64,
                 Ptr{UInt8}, Ref{Ptr{Cvoid}}),
-               h.ptr, A, M, N, mids, length(mids), scs, length(scs), ϵ, L2THR, C_NULL, res)
+               h.ptr, A, M, N, mids, length(mids), scs, length(scs), ϵ, l2_threshold(metrics), C_NULL, res)
     check(h, st)
     r = res[]
     try
@@ -189,7 +243,9 @@ function _sequence(A::Matrix{Float64}, scales, metrics, grid)
                            (Ptr{Cvoid}, Cint, Ref{Float64}, Ref{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
                            r, g, eta, root, par, C_NULL, C_NULL, C_NULL))
             EOAlgScale[(k, l)] = (eta[], bfs_digraph(par, root[]))
-            @info "$(k) at scale $(l): η = $(@sprintf("%.4g", eta[]))"
+            tt = Ref{Float64}(0)                                          # device time of the group = the reference's `tt = @elapsed`
+            check(h, ccall((:seqj_result_group_elapsed, libseqj), Cint, (Ptr{Cvoid}, Cint, Ref{Float64}), r, g, tt))
+            @info "$(k) at scale $(l): η = $(@sprintf("%.4g", eta[])) ($(@sprintf("%.2g", tt[] / 1000))s)"   # src/sequencer.jl:260
             g += 1
         end
         eta = Ref{Float64}(0); root = Ref{Int32}(0)
@@ -231,7 +287,7 @@ function autoscale(A::AbstractMatrix; scales = FIB, metrics = ALL_METRICS, grid 
     maxscale = M ÷ 10
     @assert maxscale > 0 "Matrix A contains too few rows ($(M)) for autoscale. The minimum is 10 rows. It is recommended to set scale=(1,)."
     bestscale, max_η = 1, 0.0
-    mets = metrics isa Union{B200Metric,EMD,Energy,Type} ? (metrics,) : tuple(metrics...)
+    mets = metrics isa Union{PreMetric,Type} ? (metrics,) : tuple(metrics...)
     G = ensuregrid!(A, grid)
     for s in filter(i -> i < maxscale, FIB)
         r, _ = _sequence(Asamp, (s,), mets, G)
@@ -255,15 +311,6 @@ function _cdf_distance(mid::Integer, u, v, uw, vw)
                    Vector{Float64}(v), Vector{Float64}(vw), length(v), out))
     out[]
 end
-# ---- Distances.PeriodicEuclidean(periods) on the B200 path (metric id 6; reference test/runtests.jl:189-236) ----
-const PERIODIC = B200Metric(6, "PeriodicEuclidean")
-"Set the periods used by the `PERIODIC` metric: `set_periods!(P); sequence(A; metrics=(PERIODIC,), scales=(1,))`."
-function set_periods!(periods::AbstractVector{<:Real})
-    h = handle()
-    p = Vector{Float64}(periods)
-    check(h, ccall((:seqj_set_periods, libseqj), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), h.ptr, p, length(p)))
-end
-
 "`emd(u, v, uw, vw)`: EMD between the weighted ECDFs on the grids `u`, `v` (reference :108)."
 emd(u, v, uw, vw) = _cdf_distance(1, u, v, uw, vw)
 "`emd(u, v)`: weights on the default unit grids `axes(u,1)`, `axes(v,1)` (reference :101)."
@@ -273,8 +320,8 @@ energy(u, v, uw, vw) = _cdf_distance(3, u, v, uw, vw)
 energy(u::AbstractVector, v = u) = _cdf_distance(3, collect(1.0:length(u)), collect(1.0:length(v)), u, v)
 
 # functor and four-argument forms of the types (reference src/distancemetrics.jl:46-50, 82-93, 143-162)
-(m::EMD)(u::AbstractVector, v::AbstractVector = u) = m.grid === nothing ? emd(u, v) : emd(m.grid[1], m.grid[2], u, v)
-(m::Energy)(u::AbstractVector, v::AbstractVector = u) = m.grid === nothing ? energy(u, v) : energy(m.grid[1], m.grid[2], u, v)
+(m::EMD)(u::AbstractVector, v::AbstractVector = u) = m.grids === nothing ? emd(u, v) : emd(m.grids[1], m.grids[2], u, v)
+(m::Energy)(u::AbstractVector, v::AbstractVector = u) = m.grids === nothing ? energy(u, v) : energy(m.grids[1], m.grids[2], u, v)
 EMD(u::AbstractVector, v::AbstractVector, uw::AbstractVector, vw::AbstractVector) = emd(u, v, uw, vw)
 Energy(u::AbstractVector, v::AbstractVector, uw::AbstractVector, vw::AbstractVector) = energy(u, v, uw, vw)
 

@@ -42,8 +42,8 @@ for name, fn in runs.items():
     for key, (etas, trees) in r.EOSeg.items():
         a, b = r.chunk_ranges[key] if name == "chunk" else (0, len(etas))
         same = same and np.allclose(etas, ref.EOSeg[key][0][a:b], rtol=1e-12)
-    if name != "chunk":                                          # group-major runs whole groups: bit-identical
-        same = same and worst == 0.0 and r.eta == ref.eta
+    if name != "chunk":                                          # group-major runs whole groups: the same trees, so the
+        same = same and worst == 0.0 and r.eta == ref.eta        # (integer-derived) etas are bit-identical
     print(f"rank {rank} {name}: match={same} worst group-eta rel diff={worst:.2e} groups here={len(r.EOAlgScale)} "
           f"timings={ {k: round(v, 1) for k, v in r.timings.items() if k.startswith('host')} }", flush=True)
     ok = ok and same

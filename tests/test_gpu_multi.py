@@ -44,8 +44,11 @@ def test_device_exchange_equals_host_fuse(seqj, handle):
         i, j, v = t
         o = np.lexsort((j, i))
         return i[o], j[o], v[o]
-    for a, b in zip(canon(fin.D_triplets), canon(ref.D_triplets)):
-        assert np.array_equal(a, b)
+    (fi, fj, fv), (ri, rj, rv) = canon(fin.D_triplets), canon(ref.D_triplets)
+    assert np.array_equal(fi, ri) and np.array_equal(fj, rj)
+    # values to rounding only: a rank that owns the coarse part of a cut chain computes its first scale by tiles where
+    # the single call derived it (~1e-13 relative in the matrix entries, hence in the MST weights behind D)
+    assert np.allclose(fv, rv, rtol=1e-9, atol=0.0)
     for p in parts:
         for key, (eta, tree) in p.EOAlgScale.items():
             assert eta == ref.EOAlgScale[key][0] and np.array_equal(tree.parents, ref.EOAlgScale[key][1].parents)
