@@ -149,6 +149,17 @@ int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N,
                   double eps_floor, double l2_thresh, const uint8_t* group_mask,
                   seqj_result** out);
 
+/* Float32 input (reference quirk Q2, SURVEY.md section 8: every image test of test/runtests.jl:56-186 passes a Float32
+ * matrix).  The reference then clamps and normalises in Float32 (`clamp!`, src/sequencer.jl:130; `S ./ sum(S, dims=1)`,
+ * :402-403), evaluates Euclidean / KL in Float32 and the ECDFs on Float32 weights, and only `.+ eps` (:226) promotes to
+ * Float64.  Here the PDFs are the same Float32 values -- Float32(a) / Float32(chunk sum), clamp in Float32 -- and
+ * everything after them runs in FP64, so results agree with the reference's to Float32 accuracy (~1e-6 relative)
+ * instead of carrying its Float32 accumulation noise; half the bytes cross PCIe.  Coarse scales are not derived from
+ * fine ones in this mode (the per-scale Float32 rounding breaks the exact nesting).  Single-device handles only. */
+int seqj_sequence_f32(seqj_handle* h, const float* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
+                      const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
+                      const uint8_t* group_mask, seqj_result** out);
+
 /* Same, with A already resident on the handle's device (device pointer, same layout). */
 int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M, int64_t N,
                       const int32_t* metric_ids, int nmetrics, const int32_t* scales, int nscales,

@@ -157,6 +157,67 @@ def clamp_input(A: np.ndarray) -> np.ndarray:
     return np.maximum(A, JULIA_EPS)
 
 
+def clamp_input_f32(A: np.ndarray) -> np.ndarray:
+    """Float32 input: `clamp!(A, eps(), typemax(Float32))` stays in Float32 (sequencer.jl:130)."""
+    A = np.array(A, dtype=np.float32)
+    if A.ndim != 2:
+        raise ValueError("A must be M x N")
+    if not (np.all(np.isfinite(A)) and np.all(A >= 0)):
+        raise AssertionError("Input data cannot contain negative, NaN or infinite values.")
+    return np.maximum(A, np.float32(JULIA_EPS))
+
+
+def splitnorm_f32(A32: np.ndarray, scale: int):
+    """_splitnorm on a Float32 matrix: `S ./ sum(S, dims=1)` evaluated in Float32 (sequencer.jl:402-403)."""
+    out = []
+    for r0, r1 in chunk_bounds(A32.shape[0], scale):
+        S = A32[r0:r1, :]
+        out.append((S / np.sum(S, axis=0, keepdims=True, dtype=np.float32)).astype(np.float32))
+    return out
+
+
+def pairwise_f32(metric: int, P: np.ndarray, l2_thresh: float = L2THR, block: int = 64) -> np.ndarray:
+    """The reference's arithmetic on Float32 chunks (quirk Q2): Distances evaluates Euclidean (Gram + threshold
+    recompute) and KLDivergence in Float32; EMD / Energy build ECDFs on Float32 weights (cumulative sums and the
+    division in Float32) and only the multiplication by the Float64 grid steps promotes (distancemetrics.jl:199-219).
+    Restated from the published algorithms; no Julia run pins the summation orders (parity unpinned)."""
+    P = np.asarray(P, dtype=np.float32)
+    m, N = P.shape
+    if metric == L2:
+        G = P.T @ P
+        sa2 = np.sum(P * P, axis=0, dtype=np.float32)
+        self_ = sa2[:, None] + sa2[None, :]
+        v = self_ - np.float32(2) * G
+        bad = v < np.float32(l2_thresh) * self_
+        np.fill_diagonal(bad, False)
+        bi, bj = np.nonzero(bad)
+        for i0 in range(0, len(bi), 4096):
+            ii, jj = bi[i0:i0 + 4096], bj[i0:i0 + 4096]
+            v[ii, jj] = np.sum((P[:, ii] - P[:, jj]) ** 2, axis=0, dtype=np.float32)
+        r = np.sqrt(np.maximum(v, np.float32(0)))
+        r = np.tril(r, -1)
+        return (r + r.T).astype(np.float64)
+    if metric == KLD:
+        r = np.zeros((N, N), dtype=np.float32)
+        for i in range(N):
+            col = P[:, i:i + 1]
+            r[i, :] = np.sum(col * np.log(col / P), axis=0, dtype=np.float32)
+        np.fill_diagonal(r, 0.0)
+        return r.astype(np.float64)
+    U = (np.cumsum(P, axis=0, dtype=np.float32) / np.sum(P, axis=0, keepdims=True, dtype=np.float32)).astype(np.float32)
+    U[-1, :] = 1.0
+    UT = np.ascontiguousarray(U.T)
+    r = np.zeros((N, N))
+    for i0 in range(0, N, block):
+        d = UT[i0:i0 + block, None, :] - UT[None, :, :]              # Float32 differences
+        if metric == EMD:
+            r[i0:i0 + block, :] = np.sum(np.abs(d).astype(np.float64), axis=2)
+        else:
+            r[i0:i0 + block, :] = math.sqrt(2.0) * np.sqrt(np.sum((d * d).astype(np.float64), axis=2))
+    np.fill_diagonal(r, 0.0)
+    return r
+
+
 def chunk_bounds(M: int, scale: int):
     """_splitnorm chunking (sequencer.jl:389-397): chunklen = cld(M,scale); starts 1:chunklen:M."""
     if scale > M:
@@ -513,7 +574,7 @@ def dense_from_edges(N, edges):
 
 
 def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=False,
-                  eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None):
+                  eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None, f32=False):
     """One (metric k, scale l) iteration of the double loop in _sequence (sequencer.jl:196-258).
     A is already clamped. Returns (GroupResult, min root-score gap)."""
     M, N = A.shape
@@ -522,8 +583,11 @@ def compute_group(A, k, l, faithful=False, faithful_root=True, keep_matrices=Fal
     eta_c, par_c, root_c, Dcs = [], [], [], []
     if grid is None:
         grid = np.arange(1, M + 1, dtype=np.float64)          # ensuregrid! default (sequencer.jl:298)
-    for P, (r0, r1) in zip(splitnorm(A, l), chunk_bounds(M, l)):
-        Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh, lgrid=grid[r0:r1], periods=periods)
+    for P, (r0, r1) in zip(splitnorm_f32(A, l) if f32 else splitnorm(A, l), chunk_bounds(M, l)):
+        if f32:
+            Dc = np.abs(pairwise_f32(k, P, l2_thresh)) + eps_floor
+        else:
+            Dc = chunk_distance(k, P, faithful, eps_floor, l2_thresh, lgrid=grid[r0:r1], periods=periods)
         if k == KLD:                     # Symmetric(dm): only the upper triangle is ever read
             Dsym = np.triu(Dc) + np.triu(Dc, 1).T
         else:
@@ -568,9 +632,11 @@ def _norm_args(scales, metrics):
 
 
 def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_root=True,
-                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None) -> OracleResult:
-    """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects)."""
-    A = clamp_input(A)
+                    keep_matrices=False, eps_floor=EPS_FLOOR, l2_thresh=L2THR, grid=None, periods=None,
+                    f32=False) -> OracleResult:
+    """_sequence (sequencer.jl:184-276) on an M x N matrix (columns = objects).  f32: the input is a Float32 matrix
+    and the chunk distances follow the reference's Float32 arithmetic (quirk Q2, pairwise_f32)."""
+    A = clamp_input_f32(A) if f32 else clamp_input(A)
     M, N = A.shape
     scales, metrics = _norm_args(scales, metrics)
     groups = []
@@ -578,7 +644,7 @@ def sequence_oracle(A, scales, metrics=ALL_METRICS, faithful=False, faithful_roo
     for k in metrics:
         for l in scales:
             g, gap = compute_group(A, k, l, faithful, faithful_root, keep_matrices, eps_floor, l2_thresh,
-                                   None if grid is None else np.asarray(grid, dtype=np.float64), periods)
+                                   None if grid is None else np.asarray(grid, dtype=np.float64), periods, f32)
             groups.append(g)
             min_gap = min(min_gap, gap)
     return fuse_groups(N, groups, faithful_root, min_gap)

@@ -34,6 +34,8 @@ SIGNATURES = {
     "seqj_result_probes": (C.c_int, [vp, c_dp, C.c_int64]),
     "seqj_sequence": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
                                 C.c_double, c_u8p, C.POINTER(vp)]),
+    "seqj_sequence_f32": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
+                                    C.c_double, c_u8p, C.POINTER(vp)]),
     "seqj_sequence_dev": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,
                                     C.c_double, c_u8p, C.POINTER(vp)]),
     "seqj_sequence_partial": (C.c_int, [vp, vp, C.c_int64, C.c_int64, c_ip, C.c_int, c_ip, C.c_int, C.c_double,

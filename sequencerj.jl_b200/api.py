@@ -281,8 +281,10 @@ def _layout_input(A):
         A = A.reshape(1, -1)
     if A.ndim != 2:
         raise ValueError("A must be a vector or an M x N matrix")
-    orig = A if (A.dtype == np.float64 and A.flags.writeable) else None
-    return np.ascontiguousarray(A.T, dtype=np.float64), orig      # no copy for a Fortran-ordered float64 A
+    orig = A if (A.dtype in (np.float64, np.float32) and A.flags.writeable) else None
+    # Float32 stays Float32 across the ABI (seqj_sequence_f32, quirk Q2); every other eltype is promoted to Float64
+    dt = np.float32 if A.dtype == np.float32 else np.float64
+    return np.ascontiguousarray(A.T, dtype=dt), orig              # no copy for a Fortran-ordered float64 / float32 A
 
 
 def _collect(handle, res, N, metrics, scales, want_final=True, partial=False):
@@ -405,6 +407,9 @@ def _sequence(At, scales, metrics, handle=None, group_mask=None, device_ptr=None
     elif device_ptr is not None:
         st = handle.lib.seqj_sequence_dev(handle.h, C.c_void_p(device_ptr), M, N, _lib.iptr(mids), len(mids),
                                           _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
+    elif At.dtype == np.float32:
+        st = handle.lib.seqj_sequence_f32(handle.h, At.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(mids), len(mids),
+                                          _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
     else:
         st = handle.lib.seqj_sequence(handle.h, At.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(mids), len(mids),
                                       _lib.iptr(scs), len(scs), EPS_FLOOR, L2THR, maskp, C.byref(res))
@@ -476,7 +481,7 @@ def sequence(A, scales=None, metrics=ALL_METRICS, grid=None, handle=None, rng=No
         assert 1 <= s <= M, f"Scale ({s}) cannot be larger than the number of data elements ({M})."
     r = _sequence(At, scales, metrics, handle)
     if orig is not None and r.timings.get("input_min", 1.0) < JULIA_EPS:
-        np.maximum(orig, JULIA_EPS, out=orig)            # clamp!(A, eps(), typemax): caller-visible (sequencer.jl:130)
+        np.maximum(orig, orig.dtype.type(JULIA_EPS), out=orig)     # clamp!(A, eps(), typemax): caller-visible (sequencer.jl:130)
     for (m, l), (eta, _) in r.EOAlgScale.items():       # "$(k) at scale $(l): η = ... (...s)"  (src/sequencer.jl:260)
         logger.info("%s at scale %d: η = %.4g (%.2gs)", m, l, eta, r.group_ms.get((m, l), 0.0) * 1e-3)
     logger.info("Final: η = %.4g sequence = %s", r.eta, prettyp(r.order, 5))

@@ -10,7 +10,7 @@
 // longest-processing-time-first.
 //
 // Cost model, in picoseconds per N^2 matrix entry (every term scales with N^2, so N drops out), from the measured
-// kernel rates of profiles/r02_*: EMD tiles 16.2 Tinstr/s, DMMA tiles 37.06 TFLOP/s x min(0.9, cl / (cl + 110)) for
+// kernel rates of profiles/r02_*: EMD tiles 16.2 Tinstr/s x cl / (cl + 18), DMMA tiles 37.06 TFLOP/s x min(0.9, cl / (cl + 110)) for
 // chunk length cl, derivation and combine 4.5 / 5.9 TB/s, MST 5.5 TB/s (8 bytes per entry and graph).
 #pragma once
 
@@ -28,7 +28,7 @@ inline double shard_cost_mst_combine(int nchunks) {
 }
 inline double shard_cost_tiles(int mid, int64_t M, int cl) {
   const bool direct = mid == SEQJ_EMD || mid == SEQJ_EMD_GRID || mid == SEQJ_PERIODIC;
-  if (direct) return (double)M / 16.2;
+  if (direct) return (double)M / (16.2 * (double)cl / ((double)cl + 18.0));   // per-tile fixed cost: 154 ms instead of 122 at cl = 64, N = 30,000
   const double eff = std::min(0.9, (double)cl / ((double)cl + 110.0));
   return (double)M / (37.06 * eff);
 }

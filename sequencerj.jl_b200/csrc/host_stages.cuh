@@ -162,6 +162,7 @@ struct PrepBufs {
   double *mass = nullptr, *sR = nullptr, *sT = nullptr;
   int64_t ldn = 0, rows_pad = 0;
   int* m_of_chunk = nullptr;
+  int f32_pdf = 0;               // Float32 input: PDFs rounded through Float32 as the reference computes them (Q2)
 };
 
 int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const ScaleLayout& L, PrepBufs& b,
@@ -173,6 +174,9 @@ int run_prep(Ctx& c, const double* A_dev, int64_t ldA, int M, int N, const Scale
   pp.sP = b.sP; pp.sU = b.sU; pp.H = b.H; pp.normalize = normalize;
   pp.grid = b.grid; pp.UwE = b.UwE; pp.UwG = b.UwG; pp.sUG = b.sUG;
   pp.mass = b.mass; pp.sR = b.sR; pp.sT = b.sT;
+  pp.need_log = b.logP != nullptr;
+  pp.need_cdf = b.Uc != nullptr || b.U != nullptr || b.UwE != nullptr || b.UwG != nullptr;
+  pp.f32_pdf = b.f32_pdf;
   int t = c.timer.begin(SEQJ_T_PREP);
   // rows [N, rows_pad) are read by TMA boxes of the last tiles: keep them zero
   const size_t tail = (size_t)(b.rows_pad - N) * L.ldX * 8;

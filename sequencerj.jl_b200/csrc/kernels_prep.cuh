@@ -54,6 +54,14 @@ __global__ void __launch_bounds__(256) input_stats_kernel(const double* __restri
   }
 }
 
+// Float32 input (reference quirk Q2: the image tests pass Float32 matrices): widen to the FP64 working copy.  The
+// reference's `clamp!(A, eps(), typemax(Float32))` (src/sequencer.jl:130) is the same clamp-on-load as for Float64:
+// eps() = 2^-52 is exactly representable in Float32.
+__global__ void __launch_bounds__(256) widen_f32_kernel(const float* __restrict__ A, int64_t n, double* __restrict__ out) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = (double)A[i];
+}
+
 struct PrepParams {
   const double* A;
   int64_t ldA;
@@ -68,6 +76,9 @@ struct PrepParams {
   double* sU;
   double* H;
   int normalize;
+  int need_log;           // log P and the entropy term (KL only): an FP64 log per element otherwise wasted
+  int need_cdf;           // the CDF pass (EMD / Energy operands and their per-chunk vectors)
+  int f32_pdf;            // Float32 input (quirk Q2): the PDF is the reference's Float32 quotient Float32(a) / Float32(sum)
   // explicit grid (reference: metrics passed as the TYPES EMD / Energy, src/sequencer.jl:217-219): per-row
   // deltas g_k - g_{k-1} of the chunk-local grid with g_0 = 0 (src/distancemetrics.jl:199-209).  Since the
   // deltas are positive, |U-V|*d = |d*U - d*V| and (U-V)^2*d = (sqrt(d)*U - sqrt(d)*V)^2: the grid only scales
@@ -104,11 +115,13 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
     double pv = 0.0, lp = 0.0;
     if (k < m) {
       const double a = fmax(src[k], kClampEps);
-      pv = p.normalize ? a / s : a;
-      lp = log(pv);
+      pv = p.normalize ? (p.f32_pdf ? (double)((float)a / (float)s) : a / s) : a;
       w += pv;
       sq += pv * pv;
-      h += pv * lp;
+      if (p.need_log) {
+        lp = log(pv);
+        h += pv * lp;
+      }
     }
     if (p.P) p.P[dst + k] = pv;
     if (p.logP) p.logP[dst + k] = lp;
@@ -119,14 +132,14 @@ __global__ void __launch_bounds__(256) prep_kernel(PrepParams p) {
 
   // pass 3: CDF by warp-shuffle inclusive scan with a running carry
   double su = 0.0, sug = 0.0, sr = 0.0, st = 0.0;
-  if (p.Uc || p.U || p.sU || p.UwE || p.UwG || p.sR) {
+  if (p.need_cdf) {
     double carry = 0.0;
     for (int base = 0; base < p.cl_pad; base += 32) {
       const int k = base + lane;
       double x = 0.0;
       if (k < m) {
         const double a = fmax(src[k], kClampEps);
-        x = p.normalize ? a / s : a;
+        x = p.normalize ? (p.f32_pdf ? (double)((float)a / (float)s) : a / s) : a;
       }
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {

@@ -248,7 +248,7 @@ static int check_ready(seqj_handle* h) {
 static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64_t N64, const int32_t* metric_ids,
                          int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                          const uint8_t* group_mask, const int32_t* chunk_lo, const int32_t* chunk_hi, double* S_out,
-                         int64_t S_stride, seqj_result** out, double* pack_out = nullptr) {
+                         int64_t S_stride, seqj_result** out, double* pack_out = nullptr, int f32_pdf = 0) {
   ST_TRY(check_ready(h));
   if (!A_dev || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M64 < 1 || N64 < 2 ||
       M64 > (1 << 30) || N64 > (1 << 30))
@@ -263,18 +263,6 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   *out = nullptr;
   Ctx c(h);
   const int G = nmetrics * nscales;
-  bool needP = false, needLog = false, needUc = false, needWE = false, needWG = false, needPer = false;
-  for (int k = 0; k < nmetrics; ++k) {
-    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_PERIODIC;
-    needPer |= metric_ids[k] == SEQJ_PERIODIC;
-    needLog |= metric_ids[k] == SEQJ_KLD;
-    needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;
-    needWE |= metric_ids[k] == SEQJ_EMD_GRID;
-    needWG |= metric_ids[k] == SEQJ_ENERGY_GRID;
-  }
-  if ((needWE || needWG) && (int64_t)h->grid.size() != M64)
-    return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of A. Got grid:" +
-                                      std::to_string(h->grid.size()) + " and A:" + std::to_string(M64));
   std::vector<ScaleLayout> layouts;
   int64_t max_ldX = 0;
   int max_chunks = 0;
@@ -282,15 +270,6 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     layouts.push_back(make_layout(M, scales[l]));
     max_ldX = std::max(max_ldX, layouts.back().ldX);
     max_chunks = std::max(max_chunks, layouts.back().nchunks);
-  }
-  if (needPer) {                  // PeriodicEuclidean(periods) only evaluates vectors of length(periods)
-    if ((int64_t)h->periods.size() != M64)
-      return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean needs one period per row. Got periods:" +
-                                        std::to_string(h->periods.size()) + " and A:" + std::to_string(M64));
-    for (int l = 0; l < nscales; ++l)
-      if (layouts[l].nchunks != 1)
-        return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean(periods) applies to whole columns only; scale " +
-                                          std::to_string(scales[l]) + " splits them into chunks of " + std::to_string(layouts[l].cl) + " rows");
   }
   const bool partial = (chunk_lo != nullptr);
   if (partial && (!chunk_hi || !S_out)) return fail(h, SEQJ_E_BADARG, "partial mode needs chunk_hi and S_out");
@@ -301,6 +280,30 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     return !group_mask || group_mask[k * nscales + l] != 0;
   };
   const bool do_final = (group_mask == nullptr) && !partial;
+  bool needP = false, needLog = false, needUc = false, needWE = false, needWG = false, needPer = false;
+  for (int k = 0; k < nmetrics; ++k) {
+    bool used = false;                            // operands only for the metrics this call (this rank) computes
+    for (int l = 0; l < nscales; ++l) used |= mask(k, l);
+    if (!used) continue;
+    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_PERIODIC;
+    needPer |= metric_ids[k] == SEQJ_PERIODIC;
+    needLog |= metric_ids[k] == SEQJ_KLD;
+    needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;
+    needWE |= metric_ids[k] == SEQJ_EMD_GRID;
+    needWG |= metric_ids[k] == SEQJ_ENERGY_GRID;
+  }
+  if ((needWE || needWG) && (int64_t)h->grid.size() != M64)
+    return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of A. Got grid:" +
+                                      std::to_string(h->grid.size()) + " and A:" + std::to_string(M64));
+  if (needPer) {                  // PeriodicEuclidean(periods) only evaluates vectors of length(periods)
+    if ((int64_t)h->periods.size() != M64)
+      return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean needs one period per row. Got periods:" +
+                                        std::to_string(h->periods.size()) + " and A:" + std::to_string(M64));
+    for (int l = 0; l < nscales; ++l)
+      if (layouts[l].nchunks != 1)
+        return fail(h, SEQJ_E_BADARG, "DimensionMismatch: PeriodicEuclidean(periods) applies to whole columns only; scale " +
+                                          std::to_string(scales[l]) + " splits them into chunks of " + std::to_string(layouts[l].cl) + " rows");
+  }
   if (partial) {                                   // S_out slot = rank of the group among the active ones (metric-major)
     const size_t need = (size_t)N64 * round_up(N64, 16);
     if (S_stride < (int64_t)need || (S_stride & 1)) return fail(h, SEQJ_E_BADARG, "S_stride too small (need N*roundup(N,16), even)");
@@ -341,6 +344,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
 
   hmark("stats queued");
   PrepBufs pb;
+  pb.f32_pdf = f32_pdf;
   ST_TRY(alloc_prep(c, pb, N, max_ldX, max_chunks, needP, needLog, needUc, false, needWE, needWG));
   hmark("alloc_prep");
   if (needWE || needWG) {
@@ -377,7 +381,9 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   PlanInput pin;
   pin.M = M; pin.nmetrics = nmetrics; pin.nscales = nscales; pin.metric_ids = metric_ids; pin.layouts = &layouts;
   pin.mask = mask; pin.c_lo = c_lo; pin.c_hi = c_hi; pin.partial = partial;
-  pin.hier = !(henv && atoi(henv) == 0);
+  // Float32 PDFs are rounded per scale (p = Float32(a) / Float32(sum)), so a coarse chunk is no longer an exact
+  // rescaling of its fine chunks: every scale runs the tile kernels in that mode
+  pin.hier = !(henv && atoi(henv) == 0) && !f32_pdf;
   pin.mats = (int64_t)(budget / (mat_elems * 8));
   pin.max_fine = kDeriveMaxFine;
   {
@@ -752,7 +758,7 @@ int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngro
   return SEQJ_OK;
 }
 
-static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids,
+static int sequence_host_one(seqj_handle* h, const void* A, int f32, int64_t M, int64_t N, const int32_t* metric_ids,
                              int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                              const uint8_t* group_mask, seqj_result** out);
 static int fuse_impl(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
@@ -912,32 +918,48 @@ int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const i
     return fail(h, SEQJ_E_BADARG, "bad argument");
   if (!h->peers.empty() && !group_mask && nmetrics * nscales > 1)
     return sequence_multi(h, A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, out);
-  return sequence_host_one(h, A, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
+  return sequence_host_one(h, A, 0, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
 }
 
-static int sequence_host_one(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids,
+int seqj_sequence_f32(seqj_handle* h, const float* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
+                      const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
+                      seqj_result** out) {
+  ST_TRY(check_ready(h));
+  if (!A || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M < 1 || N < 2)
+    return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (!h->peers.empty())
+    return fail(h, SEQJ_E_BADARG, "Float32 input is supported on single-device handles (convert to Float64 for a multi-device handle)");
+  return sequence_host_one(h, A, 1, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
+}
+
+static int sequence_host_one(seqj_handle* h, const void* A, int f32, int64_t M, int64_t N, const int32_t* metric_ids,
                              int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                              const uint8_t* group_mask, seqj_result** out) {
   ST_TRY(check_ready(h));
   if (!A || M < 1 || N < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
   DevPool pool(h);
   double* A_dev;
+  float* A32_dev = nullptr;
   CU_TRY(pool.alloc(&A_dev, (size_t)M * N));
+  if (f32) CU_TRY(pool.alloc(&A32_dev, (size_t)M * N));
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0); cudaEventCreate(&e1);
   cudaEventRecord(e0, h->st);
   // pinned / registered callers: one DMA; pageable callers (a Julia Matrix, a NumPy array): staged upload
-  const size_t abytes = (size_t)M * N * 8;
+  const size_t abytes = (size_t)M * N * (f32 ? 4 : 8);
+  void* dst = f32 ? static_cast<void*>(A32_dev) : static_cast<void*>(A_dev);
   const char* up = getenv("SEQJ_UPLOAD");
   const bool staged = !(up && !strcmp(up, "direct")) && abytes >= (size_t(4) << 20) && !host_pointer_is_pinned(A);
-  cudaError_t e = staged ? upload_pageable(h->upload, h->dev, A_dev, A, abytes, h->st)
-                         : cudaMemcpyAsync(A_dev, A, abytes, cudaMemcpyHostToDevice, h->st);
+  cudaError_t e = staged ? upload_pageable(h->upload, h->dev, dst, A, abytes, h->st)
+                         : cudaMemcpyAsync(dst, A, abytes, cudaMemcpyHostToDevice, h->st);
   cudaEventRecord(e1, h->st);
   if (e != cudaSuccess) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return fail(h, SEQJ_E_CUDA, std::string("H2D copy failed: ") + cudaGetErrorString(e));
   }
-  int s = seqj_sequence_dev(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, out);
+  if (f32) widen_f32_kernel<<<h->sm_count * 8, 256, 0, h->st>>>(A32_dev, (int64_t)M * N, A_dev);
+  int s = sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, nullptr,
+                        nullptr, nullptr, 0, out, nullptr, f32);
   if (s == SEQJ_OK) {
     float ms = 0;
     cudaEventElapsedTime(&ms, e0, e1);

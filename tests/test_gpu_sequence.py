@@ -445,3 +445,72 @@ def test_edge_object_counts(seqj, oracle, handle, N):
     the tile, derive, symmetric-combine, Prim, Euler-tour and fuse kernels all see the edge."""
     A = np.random.default_rng(1000 + N).random((48, N))
     _compare(seqj, oracle, A, (1, 2, 4), (0, 1, 2, 3))
+
+
+# ---- Float32 input (SURVEY quirk Q2; the reference's image tests, test/runtests.jl:56-186, all pass Float32) ----
+def _probe_all_chunks(rng, N, M, nmetrics, scales, per_chunk):
+    pg, pc, pi, pj = [], [], [], []
+    for k in range(nmetrics):
+        for l, sc in enumerate(scales):
+            cl = -(-M // sc)
+            for c in range(-(-M // cl)):
+                a, b = rng.integers(0, N, per_chunk), rng.integers(0, N, per_chunk)
+                keep = a != b
+                pg += [k * len(scales) + l] * int(keep.sum()); pc += [c] * int(keep.sum())
+                pi += np.minimum(a, b)[keep].tolist(); pj += np.maximum(a, b)[keep].tolist()
+    return tuple(np.array(x, dtype=np.int32) for x in (pg, pc, pi, pj))
+
+
+def test_float32_input_path_matches_the_float32_oracle(seqj, oracle, handle):
+    """A Float32 matrix crosses the ABI as Float32 (seqj_sequence_f32): PDFs are the reference's Float32 quotients,
+    everything after them runs in FP64.  Against the oracle's Float32 mode (the reference's Float32 arithmetic):
+    chunk-matrix entries agree to Float32 accuracy, and the result is a valid ordering with eta close to it;
+    against the FP64 path on the same values the difference is the Float32 rounding of the PDFs."""
+    img = np.load(os.path.join(GOLDEN, "colony_gray_u8.npy")).astype(np.float32) / np.float32(255)   # Gray{N0f8} -> Float32
+    img = img[:, :300] if img.shape[1] > 300 else img
+    A32 = np.asfortranarray(img)                               # zero pixels included: they are clamped to eps()
+    M, N = A32.shape
+    scales, mids = (1, 2, 4), (0, 1, 2, 3)
+    At32 = np.ascontiguousarray(A32.T)
+    probes = _probe_all_chunks(np.random.default_rng(5), N, M, 4, scales, 200)
+    r32 = seqj.api._sequence(At32, scales, seqj.ALL_METRICS, handle, probes=probes)
+    assert r32.timings["derived_groups"] == 0                  # per-scale Float32 rounding: no derivation in this mode
+    Ac = oracle.clamp_input_f32(A32)
+    pg, pc, pi, pj = probes
+    for g in np.unique(pg):
+        k, l = divmod(int(g), len(scales))
+        chunks = oracle.splitnorm_f32(Ac, scales[l])
+        for c in np.unique(pc[pg == g]):
+            sel = (pg == g) & (pc == c)
+            ref = np.abs(oracle.pairwise_f32(mids[k], chunks[int(c)])) + 1e-6
+            if mids[k] == 2:
+                ref = np.triu(ref) + np.triu(ref, 1).T
+            # Float32 accumulation noise of the reference path (sequential Float32 cumsum over the chunk's rows):
+            # up to ~1e-4 relative on distances, more on tiny KL values
+            atol = 3e-3 if mids[k] in (1, 3) else 5e-5        # Float32 CDFs: ~m * 6e-8 per value, summed over m rows
+            np.testing.assert_allclose(r32.probes[sel], ref[pi[sel], pj[sel]], rtol=1e-3, atol=atol)
+            # and exactly (1e-9) the FP64 formulas on the SAME Float32 PDFs
+            P = chunks[int(c)].astype(np.float64)
+            exact = np.abs(oracle.pairwise_vec(mids[k], P)) + 1e-6
+            if mids[k] == 2:
+                exact = np.triu(exact) + np.triu(exact, 1).T
+            rel_close(r32.probes[sel], exact[pi[sel], pj[sel]], 1e-9, atol=64 * P.shape[0] * 2.0 ** -53)
+    assert sorted(r32.order.tolist()) == list(range(N))
+    r64 = seqj.sequence(A32.astype(np.float64), scales=scales, metrics=seqj.ALL_METRICS, handle=handle)
+    for key, (eta, _) in r64.EOAlgScale.items():
+        assert abs(r32.EOAlgScale[key][0] - eta) <= 0.2 * eta      # same data to 1e-7: elongations of the same order
+
+
+def test_float32_hummingbird_exact_recovery(seqj, handle):
+    """The reference's only exact end-to-end test (test/runtests.jl:167-175) as the reference runs it: a Float32
+    image, shuffled columns, (L2, KLD), scales (1,2,4): the original order comes back exactly, un-mirrored."""
+    img = (np.load(os.path.join(GOLDEN, "hummingbird_gray_u8.npy")).astype(np.float32) / np.float32(255)).T   # transposed, as the test does
+    M, N = img.shape
+    perm = np.random.default_rng(12).permutation(N)
+    A = np.asfortranarray(img[:, perm])
+    B = A.copy()
+    r = seqj.sequence(B, scales=(1, 2, 4), metrics=(seqj.L2, seqj.KLD), handle=handle)
+    assert B.dtype == np.float32 and (A.min() > 0 or B.min() == np.float32(2.220446049250313e-16))   # caller-visible clamp!
+    rec = perm[r.order]
+    assert np.array_equal(rec, np.arange(N)) or np.array_equal(rec, np.arange(N)[::-1])
+    assert r.eta == float(N)

@@ -272,3 +272,29 @@ def test_oracle_invariances(oracle):
     edges = {(min(a, b), max(a, b)) for a, b in zip(r.mst[0].tolist(), r.mst[1].tolist())}
     edges_q = {(min(q[a], q[b]), max(q[a], q[b])) for a, b in zip(rq.mst[0].tolist(), rq.mst[1].tolist())}
     assert edges == edges_q
+
+
+def test_float32_oracle_mode(oracle):
+    """Quirk Q2: with a Float32 image the reference's chunk distances carry Float32 arithmetic.  The oracle's Float32
+    mode (pairwise_f32; parity unpinned, restated from the packages' algorithms) stays within Float32 accuracy of the
+    FP64 formulas on the same Float32 PDFs, and the Hummingbird recovery (test/runtests.jl:167-175, which runs on a
+    Float32 image) still holds in that mode."""
+    img = np.load(os.path.join(GOLDEN, "hummingbird_gray_u8.npy"))
+    BIG = (img.astype(np.float32) / np.float32(255)).T
+    A = oracle.clamp_input_f32(BIG[:, :120])
+    assert A.dtype == np.float32
+    for scale in (1, 4):
+        for P32 in oracle.splitnorm_f32(A, scale):
+            assert P32.dtype == np.float32
+            for met in (oracle.L2, oracle.EMD, oracle.KLD, oracle.ENERGY):
+                d32 = oracle.pairwise_f32(met, P32)
+                d64 = oracle.pairwise_vec(met, P32.astype(np.float64))
+                # a sequential Float32 cumsum over m rows is off by up to ~m * 6e-8 per CDF value, i.e. ~1e-3 absolute on
+                # an EMD summed over m = 640 rows: that noise is the reference's own in this mode
+                atol = 3e-3 if met in (oracle.EMD, oracle.ENERGY) else 5e-5      # Float32 Gram form: cancellation near the threshold
+                assert np.allclose(d32, d64, rtol=5e-4, atol=atol), (scale, met, np.abs(d32 - d64).max())
+    idx = np.random.default_rng(0).permutation(BIG.shape[1])
+    sh = BIG[:, idx]
+    r = oracle.sequence_oracle(sh, (1, 2, 4), metrics=(oracle.L2, oracle.KLD), f32=True)
+    assert np.array_equal(sh[:, r.order], BIG)
+    assert r.eta == 427.0

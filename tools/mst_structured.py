@@ -32,9 +32,12 @@ for name, A in (("smooth family", smooth()), ("50 tight clusters", clustered()))
     for mode in MODES:
         os.environ.pop("SEQJ_MST", None)
         os.environ.pop("SEQJ_KNN_ROUNDS", None)
+        os.environ.pop("SEQJ_KNN_BUDGET", None)
         for part in filter(None, mode.split(",")):
             if part.startswith("rounds="):
                 os.environ["SEQJ_KNN_ROUNDS"] = part[7:]
+            elif part.startswith("budget="):          # rows a graph of a large batch may rescan before Prim takes it
+                os.environ["SEQJ_KNN_BUDGET"] = part[7:]
             else:
                 os.environ["SEQJ_MST"] = part
         for _ in range(2):
@@ -43,5 +46,5 @@ for name, A in (("smooth family", smooth()), ("50 tight clusters", clustered()))
             ref = r
         same = np.array_equal(r.order, ref.order) and r.eta == ref.eta and all(
             r.EOAlgScale[k][0] == ref.EOAlgScale[k][0] for k in ref.EOAlgScale)
-        print(f"{name:18s} SEQJ_MST={mode or 'default':7s} total {r.timings['total']:.1f} ms prim {r.timings['prim']:.1f} ms "
+        print(f"{name:18s} SEQJ_MST={mode or 'default':16s} total {r.timings['total']:.1f} ms prim {r.timings['prim']:.1f} ms "
               f"identical_to_prim={same}", flush=True)
