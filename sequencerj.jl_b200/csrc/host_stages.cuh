@@ -94,10 +94,14 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
   const dim3 grid_rescan((unsigned)gx, (unsigned)nb);
+  // rescans keep the graph's component labels in shared memory when they fit next to a few resident CTAs
+  const size_t rescan_smem = ((size_t)g.N * 4 + 1024 <= h->max_smem) ? (size_t)g.N * 4 : 0;
+  kp.comp_in_smem = rescan_smem != 0;
+  if (rescan_smem) CU_TRY(cudaFuncSetAttribute(knn_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rescan_smem));
   knn_rows_kernel<false><<<grid_all, kKnnWarps * 32, 0, c.st>>>(kp);
   const int rounds = getenv("SEQJ_KNN_ROUNDS") ? std::max(1, atoi(getenv("SEQJ_KNN_ROUNDS"))) : kKnnRounds;
   for (int r = 0; r < rounds; ++r) {
-    if (r > 0) knn_rows_kernel<true><<<grid_rescan, kKnnWarps * 32, 0, c.st>>>(kp);
+    if (r > 0) knn_rows_kernel<true><<<grid_rescan, kKnnWarps * 32, rescan_smem, c.st>>>(kp);
     bp.first = (r == 0);
     boruvka_knn_kernel<<<nb, kBorKnnThreads, g.knn_smem, c.st>>>(bp);
   }

@@ -47,6 +47,7 @@ struct KnnParams {
   const int* needy;
   const int* ncount;
   const int* done;
+  int comp_in_smem;            // rescan: the CTA stages the graph's component labels in dynamic shared memory (4 N bytes)
 };
 
 // One warp per row.  Lane l owns the 16-byte pairs l, l + 32, ... of the row (coalesced 512-byte requests, four in
@@ -62,6 +63,7 @@ struct KnnParams {
 // into each of the 16 nearest components.
 template <bool RESCAN>
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
+  extern __shared__ int knn_comp_sm[];
   const int g = blockIdx.y, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int N = p.N;
   const int64_t gofs = (int64_t)g * p.ldv;
@@ -70,6 +72,18 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
   const int slot = p.mat_slot ? p.mat_slot[g] : g;
   const double* __restrict__ D = p.D + (int64_t)slot * p.strideD;
   const int* __restrict__ comp = RESCAN ? p.comp + gofs : nullptr;
+  if (RESCAN) {
+    // Every entry of the row that lies inside the row's own component is smaller than anything the list will keep
+    // (that is why the row ran dry), so it passes the cheap test and needs its label: on clustered data that is a
+    // dependent global load per element of a whole cluster.  The CTA therefore stages the labels once (CTA-uniform
+    // conditions: done / row count depend on the graph and blockIdx only).
+    if ((int)(blockIdx.x * kKnnWarps) >= nrows) return;
+    if (p.comp_in_smem) {
+      for (int i = threadIdx.x; i < N; i += kKnnWarps * 32) knn_comp_sm[i] = comp[i];
+      __syncthreads();
+      comp = knn_comp_sm;
+    }
+  }
   const unsigned long long eps_bits = (unsigned long long)__double_as_longlong(p.eps_floor);
   constexpr int U = 4;
   for (int r = blockIdx.x * kKnnWarps + warp; r < nrows; r += gridDim.x * kKnnWarps) {
