@@ -28,13 +28,14 @@
 extern "C" {
 #endif
 
-#define SEQJ_VERSION 100 /* 0.1.0 */
+#define SEQJ_VERSION 200 /* 0.2.0 */
 
 /* status codes */
 #define SEQJ_OK 0
 #define SEQJ_E_BADARG (-1)
 #define SEQJ_E_CUDA (-2)
-#define SEQJ_E_NCCL (-3)
+/* -3 is unused: the library issues no collective itself; the multi-process exchange (one all-gather of packed group
+ * results) belongs to the caller, see seqj_sequence_shard / seqj_fuse_dev, and the single-process path uses peer copies */
 #define SEQJ_E_OOM (-4)
 #define SEQJ_E_INTERNAL (-5)
 #define SEQJ_E_DOMAIN (-6) /* input has negative, NaN or infinite values (AssertionError in the reference) */

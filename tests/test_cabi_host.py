@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(seqj):
     assert sorted(_lib.SIGNATURES) == names          # the ctypes binding covers the whole header
     for n in names:
         assert getattr(lib, n) is not None
-    assert lib.seqj_version() == 100
+    assert lib.seqj_version() == 200
 
 
 def test_no_cpu_fallback(seqj):
