@@ -492,7 +492,11 @@ int run_fuse(Ctx& c, GraphWS& gws, double* Sbuf, int64_t ldD, int N, int G, cons
     bp.N = N; bp.G = G; bp.ldp = ldp; bp.mi = mst_i; bp.mj = mst_j; bp.val = edge_val; bp.eps_floor = eps_floor;
     bp.comp = gws.anc0; bp.best = reinterpret_cast<unsigned long long*>(gws.wd); bp.bestp = reinterpret_cast<unsigned long long*>(gws.wd2);
     bp.out_i = gws.dep0; bp.out_j = gws.dep1; bp.out_w = gws.S; bp.out_count = gws.size;
-    boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
+    const char* fenv = getenv("SEQJ_FUSE_MST");
+    if (N >= 2048 && !(fenv && !strcmp(fenv, "single")))
+      boruvka_sparse_cluster_kernel<<<kBoruvkaCluster, kBoruvkaThreads, 0, c.st>>>(bp);     // one cluster of 8 CTAs
+    else
+      boruvka_sparse_kernel<<<1, kBoruvkaThreads, 0, c.st>>>(bp);
     RootTreeParams rp;
     rp.N = N; rp.ei = gws.dep0; rp.ej = gws.dep1; rp.ew = gws.S;
     rp.scratch = gws.fuse_i0;

@@ -253,3 +253,20 @@ def test_autoscale_matches_oracle(seqj, oracle, handle):
         if ref.eta > ref_max:
             ref_max, ref_best = ref.eta, s
     assert best == ref_best
+
+
+def test_fuse_cluster_boruvka_equals_single_cta(seqj, handle, monkeypatch):
+    """The final MST on the sparse edge union runs on a cluster of 8 CTAs for N >= 2048 (boruvka_sparse_cluster_kernel);
+    the single-CTA kernel (SEQJ_FUSE_MST=single) must give the identical tree, root, eta and order -- on random data
+    (bushy final tree) and on an ordered family (path-like final tree)."""
+    rng = np.random.default_rng(31)
+    for A in (np.asfortranarray(rng.random((256, 5000))), _planted(4096, 192, 5)[0]):
+        a = seqj.sequence(A, scales=(1, 2, 4), metrics=seqj.ALL_METRICS, handle=handle)
+        monkeypatch.setenv("SEQJ_FUSE_MST", "single")
+        b = seqj.sequence(A, scales=(1, 2, 4), metrics=seqj.ALL_METRICS, handle=handle)
+        monkeypatch.delenv("SEQJ_FUSE_MST")
+        assert np.array_equal(a.order, b.order) and a.eta == b.eta and a.root == b.root
+        assert np.array_equal(a.parents, b.parents)
+        ea = set(zip(a.mst.src.tolist(), a.mst.dst.tolist(), a.mst.weight.tolist()))
+        eb = set(zip(b.mst.src.tolist(), b.mst.dst.tolist(), b.mst.weight.tolist()))
+        assert ea == eb
