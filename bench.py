@@ -385,8 +385,9 @@ def main():
             tc = time.perf_counter()
             rr = step_e2e()
             walls.append((time.perf_counter() - tc) * 1e3)
-            for k in ("total", "h2d", "d2h"):
-                e2e_ph[k] = e2e_ph.get(k, 0.0) + rr.timings.get(k, 0.0) / args.steps
+            for k in ("total", "h2d", "d2h", "host_upload_ms", "host_local_ms", "host_gather_ms", "host_fuse_ms"):
+                if k in rr.timings:
+                    e2e_ph[k] = e2e_ph.get(k, 0.0) + rr.timings[k] / args.steps
         barrier()
         el = time.perf_counter() - t0
         if dist is not None:

@@ -90,6 +90,11 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   // stay well below that (profiles/r02_mst.md)
   const char* benv = getenv("SEQJ_KNN_BUDGET");
   bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : 2 * g.N);
+  // A graph of a large batch that is blocked with more than half of its vertices needy is the signature of tight
+  // clusters of near-equidistant objects (every vertex of a cluster runs dry when the cluster has merged); measured
+  // at config-3 size (profiles/r02_mst.md) those cost 81 ms with unlimited rescans, 64 ms when handed to Prim at that
+  // point, 42 ms with Prim alone; smooth families and images never ask for that many rows at once.
+  bp.rescan_once = (benv || nb * 3 <= h->sm_count) ? 0x7fffffff : g.N / 2;
   bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));

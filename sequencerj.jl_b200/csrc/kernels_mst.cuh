@@ -218,6 +218,7 @@ struct BorKnnParams {
   int* done;                   // [graph] 1 = all N-1 edges found, 2 = handed back to Prim (rescan budget used up)
   int* nresc;                  // [graph] rows rescanned so far
   int rescan_budget;           // rows a graph may have rescanned in total before it is handed to the batched Prim
+  int rescan_once;             // ... and rows it may ask for in ONE request (blocked with most of its vertices needy)
   int* out_i;                  // [graph][ldv] MST edges (i < j)
   int* out_j;
   double* out_w;
@@ -333,7 +334,7 @@ __global__ void __launch_bounds__(kBorKnnThreads, 1) boruvka_knn_kernel(BorKnnPa
     // batched Prim instead (done = 2: the list kernels and later rounds skip it, Prim does not).
     int nd = (status == 2) ? s_needy : 0, dn = (status == 1) ? 1 : 0;
     const int used = p.first ? 0 : p.nresc[g];
-    if (nd > 0 && used + nd > p.rescan_budget) { nd = 0; dn = 2; }
+    if (nd > 0 && (used + nd > p.rescan_budget || nd > p.rescan_once)) { nd = 0; dn = 2; }
     p.nresc[g] = used + nd;
     p.ecount[g] = s_count;
     p.ncount[g] = nd;

@@ -490,8 +490,12 @@ def test_float32_input_path_matches_the_float32_oracle(seqj, oracle, handle):
             # Float32 CDFs: ~m * 6e-8 per value, summed over m rows; Float32 Gram form: sqrt(6e-8 * selfterms) near 0
             atol = 3e-3 if mids[k] in (1, 3) else 1e-3
             np.testing.assert_allclose(r32.probes[sel], ref[pi[sel], pj[sel]], rtol=1e-3, atol=atol)
-            # and exactly (1e-9) the FP64 formulas on the SAME Float32 PDFs
-            P = chunks[int(c)].astype(np.float64)
+            # and exactly (1e-9) the FP64 formulas on the library's Float32 PDFs: Float32(a) / Float32(chunk sum), the
+            # sum correctly rounded (Julia's / NumPy's Float32 pairwise sum can be one Float32 ulp off, which scales a
+            # whole column by 6e-8: inside the Float32 band above, outside 1e-9)
+            r0 = int(c) * (-(-M // scales[l]))
+            S = Ac[r0:r0 + chunks[int(c)].shape[0], :]
+            P = (S / S.astype(np.float64).sum(axis=0, keepdims=True).astype(np.float32)).astype(np.float32).astype(np.float64)
             exact = np.abs(oracle.pairwise_vec(mids[k], P)) + 1e-6
             if mids[k] == 2:
                 exact = np.triu(exact) + np.triu(exact, 1).T
