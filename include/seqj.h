@@ -15,7 +15,8 @@
  *     (column) j is the contiguous run A[j*M .. j*M+M-1].  N x N matrices are column-major too
  *     (for symmetric matrices this equals row-major).
  *   - all vertex / column indices are 0-based on the C side; the Julia wrapper adds 1.
- *   - calls are blocking; a handle is not thread-safe; there is no global state.
+ *   - calls are blocking; calls on one handle are serialised by the library (a per-handle lock), different handles
+ *     run concurrently; there is no global state.
  *   - there is NO CPU fallback: every compute entry point fails with SEQJ_E_CUDA when no
  *     sm_100 device is usable.
  */

@@ -3,6 +3,8 @@
 // ---- unit-level entry points ------------------------------------------------------------------
 int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, int32_t scale, double* P_out,
                    double* U_out, int32_t* nchunks_out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!A || M64 < 1 || N64 < 1 || scale < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   if (scale > M64)
@@ -33,6 +35,8 @@ int seqj_splitnorm(seqj_handle* h, const double* A, int64_t M64, int64_t N64, in
 
 int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m64, int64_t N64, int normalize,
                   int kl_full, double eps_floor, double l2_thresh, double* D_out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "bad argument");
   const bool grid_metric = metric == SEQJ_EMD_GRID || metric == SEQJ_ENERGY_GRID;
@@ -72,6 +76,8 @@ int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m
 
 int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N64, double eps_floor, double* eta, int32_t* root,
                     int32_t* parents, int32_t* mst_i, int32_t* mst_j, double* mst_w, int32_t* order) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!D || N64 < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
   const int N = (int)N64;
@@ -101,6 +107,8 @@ int seqj_measure_dm(seqj_handle* h, const double* D, int64_t N64, double eps_flo
 }
 
 int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, int n, int64_t N64, double* Dkl_out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!Dchunks || !etas || !Dkl_out || n < 1 || N64 < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   const int N = (int)N64;
@@ -126,6 +134,8 @@ int seqj_accumulate(seqj_handle* h, const double* Dchunks, const double* etas, i
 
 int seqj_cdf_distance(seqj_handle* h, int32_t metric, const double* u, const double* uw, int64_t nu64, const double* v,
                       const double* vw, int64_t nv64, double* out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!u || !uw || !v || !vw || !out || nu64 < 1 || nv64 < 1 || nu64 + nv64 >= (1ll << 26))
     return fail(h, SEQJ_E_BADARG, "bad argument");

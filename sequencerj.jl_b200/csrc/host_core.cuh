@@ -46,6 +46,8 @@ struct DeviceWorker {
 };
 
 struct seqj_handle {
+  std::recursive_mutex mu;       // serialises the public entry points on this handle: its workspace cache, streams, pinned
+                                 // buffers, grid / periods / probes and error string are per-handle state
   int dev = 0;
   cudaStream_t st = nullptr;     // compute stream: prep + distance tiles
   cudaStream_t st2 = nullptr;    // graph stream (higher priority): Prim, tree, combine, fuse

@@ -143,12 +143,16 @@ const char* seqj_last_error(const seqj_handle* h) { return h ? h->err.c_str() : 
 
 int seqj_release_workspace(seqj_handle* h) {
   if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
+  if (!h) return SEQJ_E_BADARG;
   if (h->st) cudaStreamSynchronize(h->st);
   release_cache(h);
   return SEQJ_OK;
 }
 
 int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   if (!h) return SEQJ_E_BADARG;
   h->grid.clear();
   if (!grid || M <= 0) return SEQJ_OK;
@@ -165,6 +169,8 @@ int seqj_set_grid(seqj_handle* h, const double* grid, int64_t M) {
 
 int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M) {
   if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
+  if (!h) return SEQJ_E_BADARG;
   h->periods.clear();
   if (!periods || M <= 0) return SEQJ_OK;
   for (int64_t i = 0; i < M; ++i)
@@ -174,6 +180,8 @@ int seqj_set_periods(seqj_handle* h, const double* periods, int64_t M) {
 }
 
 int seqj_set_probes(seqj_handle* h, const int32_t* group, const int32_t* chunk, const int32_t* i, const int32_t* j, int64_t n) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   if (!h) return SEQJ_E_BADARG;
   h->probe_g.clear(); h->probe_c.clear(); h->probe_i.clear(); h->probe_j.clear();
   if (n <= 0 || !group) return SEQJ_OK;
@@ -230,6 +238,8 @@ int seqj_plan_shards(int64_t M, const int32_t* metric_ids, int nmetrics, const i
 }
 
 int seqj_set_workspace_limit(seqj_handle* h, uint64_t bytes) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   if (!h) return SEQJ_E_BADARG;
   h->ws_limit = bytes;
   return SEQJ_OK;
@@ -707,6 +717,8 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
 int seqj_sequence_dev(seqj_handle* h, const double* A_dev, int64_t M, int64_t N, const int32_t* metric_ids,
                       int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                       const uint8_t* group_mask, seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, nullptr,
                        nullptr, nullptr, 0, out);
 }
@@ -715,6 +727,8 @@ int seqj_sequence_partial(seqj_handle* h, const double* A_dev, int64_t M, int64_
                           int nmetrics, const int32_t* scales, int nscales, double eps_floor, double l2_thresh,
                           const int32_t* chunk_lo, const int32_t* chunk_hi, double* S_out_dev, int64_t S_stride,
                           seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   if (!chunk_lo || !chunk_hi || !S_out_dev) return fail(h, SEQJ_E_BADARG, "bad argument");
   return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, nullptr, chunk_lo,
                        chunk_hi, S_out_dev, S_stride, out);
@@ -723,6 +737,8 @@ int seqj_sequence_partial(seqj_handle* h, const double* A_dev, int64_t M, int64_
 int seqj_groups_finish(seqj_handle* h, double* S_dev, int64_t S_stride, int ngroups, const int32_t* slots, int64_t N64,
                        const double* eta_sum, double eps_floor, double* eta, int32_t* root, int32_t* parents,
                        int32_t* mst_i, int32_t* mst_j, double* mst_w) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!S_dev || !eta_sum || ngroups < 1 || N64 < 2) return fail(h, SEQJ_E_BADARG, "bad argument");
   const int N = (int)N64, ng = ngroups;
@@ -913,6 +929,8 @@ static int sequence_multi(seqj_handle* h, const double* A, int64_t M, int64_t N,
 int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
                   const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
                   seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!A || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M < 1 || N < 2)
     return fail(h, SEQJ_E_BADARG, "bad argument");
@@ -924,6 +942,8 @@ int seqj_sequence(seqj_handle* h, const double* A, int64_t M, int64_t N, const i
 int seqj_sequence_f32(seqj_handle* h, const float* A, int64_t M, int64_t N, const int32_t* metric_ids, int nmetrics,
                       const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
                       seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
   if (!A || !metric_ids || !scales || !out || nmetrics < 1 || nscales < 1 || M < 1 || N < 2)
     return fail(h, SEQJ_E_BADARG, "bad argument");
@@ -1038,6 +1058,8 @@ static int fuse_impl(seqj_handle* h, int64_t N64, int ngroups, const double* eta
 int seqj_fuse(seqj_handle* h, int64_t N64, int ngroups, const double* eta_group, const int32_t* mst_i,
               const int32_t* mst_j, const double* mst_w, double eps_floor, seqj_result** out) {
   if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
+  if (!h) return SEQJ_E_BADARG;
   if (!eta_group || !mst_i || !mst_j || !mst_w || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   return fuse_impl(h, N64, ngroups, eta_group, mst_i, mst_j, mst_w, nullptr, nullptr, eps_floor, out);
 }
@@ -1048,6 +1070,8 @@ int seqj_sequence_shard(seqj_handle* h, const double* A_dev, int64_t M, int64_t 
                         const int32_t* scales, int nscales, double eps_floor, double l2_thresh, const uint8_t* group_mask,
                         double* pack_dev, seqj_result** out) {
   if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
+  if (!h) return SEQJ_E_BADARG;
   if (!group_mask || !pack_dev) return fail(h, SEQJ_E_BADARG, "seqj_sequence_shard needs a group mask and a pack buffer");
   return sequence_impl(h, A_dev, M, N, metric_ids, nmetrics, scales, nscales, eps_floor, l2_thresh, group_mask, nullptr,
                        nullptr, nullptr, 0, out, pack_dev);
@@ -1055,6 +1079,8 @@ int seqj_sequence_shard(seqj_handle* h, const double* A_dev, int64_t M, int64_t 
 
 int seqj_fuse_dev(seqj_handle* h, int64_t N64, int ngroups, const double* pack_dev, const int32_t* slot_of_group,
                   double eps_floor, seqj_result** out) {
+  if (!h) return SEQJ_E_BADARG;
+  std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   if (!h) return SEQJ_E_BADARG;
   if (!pack_dev || !slot_of_group || !out || N64 < 2 || ngroups < 1) return fail(h, SEQJ_E_BADARG, "bad argument");
   return fuse_impl(h, N64, ngroups, nullptr, nullptr, nullptr, nullptr, pack_dev, slot_of_group, eps_floor, out);

@@ -270,3 +270,20 @@ def test_fuse_cluster_boruvka_equals_single_cta(seqj, handle, monkeypatch):
         ea = set(zip(a.mst.src.tolist(), a.mst.dst.tolist(), a.mst.weight.tolist()))
         eb = set(zip(b.mst.src.tolist(), b.mst.dst.tolist(), b.mst.weight.tolist()))
         assert ea == eb
+
+
+def test_config4_full_size_streamed_sampled_entries(seqj, oracle, handle):
+    """BASELINE config 4 at its real size on ONE GPU: N = 30,000 x L = 2,048, EMD + Energy, scales 1..32 = 126 chunk
+    matrices of 7.2 GB (907 GB in total) streamed through ~24 pool slots.  The Energy chain runs block waves + a top
+    wave (host_plan.cuh) with all five coarse scales derived; sampled chunk- and group-matrix entries of both metrics at
+    every scale equal the direct formulas at 1e-9, and the order is a permutation."""
+    N, L = 30000, 2048
+    mids, scales = (1, 3), (1, 2, 4, 8, 16, 32)
+    At = oracle_clamp(np.random.default_rng(2738).random((N, L)))
+    probes = _probe_plan(np.random.default_rng(14), N, L, mids, scales, per_chunk=40, per_group=60)
+    r = seqj.api._sequence(At, scales, (seqj.WASS1D, seqj.ENERGY), handle, probes=probes)
+    assert r.timings["waves"] >= 9 and r.timings["derived_groups"] == 5
+    assert sorted(r.order.tolist()) == list(range(N))
+    assert len(r.EOAlgScale) == 12 and sum(len(v[0]) for v in r.EOSeg.values()) == 126
+    _check_probes(seqj, oracle, At.T, mids, scales, r, probes)
+    handle.check(handle.lib.seqj_release_workspace(handle.h))          # give the 170 GB back to the other tests
