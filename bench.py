@@ -323,16 +323,20 @@ def main():
     sampler.start()
     for _ in range(args.warmup):
         r = step_dev()
+    step_dev_ms = []
+
     def timed_region():
         """EXACTLY args.steps steps between two barriers; returns the wall time and the per-step records."""
         barrier()
         sampler.mark()
         t0 = time.perf_counter()
         phases, launches, step_walls, derived, r = {}, 0, [], 0, None
+        step_dev_ms.clear()
         for _ in range(args.steps):
             tc = time.perf_counter()
             r = step_dev()
             step_walls.append(round((time.perf_counter() - tc) * 1e3, 1))
+            step_dev_ms.append(round(r.timings.get("total", 0.0), 1))   # device-side span of the call (CUDA events)
             launches += r.launches
             for k, v in r.timings.items():
                 if k not in ("input_min", "derived_groups", "waves"):
@@ -520,7 +524,7 @@ def main():
            "config": {"workload": cfg["name"], "pairs_per_step": pairs,
                       "cache": "inputs (8*N*L bytes) and every N x N chunk matrix are larger than the 126 MB L2; no flush needed",
                       "parallelism": f"{args.sharding}-major over {world} GPU(s)"},
-           "sequence_wall_s": elapsed / args.steps, "wall_ms_each_step": step_walls, "retimed_after_unsettled_first_attempt": first_attempt,
+           "sequence_wall_s": elapsed / args.steps, "wall_ms_each_step": step_walls, "device_ms_each_step": step_dev_ms, "retimed_after_unsettled_first_attempt": first_attempt,
            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof_main,
            "roofline_emd": roofs["emd"], "roofline_gemm": roofs["gemm"], "roofline_mst": roofs["mst"],
            "roofline_derive": roofs["derive"], "roofline_combine": roofs["combine"],

@@ -51,6 +51,14 @@ extern "C" {
 #define SEQJ_EMD_GRID 4
 #define SEQJ_ENERGY_GRID 5
 #define SEQJ_PERIODIC 6 /* Distances.PeriodicEuclidean(periods), set with seqj_set_periods (test/runtests.jl:189-236) */
+/* further element-wise Distances.jl (semi)metrics a caller can pass in `metrics` (any Distances.PreMetric is accepted
+ * by the reference's `pairwise` call, src/sequencer.jl:226): evaluated on the chunk PDFs
+ * by the direct tile kernel, no Gram form */
+#define SEQJ_CITYBLOCK 7      /* Distances.Cityblock():      sum |a - b|       */
+#define SEQJ_TOTALVARIATION 8 /* Distances.TotalVariation(): sum |a - b| / 2   */
+#define SEQJ_CHEBYSHEV 9      /* Distances.Chebyshev():      max |a - b|       */
+#define SEQJ_SQEUCLIDEAN 10   /* Distances.SqEuclidean():    sum (a - b)^2     */
+#define SEQJ_METRIC_MAX 10
 
 /* phase timers returned by seqj_result_timings (milliseconds, CUDA events on the library's streams) */
 #define SEQJ_T_TOTAL 0    /* whole seqj_sequence call, device side (H2D .. results ready) */

@@ -48,6 +48,8 @@ FLOATMAX32 = 3.4028234663852886e38  # floatmax(Float32), sequencer.jl:351-352
 L2, EMD, KLD, ENERGY = 0, 1, 2, 3
 EMD_GRID, ENERGY_GRID = 4, 5                   # the TYPES EMD / Energy + explicit grid (sequencer.jl:217-219)
 PERIODIC = 6                                   # Distances.PeriodicEuclidean(periods) (test/runtests.jl:189-236)
+# further element-wise Distances.jl metrics a caller may pass (`pairwise` takes any PreMetric, sequencer.jl:226)
+CITYBLOCK, TOTALVARIATION, CHEBYSHEV, SQEUCLIDEAN = 7, 8, 9, 10
 ALL_METRICS = (L2, EMD, KLD, ENERGY)           # distancemetrics.jl:257 (order matters)
 METRIC_NAMES = {L2: "Euclidean", EMD: "EMD", KLD: "KLDivergence", ENERGY: "Energy"}
 FIB = [1, 2, 3, 5, 8, 13, 21, 34, 55, 89, 144, 233, 377, 610, 987, 1597, 2584, 5168]  # sequencer.jl:148
@@ -371,8 +373,30 @@ def pairwise_periodic(P: np.ndarray, periods, faithful: bool = False) -> np.ndar
     return r
 
 
+def pairwise_elementwise(metric: int, P: np.ndarray, block: int = 64) -> np.ndarray:
+    """Distances.jl Cityblock / TotalVariation / Chebyshev / SqEuclidean (published definitions: sum |a-b|,
+    sum |a-b| / 2, max |a-b|, sum (a-b)^2), evaluated pair by pair over the columns as `pairwise` does."""
+    m, N = P.shape
+    PT = np.ascontiguousarray(P.T)
+    r = np.zeros((N, N))
+    for i0 in range(0, N, block):
+        d = PT[i0:i0 + block, None, :] - PT[None, :, :]
+        if metric == CITYBLOCK:
+            r[i0:i0 + block] = np.abs(d).sum(axis=2)
+        elif metric == TOTALVARIATION:
+            r[i0:i0 + block] = np.abs(d).sum(axis=2) / 2
+        elif metric == CHEBYSHEV:
+            r[i0:i0 + block] = np.abs(d).max(axis=2)
+        else:
+            r[i0:i0 + block] = (d * d).sum(axis=2)
+    np.fill_diagonal(r, 0.0)
+    return r
+
+
 def chunk_distance(metric: int, P: np.ndarray, faithful: bool = False,
                    eps_floor: float = EPS_FLOOR, l2_thresh: float = L2THR, lgrid=None, periods=None) -> np.ndarray:
+    if metric in (CITYBLOCK, TOTALVARIATION, CHEBYSHEV, SQEUCLIDEAN):
+        return np.abs(pairwise_elementwise(metric, P)) + eps_floor
     if metric == PERIODIC:
         return np.abs(pairwise_periodic(P, periods, faithful)) + eps_floor
     if metric in (EMD_GRID, ENERGY_GRID):

@@ -49,7 +49,13 @@ ALL_METRICS = (L2, WASS1D, KLD, ENERGY)    # distancemetrics.jl:257
 # chunk-local slice of `grid` (sequencer.jl:217-219) -- delta-weighted CDF distances on the explicit grid
 EMD_GRID = Metric(4, "EMD(grid)")
 ENERGY_GRID = Metric(5, "Energy(grid)")
-_BY_ID = {m.id: m for m in ALL_METRICS + (EMD_GRID, ENERGY_GRID)}
+# further element-wise Distances.jl metrics (the reference hands any PreMetric to `pairwise`, sequencer.jl:226):
+# evaluated on the chunk PDFs by the direct tile kernel
+CITYBLOCK = Metric(7, "Cityblock()")
+TOTALVARIATION = Metric(8, "TotalVariation()")
+CHEBYSHEV = Metric(9, "Chebyshev()")
+SQEUCLIDEAN = Metric(10, "SqEuclidean()")
+_BY_ID = {m.id: m for m in ALL_METRICS + (EMD_GRID, ENERGY_GRID, CITYBLOCK, TOTALVARIATION, CHEBYSHEV, SQEUCLIDEAN)}
 
 
 class PeriodicEuclidean(Metric):
@@ -236,8 +242,9 @@ def _normalize_metrics(metrics):
         elif isinstance(m, (EMD, Energy)) and m.grids is None:      # EMD() / Energy() instances == WASS1D / ENERGY
             out.append(WASS1D if isinstance(m, EMD) else ENERGY)
         else:
-            raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY and the "
-                            "EMD / Energy types with an explicit grid")
+            raise TypeError(f"unsupported metric {m!r}: the B200 path implements L2, WASS1D, KLD, ENERGY, the EMD / Energy "
+                            "types with an explicit grid, PeriodicEuclidean, Cityblock, TotalVariation, Chebyshev and "
+                            "SqEuclidean (no CPU fallback)")
     return tuple(out)
 
 

@@ -38,7 +38,7 @@ int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m
   if (!h) return SEQJ_E_BADARG;
   std::lock_guard<std::recursive_mutex> lock__(h->mu);      // one call at a time per handle
   ST_TRY(check_ready(h));
-  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "bad argument");
+  if (!chunk || !D_out || m64 < 1 || N64 < 1 || metric < 0 || metric > SEQJ_METRIC_MAX) return fail(h, SEQJ_E_BADARG, "bad argument");
   const bool grid_metric = metric == SEQJ_EMD_GRID || metric == SEQJ_ENERGY_GRID;
   if (grid_metric && (int64_t)h->grid.size() != m64)
     return fail(h, SEQJ_E_BADARG, "Grid length must match dims 1 (row count) of the chunk");
@@ -48,7 +48,7 @@ int seqj_pairwise(seqj_handle* h, int32_t metric, const double* chunk, int64_t m
   Ctx c(h);
   ScaleLayout L = make_layout(m, 1);
   PrepBufs pb;
-  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD || metric == SEQJ_PERIODIC, metric == SEQJ_KLD,
+  ST_TRY(alloc_prep(c, pb, N, L.ldX, 1, metric == SEQJ_L2 || metric == SEQJ_KLD || metric == SEQJ_PERIODIC || metric >= SEQJ_CITYBLOCK, metric == SEQJ_KLD,
                     metric == SEQJ_EMD || metric == SEQJ_ENERGY, false, metric == SEQJ_EMD_GRID, metric == SEQJ_ENERGY_GRID));
   if (metric == SEQJ_PERIODIC) ST_TRY(upload_periods(c, pb, h->periods, L.cl_pad));
   if (grid_metric) {

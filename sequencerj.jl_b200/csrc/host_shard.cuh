@@ -27,7 +27,7 @@ inline double shard_cost_mst_combine(int nchunks) {
   return mst + comb;
 }
 inline double shard_cost_tiles(int mid, int64_t M, int cl) {
-  const bool direct = mid == SEQJ_EMD || mid == SEQJ_EMD_GRID || mid == SEQJ_PERIODIC;
+  const bool direct = mid == SEQJ_EMD || mid == SEQJ_EMD_GRID || mid == SEQJ_PERIODIC || mid >= SEQJ_CITYBLOCK;
   if (direct) return (double)M / (16.2 * (double)cl / ((double)cl + 18.0));   // per-tile fixed cost: 154 ms instead of 122 at cl = 64, N = 30,000
   const double eff = std::min(0.9, (double)cl / ((double)cl + 110.0));
   return (double)M / (37.06 * eff);

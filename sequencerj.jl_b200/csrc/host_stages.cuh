@@ -90,11 +90,10 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   // stay well below that (profiles/r02_mst.md)
   const char* benv = getenv("SEQJ_KNN_BUDGET");
   bp.rescan_budget = benv ? atoi(benv) : ((nb * 3 <= h->sm_count) ? 0x7fffffff : 2 * g.N);
-  // A graph of a large batch that is blocked with more than half of its vertices needy is the signature of tight
-  // clusters of near-equidistant objects (every vertex of a cluster runs dry when the cluster has merged); measured
-  // at config-3 size (profiles/r02_mst.md) those cost 81 ms with unlimited rescans, 64 ms when handed to Prim at that
-  // point, 42 ms with Prim alone; smooth families and images never ask for that many rows at once.
-  bp.rescan_once = (benv || nb * 3 <= h->sm_count) ? 0x7fffffff : g.N / 2;
+  // A cap on a single request was tried and dropped: with rescans only when a graph is blocked, the smooth family
+  // also asks for more than N/2 rows at once (80 ms instead of 44 with the cap, profiles/r02_mst.md)
+  const char* oenv = getenv("SEQJ_KNN_ONCE");
+  bp.rescan_once = oenv ? atoi(oenv) : 0x7fffffff;
   bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
   const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
@@ -263,6 +262,24 @@ int run_distance(Ctx& c, int metric, const ScaleLayout& L, const PrepBufs& pb, c
   dp.mirror = 1; dp.kl_swap = 0;
   dp.tile_flags = nullptr; dp.tile_flag_stride = ntiles; dp.dense_thresh = 0x7fffffff; dp.dense_list = nullptr; dp.dense_count = nullptr;
   dp.fix_list = fb.list; dp.fix_count = fb.count; dp.fix_cap = fb.cap; dp.fix_overflow = fb.overflow;
+  dp.out_scale = 1.0;
+  if (metric >= SEQJ_CITYBLOCK && metric <= SEQJ_SQEUCLIDEAN) {
+    // element-wise Distances.jl metrics on the PDFs: direct tiles (same TMA pipeline and register tile as EMD), timed
+    // with the Euclidean phase
+    CUtensorMap tmP;
+    ST_TRY(make_tmap(h, &tmP, pb.P, L.ldX, pb.rows_pad));
+    dp.normA = nullptr; dp.tau = 0; dp.period = nullptr;
+    int t0 = c.timer.begin(SEQJ_T_DIST_L2);
+    dim3 grid0(ntiles, nb);
+    if (metric == SEQJ_CITYBLOCK) direct_dist_kernel<OP_L1><<<grid0, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp);
+    else if (metric == SEQJ_TOTALVARIATION) { dp.out_scale = 0.5; direct_dist_kernel<OP_L1><<<grid0, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp); }
+    else if (metric == SEQJ_CHEBYSHEV) direct_dist_kernel<OP_MAX><<<grid0, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp);
+    else direct_dist_kernel<OP_SQ_RAW><<<grid0, kTileThreads, kTileSmemBytes, c.st>>>(tmP, dp);
+    c.launches++;
+    CU_TRY(cudaGetLastError());
+    c.timer.end(t0);
+    return SEQJ_OK;
+  }
   const bool periodic = metric == SEQJ_PERIODIC;
   if (periodic) metric = SEQJ_L2;                      // timed with the Euclidean phase
   const bool on_grid = metric >= SEQJ_EMD_GRID;        // EMD / Energy on the explicit grid: pre-scaled operands
@@ -424,6 +441,8 @@ int set_kernel_attrs(seqj_handle* h) {
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_ENERGY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_PERIODIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_MAX>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
+  CU_TRY(cudaFuncSetAttribute(direct_dist_kernel<OP_SQ_RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTileSmemBytes));
   CU_TRY(cudaFuncSetAttribute(kl_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kKlSmemBytes));
   CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_L2, kDeriveMaxFine)));
   CU_TRY(cudaFuncSetAttribute(derive_kernel<MODE_KL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)derive_smem_bytes(MODE_KL, kDeriveMaxFine)));

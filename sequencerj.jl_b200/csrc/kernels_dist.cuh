@@ -55,6 +55,7 @@ struct DistParams {
   unsigned int fix_cap;
   int* fix_overflow;
   const double* period; // OP_PERIODIC: period of every row of the (single) chunk, padded to cl_pad with 1.0
+  double out_scale = 1.0;  // OP_L1: factor on the sum (a power of two)
 };
 
 // rho: logical fragment row g -> physical row inside an 8-row group, chosen so that the two rows
@@ -250,7 +251,9 @@ __global__ void compact_flags_kernel(const unsigned char* __restrict__ flags, in
 // thread T of the 128 consumers: ti = T>>4 (rows 8ti..8ti+7), tj = T&15 (cols (tj&7)+8(tj>>3)+16bb).
 // OP_L1: EMD.  OP_SQ / OP_SQ_ENERGY: sum_k (a-b)^2 -> Euclidean / Energy computed WITHOUT the Gram form; used
 // as the fix-up of whole tiles that the DMMA epilogue (or derive_kernel) found full of cancelling entries.
-enum DirectOp { OP_L1 = 0, OP_SQ = 1, OP_SQ_ENERGY = 2, OP_PERIODIC = 3 };
+enum DirectOp { OP_L1 = 0, OP_SQ = 1, OP_SQ_ENERGY = 2, OP_PERIODIC = 3, OP_MAX = 4, OP_SQ_RAW = 5 };
+// OP_MAX: max_k |a - b| (Chebyshev); OP_SQ_RAW: sum (a - b)^2 without the root (SqEuclidean); OP_L1 with out_scale = 0.5
+// is TotalVariation, OP_L1 on the PDFs Cityblock.
 
 // |a - b| mod p folded onto [0, p/2] (Distances.PeriodicEuclidean eval_op): the mod is exact (fmod) and only
 // taken when the difference reaches the period.
@@ -327,6 +330,8 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
             if (OP == OP_L1) {
               acc[a][b] += fabs(fa.x - fb[cur][b].x);
               acc[a][b] += fabs(fa.y - fb[cur][b].y);
+            } else if (OP == OP_MAX) {
+              acc[a][b] = fmax(acc[a][b], fmax(fabs(fa.x - fb[cur][b].x), fabs(fa.y - fb[cur][b].y)));
             } else if (OP == OP_PERIODIC) {
               const double sx = periodic_fold(fa.x - fb[cur][b].x, per.x), sy = periodic_fold(fa.y - fb[cur][b].y, per.y);
               acc[a][b] = fma(sx, sx, acc[a][b]);
@@ -353,8 +358,9 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
         const int j = j0 + jrow0 + 16 * b;
         if (j >= N || i > j) continue;
         double d = acc[a][b];
-        if (OP != OP_L1) d = fast_sqrt(d);
+        if (OP != OP_L1 && OP != OP_MAX && OP != OP_SQ_RAW) d = fast_sqrt(d);
         if (OP == OP_SQ_ENERGY) d = 1.4142135623730951 * d;
+        if (OP == OP_L1) d *= p.out_scale;                               // 1 (EMD, Cityblock) or 1/2 (TotalVariation): exact
         const double out = (i == j) ? p.eps_floor : fabs(d) + p.eps_floor;
         D[(int64_t)i * p.ldD + j] = out;
         if (i != j) D[(int64_t)j * p.ldD + i] = out;

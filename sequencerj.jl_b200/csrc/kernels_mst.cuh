@@ -109,32 +109,35 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
               } else { k3 = x; j3 = idx; }
             }
           }
-        } else if (idx < N) {
-          const int cc = comp[idx];
-          if (cc != cv) {
-            x = max(x, eps_bits);
-            if (x < k3) {
-              // position of an entry of the same component, if the lane keeps one (4 = none)
-              const int q = (cc == c0) ? 0 : (cc == c1) ? 1 : (cc == c2) ? 2 : (cc == c3) ? 3 : 4;
-              const unsigned long long kq = (q == 0) ? k0 : (q == 1) ? k1 : (q == 2) ? k2 : k3;
-              if (q == 4 || x < kq) {
-                // remove entry q (or the last one) by shifting the tail up, then insert (x, idx, cc) in order
-                if (q <= 0) { k0 = k1; j0 = j1; c0 = c1; }
-                if (q <= 1) { k1 = k2; j1 = j2; c1 = c2; }
-                if (q <= 2) { k2 = k3; j2 = j3; c2 = c3; }
-                // now three sorted entries in 0..2 (slot 3 is free); x < old k3 or x < old kq
-                if (x < k2) {
-                  k3 = k2; j3 = j2; c3 = c2;
-                  if (x < k1) {
-                    k2 = k1; j2 = j1; c2 = c1;
-                    if (x < k0) { k1 = k0; j1 = j0; c1 = c0; k0 = x; j0 = idx; c0 = cc; }
-                    else { k1 = x; j1 = idx; c1 = cc; }
-                  } else { k2 = x; j2 = idx; c2 = cc; }
-                } else { k3 = x; j3 = idx; c3 = cc; }
-              }
-            }
-          }
         }
+      }
+    };
+    // Rescan: the test against the fourth kept entry is no filter here -- with one entry per component the fourth entry
+    // is the lightest edge into the FOURTH nearest component, so every vertex of the three nearest components (and of
+    // the row's own) passes it, some lane of the warp takes the divergent insertion in nearly every step and the kernel
+    // ran at 2.3 TB/s on clustered data (profiles/r02_mst.md).  The label is therefore looked up for every element
+    // (shared memory) and a branch-free prefilter drops what cannot change the lane's list: own component, or a
+    // component the lane already holds with an edge that is not heavier.
+    auto consider_rescan = [&](unsigned long long x, int idx) {
+      const int cc = comp[min(idx, N - 1)];
+      x = max(x, eps_bits);
+      const bool useful = (idx < N) & (x < k3) & (cc != cv) &
+                          !(((cc == c0) & (x >= k0)) | ((cc == c1) & (x >= k1)) | ((cc == c2) & (x >= k2)));
+      if (useful) {
+        // position of an entry of the same component, if the lane keeps one (4 = none)
+        const int q = (cc == c0) ? 0 : (cc == c1) ? 1 : (cc == c2) ? 2 : (cc == c3) ? 3 : 4;
+        // remove entry q (or the last one) by shifting the tail up, then insert (x, idx, cc) in order
+        if (q <= 0) { k0 = k1; j0 = j1; c0 = c1; }
+        if (q <= 1) { k1 = k2; j1 = j2; c1 = c2; }
+        if (q <= 2) { k2 = k3; j2 = j3; c2 = c3; }
+        if (x < k2) {
+          k3 = k2; j3 = j2; c3 = c2;
+          if (x < k1) {
+            k2 = k1; j2 = j1; c2 = c1;
+            if (x < k0) { k1 = k0; j1 = j0; c1 = c0; k0 = x; j0 = idx; c0 = cc; }
+            else { k1 = x; j1 = idx; c1 = cc; }
+          } else { k2 = x; j2 = idx; c2 = cc; }
+        } else { k3 = x; j3 = idx; c3 = cc; }
       }
     };
     for (int base = 2 * lane; base < N; base += 64 * U) {
@@ -147,7 +150,10 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_rows_kernel(KnnParams p) {
 #pragma unroll
       for (int q = 0; q < U; ++q) {
         const int idx = base + 64 * q;
-        if (idx < N) { consider(dv[q].x, idx); consider(dv[q].y, idx + 1); }
+        if (idx < N) {
+          if (RESCAN) { consider_rescan(dv[q].x, idx); consider_rescan(dv[q].y, idx + 1); }
+          else { consider(dv[q].x, idx); consider(dv[q].y, idx + 1); }
+        }
       }
     }
     // L = the smallest (k3, j3) among the lanes whose list is full: whatever such a lane did not list is larger

@@ -265,7 +265,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     return fail(h, SEQJ_E_BADARG, "bad argument (need M >= 1, N >= 2, at least one metric and one scale)");
   const int M = (int)M64, N = (int)N64;
   for (int k = 0; k < nmetrics; ++k)
-    if (metric_ids[k] < 0 || metric_ids[k] > SEQJ_PERIODIC) return fail(h, SEQJ_E_BADARG, "unknown metric id");
+    if (metric_ids[k] < 0 || metric_ids[k] > SEQJ_METRIC_MAX) return fail(h, SEQJ_E_BADARG, "unknown metric id");
   for (int l = 0; l < nscales; ++l)
     if (scales[l] < 1 || scales[l] > M)
       return fail(h, SEQJ_E_BADARG, "Scale (" + std::to_string(scales[l]) +
@@ -295,7 +295,8 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
     bool used = false;                            // operands only for the metrics this call (this rank) computes
     for (int l = 0; l < nscales; ++l) used |= mask(k, l);
     if (!used) continue;
-    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_PERIODIC;
+    needP |= metric_ids[k] == SEQJ_L2 || metric_ids[k] == SEQJ_KLD || metric_ids[k] == SEQJ_PERIODIC ||
+             (metric_ids[k] >= SEQJ_CITYBLOCK && metric_ids[k] <= SEQJ_SQEUCLIDEAN);
     needPer |= metric_ids[k] == SEQJ_PERIODIC;
     needLog |= metric_ids[k] == SEQJ_KLD;
     needUc |= metric_ids[k] == SEQJ_EMD || metric_ids[k] == SEQJ_ENERGY;

@@ -61,11 +61,15 @@ Base.show(io::IO, s::PeriodicEuclidean) = write(io, "PeriodicEuclidean($(length(
 metric_id(::Distances.Euclidean) = Int32(0)        # any threshold: `Euclidean(thr)` passes thr as l2_thresh
 metric_id(::Distances.KLDivergence) = Int32(2)
 metric_id(::Distances.PeriodicEuclidean) = Int32(6)   # periods are handed to the library by `_sequence`
+metric_id(::Distances.Cityblock) = Int32(7)           # further element-wise Distances.jl metrics (direct tile kernel)
+metric_id(::Distances.TotalVariation) = Int32(8)
+metric_id(::Distances.Chebyshev) = Int32(9)
+metric_id(::Distances.SqEuclidean) = Int32(10)
 metric_id(::Type{EMD}) = Int32(4)
 metric_id(::Type{Energy}) = Int32(5)
 metric_id(m::EMD) = m.grids === nothing ? Int32(1) : error("EMD with explicit grids is a pair functor; pass the TYPE `EMD` and `grid=` to sequence")
 metric_id(m::Energy) = m.grids === nothing ? Int32(3) : error("Energy with explicit grids is a pair functor; pass the TYPE `Energy` and `grid=` to sequence")
-metric_id(m) = error("unsupported metric $(m): the B200 path implements Euclidean, KLDivergence, PeriodicEuclidean, EMD and Energy (no CPU fallback)")
+metric_id(m) = error("unsupported metric $(m): the B200 path implements Euclidean, KLDivergence, PeriodicEuclidean, Cityblock, TotalVariation, Chebyshev, SqEuclidean, EMD and Energy (no CPU fallback)")
 l2_threshold(metrics) = (t = L2THR; for m in metrics; m isa Distances.Euclidean && (t = m.thresh); end; t)
 
 "Scales used in the autoscale option (reference src/sequencer.jl:148)."

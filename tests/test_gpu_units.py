@@ -340,3 +340,28 @@ def test_accumulate_matches_reference_formula(seqj, handle):
     for e in etas:
         tot += e
     assert np.array_equal(seqj.accumulate(Ds, etas), S / tot)     # same order of operations: bit-exact
+
+
+@pytest.mark.parametrize("name", ["CITYBLOCK", "TOTALVARIATION", "CHEBYSHEV", "SQEUCLIDEAN"])
+def test_elementwise_distances_metrics(seqj, oracle, handle, name):
+    """the reference hands any Distances.PreMetric to `pairwise` (src/sequencer.jl:226).
+    Cityblock, TotalVariation, Chebyshev and SqEuclidean run on the direct tile kernel; chunk matrices against the
+    published definitions, and a whole `sequence` against the oracle (trees, eta, order)."""
+    met = getattr(seqj, name)
+    mid = getattr(oracle, name)
+    rng = np.random.default_rng(17)
+    for (m, N) in ((37, 150), (256, 333)):
+        A = oracle.clamp_input(rng.random((m, N)))
+        Dm = seqj.pairwise(met, A, normalize=True)
+        P = A / A.sum(axis=0, keepdims=True)
+        ref = oracle.chunk_distance(mid, P)
+        assert np.array_equal(Dm, Dm.T) and np.all(np.diag(Dm) == 1e-6)
+        rel_close(Dm, ref, 1e-9, atol=64 * m * 2.0 ** -53)
+    A = rng.random((48, 90))
+    r = seqj.sequence(A.copy(), scales=(1, 2, 3), metrics=(met, seqj.WASS1D), handle=handle)
+    ref = oracle.sequence_oracle(A, (1, 2, 3), (mid, 1))
+    assert np.array_equal(r.order, ref.order) and abs(r.eta - ref.eta) <= 1e-9 * ref.eta
+    for g in ref.groups:
+        key = (met if g.metric == mid else seqj.WASS1D, g.scale)
+        rel_close(r.EOSeg[key][0], g.eta_chunk, 1e-9)
+        assert np.array_equal(r.EOAlgScale[key][1].parents, g.parents)
