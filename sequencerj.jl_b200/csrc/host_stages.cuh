@@ -96,7 +96,11 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   bp.rescan_once = oenv ? atoi(oenv) : 0x7fffffff;
   bp.out_i = g.knn_ei; bp.out_j = g.knn_ej; bp.out_w = g.S2; bp.use_smem = g.knn_use_smem; bp.first = 1;
   const dim3 grid_all((unsigned)((g.N + kKnnWarps - 1) / kKnnWarps), (unsigned)nb);
-  const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, h->sm_count * 8 / nb));
+  // Rescan grid: at least 64 CTAs per graph.  The needy rows are spread very unevenly over the graphs of a batch (on
+  // the clustered input a third of the 124 graphs asks for all N rows, the rest for none), and with SMs*8/nb = 9 CTAs
+  // per graph the busy graphs kept 2-3 CTAs per SM in flight: 45 ms for one pass that the list kernel does in 17
+  // (profiles/r02_mst.md).  CTAs without rows return at once.
+  const int gx = std::max(1, std::min((g.N + kKnnWarps - 1) / kKnnWarps, std::max(h->sm_count * 8 / nb, 64)));
   const dim3 grid_rescan((unsigned)gx, (unsigned)nb);
   // rescans keep the graph's component labels in shared memory when they fit next to a few resident CTAs
   const size_t rescan_smem = ((size_t)g.N * 4 + 1024 <= h->max_smem) ? (size_t)g.N * 4 : 0;

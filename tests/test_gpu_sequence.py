@@ -295,7 +295,7 @@ def test_cabi_error_paths(seqj, handle):
     call = lambda M, N, m, s: lib.seqj_sequence(h, A.ctypes.data_as(C.c_void_p), M, N, _lib.iptr(m), len(m), _lib.iptr(s), len(s),
                                                 1e-6, 1e-7, None, C.byref(res))
     assert call(30, 1, mids, scs) == -1                                   # N < 2
-    assert call(30, 20, np.array([9], dtype=np.int32), scs) == -1         # unknown metric
+    assert call(30, 20, np.array([99], dtype=np.int32), scs) == -1        # unknown metric
     assert call(30, 20, mids, np.array([31], dtype=np.int32)) == -1       # scale > M
     assert b"cannot be larger than the number of data elements" in lib.seqj_last_error(h)
     bad = A.copy(); bad[3, 4] = -1.0
