@@ -65,17 +65,18 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index=0):
+    def __init__(self, index=0, period_ms=250):
         self.proc = None
         self.lines = []
         self.index = index
+        self.period_ms = period_ms
 
     def start(self):
         if os.environ.get("BENCH_NO_SAMPLER"):
             return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", "250")],
+                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", str(self.period_ms))],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -117,7 +118,7 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         hi = sorted(sm)[len(sm) // 2:]        # samples under load = upper half
         return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "period_ms": int(os.environ.get("BENCH_SMI_MS", self.period_ms)), "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -319,7 +320,11 @@ def main():
     # does not land in the timed region; it samples every 250 ms until the timed steps are done (at 100 ms the
     # polling itself cost 3-20 ms per sequence() call of host-side launch stalls, measured with BENCH_SMI_MS /
     # BENCH_NO_SAMPLER)
-    sampler = ClockSampler(local)
+    # Long steps (>= ~150 ms: config 3 on 1-2 GPUs, config 4) are sampled once a second, short ones every 250 ms: with 250 ms
+    # polling about one 230 ms step in 30 ran 10-50 ms longer ON THE DEVICE (profiles/r02_bench_noise.md: 0 of 40 such
+    # steps at 1000 ms or without the sampler, 3 of 40 at 250 ms), while a short timed region needs the denser samples
+    long_steps = pairs_per_step(cfg) * cfg["L"] / max(world, 1) > 1.5e12
+    sampler = ClockSampler(local, 1000 if long_steps else 250)
     sampler.start()
     for _ in range(args.warmup):
         r = step_dev()
