@@ -23,3 +23,4 @@ else:
     A = np.asfortranarray(np.abs(A[:, rng.permutation(A.shape[1])]))
 r = s.sequence(A, scales=(1, 2, 4, 8, 16), metrics=s.ALL_METRICS)
 print(kind, "total", round(r.timings["total"], 1), "prim", round(r.timings["prim"], 1))
+print({k: round(v, 1) for k, v in r.timings.items()})
