@@ -113,14 +113,28 @@ __device__ __forceinline__ void tile_issue(const CUtensorMap* tmA, const CUtenso
   tma_load_2d(sb, tmB, &s.full[st], k0, j0);
   tma_load_2d(sb + kStageBytesA, tmB, &s.full[st], k0, j0 + kTileM);
 }
-// Called by the elected thread at the top of consumer iteration `it`: refill the slot that was
-// consumed in iteration it-1 (all consumer warps have normally released it by now).
-__device__ __forceinline__ void tile_refill(const CUtensorMap* tmA, const CUtensorMap* tmB, const TileSmem& s,
-                                            int it, int nk, int kbase, int i0, int j0) {
+// Consumer release + producer refill, called by EVERY consumer thread (warp-converged) of iteration `it` right after
+// its wait on full[it % kStages]: the warp releases the slot it consumed in iteration it-1 and the elected thread
+// refills it with k-stage it-1+kStages.
+// Why the release trails by one wait: ptxas schedules `mbarrier.arrive` directly behind the last `ld.shared` of the
+// iteration, ahead of the math instructions that consume the loaded fragments, and attaches no scoreboard wait to it
+// (SASS: LDS.128 x3, SYNCS.ARRIVE, DMMA ...).  The arrive can then be performed while those loads are still queued,
+// and once the last warp has arrived the refill's TMA write may land in the slot before they are served: the last
+// fragment rows of a k-stage were occasionally read from the NEXT k-stage (seen on B200 in the first call of a
+// process, GPU clocks still ramping: a few 24 x 32 blocks of a 10k x 10k Euclidean matrix off by ~2 %;
+// tools/determinism_stress.py, profiles/r02_pipeline_race.md).  Placed after the next full-wait, the arrive follows a
+// spin loop that itself follows every math instruction of iteration it-1 in the instruction stream, and those were
+// only issued once their operands had arrived from shared memory.
+__device__ __forceinline__ void tile_release_refill(const CUtensorMap* tmA, const CUtensorMap* tmB, const TileSmem& s,
+                                                    int it, int nk, int kbase, int i0, int j0) {
   const int nxt = it - 1 + kStages;
-  if (it >= 1 && nxt < nk) {
-    mbar_wait(&s.empty[(it - 1) % kStages], ((it - 1) / kStages) & 1);
-    tile_issue(tmA, tmB, s, nxt, kbase, i0, j0);
+  if (it >= 1 && nxt < nk) {                    // slots that are never refilled need no release
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(&s.empty[(it - 1) % kStages]);
+    if (threadIdx.x == 0) {
+      mbar_wait(&s.empty[(it - 1) % kStages], ((it - 1) / kStages) & 1);
+      tile_issue(tmA, tmB, s, nxt, kbase, i0, j0);
+    }
   }
 }
 

@@ -207,8 +207,8 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   for (int it = 0; it < p.nk; ++it) {
     const int st = it % kStages;
     const uint32_t ph = (it / kStages) & 1;
-    if (threadIdx.x == 0) tile_refill(&tmA, &tmB, s, it, p.nk, kbase, i0, j0);
     mbar_wait(&s.full[st], ph);
+    tile_release_refill(&tmA, &tmB, s, it, p.nk, kbase, i0, j0);
     const uint32_t sa = stages_u32 + st * kStageBytes;
     const uint32_t sb = sa + kStageBytesA + warp * (32 * 128);
 #pragma unroll
@@ -227,8 +227,6 @@ gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int b = 0; b < 4; ++b) dmma884(acc[a][b][0], acc[a][b][1], fa[a].y, fb[b].y);
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&s.empty[st]);
   }
 
   // ---- fused epilogue ----
@@ -303,8 +301,8 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
     for (int it = 0; it < p.nk; ++it) {
       const int st = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
-      if (threadIdx.x == 0) tile_refill(&tmU, &tmU, s, it, p.nk, kbase, i0, j0);
       mbar_wait(&s.full[st], ph);
+      tile_release_refill(&tmU, &tmU, s, it, p.nk, kbase, i0, j0);
       const uint32_t sa = stages_u32 + st * kStageBytes + (8 * ti) * 128;
       const uint32_t sb = stages_u32 + st * kStageBytes + kStageBytesA + jrow0 * 128;
       // The j-side fragments of chunk c + 1 are loaded while chunk c is being accumulated (two register sets,
@@ -344,8 +342,6 @@ direct_dist_kernel(const __grid_constant__ CUtensorMap tmU, DistParams p) {
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s.empty[st]);
     }
 
     double* __restrict__ D = p.D + (int64_t)chunk_local * p.strideD;
@@ -431,14 +427,18 @@ kl_direct_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
     for (int it = 0; it < p.nk; ++it) {
       const int st = it % kKlStages;
       const uint32_t ph = (it / kKlStages) & 1;
-      if (threadIdx.x == 0) {
+      mbar_wait(&full[st], ph);
+      {                                            // release of slot it-1 trails its reads by one wait: see tile_release_refill
         const int nxt = it - 1 + kKlStages;
         if (it >= 1 && nxt < p.nk) {
-          mbar_wait(&empty[(it - 1) % kKlStages], ((it - 1) / kKlStages) & 1);
-          kl_issue(&tmP, &tmL, stages, full, nxt, kbase, i0, j0);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[(it - 1) % kKlStages]);
+          if (threadIdx.x == 0) {
+            mbar_wait(&empty[(it - 1) % kKlStages], ((it - 1) / kKlStages) & 1);
+            kl_issue(&tmP, &tmL, stages, full, nxt, kbase, i0, j0);
+          }
         }
       }
-      mbar_wait(&full[st], ph);
       const uint32_t sp = stages_u32 + st * kKlStageBytes + (8 * ti) * 128;       // P rows i
       const uint32_t sl = sp + kStageBytesA;                                        // log P rows i
       const uint32_t sb = stages_u32 + st * kKlStageBytes + 2 * kStageBytesA + jrow0 * 128;   // log P rows j
@@ -459,8 +459,6 @@ kl_direct_kernel(const __grid_constant__ CUtensorMap tmP, const __grid_constant_
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[st]);
     }
 
     double* __restrict__ D = p.D + (int64_t)chunk_local * p.strideD;

@@ -111,7 +111,7 @@ template <int R>
 __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
   extern __shared__ unsigned long long prim_sm[];
   __shared__ unsigned long long rk[2][32];
-  __shared__ int rv[2][32];
+  __shared__ int rv[2][32], rf[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = p.N;
   const int Npad = (N + 1) & ~1;
@@ -187,11 +187,14 @@ __global__ void __launch_bounds__(kPrimThreads, 1) prim_kernel(PrimParams p) {
     }
     auto getf = [&](int v) { return from[v]; };
     warp_argmin_edge(bk, bv, getf);
-    if (lane == 0) { rk[par][warp] = bk; rv[par][warp] = bv; }
+    // The tree endpoint of the warp's candidate travels with it: after the barrier a faster warp may already be relaxing
+    // from[] for the next step while a slower one still orders tied candidates.
+    if (lane == 0) { rk[par][warp] = bk; rv[par][warp] = bv; rf[par][warp] = (bv != 0x7fffffff) ? from[bv] : 0x7fffffff; }
     __syncthreads();
     bk = rk[par][lane];
     bv = rv[par][lane];
-    warp_argmin_edge(bk, bv, getf);
+    const int bf = rf[par][lane];
+    warp_argmin_edge(bk, bv, [&](int) { return bf; });
     u = bv;
     if (((u >> 1) & (kPrimThreads - 1)) == tid) {       // the owner of key[u] retires it
       order[step] = u;

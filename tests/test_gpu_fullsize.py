@@ -287,3 +287,57 @@ def test_config4_full_size_streamed_sampled_entries(seqj, oracle, handle):
     assert len(r.EOAlgScale) == 12 and sum(len(v[0]) for v in r.EOSeg.values()) == 126
     _check_probes(seqj, oracle, At.T, mids, scales, r, probes)
     handle.check(handle.lib.seqj_release_workspace(handle.h))          # give the 170 GB back to the other tests
+
+
+@pytest.mark.parametrize("metric", [0, 3, 1, 2])
+def test_fullsize_whole_chunk_matrix_cold_and_warm(seqj, oracle, handle, metric):
+    """Every one of the 10^8 entries of a config-3 chunk matrix (N = 10,000, chunk length 256), computed right after the
+    GPU has idled (clocks down, as in the first call of a process) and again at once: both runs bit-identical, and for
+    the contraction metrics that NumPy can evaluate over the whole matrix (Euclidean, Energy: Gram form on the host,
+    no cancellation on random data) every entry within 1e-9.  Round 2 found the TMA pipeline of the tile kernels
+    releasing a slot before its last shared-memory reads were served: a handful of 24 x 32 blocks of the FIRST matrix a
+    process computed were off by ~2 % (profiles/r02_pipeline_race.md); sampled entries never saw it."""
+    import time
+    N, m = 10000, 256
+    A = oracle.clamp_input(np.random.default_rng(2732).random((m, N)))
+    time.sleep(3.0)
+    cold = seqj.pairwise(metric, A, normalize=True, kl_full=False)
+    warm = seqj.pairwise(metric, A, normalize=True, kl_full=False)
+    assert np.array_equal(cold, warm)
+    if metric in (0, 3):
+        P = A / A.sum(axis=0, keepdims=True)
+        X = P if metric == 0 else oracle.chunk_cdf(P) - (np.arange(1, m + 1) / m)[:, None]   # CDFs centred on the ramp
+        s = (X * X).sum(axis=0)
+        G = X.T @ X
+        G *= -2.0
+        G += s[:, None]
+        G += s[None, :]
+        np.maximum(G, 0.0, out=G)
+        np.sqrt(G, out=G)
+        if metric == 3:
+            G *= np.sqrt(2.0)
+        G += 1e-6
+        np.fill_diagonal(G, 1e-6)
+        G -= cold
+        np.abs(G, out=G)
+        cold *= 1e-9
+        assert np.all(G <= cold + 1e-12), f"{int((G > cold + 1e-12).sum())} entries off, max {G.max()}"
+
+
+def test_config3_random_cold_and_warm_identical(seqj, handle):
+    """Config 3 on random data right after the GPU has idled and again at once: every chunk eta / root / BFS tree, every
+    group result and the final order are identical (the trees of i.i.d. data hang on thousands of near-ties, so any
+    glitched distance entry shows)."""
+    import time
+    N, L = 10000, 4096
+    A = np.asfortranarray(np.maximum(np.random.default_rng(99).random((L, N)), 2.220446049250313e-16))
+    time.sleep(3.0)
+    r1 = seqj.sequence(A, scales=(1, 2, 4, 8, 16), metrics=seqj.ALL_METRICS)
+    r2 = seqj.sequence(A, scales=(1, 2, 4, 8, 16), metrics=seqj.ALL_METRICS)
+    assert np.array_equal(r1.order, r2.order) and r1.eta == r2.eta
+    for key in r1.EOSeg:
+        assert r1.EOSeg[key][0] == r2.EOSeg[key][0], key
+        for t1, t2 in zip(r1.EOSeg[key][1], r2.EOSeg[key][1]):
+            assert t1.root == t2.root and np.array_equal(t1.parents, t2.parents), key
+        assert r1.EOAlgScale[key][0] == r2.EOAlgScale[key][0], key
+        assert np.array_equal(r1.EOAlgScale[key][1].parents, r2.EOAlgScale[key][1].parents), key
