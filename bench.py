@@ -342,6 +342,9 @@ def main():
             r = step_dev()
             step_walls.append(round((time.perf_counter() - tc) * 1e3, 1))
             step_dev_ms.append(round(r.timings.get("total", 0.0), 1))   # device-side span of the call (CUDA events)
+            if os.environ.get("BENCH_STEP_PHASES"):                      # which phase a slow step was slow in
+                print("step phases", {k: round(v, 1) for k, v in r.timings.items() if v and k not in ("input_min", "waves")},
+                      file=sys.stderr, flush=True)
             launches += r.launches
             for k, v in r.timings.items():
                 if k not in ("input_min", "derived_groups", "waves"):

@@ -274,6 +274,12 @@ struct GraphWS {
   size_t knn_smem = 0;
   unsigned long long* knn_lk = nullptr;
   int *knn_lj = nullptr, *knn_ei = nullptr, *knn_ej = nullptr, *knn_root = nullptr, *knn_flags = nullptr;
+  // first list pass from the upper triangle (knn_sample / knn_tiles / knn_merge kernels): candidate scratch for knn_tile_graphs
+  // graphs at a time, nullptr = the row kernel reads the full matrices
+  KnnCand* knn_cand = nullptr;
+  unsigned long long* knn_tau = nullptr;
+  int* knn_cnt = nullptr;
+  int knn_tile_graphs = 0;
 };
 
 constexpr int kKnnRounds = 12;      // Boruvka launches per measurement (each runs rounds until rows need a rescan)

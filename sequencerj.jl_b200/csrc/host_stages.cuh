@@ -60,6 +60,17 @@ int graphws_alloc(Ctx& c, GraphWS& g, int cap, int N) {
     g.knn_use_smem = g.knn_smem + 1024 <= h->max_smem;
     if (!g.knn_use_smem) g.knn_smem = 0;
     CU_TRY(cudaFuncSetAttribute(boruvka_knn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.knn_smem));
+    // Upper-triangle list pass (0.64 of the row kernel's bytes): thresholds from an N/8 sample of every row, so it
+    // is used where that sample is large enough to be representative, N >= 6144.  SEQJ_KNN=rows / tiles forces either.
+    const char* kenv = getenv("SEQJ_KNN");
+    const bool tiles = kenv ? !strcmp(kenv, "tiles") : N >= 6144;
+    if (tiles) {
+      const size_t per = (size_t)N * kKtCap * sizeof(KnnCand);
+      g.knn_tile_graphs = (int)std::max<size_t>(1, std::min<size_t>((size_t)g.knn_cap, (size_t(512) << 20) / per));
+      CU_TRY(c.pool.alloc(&g.knn_cand, (size_t)N * kKtCap * g.knn_tile_graphs));
+      CU_TRY(c.pool.alloc(&g.knn_tau, (size_t)N * g.knn_tile_graphs));
+      CU_TRY(c.pool.alloc(&g.knn_cnt, (size_t)N * g.knn_tile_graphs));
+    }
   }
   return SEQJ_OK;
 }
@@ -106,7 +117,28 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   const size_t rescan_smem = ((size_t)g.N * 4 + 1024 <= h->max_smem) ? (size_t)g.N * 4 : 0;
   kp.comp_in_smem = rescan_smem != 0;
   if (rescan_smem) CU_TRY(cudaFuncSetAttribute(knn_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rescan_smem));
-  knn_rows_kernel<false><<<grid_all, kKnnWarps * 32, 0, c.st>>>(kp);
+  int list_launches = 1;
+  if (g.knn_cand) {
+    KnnTileParams tp{};
+    tp.D = D; tp.ldD = ldD; tp.strideD = strideD; tp.mat_slot = mat_slot; tp.N = g.N; tp.eps_floor = eps_floor;
+    tp.nblk = (g.N + kKtB - 1) / kKtB; tp.ntiles = tp.nblk * (tp.nblk + 1) / 2;
+    tp.tau = g.knn_tau; tp.cnt = g.knn_cnt; tp.cand = g.knn_cand;
+    list_launches = 0;
+    const unsigned rows_grid = (unsigned)((g.N + kKnnWarps - 1) / kKnnWarps);
+    for (int g0 = 0; g0 < nb; g0 += g.knn_tile_graphs) {
+      const int gb = std::min(g.knn_tile_graphs, nb - g0);
+      tp.g0 = g0;
+      CU_TRY(cudaMemsetAsync(g.knn_cnt, 0, sizeof(int) * (size_t)g.N * gb, c.st));
+      knn_sample_kernel<<<dim3(rows_grid, (unsigned)gb), kKnnWarps * 32, 0, c.st>>>(tp);
+      const dim3 tgrid((unsigned)((tp.ntiles + kKtWarps - 1) / kKtWarps), (unsigned)gb);
+      // 4 rows per register set, 4 CTAs per SM: 19.99 ms for the MST stage of config 3; 8 rows / 2 CTAs: 22.8 ms
+      knn_tiles_kernel<4, 4><<<tgrid, kKtWarps * 32, 0, c.st>>>(tp);
+      knn_merge_kernel<<<dim3(rows_grid, (unsigned)gb), kKnnWarps * 32, 0, c.st>>>(kp, tp);
+      list_launches += 3;
+    }
+  } else {
+    knn_rows_kernel<false><<<grid_all, kKnnWarps * 32, 0, c.st>>>(kp);
+  }
   const int rounds = getenv("SEQJ_KNN_ROUNDS") ? std::max(1, atoi(getenv("SEQJ_KNN_ROUNDS"))) : kKnnRounds;
   for (int r = 0; r < rounds; ++r) {
     if (r > 0) knn_rows_kernel<true><<<grid_rescan, kKnnWarps * 32, rescan_smem, c.st>>>(kp);
@@ -118,7 +150,7 @@ int run_knn_mst(Ctx& c, GraphWS& g, const double* D, int64_t ldD, int64_t stride
   rp.parent = g.parent; rp.weight = g.weight; rp.order = g.order;
   rp.ld_e = g.ldv; rp.ld_s = (int64_t)16 * g.N + 64; rp.ld_o = g.ldv; rp.done = done;
   root_tree_kernel<<<nb, 1024, 0, c.st>>>(rp);
-  c.launches += 2 * rounds + 1;
+  c.launches += 2 * rounds + list_launches;
   CU_TRY(cudaGetLastError());
   return SEQJ_OK;
 }

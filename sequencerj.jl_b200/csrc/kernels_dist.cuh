@@ -91,12 +91,18 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
       const int j = jbase + 8 * b + 4 * e;
       nj[b][e] = (INTERIOR || j < N) ? nrm[j] : 0.0;
     }
-  // phase A: distances in place of the accumulators + one flag bit per entry
+  // One pass: every entry is finished and stored (direct + mirrored) as soon as it is computed, so that the
+  // accumulators die row by row and the epilogue needs no registers beyond the main loop's (168 per thread = three
+  // CTAs per SM for every metric; the two-phase version kept all 64 distances alive across the tile-level decision and
+  // spilled ~1 KB per thread for L2 / Energy there).  Only the flag bits survive; flagged entries are listed afterwards.
   unsigned long long flags = 0ull;
 #pragma unroll
   for (int a = 0; a < 8; ++a) {
     const int i = i0 + 8 * a + rg;
-    const double ni = (INTERIOR || i < N) ? nrm[i] : 0.0;
+    const bool irow = INTERIOR || i < N;
+    const double ni = irow ? nrm[i] : 0.0;
+    double* __restrict__ drow = D + (int64_t)i * p.ldD + jbase;          // direct stores: drow[8b + 4e]
+    double* __restrict__ dcol = D + (int64_t)jbase * p.ldD + i;          // mirrored stores: dcol[(8b + 4e) * ldD]
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
 #pragma unroll
@@ -117,8 +123,14 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
           d = fast_sqrt(v);
           if (MODE == MODE_ENERGY) d = 1.4142135623730951 * d;   // sqrt(2) * sqrt(sum)
         }
-        acc[a][b][e] = fabs(d) + p.eps_floor;
         if (live && flag) flags |= 1ull << (a * 8 + b * 2 + e);
+        if (!INTERIOR) {
+          if (!irow || j >= N) continue;
+          if (p.mirror && i > j) continue;
+        }
+        const double out = (!INTERIOR && i == j) ? p.eps_floor : fabs(d) + p.eps_floor;   // pairwise sets the diagonal to 0, then .+ eps
+        drow[8 * b + 4 * e] = out;
+        if (INTERIOR || (p.mirror && i != j)) dcol[(int64_t)(8 * b + 4 * e) * p.ldD] = out;
       }
     }
   }
@@ -130,34 +142,20 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
     dense = *s_cnt > p.dense_thresh;
     if (dense && threadIdx.x == 0) p.tile_flags[(size_t)blockIdx.y * p.tile_flag_stride + blockIdx.x] = 1;
   }
-  // phase B: stores (+ per-entry fix-up list when the tile is not dense)
-#pragma unroll
-  for (int a = 0; a < 8; ++a) {
-    const int i = i0 + 8 * a + rg;
-    if (!INTERIOR && i >= N) continue;
-    double* __restrict__ drow = D + (int64_t)i * p.ldD + jbase;          // direct stores: drow[8b + 4e]
-    double* __restrict__ dcol = D + (int64_t)jbase * p.ldD + i;          // mirrored stores: dcol[(8b + 4e) * ldD]
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int j = jbase + 8 * b + 4 * e;
-        if (!INTERIOR) {
-          if (j >= N) continue;
-          if (p.mirror && i > j) continue;
-        }
-        double out = (!INTERIOR && i == j) ? p.eps_floor : acc[a][b][e];   // pairwise sets the diagonal to 0, then .+ eps
-        if (!dense && ((flags >> (a * 8 + b * 2 + e)) & 1ull)) {
-          const unsigned int idx = atomicAdd(p.fix_count, 1u);
-          if (idx < p.fix_cap) {
-            p.fix_list[idx] = make_int4((int)blockIdx.y, i, j, p.kl_swap);
-          } else {
-            *p.fix_overflow = 1;
-            out = -1.0;     // marker for the dense fix-up pass
-          }
-        }
-        drow[8 * b + 4 * e] = out;
-        if (INTERIOR || (p.mirror && i != j)) dcol[(int64_t)(8 * b + 4 * e) * p.ldD] = out;
+  // per-entry fix-up list when the tile is not dense (rare: nothing is flagged on unstructured data)
+  if (!dense && flags) {
+#pragma unroll 1
+    for (unsigned long long f = flags; f; f &= f - 1) {
+      const int bit = __ffsll((long long)f) - 1;
+      const int a = bit >> 3, b = (bit >> 1) & 3, e = bit & 1;
+      const int i = i0 + 8 * a + rg, j = jbase + 8 * b + 4 * e;
+      const unsigned int idx = atomicAdd(p.fix_count, 1u);
+      if (idx < p.fix_cap) {
+        p.fix_list[idx] = make_int4((int)blockIdx.y, i, j, p.kl_swap);
+      } else {
+        *p.fix_overflow = 1;                                // marker for the dense fix-up pass
+        D[(int64_t)i * p.ldD + j] = -1.0;
+        if (INTERIOR || (p.mirror && i != j)) D[(int64_t)j * p.ldD + i] = -1.0;
       }
     }
   }
@@ -166,7 +164,7 @@ __device__ __forceinline__ void gemm_epilogue(const DistParams& p, double (&acc)
 template <int MODE>
 // KL runs 3 CTAs per SM (168 registers, the few spills land outside the DMMA loop: measured 13.6 -> 12.4 ms at config 3);
 // the sqrt epilogue of L2 / Energy spills more at 168 and is faster at 2 CTAs (14.2 vs 14.9 ms).
-__global__ void __launch_bounds__(kTileThreads, (MODE == MODE_KL) ? 3 : 2)
+__global__ void __launch_bounds__(kTileThreads, 3)
 gemm_dist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, DistParams p) {
   __shared__ int s_cnt;
   extern __shared__ uint8_t smem_raw[];

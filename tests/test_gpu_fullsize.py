@@ -341,3 +341,24 @@ def test_config3_random_cold_and_warm_identical(seqj, handle):
             assert t1.root == t2.root and np.array_equal(t1.parents, t2.parents), key
         assert r1.EOAlgScale[key][0] == r2.EOAlgScale[key][0], key
         assert np.array_equal(r1.EOAlgScale[key][1].parents, r2.EOAlgScale[key][1].parents), key
+
+
+def test_config3_tile_list_pass_equals_row_list_pass(seqj, handle, monkeypatch):
+    """Config 3 on random data with the two first list passes of the kNN-filtered Boruvka: the default at this size
+    (upper-triangle blocks, knn_tiles_kernel + knn_merge_kernel) and the row kernel that reads the full matrices
+    (SEQJ_KNN=rows).  The lists differ, the MST under the reference's edge order does not: every chunk / group tree,
+    eta and the final order are identical."""
+    N, L = 10000, 4096
+    A = np.asfortranarray(np.maximum(np.random.default_rng(41).random((L, N)), 2.220446049250313e-16))
+    monkeypatch.delenv("SEQJ_KNN", raising=False)
+    a = seqj.sequence(A, scales=(1, 2, 4, 8, 16), metrics=seqj.ALL_METRICS)
+    monkeypatch.setenv("SEQJ_KNN", "rows")
+    b = seqj.sequence(A, scales=(1, 2, 4, 8, 16), metrics=seqj.ALL_METRICS)
+    monkeypatch.delenv("SEQJ_KNN", raising=False)
+    assert np.array_equal(a.order, b.order) and a.eta == b.eta
+    for key in a.EOSeg:
+        assert a.EOSeg[key][0] == b.EOSeg[key][0], key
+        for t1, t2 in zip(a.EOSeg[key][1], b.EOSeg[key][1]):
+            assert t1.root == t2.root and np.array_equal(t1.parents, t2.parents), key
+        assert a.EOAlgScale[key][0] == b.EOAlgScale[key][0], key
+        assert np.array_equal(a.EOAlgScale[key][1].parents, b.EOAlgScale[key][1].parents), key

@@ -362,13 +362,16 @@ def test_mst_back_ends_agree(seqj, handle, monkeypatch, kind):
         A = np.concatenate([B, B, B[:, :60]], axis=1)[:, rng.permutation(300)]     # smooth family with duplicates
     scales = (1, 2, 4, 8)                                    # 4 metrics x 15 chunks = 60 chunk graphs, then 16 groups
     runs = []
-    for mode in ("prim", None, "knn"):
-        if mode is None:
-            monkeypatch.delenv("SEQJ_MST", raising=False)
-        else:
+    for mode in ("prim", None, "knn", "tiles"):             # tiles: the upper-triangle list pass forced at this small N
+        monkeypatch.delenv("SEQJ_MST", raising=False)
+        monkeypatch.delenv("SEQJ_KNN", raising=False)
+        if mode == "tiles":
+            monkeypatch.setenv("SEQJ_KNN", "tiles")
+        elif mode is not None:
             monkeypatch.setenv("SEQJ_MST", mode)
         runs.append(seqj.sequence(A.copy(), scales=scales, metrics=seqj.ALL_METRICS))
     monkeypatch.delenv("SEQJ_MST", raising=False)
+    monkeypatch.delenv("SEQJ_KNN", raising=False)
     a = runs[0]
     for b in runs[1:]:
         assert np.array_equal(a.order, b.order) and a.eta == b.eta

@@ -225,19 +225,22 @@ def _edge_set(t):
     return set(zip(np.minimum(t.src, t.dst).tolist(), np.maximum(t.src, t.dst).tolist()))
 
 
-MST_MODES = ("auto", "prim")      # auto = kNN-filtered Boruvka for a single graph (kernels_mst.cuh); prim = the Prim kernels
+# auto = kNN-filtered Boruvka with the row list kernel at these sizes (kernels_mst.cuh); tiles = the same with the
+# upper-triangle list pass (knn_tiles_kernel + knn_merge_kernel, the default from N = 6144) forced; prim = the Prim kernels
+MST_MODES = ("auto", "tiles", "prim")
 
 
 def _measure_modes(seqj, monkeypatch, Dm, **kw):
     """`_measure_dm` through both MST back ends of the library (SEQJ_MST is read at every call)."""
     out = []
     for mode in MST_MODES:
-        if mode == "auto":
-            monkeypatch.delenv("SEQJ_MST", raising=False)
-        else:
+        monkeypatch.delenv("SEQJ_MST", raising=False)
+        monkeypatch.setenv("SEQJ_KNN", "tiles" if mode == "tiles" else "rows")
+        if mode == "prim":
             monkeypatch.setenv("SEQJ_MST", mode)
         out.append(seqj.measure_dm(Dm, **kw))
     monkeypatch.delenv("SEQJ_MST", raising=False)
+    monkeypatch.delenv("SEQJ_KNN", raising=False)
     return out
 
 
@@ -278,8 +281,9 @@ def test_measure_dm_structured_inputs_take_the_rescan_path(seqj, oracle, handle,
     for got in _measure_modes(seqj, monkeypatch, Dm, want_order=True):
         assert _edge_set(got.mst) == set(zip(ref.mst_i.tolist(), ref.mst_j.tolist()))
         assert got.eta == ref.eta
-    a, b = _measure_modes(seqj, monkeypatch, Dm, want_order=True)
-    assert a.root == b.root and np.array_equal(a.bfs.parents, b.bfs.parents) and np.array_equal(a.order, b.order)
+    a, *rest = _measure_modes(seqj, monkeypatch, Dm, want_order=True)
+    for b in rest:
+        assert a.root == b.root and np.array_equal(a.bfs.parents, b.bfs.parents) and np.array_equal(a.order, b.order)
 
 
 @pytest.mark.parametrize("N,levels", [(7, 2), (64, 3), (300, 4), (1031, 3), (2500, 5), (4099, 2)])

@@ -116,3 +116,28 @@ def test_streaming_threshold_variant_keeps_the_list_contract(oracle):
         edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True)
         ei, ej, _ = oracle.kruskal_mst(D)
         assert ncomp == 1 and {(a, b) for a, b, _ in edges} == set(zip(ei.tolist(), ej.tolist()))
+
+
+def test_threshold_lists_keep_the_list_contract(oracle):
+    """Round 2, the upper-triangle list pass (kernels_mst.cuh: knn_sample / knn_tiles / knn_merge kernels, modelled by
+    tools/knn_boruvka_proto.py:threshold_lists): every list holds exactly the smallest entries of its row in
+    (weight, j) order, every unlisted edge weighs >= the bound, rows that overflow the candidate buffer come back empty
+    with bound 0 (= rescan me), and Boruvka on these lists returns the reference's tree -- random weights, heavy ties
+    (every row overflows) and duplicated objects."""
+    rng = np.random.default_rng(11)
+    base = _sym(rng.random((60, 60)) + 0.01)
+    cases = (_sym(rng.random((300, 300)) + 0.01), _sym(rng.integers(1, 4, (130, 130)).astype(float)),
+             np.kron(np.ones((3, 3)), base))
+    for D in cases:
+        np.fill_diagonal(D, 1e-6)
+        N = D.shape[0]
+        W = model.bits(np.maximum(D, model.EPS))
+        for cap, div in ((96, 8), (8, 8), (96, 2)):
+            lists, bound = model.threshold_lists(D, sample_div=div, cap=cap)
+            for v in range(N):
+                allv = sorted((int(W[v, j]), j) for j in range(N) if j != v)
+                assert lists[v] == allv[:len(lists[v])]
+                assert all(w >= int(bound[v]) for w, _ in allv[len(lists[v]):])
+            edges, ncomp, _ = model.boruvka(D, lists, bound, rescan=True)
+            ei, ej, _ = oracle.kruskal_mst(D)
+            assert ncomp == 1 and {(a, b) for a, b, _ in edges} == set(zip(ei.tolist(), ej.tolist()))

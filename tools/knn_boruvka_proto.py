@@ -131,6 +131,49 @@ def knn_lists(D):
     return lists, bound
 
 
+def threshold_lists(D, sample_div=8, sample_k=3, cap=96, block=128):
+    """Round 2: the first list pass from the UPPER TRIANGLE (kernels_mst.cuh: knn_sample / knn_tiles / knn_merge
+    kernels).  tau_v = the sample_k-th smallest of a contiguous sample of N / sample_div entries of row v; every entry
+    (i, j), i < j, is read once and offered to both ends: it becomes a candidate of row i when it is <= tau_i and of
+    row j when it is <= tau_j.  The list = the K smallest candidates in (weight, j) order, bound = the K-th weight or
+    tau_v (every entry <= tau_v is a candidate).  A row without a threshold or with more than `cap` candidates gets an
+    empty list with bound 0, i.e. it is rescanned in the first round.  Returns (lists, bound) like knn_lists."""
+    N = D.shape[0]
+    W = bits(np.maximum(D, EPS))
+    m = max(64, (N // sample_div + 63) // 64 * 64)
+    tau = np.empty(N, dtype=np.uint64)
+    for v in range(N):
+        s0 = (v // block) * block
+        if s0 + m > N:
+            s0 = max(0, ((N - m) + 1) & ~1)
+        js = [j for j in range(s0, min(N, s0 + m)) if j != v]
+        ws = sorted(int(W[v, j]) for j in js)
+        tau[v] = ws[sample_k - 1] if len(ws) >= sample_k else NONE
+        if len(ws) >= sample_k and ws[0] == ws[sample_k - 1]:
+            tau[v] = 0                                      # the smallest sample entries tie: straight to the rescan
+    cands = [[] for _ in range(N)]
+    for i in range(N):                                     # one visit per unordered pair
+        for j in range(i + 1, N):
+            w = int(W[i, j])
+            if w <= int(tau[i]):
+                cands[i].append((w, j))
+            if w <= int(tau[j]):
+                cands[j].append((w, i))
+    lists, bound = [], np.empty(N, dtype=np.uint64)
+    for v in range(N):
+        if tau[v] == NONE or tau[v] == 0 or len(cands[v]) > cap:
+            lists.append([]); bound[v] = 0
+            continue
+        c = sorted(cands[v])
+        if len(c) >= K:
+            c = c[:K]
+            bound[v] = c[-1][0]
+        else:
+            bound[v] = tau[v]
+        lists.append(c)
+    return lists, bound
+
+
 def boruvka(D, lists, bound, verbose=False, rescan=True, dedupe=False, lazy=False):
     """dedupe: rescanned lists hold one entry per component; lazy: rescan only when no component can hook any more
     (the round-2 kernels do both; the round-1 behaviour is dedupe=False, lazy=False)."""

@@ -11,7 +11,9 @@ import sequencerj_b200 as s  # noqa: E402
 N, L = 10000, 4096
 rng = np.random.default_rng(7)
 kind = sys.argv[1] if len(sys.argv) > 1 else "clusters"
-if kind == "smooth":
+if kind == "random":
+    A = np.asfortranarray(np.maximum(rng.random((L, N)), 2.220446049250313e-16))
+elif kind == "smooth":
     x = np.arange(L)[:, None]
     mu = np.linspace(0.15 * L, 0.85 * L, N)[None, :]
     A = np.exp(-0.5 * ((x - mu) / (0.05 * L)) ** 2) + 1e-3

@@ -33,9 +33,12 @@ for name, A in (("smooth family", smooth()), ("50 tight clusters", clustered()))
         os.environ.pop("SEQJ_MST", None)
         os.environ.pop("SEQJ_KNN_ROUNDS", None)
         os.environ.pop("SEQJ_KNN_BUDGET", None)
+        os.environ.pop("SEQJ_KNN", None)
         for part in filter(None, mode.split(",")):
             if part.startswith("rounds="):
                 os.environ["SEQJ_KNN_ROUNDS"] = part[7:]
+            elif part.startswith("lists="):           # first list pass: rows (full matrices) | tiles (upper triangle)
+                os.environ["SEQJ_KNN"] = part[6:]
             elif part.startswith("budget="):          # rows a graph of a large batch may rescan before Prim takes it
                 os.environ["SEQJ_KNN_BUDGET"] = part[7:]
             else:
