@@ -61,27 +61,70 @@ def pairs_per_step(cfg):
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock, power and throttle reasons during the timed region (B200_PROFILING.md recipe).
+
+    Read through NVML inside this process (pynvml, the library nvidia-smi itself sits on): a thread polls the four
+    values every `period_ms`.  The `nvidia-smi -lms` child process used before stalled this process's kernel launches
+    for 50-130 ms at every poll on some boxes -- the slow steps had unchanged kernel times and idle gaps between the
+    kernels (profiles/r02_bench_noise.md).  BENCH_SAMPLER=smi selects the child process again; it is also the fallback
+    when pynvml is missing.  BENCH_NO_SAMPLER=1 turns sampling off."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index=0, period_ms=250):
         self.proc = None
-        self.lines = []
+        self.nvml = None
+        self.lines = []              # smi: csv lines; nvml: (sm, max, watts, [reasons]) tuples
         self.index = index
-        self.period_ms = period_ms
+        self.period_ms = int(os.environ.get("BENCH_SMI_MS", period_ms))
+        self.running = False
+
+    def _nvml_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [x for x in vis.split(",") if x.strip() != ""]
+        if ids and all(x.strip().isdigit() for x in ids) and self.index < len(ids):
+            return int(ids[self.index])
+        return self.index
 
     def start(self):
         if os.environ.get("BENCH_NO_SAMPLER"):
             return
+        if os.environ.get("BENCH_SAMPLER", "nvml") != "smi":
+            try:
+                import pynvml
+                pynvml.nvmlInit()
+                self.nvml = pynvml
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(self._nvml_index())
+                self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+                self.running = True
+                self.t = threading.Thread(target=self._poll, daemon=True)
+                self.t.start()
+                return
+            except Exception:
+                self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", os.environ.get("BENCH_SMI_MS", str(self.period_ms))],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nvml
+        bits = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown, "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown, "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while self.running:
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.lines.append((sm, self.max_sm, pw, [n for n, b in bits.items() if mask & b]))
+            except Exception:
+                pass
+            time.sleep(self.period_ms / 1000.0)
 
     def _read(self):
         for ln in self.proc.stdout:
@@ -93,17 +136,23 @@ class ClockSampler:
         self.start_idx = len(self.lines)
 
     def stop(self):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
+        if self.nvml is None and not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no sampler"]}
+        if self.nvml is not None:
+            self.running = False
+            self.t.join(timeout=2)
+        else:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         lines = self.lines[getattr(self, "start_idx", 0):] or self.lines[-1:]
         for ln in lines:
+            if isinstance(ln, tuple):
+                sm.append(ln[0]); mx.append(ln[1]); pw.append(ln[2]); reasons.update(ln[3])
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -111,14 +160,15 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         hi = sorted(sm)[len(sm) // 2:]        # samples under load = upper half
         return {"sm_mhz": float(np.median(hi)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
-                "samples": len(sm), "period_ms": int(os.environ.get("BENCH_SMI_MS", self.period_ms)), "reasons": sorted(reasons)}
+                "samples": len(sm), "period_ms": self.period_ms, "source": "nvml (in-process)" if self.nvml is not None else "nvidia-smi",
+                "reasons": sorted(reasons)}
 
 
 # --------------------------------------------------------------------------------------------
@@ -324,7 +374,7 @@ def main():
     # polling about one 230 ms step in 30 ran 10-50 ms longer ON THE DEVICE (profiles/r02_bench_noise.md: 0 of 40 such
     # steps at 1000 ms or without the sampler, 3 of 40 at 250 ms), while a short timed region needs the denser samples
     long_steps = pairs_per_step(cfg) * cfg["L"] / max(world, 1) > 1.5e12
-    sampler = ClockSampler(local, 1000 if long_steps else 250)
+    sampler = ClockSampler(local, (1000 if long_steps else 250) if os.environ.get("BENCH_SAMPLER") == "smi" else 200)
     sampler.start()
     for _ in range(args.warmup):
         r = step_dev()
