@@ -386,7 +386,11 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   CU_TRY(cudaMemGetInfo(&free_b, &total_b));
   hmark("memgetinfo");
   free_b += h->cached_bytes;                    // blocks cached from the previous call are reusable
-  size_t budget = free_b > (size_t(4) << 30) ? free_b - (size_t(4) << 30) : free_b / 2;
+  // 5 GB stay outside the matrix pool: the graph workspace (lists, candidate scratch of the upper-triangle list pass:
+  // up to 0.6 GB), result staging and whatever the host framework allocates next to the library (the sharded upload of
+  // config 4 needs 0.55 GB of torch tensors per rank; with 4 GB it no longer fitted once the candidate scratch existed)
+  const size_t reserve_b = size_t(5) << 30;
+  size_t budget = free_b > reserve_b ? free_b - reserve_b : free_b / 2;
   if (h->ws_limit && h->ws_limit < budget) budget = h->ws_limit;
   const char* henv = getenv("SEQJ_HIER");
   PlanInput pin;
