@@ -294,7 +294,19 @@ def rank_work(r, N, L, scales, derived):
                 der_bytes += 8.0 * (sharding.nchunks(L, fine) * npair + sharding.nchunks(L, coarse) * N * N)
                 left -= 1
     return {"emd_instr": 2.0 * emd_rows * npair, "gemm_flops": 2.0 * max(gemm_rows, 0) * npair, "gemm_groups": max(gemm_groups, 0),
-            "mst_bytes": 8.0 * N * N * graphs, "graphs": graphs, "derive_bytes": der_bytes, "combine_bytes": comb}
+            "mst_bytes": mst_bytes_per_graph(N) * graphs, "graphs": graphs, "derive_bytes": der_bytes, "combine_bytes": comb}
+
+
+def mst_bytes_per_graph(N):
+    """Algorithmic bytes the first list pass of the MST reads per graph (csrc/kernels_mst.cuh).  From N = 6144 (unless
+    SEQJ_KNN=rows): the 128 x 128 blocks of the upper triangle incl. the diagonal blocks, once, plus the N/8-entry sample
+    of every row; below: every row in full."""
+    tiles = N >= 6144 if os.environ.get("SEQJ_KNN") is None else os.environ["SEQJ_KNN"] == "tiles"
+    if not tiles:
+        return 8.0 * N * N
+    nblk = -(-N // 128)
+    m = max(64, -(-(N // 8) // 64) * 64)
+    return 8.0 * (nblk * (nblk + 1) // 2 * 128 * 128 + N * min(m, N))
 
 
 METRIC_NAME = "sequence() distance throughput at N=10k,L=4k all metrics (wall-s per call in sequence_wall_s)"
@@ -303,7 +315,7 @@ METRIC_NAME = "sequence() distance throughput at N=10k,L=4k all metrics (wall-s 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3)
@@ -549,9 +561,10 @@ def main():
         "gemm": roof("gemm_dist_kernel<L2|KL|Energy> (DMMA tiles + fix-up)", "tensor", work["gemm_flops"], gemm_ms,
                      peaks.get("dmma884_sustained_tflops", 37.06), "TFLOP/s", 1e12, fp64_note, "gemm",
                      note=f"{work['gemm_groups']} tile launches per step, {int(derived)} groups derived instead"),
-        "mst": roof("MST stage: knn_rows_kernel + boruvka_knn_kernel (+ prim_kernel for graphs over the rescan budget)", "hbm",
-                    work["mst_bytes"], phases.get("prim", 0), hbm, "GB/s", 1e9, hbm_src, "knn_rows",
-                    note="8 N^2 bytes per graph (every matrix read once)"),
+        "mst": roof("MST stage: knn_sample / knn_tiles / knn_merge kernels + boruvka_knn_kernel (+ rescans, + prim_kernel for graphs "
+                    "over the rescan budget)", "hbm", work["mst_bytes"], phases.get("prim", 0), hbm, "GB/s", 1e9, hbm_src, "knn_tiles",
+                    note="algorithmic bytes of the list pass: upper-triangle blocks read once (4 N^2 + diagonal blocks) + N^2 for the "
+                         "row samples from N = 6144, 8 N^2 below; the stage's time also holds the Boruvka rounds, the rooting and rescans"),
         "derive": roof("derive_kernel<L2|KL|Energy> (coarse scales from the next finer one)", "hbm", work["derive_bytes"],
                        phases.get("derive", 0), hbm, "GB/s", 1e9, hbm_src, "derive",
                        note="8 bytes x (upper halves of the fine matrices read + whole coarse matrices written)"),

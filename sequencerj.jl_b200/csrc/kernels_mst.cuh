@@ -337,11 +337,12 @@ __global__ void __launch_bounds__(kKtWarps * 32, MINB) knn_tiles_kernel(KnnTileP
   const int i0 = I * kKtB, j0 = J * kKtB;
   const int nr = min(kKtB, N - i0);
   const bool diag = (I == J);
-  // the lane's four columns are adjacent (32 contiguous bytes per row; the interleaved mapping -- 16-byte pairs lane and
-  // lane + 32, 512 contiguous bytes per load instruction -- measured slower: MST stage 21.9 instead of 20.0 ms)
-  const int jc = j0 + 4 * lane;
-  auto col = [&](int c) { return jc + c; };
-  const bool ld_ok = jc < N, ld_ok2 = ld_ok;               // jc + 3 < ldD: ldD is a multiple of 16
+  // The lane's four columns are adjacent (32 contiguous bytes per row).  Measured and rejected: the interleaved mapping
+  // (16-byte pairs lane and lane + 32, so that each load instruction covers 512 contiguous bytes): MST stage 21.9
+  // instead of 20.0 ms; and loads written as conditional expressions instead of under one branch per row (the
+  // compiler then waits for each volatile load before the next): 22.9 ms.
+  const int jc = j0 + 4 * lane;                            // first of the lane's four columns
+  const bool ld_ok = jc < N;                               // jc + 3 < ldD: ldD is a multiple of 16
   const double* __restrict__ base = p.D + (int64_t)slot * p.strideD + (int64_t)i0 * p.ldD + jc;
   const unsigned long long* __restrict__ tau = p.tau + (int64_t)blockIdx.y * N;
   int* __restrict__ cnt = p.cnt + (int64_t)blockIdx.y * N;
@@ -352,7 +353,7 @@ __global__ void __launch_bounds__(kKtWarps * 32, MINB) knn_tiles_kernel(KnnTileP
   unsigned tjh[4];
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
-    tj[c] = (col(c) < N) ? tau[col(c)] : 0ull;
+    tj[c] = (jc + c < N) ? tau[jc + c] : 0ull;
     tjh[c] = (unsigned)(tj[c] >> 32);
   }
   // Hits are rare (~5 per 1,000 entries) and everything about them is kept out of the streaming loop, which only
@@ -396,10 +397,11 @@ __global__ void __launch_bounds__(kKtWarps * 32, MINB) knn_tiles_kernel(KnnTileP
   auto load_rows = [&](int r0) {
 #pragma unroll
     for (int u = 0; u < U; ++u)
-      {
-        const bool rok = r0 + u < nr;
-        na[u] = (rok && ld_ok) ? ldg_stream_u64x2(base + (int64_t)(r0 + u) * p.ldD) : make_ulonglong2(kKnnNone, kKnnNone);
-        nb[u] = (rok && ld_ok2) ? ldg_stream_u64x2(base + (int64_t)(r0 + u) * p.ldD + 2) : make_ulonglong2(kKnnNone, kKnnNone);
+      if (ld_ok && r0 + u < nr) {
+        na[u] = ldg_stream_u64x2(base + (int64_t)(r0 + u) * p.ldD);
+        nb[u] = ldg_stream_u64x2(base + (int64_t)(r0 + u) * p.ldD + 2);
+      } else {
+        na[u] = nb[u] = make_ulonglong2(kKnnNone, kKnnNone);
       }
   };
   load_rows(0);
@@ -429,9 +431,9 @@ __global__ void __launch_bounds__(kKtWarps * 32, MINB) knn_tiles_kernel(KnnTileP
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(base + (int64_t)r * p.ldD);
 #pragma unroll 1
         for (int c = 0; c < 4; ++c) {
-          const int j = col(c);
+          const int j = jc + c;
           if (j >= N || j == i) continue;
-          const unsigned long long xc = __ldg(src + (j - jc));
+          const unsigned long long xc = __ldg(src + c);
           const unsigned long long xv = max(xc, eps_bits);
           // the diagonal block holds (i, j) and (j, i): each entry is offered to its row only
           if (xv <= tir) offer(i, xv, j);

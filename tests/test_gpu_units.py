@@ -369,3 +369,27 @@ def test_elementwise_distances_metrics(seqj, oracle, handle, name):
         key = (met if g.metric == mid else seqj.WASS1D, g.scale)
         rel_close(r.EOSeg[key][0], g.eta_chunk, 1e-9)
         assert np.array_equal(r.EOAlgScale[key][1].parents, g.parents)
+
+
+def test_measure_dm_default_list_pass_at_a_ragged_size(seqj, handle, monkeypatch):
+    """N = 6150 (>= 6144: the upper-triangle list pass is the default; 6150 is neither a multiple of 4 nor of the
+    128-entry block edge, so the last block row / column and the row samples of the last rows are ragged): the tree, its
+    root, eta and the order equal the Prim kernels' on a random matrix and on one with a block of duplicated objects."""
+    rng = np.random.default_rng(17)
+    N = 6150
+    X = rng.random((N, 4))
+    X[5000:5100] = X[100:200]                                  # 100 duplicated objects: exact ties at the eps floor
+    G = X @ X.T
+    sq = np.diag(G).copy()
+    Dm = np.sqrt(np.maximum(sq[:, None] + sq[None, :] - 2.0 * G, 0.0)) + 1e-6
+    np.fill_diagonal(Dm, 1e-6)
+    Dm = np.triu(Dm, 1); Dm = Dm + Dm.T
+    monkeypatch.delenv("SEQJ_KNN", raising=False)
+    monkeypatch.delenv("SEQJ_MST", raising=False)
+    a = seqj.measure_dm(Dm, want_order=True)
+    monkeypatch.setenv("SEQJ_MST", "prim")
+    b = seqj.measure_dm(Dm, want_order=True)
+    monkeypatch.delenv("SEQJ_MST", raising=False)
+    assert _edge_set(a.mst) == _edge_set(b.mst)
+    assert a.root == b.root and a.eta == b.eta
+    assert np.array_equal(a.bfs.parents, b.bfs.parents) and np.array_equal(a.order, b.order)
