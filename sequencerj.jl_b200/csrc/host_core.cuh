@@ -154,15 +154,26 @@ struct DevPool {
       h->cached_bytes += b.first;
     }
   }
+  // `larger_ok`: the request may be served by a larger cached block.  Used for the N x N buffers that dominate a call
+  // -- the matrix pool of seqj_sequence, the proximity matrix of seqj_fuse / seqj_fuse_dev -- so that they hand the
+  // same block (nearly all of the device memory) back and forth.  Without it the fuse's request went to cudaMalloc,
+  // failed, released the whole cache, and the next seqj_sequence call did the same in the other direction: two full
+  // free / malloc cycles of ~170 GB per step (seen at config 4 on 2 GPUs once the sharded upload had forced a
+  // re-plan).  The block keeps its own size in the cache.
   template <typename T>
-  cudaError_t alloc(T** out, size_t count) {
+  cudaError_t alloc(T** out, size_t count, bool larger_ok = false) {
     const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~size_t(255);
     void* p = nullptr;
     auto it = h->cache.find(bytes);
+    if (it == h->cache.end() && larger_ok) it = h->cache.lower_bound(bytes);
     if (it != h->cache.end()) {
       p = it->second;
+      const size_t have = it->first;
       h->cache.erase(it);
-      h->cached_bytes -= bytes;
+      h->cached_bytes -= have;
+      blocks.emplace_back(have, p);
+      *out = static_cast<T*>(p);
+      return cudaSuccess;
     } else {
       cudaError_t e = cudaMalloc(&p, bytes);
       if (e == cudaErrorMemoryAllocation && !h->cache.empty()) {

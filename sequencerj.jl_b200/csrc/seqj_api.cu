@@ -479,7 +479,7 @@ static int sequence_impl(seqj_handle* h, const double* A_dev, int64_t M64, int64
   }
   // ONE pool of N x N matrices: every phase of the plan keeps its accumulators, wave slots and carry slots in it
   double* Mpool;
-  CU_TRY(c.pool.alloc(&Mpool, mat_elems * (size_t)plan.pool_slots));
+  CU_TRY(c.pool.alloc(&Mpool, mat_elems * (size_t)plan.pool_slots, /*larger_ok=*/true));
   GraphWS gws;
   ST_TRY(graphws_alloc(c, gws, std::max(plan.max_tasks, std::max(1, plan.max_done)), N));
 
@@ -1011,7 +1011,7 @@ static int fuse_impl(seqj_handle* h, int64_t N64, int ngroups, const double* eta
   CU_TRY(c.pool.alloc(&eta_f, 1)); CU_TRY(c.pool.alloc(&root_f, 1)); CU_TRY(c.pool.alloc(&par_f, (size_t)ldp));
   CU_TRY(c.pool.alloc(&fmst_i, (size_t)ldp)); CU_TRY(c.pool.alloc(&fmst_j, (size_t)ldp));
   CU_TRY(c.pool.alloc(&fmst_w, (size_t)ldp)); CU_TRY(c.pool.alloc(&order_f, (size_t)ldp));
-  CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&Sbuf, (size_t)N * ldD));
+  CU_TRY(c.pool.alloc(&edge_val, (size_t)G * ldp)); CU_TRY(c.pool.alloc(&Sbuf, (size_t)N * ldD, /*larger_ok=*/true));
   if (pack_dev) {
     int* slot_d;
     CU_TRY(c.pool.alloc(&slot_d, (size_t)G));

@@ -7,6 +7,7 @@ combination stay on the GPU that owns it.  The only exchange is the per-group re
 """
 from __future__ import annotations
 
+import os
 import time
 
 import numpy as np
@@ -202,6 +203,12 @@ def _finish_sharded(final, local, t0, t1, t2, t3, t_up=0.0):
     return final
 
 
+def _torch_cached_free(device) -> int:
+    """Bytes torch's caching allocator holds without using them (it serves new tensors from there first)."""
+    import torch
+    return int(torch.cuda.memory_reserved(device) - torch.cuda.memory_allocated(device))
+
+
 def _sequence_sharded_device(At, scales, metrics, rank, world, handle, device_ptr, dist, device, owner, mask):
     import torch
     N, M = At.shape
@@ -215,8 +222,27 @@ def _sequence_sharded_device(At, scales, metrics, rank, world, handle, device_pt
     tu = time.perf_counter()
     keep = None
     if device_ptr is None:
+        # The library keeps its workspace cached between calls and sizes it from the memory that was free when it was
+        # planned; if the upload buffers do not fit next to it (config 4: 0.74 GB per rank), every rank gives the cache
+        # back and the next call plans around them.  The decision is collective: the all-gather below needs every rank.
+        if cuda:
+            h = handle or api.default_handle()
+            rows = -(-N // world)
+            need = (rows + world * rows) * M * 8 + (16 << 20)         # shard + gathered copy (+ allocator slack)
+            tight = torch.zeros(1, dtype=torch.int32, device=device)
+            if torch.cuda.mem_get_info(device)[0] + _torch_cached_free(device) < need:
+                tight += 1
+            dist.all_reduce(tight, op=dist.ReduceOp.MAX)
+            if int(tight.item()):
+                h.check(h.lib.seqj_release_workspace(h.h))
+            if os.environ.get("SEQJ_TRACE_SHARD"):
+                print(f"[shard {rank}] free {torch.cuda.mem_get_info(device)[0] >> 20} MiB, torch cache {_torch_cached_free(device) >> 20} MiB, "
+                      f"need {need >> 20} MiB, released {int(tight.item())}, {1e3 * (time.perf_counter() - tu):.1f} ms", flush=True)
         keep = upload_sharded(At, rank, world, dist, device)
         device_ptr = keep.data_ptr()
+        if cuda and os.environ.get("SEQJ_TRACE_SHARD"):
+            torch.cuda.synchronize(device)
+            print(f"[shard {rank}] upload done at {1e3 * (time.perf_counter() - tu):.1f} ms", flush=True)
     cap = int(max(int((owner == r).sum()) for r in range(world)))
     stride = 2 * N                                                  # seqj_pack_stride(N)
     pack = torch.zeros((cap, stride), dtype=torch.float64, device=device)
